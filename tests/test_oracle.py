@@ -1,0 +1,65 @@
+"""Pins oracle/lpformer_oracle.py (and oracle/ref_port.py) to the golden vectors
+generated from the unmodified reference (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from oracle import lpformer_oracle as O
+
+
+def graph_of(g):
+    e, n = g["edges"], g.n
+    row = np.concatenate([e[0], e[1]])
+    col = np.concatenate([e[1], e[0]])
+    w = np.concatenate([g["edge_weight"], g["edge_weight"]])
+    adj = O.CSR.from_coo(row, col, None, n)
+    adj_w = O.CSR.from_coo(row, col, w, n)
+    ppr = O.CSR.from_coo(g["ppr_row"], g["ppr_col"], g["ppr_val"], n)
+    return adj, adj_w, ppr
+
+
+def test_selection_bit_exact(golden):
+    g = golden
+    adj, _, ppr = graph_of(g)
+    mode, sets = O.select_sets(adj, ppr, g["links"], g.cfg["thresh_cn"], g.cfg["thresh_1hop"], g.cfg["thresh_non1hop"])
+    assert mode == g.cfg["mask"]
+    ref = g.sets()
+    assert set(ref) == set(sets)
+    for t, (ix, src, tgt) in ref.items():
+        li, nd, qa, qb = sets[t]
+        assert np.array_equal(ix[0], li), t
+        assert np.array_equal(ix[1], nd), t
+        assert np.array_equal(src.view(np.uint32), qa.view(np.uint32)), t   # bit-exact fp32
+        assert np.array_equal(tgt.view(np.uint32), qb.view(np.uint32)), t
+    counts = O.structure_counts(sets, mode, g["links"].shape[1])
+    assert np.array_equal(counts, g["counts"])
+
+
+def test_propagate(golden):
+    g = golden
+    _, adj_w, _ = graph_of(g)
+    X = O.propagate(g["x"], adj_w, g.model_params, g.cfg)
+    np.testing.assert_allclose(X, g["X_node"], rtol=1e-4, atol=2e-5)
+
+
+def test_features_and_scores(golden):
+    g = golden
+    adj, _, ppr = graph_of(g)
+    feats, _, counts, alpha = O.link_features(g["links"], g["X_node"], adj, ppr, g.model_params, g.cfg)
+    d = g.cfg["dim"]
+    np.testing.assert_allclose(feats[:, :d], g["el"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(feats[:, d:], g["pw"], rtol=1e-4, atol=2e-5)
+    logit, prob = O.mlp_score(feats, g.score_params)
+    np.testing.assert_allclose(prob, g["prob"], rtol=1e-4, atol=1e-6)
+    # attention weights (debug output of the last layer): [2, S] = (link idx, head-mean alpha)
+    aw = g["att_weights"]
+    np.testing.assert_allclose(alpha.mean(1), aw[1], rtol=1e-4, atol=1e-6)
+
+
+def test_ppr_push_matches_reference_kernel(golden):
+    g = golden
+    if g.cfg["eps"] < 1e-4:
+        pytest.skip("pure-Python push is slow for tiny eps; covered by the C oracle test")
+    adj, _, _ = graph_of(g)
+    ppr = O.ppr_push(adj.indptr, adj.indices, g.cfg["alpha"], g.cfg["eps"])
+    assert np.array_equal(ppr.indices, g["ppr_col"])
+    assert np.array_equal(ppr.val.view(np.uint32), g["ppr_val"].view(np.uint32))
