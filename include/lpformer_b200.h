@@ -1,0 +1,160 @@
+/*
+ * lpformer_b200 — C ABI of the B200 (sm_100a) kernels behind LPFormer's per-link
+ * pairwise-encoding path.
+ *
+ * The reference (HarryShomer/LPFormer) has no FFI: its hot path is Python calling
+ * torch.sparse / torch_scatter / PyG library kernels.  Each entry point below names
+ * the reference code it replaces (paths relative to the reference's src/).  The
+ * Python module lpformer_b200.LinkTransformer binds these through ctypes with
+ * tensor.data_ptr() values; nothing torch-typed crosses this boundary.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - no entry point allocates, synchronises or keeps global state (except the
+ *     thread-local last-error string); launches are stream-ordered;
+ *   - return value: 0 = success, negative = error (see lpf_last_error());
+ *   - CSR tables: rowptr int64 [n+1], col int32 [nnz] ascending within a row,
+ *     val fp32 [nnz];
+ *   - links: int64 [2, BS] row-major (row 0 = source a, row 1 = target b), the
+ *     layout of `batch` in models/link_transformer.py:82;
+ *   - dense matrices are fp32 row-major with an explicit leading dimension.
+ */
+#ifndef LPFORMER_B200_H
+#define LPFORMER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LPF_OK 0
+#define LPF_ERR_INVALID -1   /* bad argument */
+#define LPF_ERR_CUDA -2      /* CUDA runtime error (launch/config) */
+#define LPF_ERR_UNSUPPORTED -3
+
+/* selection modes, models/link_transformer.py:39-44 */
+#define LPF_MODE_CN 0
+#define LPF_MODE_1HOP 1
+#define LPF_MODE_ALL 2
+
+/* node-set types, concatenation order of models/link_transformer.py:161 */
+#define LPF_T_CN 0
+#define LPF_T_1HOP 1
+#define LPF_T_NON1HOP 2
+
+/* GEMM epilogue flags */
+#define LPF_EPI_NONE 0
+#define LPF_EPI_RELU 1
+#define LPF_EPI_SIGMOID 2
+
+int lpf_abi_version(void);
+/* Thread-local description of the last error returned on this thread. */
+const char* lpf_last_error(void);
+/* 1 if a CUDA device of compute capability 10.x is current, else 0 (no error set). */
+int lpf_device_ok(void);
+
+/* ------------------------------------------------------------------------- *
+ * K1  node selection — replaces compute_node_mask / get_ppr_vals /
+ *     get_non_1hop_ppr (models/link_transformer.py:214-319, :434-481) and the
+ *     scatter counts of get_structure_cnts/get_count (:340-386).
+ *
+ * Pass 1 (count): counts[t*BS + i] = |set_t(link i)| for t in {CN,1HOP,NON1HOP}
+ *                 (types the mode does not produce are written as 0).
+ * Scan          : ptr[0..3*BS] = exclusive prefix sum of counts (int64), so type t
+ *                 of link i owns rows [ptr[t*BS+i], ptr[t*BS+i+1]) of the pair
+ *                 arrays; the pair arrays are therefore ordered type-major, then
+ *                 by (link, node) — the order of torch.cat((cn, onehop, non1hop)).
+ * Pass 2 (fill) : node[s], src_ppr[s], tgt_ppr[s] (and link[s] if non-NULL).
+ * src_ppr/tgt_ppr are q(P(a,u)), q(P(b,u)) with q(p) = fl32(p+1)-1 (absent -> 0),
+ * the value the reference thresholds and feeds to the RPE MLPs.
+ * ------------------------------------------------------------------------- */
+int lpf_select_count(const int64_t* links, int64_t bs,
+                     const int64_t* adj_rowptr, const int32_t* adj_col,
+                     const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val,
+                     float th_cn, float th_1hop, float th_non1hop, int mode,
+                     int32_t* counts, void* stream);
+
+/* Exclusive scan of n int32 counts into n+1 int64 offsets (single launch).
+ * `scratch` must hold lpf_scan_scratch_bytes(n) bytes. */
+int64_t lpf_scan_scratch_bytes(int64_t n);
+int lpf_scan_counts(const int32_t* counts, int64_t n, int64_t* ptr, void* scratch, void* stream);
+
+int lpf_select_fill(const int64_t* links, int64_t bs,
+                    const int64_t* adj_rowptr, const int32_t* adj_col,
+                    const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val,
+                    float th_cn, float th_1hop, float th_non1hop, int mode,
+                    const int64_t* ptr,
+                    int32_t* node, float* src_ppr, float* tgt_ppr, int32_t* link /* may be NULL */,
+                    void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * RPE hidden vector — first half of get_pos_encodings (models/link_transformer.py
+ * :182-211) with MLP = Linear(2,d) -> LayerNorm -> ReLU (models/other_models.py
+ * :125-133):  hsum[s,:] = h(pa,pb) + h(pb,pa),  h(x,y) = ReLU(LN(W1 [x,y] + b1)).
+ * The second Linear and lin_r's PE half are folded into one contraction done by
+ * lpf_gemm.  w1 is the [d,2] weight, b1/ln_w/ln_b are [d].
+ * Rows [row0, row0+rows) of the pair arrays are processed (one type at a time).
+ * ------------------------------------------------------------------------- */
+int lpf_rpe_hidden(const float* src_ppr, const float* tgt_ppr, int64_t row0, int64_t rows,
+                   const float* w1, const float* b1, const float* ln_w, const float* ln_b,
+                   int32_t d, float* hsum, int64_t ld_hsum, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Dense contraction  C[M,N] = epi( A[M,K] . W[N,K]^T + bias[N] )  — every
+ * nn.Linear on the path (modules/layers.py:130-131,208-214; models/other_models.py
+ * :125-138,173-179; GCNConv.lin).  W is the nn.Linear weight layout.  bias may be
+ * NULL.  `bias_scale` multiplies the bias (2.0 for lin_l(e1)+lin_l(e2)).
+ * ------------------------------------------------------------------------- */
+int lpf_gemm(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+             float bias_scale, float* C, int64_t ldc, int64_t M, int32_t N, int32_t K,
+             int epilogue, void* stream);
+
+/* Row-wise LayerNorm (eps 1e-5) over the first `n` columns, optional ReLU, in place
+ * or out of place (X may equal Y).  nn.LayerNorm + F.relu of MLP/GCN/gnn_norm.
+ * If `residual` is non-NULL the result is residual + act(LN(x)) (GCN.forward :71).
+ * gamma == beta == NULL skips the normalisation (GCN with layer_norm=False). */
+int lpf_layernorm_act(const float* X, int64_t ldx, const float* gamma, const float* beta,
+                      const float* residual, int64_t ldr, float* Y, int64_t ldy,
+                      int64_t rows, int32_t n, int relu, void* stream);
+
+/* Link-level gathers (models/link_transformer.py:101-102,143-144; train/testing.py:29,113):
+ * xsum[i,:] = X[a_i,:] + X[b_i,:]   (input of lin_l, since lin_l(e1)+lin_l(e2) = W_l(e1+e2)+2b)
+ * xprod[i,:] = X[a_i,:] * X[b_i,:]  (input of elementwise_lin).  Either output may be NULL. */
+int lpf_gather_links(const int64_t* links, int64_t bs, const float* X, int64_t ldx, int32_t d,
+                     float* xsum, int64_t ld_sum, float* xprod, int64_t ld_prod, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * K4  fused per-link attention — replaces LinkTransformerLayer.forward +
+ * LinkAttention.forward/message (modules/layers.py:39-82,161-224): for link i and
+ * each selected pair s (all three type segments):
+ *     v_s   = KV[node[s],:] + R[s,:]                     (lin_r, split as in App. B)
+ *     sc_sh = sum_c att[h,c] * leaky_relu(v_s[h,c] * Q[i,h,c], 0.2)
+ *     alpha = segment softmax over the link's pairs (max-subtracted, denom + 1e-16)
+ *     out_i = LayerNorm_{H*C}( sum_s alpha_s v_s + bias )
+ * and appends the set counts (get_structure_cnts) as fp32 columns after the H*C
+ * outputs: mode ALL -> (cn, 1hop, non1hop, cn+1hop); 1HOP -> (cn, 1hop, cn+1hop);
+ * CN -> (cn); pass write_counts=0 for inner layers of a multi-layer stack.
+ * alpha_out (may be NULL) receives the head-mean attention weight per pair.
+ * ------------------------------------------------------------------------- */
+int lpf_attend_fused(const int64_t* ptr, int64_t bs, const int32_t* node,
+                     const float* KV, int64_t ld_kv, const float* R, int64_t ld_r,
+                     const float* Q, int64_t ld_q,
+                     const float* att, const float* bias, const float* ln_w, const float* ln_b,
+                     int32_t heads, int32_t ch, int mode, int write_counts,
+                     float* out, int64_t ld_out, float* alpha_out, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * K2  GCN message passing — GCNConv's SpMM (models/other_models.py:66 via
+ * torch_sparse.matmul): Y[r,:] = sum_k val[k] * XW[col[k],:] + bias over CSR row r,
+ * for rows [row0, row0+rows) (row sharding for multi-GPU).
+ * ------------------------------------------------------------------------- */
+int lpf_gcn_spmm(const int64_t* rowptr, const int32_t* col, const float* val,
+                 int64_t row0, int64_t rows, const float* XW, int64_t ld_xw, const float* bias,
+                 int32_t d, float* Y, int64_t ldy, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LPFORMER_B200_H */

@@ -1,0 +1,242 @@
+// K4 — fused per-link attention: gather -> score -> segment softmax -> weighted sum ->
+// +bias -> LayerNorm (+ set counts), one warp per link, each link's set kept on chip.
+//
+// Replaces LinkTransformerLayer.forward + LinkAttention.forward/message (reference
+// modules/layers.py:39-82, :161-224), which materialise [S,2d] gathers, run lin_l / lin_r
+// per pair and use three scatter passes for the softmax.  Algebra as in SURVEY App. B:
+//   v_s = KV[node_s] + R_s   (R_s carries the RPE contraction and lin_r's bias)
+//   sc_{s,h} = sum_c att[h,c] * leaky_relu(v_s[h,c] * Q_i[h,c], 0.2)
+//   out_i = LN( sum_s softmax_s(sc)_h v_s[h,:] + bias )     (empty set -> LN(bias))
+// The softmax is evaluated online (running max / sum), which is the same quantity as the
+// reference's max-subtracted form exp(sc-max)/(sum+1e-16).
+#include "common.cuh"
+
+namespace lpf {
+
+struct AttendParams {
+    const int64_t* ptr;
+    int64_t bs;
+    const int32_t* node;
+    const float* KV;
+    int64_t ld_kv;
+    const float* R;
+    int64_t ld_r;
+    const float* Q;
+    int64_t ld_q;
+    const float* att;
+    const float* bias;
+    const float* ln_w;
+    const float* ln_b;
+    int heads, ch, mode, write_counts;
+    float* out;
+    int64_t ld_out;
+    float* alpha_out;
+};
+
+constexpr int kAttWarps = 8;
+
+template <int H, int KC>
+__global__ void __launch_bounds__(kAttWarps * 32) attend_kernel(AttendParams p) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int C = p.ch, HC = H * C;
+    float att[H][KC];
+#pragma unroll
+    for (int h = 0; h < H; ++h)
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            const int c = lane + 32 * k;
+            att[h][k] = (c < C) ? __ldg(p.att + h * C + c) : 0.f;
+        }
+
+    for (int64_t i = (int64_t)blockIdx.x * kAttWarps + warp; i < p.bs; i += (int64_t)gridDim.x * kAttWarps) {
+        float q[H][KC], acc[H][KC], mx[H], den[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            mx[h] = -INFINITY;
+            den[h] = 0.f;
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                const int c = lane + 32 * k;
+                q[h][k] = (c < C) ? __ldg(p.Q + i * p.ld_q + h * C + c) : 0.f;
+                acc[h][k] = 0.f;
+            }
+        }
+        int64_t seg_lo[3], seg_hi[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            seg_lo[t] = __ldg(p.ptr + t * p.bs + i);
+            seg_hi[t] = __ldg(p.ptr + t * p.bs + i + 1);
+        }
+
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            for (int64_t s0 = seg_lo[t]; s0 < seg_hi[t]; s0 += 32) {
+                const int cnt = (int)min((int64_t)32, seg_hi[t] - s0);
+                const int32_t my_node = (lane < cnt) ? __ldg(p.node + s0 + lane) : 0;
+                for (int j = 0; j < cnt; ++j) {
+                    const int64_t u = __shfl_sync(kFull, my_node, j);
+                    const float* kv = p.KV + u * p.ld_kv;
+                    const float* rr = p.R + (s0 + j) * p.ld_r;
+                    float v[H][KC], sc[H];
+#pragma unroll
+                    for (int h = 0; h < H; ++h) {
+                        float part = 0.f;
+#pragma unroll
+                        for (int k = 0; k < KC; ++k) {
+                            const int c = lane + 32 * k;
+                            float val = 0.f;
+                            if (c < C) val = __ldg(kv + h * C + c) + __ldg(rr + h * C + c);
+                            v[h][k] = val;
+                            float x = val * q[h][k];
+                            x = (x > 0.f) ? x : 0.2f * x;
+                            part = fmaf(att[h][k], x, part);
+                        }
+                        sc[h] = warp_sum(part);
+                    }
+#pragma unroll
+                    for (int h = 0; h < H; ++h) {
+                        const float m_new = fmaxf(mx[h], sc[h]);
+                        const float scale = expf(mx[h] - m_new);  // exp(-inf) = 0 on the first pair
+                        const float w = expf(sc[h] - m_new);
+                        den[h] = fmaf(den[h], scale, w);
+#pragma unroll
+                        for (int k = 0; k < KC; ++k) acc[h][k] = fmaf(acc[h][k], scale, w * v[h][k]);
+                        mx[h] = m_new;
+                    }
+                }
+            }
+        }
+
+        // head-mean attention weights (debug output of the reference, modules/layers.py:73-75)
+        if (p.alpha_out) {
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                for (int64_t s = seg_lo[t]; s < seg_hi[t]; ++s) {
+                    const int64_t u = __ldg(p.node + s);
+                    const float* kv = p.KV + u * p.ld_kv;
+                    const float* rr = p.R + s * p.ld_r;
+                    float mean_alpha = 0.f;
+#pragma unroll
+                    for (int h = 0; h < H; ++h) {
+                        float part = 0.f;
+#pragma unroll
+                        for (int k = 0; k < KC; ++k) {
+                            const int c = lane + 32 * k;
+                            float val = 0.f;
+                            if (c < C) val = __ldg(kv + h * C + c) + __ldg(rr + h * C + c);
+                            float x = val * q[h][k];
+                            x = (x > 0.f) ? x : 0.2f * x;
+                            part = fmaf(att[h][k], x, part);
+                        }
+                        const float sc = warp_sum(part);
+                        mean_alpha += expf(sc - mx[h]) / (den[h] + 1e-16f);
+                    }
+                    if (lane == 0) p.alpha_out[s] = mean_alpha / (float)H;
+                }
+            }
+        }
+
+        // out = LN(acc / (den + 1e-16) + bias)
+        float o[H][KC];
+        float sum = 0.f;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            const float inv = 1.0f / (den[h] + 1e-16f);
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                const int c = lane + 32 * k;
+                o[h][k] = (c < C) ? fmaf(acc[h][k], inv, __ldg(p.bias + h * C + c)) : 0.f;
+                sum += o[h][k];
+            }
+        }
+        const float mean = warp_sum(sum) / (float)HC;
+        float var = 0.f;
+#pragma unroll
+        for (int h = 0; h < H; ++h)
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                const float dlt = (lane + 32 * k < C) ? o[h][k] - mean : 0.f;
+                var = fmaf(dlt, dlt, var);
+            }
+        const float rstd = rsqrtf(warp_sum(var) / (float)HC + 1e-5f);
+        float* out = p.out + i * p.ld_out;
+#pragma unroll
+        for (int h = 0; h < H; ++h)
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                const int c = lane + 32 * k;
+                if (c < C) out[h * C + c] = fmaf((o[h][k] - mean) * rstd, __ldg(p.ln_w + h * C + c), __ldg(p.ln_b + h * C + c));
+            }
+        if (p.write_counts && lane == 0) {
+            // get_structure_cnts / get_count (reference models/link_transformer.py:340-386),
+            // column order of :155, :173, :175
+            const float n_cn = (float)(seg_hi[0] - seg_lo[0]);
+            const float n_1h = (float)(seg_hi[1] - seg_lo[1]);
+            const float n_n1 = (float)(seg_hi[2] - seg_lo[2]);
+            if (p.mode == LPF_MODE_CN) {
+                out[HC] = n_cn;
+            } else if (p.mode == LPF_MODE_1HOP) {
+                out[HC] = n_cn;
+                out[HC + 1] = n_1h;
+                out[HC + 2] = n_cn + n_1h;
+            } else {
+                out[HC] = n_cn;
+                out[HC + 1] = n_1h;
+                out[HC + 2] = n_n1;
+                out[HC + 3] = n_cn + n_1h;
+            }
+        }
+    }
+}
+
+template <int H>
+static int launch_attend_h(const AttendParams& p, cudaStream_t st) {
+    int64_t blocks = (p.bs + kAttWarps - 1) / kAttWarps;
+    const int64_t cap = (int64_t)kNumSMs * 8 * 4;
+    if (blocks > cap) blocks = cap;
+    const unsigned g = (unsigned)blocks;
+    const int kc = (p.ch + 31) / 32;
+    if (kc * H > 16) {
+        set_error("lpf_attend_fused: heads*ceil(ch/32) = %d exceeds 16", kc * H);
+        return LPF_ERR_UNSUPPORTED;
+    }
+    if (kc <= 1) attend_kernel<H, 1><<<g, kAttWarps * 32, 0, st>>>(p);
+    else if (kc <= 2) { if constexpr (H * 2 <= 16) attend_kernel<H, 2><<<g, kAttWarps * 32, 0, st>>>(p); }
+    else if (kc <= 4) { if constexpr (H * 4 <= 16) attend_kernel<H, 4><<<g, kAttWarps * 32, 0, st>>>(p); }
+    else if (kc <= 8) { if constexpr (H * 8 <= 16) attend_kernel<H, 8><<<g, kAttWarps * 32, 0, st>>>(p); }
+    else { if constexpr (H * 16 <= 16) attend_kernel<H, 16><<<g, kAttWarps * 32, 0, st>>>(p); }
+    return check_launch("lpf_attend_fused");
+}
+
+}  // namespace lpf
+
+using namespace lpf;
+
+extern "C" int lpf_attend_fused(const int64_t* ptr, int64_t bs, const int32_t* node, const float* KV, int64_t ld_kv,
+                                const float* R, int64_t ld_r, const float* Q, int64_t ld_q, const float* att,
+                                const float* bias, const float* ln_w, const float* ln_b, int32_t heads, int32_t ch,
+                                int mode, int write_counts, float* out, int64_t ld_out, float* alpha_out,
+                                void* stream) {
+    LPF_REQUIRE(bs >= 0, "negative batch size");
+    if (bs == 0) return LPF_OK;
+    LPF_REQUIRE(ptr && KV && Q && att && bias && ln_w && ln_b && out, "NULL argument");
+    LPF_REQUIRE(heads >= 1 && ch >= 1, "bad heads/ch");
+    LPF_REQUIRE(mode == LPF_MODE_CN || mode == LPF_MODE_1HOP || mode == LPF_MODE_ALL, "bad mode");
+    const int hc = heads * ch;
+    const int cd = !write_counts ? 0 : (mode == LPF_MODE_CN ? 1 : (mode == LPF_MODE_1HOP ? 3 : 4));
+    LPF_REQUIRE(ld_kv >= hc && ld_q >= hc && ld_out >= hc + cd, "leading dimension too small");
+    LPF_REQUIRE(R == nullptr || ld_r >= hc, "ld_r too small");
+    // node / R may be NULL only if every set is empty; the kernel never dereferences them then.
+    AttendParams p{ptr, bs, node, KV, ld_kv, R, ld_r, Q, ld_q, att, bias, ln_w, ln_b,
+                   heads, ch, mode, write_counts, out, ld_out, alpha_out};
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (heads) {
+        case 1: return launch_attend_h<1>(p, st);
+        case 2: return launch_attend_h<2>(p, st);
+        case 4: return launch_attend_h<4>(p, st);
+        case 8: return launch_attend_h<8>(p, st);
+        default:
+            set_error("lpf_attend_fused: heads must be 1, 2, 4 or 8 (got %d)", heads);
+            return LPF_ERR_UNSUPPORTED;
+    }
+}

@@ -1,0 +1,332 @@
+// K1 — per-link node selection on sorted CSR rows (count pass / fill pass).
+//
+// Replaces the sparse-COO algebra of compute_node_mask / get_ppr_vals /
+// get_non_1hop_ppr (reference models/link_transformer.py:214-319, :434-481): for a
+// link (a,b) the reference slices rows a,b out of the N x N COO adjacency mask and PPR
+// matrix, adds / multiplies / coalesces them (a sort over every entry of the batch)
+// and filters by threshold.  Here one warp owns one link and walks the two sorted
+// adjacency rows (and, in mode ALL, the two sorted PPR rows) with a warp-cooperative
+// merge-path over shared-memory windows; membership / PPR look-ups are binary searches
+// into the other rows.  Output order (type-major, then link, then ascending node id)
+// and values (q(p) = fl32(p+1)-1) are bit-identical to the reference's.
+#include <limits.h>
+
+#include "common.cuh"
+
+namespace lpf {
+
+struct SelectParams {
+    const int64_t* links;
+    int64_t bs;
+    const int64_t* adj_rowptr;
+    const int32_t* adj_col;
+    const int64_t* ppr_rowptr;
+    const int32_t* ppr_col;
+    const float* ppr_val;
+    float th_cn, th_1hop, th_non1hop;
+    int mode;
+    int32_t* counts;     // count pass: [3*bs]
+    const int64_t* ptr;  // fill pass: [3*bs+1]
+    int32_t* node;
+    float* pa;
+    float* pb;
+    int32_t* link;
+};
+
+constexpr int kSelWarps = 8;  // warps (= links in flight) per CTA
+
+// Walks the sorted union of two duplicate-free ascending rows A[0..na) and B[0..nb), 32
+// union slots per step.  All 32 lanes call f(valid, u, inA, idxA, inB, idxB) convergently
+// (so f may use warp collectives); slots are in ascending order of u across lanes and
+// steps, each distinct u is valid exactly once.  wa/wb: 32-int shared windows of this warp.
+template <class F>
+__device__ __forceinline__ void warp_union(const int32_t* __restrict__ A, int na,
+                                           const int32_t* __restrict__ B, int nb,
+                                           int32_t* wa, int32_t* wb, int lane, F&& f) {
+    int ia = 0, ib = 0;
+    int32_t prev_a = -1;  // last element of A consumed by earlier windows
+    while (ia < na || ib < nb) {
+        const int32_t la = (ia + lane < na) ? __ldg(A + ia + lane) : INT_MAX;
+        const int32_t lb = (ib + lane < nb) ? __ldg(B + ib + lane) : INT_MAX;
+        __syncwarp();
+        wa[lane] = la;
+        wb[lane] = lb;
+        __syncwarp();
+        // merge-path split of diagonal `lane` (ties: A first): i = #A among the first `lane` slots
+        int lo = 0, hi = lane;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (wa[mid] <= wb[lane - 1 - mid]) lo = mid + 1; else hi = mid;
+        }
+        const int i = lo, j = lane - lo;
+        const int32_t av = wa[i], bv = wb[j];
+        const bool take_a = av <= bv;
+        const int32_t u = take_a ? av : bv;
+        bool valid = u != INT_MAX;
+        bool in_a, in_b;
+        if (take_a) {
+            in_a = true;
+            in_b = (bv == u);
+        } else {
+            in_a = false;
+            in_b = true;
+            const int32_t before = (i > 0) ? wa[i - 1] : prev_a;
+            if (before == u) valid = false;  // B's copy of a common element: already emitted
+        }
+        f(valid, u, in_a, ia + i, in_b, ib + j);
+        const int n_a = __shfl_sync(kFull, i + (take_a ? 1 : 0), 31);
+        if (n_a > 0) prev_a = wa[n_a - 1];
+        ia += n_a;
+        ib += 32 - n_a;
+    }
+}
+
+// (present, q(P(x,u))) by binary search in a PPR row
+__device__ __forceinline__ float ppr_lookup_q(const int32_t* __restrict__ pc, const float* __restrict__ pv,
+                                              int n, int32_t u) {
+    const int k = lower_bound(pc, n, u);
+    if (k < n && __ldg(pc + k) == u) return quantise(__ldg(pv + k));
+    return 0.0f;
+}
+__device__ __forceinline__ bool row_contains(const int32_t* __restrict__ c, int n, int32_t u) {
+    const int k = lower_bound(c, n, u);
+    return k < n && __ldg(c + k) == u;
+}
+__device__ __forceinline__ float fsign(float v) { return (v > 0.0f) ? 1.0f : ((v < 0.0f) ? -1.0f : 0.0f); }
+
+template <bool FILL>
+__global__ void __launch_bounds__(kSelWarps * 32) select_kernel(SelectParams p) {
+    __shared__ int32_t win[kSelWarps][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int32_t* wa = win[warp];
+    int32_t* wb = win[warp] + 32;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    for (int64_t i = (int64_t)blockIdx.x * kSelWarps + warp; i < p.bs; i += (int64_t)gridDim.x * kSelWarps) {
+        const int64_t a = __ldg(p.links + i), b = __ldg(p.links + p.bs + i);
+        const int64_t a0 = __ldg(p.adj_rowptr + a), b0 = __ldg(p.adj_rowptr + b);
+        const int na = (int)(__ldg(p.adj_rowptr + a + 1) - a0), nb = (int)(__ldg(p.adj_rowptr + b + 1) - b0);
+        const int64_t pa0 = __ldg(p.ppr_rowptr + a), pb0 = __ldg(p.ppr_rowptr + b);
+        const int npa = (int)(__ldg(p.ppr_rowptr + a + 1) - pa0), npb = (int)(__ldg(p.ppr_rowptr + b + 1) - pb0);
+        const int32_t* Aa = p.adj_col + a0;
+        const int32_t* Ab = p.adj_col + b0;
+        const int32_t* Pac = p.ppr_col + pa0;
+        const int32_t* Pbc = p.ppr_col + pb0;
+        const float* Pav = p.ppr_val + pa0;
+        const float* Pbv = p.ppr_val + pb0;
+
+        int c_cn = 0, c_1h = 0, c_n1 = 0;  // warp-uniform running sizes
+        int64_t o_cn = 0, o_1h = 0, o_n1 = 0;
+        if (FILL) {
+            o_cn = __ldg(p.ptr + i);
+            o_1h = __ldg(p.ptr + p.bs + i);
+            o_n1 = __ldg(p.ptr + 2 * p.bs + i);
+        }
+        const bool want_1h = p.mode != LPF_MODE_CN;
+
+        // ---- CN (in both adjacency rows) and 1-hop (in exactly one), :229-250, :279-319
+        warp_union(Aa, na, Ab, nb, wa, wb, lane,
+                   [&](bool valid, int32_t u, bool in_a, int, bool in_b, int) {
+                       const bool is_cn = valid && in_a && in_b;
+                       const bool is_1h = valid && want_1h && (in_a != in_b);
+                       float qa = 0.0f, qb = 0.0f;
+                       if (is_cn || is_1h) {
+                           qa = ppr_lookup_q(Pac, Pav, npa, u);
+                           qb = ppr_lookup_q(Pbc, Pbv, npb, u);
+                       }
+                       const bool k_cn = is_cn && qa >= p.th_cn && qb >= p.th_cn;
+                       const bool k_1h = is_1h && qa >= p.th_1hop && qb >= p.th_1hop;
+                       const unsigned m_cn = __ballot_sync(kFull, k_cn);
+                       const unsigned m_1h = __ballot_sync(kFull, k_1h);
+                       if (FILL) {
+                           if (k_cn || k_1h) {
+                               const int64_t s = k_cn ? o_cn + c_cn + __popc(m_cn & lt_mask)
+                                                      : o_1h + c_1h + __popc(m_1h & lt_mask);
+                               p.node[s] = u;
+                               p.pa[s] = qa;
+                               p.pb[s] = qb;
+                               if (p.link) p.link[s] = (int32_t)i;
+                           }
+                       }
+                       c_cn += __popc(m_cn);
+                       c_1h += __popc(m_1h);
+                   });
+
+        // ---- >1-hop: union of the two PPR rows, entries on A(a) U A(b) zeroed, :443-481
+        if (p.mode == LPF_MODE_ALL) {
+            warp_union(Pac, npa, Pbc, npb, wa, wb, lane,
+                       [&](bool valid, int32_t u, bool in_a, int ka, bool in_b, int kb) {
+                           float va = 0.0f, vb = 0.0f;
+                           bool keep = false;
+                           if (valid) {
+                               if (in_a) va = __ldg(Pav + ka);
+                               if (in_b) vb = __ldg(Pbv + kb);
+                               if (row_contains(Aa, na, u) || row_contains(Ab, nb, u)) { va = 0.0f; vb = 0.0f; }
+                               const float sv = __fsub_rn(__fadd_rn(va, fsign(vb)), 1.0f);
+                               const float tv = __fsub_rn(__fadd_rn(vb, fsign(va)), 1.0f);
+                               keep = sv >= p.th_non1hop && tv >= p.th_non1hop;
+                               va = sv;
+                               vb = tv;
+                           }
+                           const unsigned m = __ballot_sync(kFull, keep);
+                           if (FILL && keep) {
+                               const int64_t s = o_n1 + c_n1 + __popc(m & lt_mask);
+                               p.node[s] = u;
+                               p.pa[s] = va;
+                               p.pb[s] = vb;
+                               if (p.link) p.link[s] = (int32_t)i;
+                           }
+                           c_n1 += __popc(m);
+                       });
+        }
+
+        if (!FILL && lane == 0) {
+            p.counts[i] = c_cn;
+            p.counts[p.bs + i] = c_1h;
+            p.counts[2 * p.bs + i] = c_n1;
+        }
+    }
+}
+
+static int launch_select(bool fill, const SelectParams& p, cudaStream_t st) {
+    if (p.bs == 0) return LPF_OK;
+    int64_t blocks = (p.bs + kSelWarps - 1) / kSelWarps;
+    const int64_t cap = (int64_t)kNumSMs * 8 * 4;  // 8 CTAs/SM resident, 4 waves
+    if (blocks > cap) blocks = cap;
+    if (fill) select_kernel<true><<<(unsigned)blocks, kSelWarps * 32, 0, st>>>(p);
+    else select_kernel<false><<<(unsigned)blocks, kSelWarps * 32, 0, st>>>(p);
+    return check_launch(fill ? "lpf_select_fill" : "lpf_select_count");
+}
+
+// ---------------------------------------------------------------------------------------
+// exclusive scan int32 -> int64 (two launches: tile sums, then per-tile scan + carry-in)
+// ---------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const int32_t* __restrict__ in, int64_t n,
+                                                              int64_t* __restrict__ tile_sums) {
+    __shared__ int64_t red[kScanThreads / 32];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile;
+    int64_t s = 0;
+    for (int k = 0; k < kScanItems; ++k) {
+        const int64_t idx = base + k * kScanThreads + threadIdx.x;
+        if (idx < n) s += in[idx];
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t t = 0;
+        for (int w = 0; w < kScanThreads / 32; ++w) t += red[w];
+        tile_sums[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tiles(const int32_t* __restrict__ in, int64_t n,
+                                                          const int64_t* __restrict__ tile_sums,
+                                                          int64_t* __restrict__ out) {
+    __shared__ int64_t red[kScanThreads / 32];
+    __shared__ int64_t carry_s;
+    // carry-in = sum of the sums of all earlier tiles
+    int64_t c = 0;
+    for (int t = threadIdx.x; t < (int)blockIdx.x; t += kScanThreads) c += tile_sums[t];
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t t = 0;
+        for (int w = 0; w < kScanThreads / 32; ++w) t += red[w];
+        carry_s = t;
+    }
+    __syncthreads();
+    const int64_t carry = carry_s;
+    __syncthreads();
+
+    // each thread owns kScanItems consecutive elements
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    int32_t v[kScanItems];
+    int64_t local = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        local += v[k];
+    }
+    // warp inclusive scan of `local`
+    int64_t inc = local;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int64_t t = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) red[warp] = inc;
+    __syncthreads();
+    int64_t warp_off = 0;
+    for (int w = 0; w < warp; ++w) warp_off += red[w];
+    int64_t run = carry + warp_off + inc - local;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+        if (base + k == n - 1) out[n] = run;
+    }
+    if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) out[0] = 0;
+}
+
+}  // namespace lpf
+
+using namespace lpf;
+
+static int check_select_args(const int64_t* links, int64_t bs, const void* arp, const void* ac, const void* prp,
+                             const void* pc, const void* pv, int mode) {
+    LPF_REQUIRE(bs >= 0, "negative batch size");
+    LPF_REQUIRE(bs == 0 || links, "links is NULL");
+    LPF_REQUIRE(arp && prp, "rowptr is NULL");
+    (void)ac; (void)pc; (void)pv;  // may be NULL for graphs without edges / PPR entries
+    LPF_REQUIRE(mode == LPF_MODE_CN || mode == LPF_MODE_1HOP || mode == LPF_MODE_ALL, "bad mode");
+    return LPF_OK;
+}
+
+extern "C" int lpf_select_count(const int64_t* links, int64_t bs, const int64_t* adj_rowptr, const int32_t* adj_col,
+                                const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val, float th_cn,
+                                float th_1hop, float th_non1hop, int mode, int32_t* counts, void* stream) {
+    int rc = check_select_args(links, bs, adj_rowptr, adj_col, ppr_rowptr, ppr_col, ppr_val, mode);
+    if (rc) return rc;
+    LPF_REQUIRE(bs == 0 || counts, "counts is NULL");
+    SelectParams p{links, bs, adj_rowptr, adj_col, ppr_rowptr, ppr_col, ppr_val, th_cn, th_1hop, th_non1hop,
+                   mode, counts, nullptr, nullptr, nullptr, nullptr, nullptr};
+    return launch_select(false, p, (cudaStream_t)stream);
+}
+
+extern "C" int lpf_select_fill(const int64_t* links, int64_t bs, const int64_t* adj_rowptr, const int32_t* adj_col,
+                               const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val, float th_cn,
+                               float th_1hop, float th_non1hop, int mode, const int64_t* ptr, int32_t* node,
+                               float* src_ppr, float* tgt_ppr, int32_t* link, void* stream) {
+    int rc = check_select_args(links, bs, adj_rowptr, adj_col, ppr_rowptr, ppr_col, ppr_val, mode);
+    if (rc) return rc;
+    LPF_REQUIRE(bs == 0 || ptr, "ptr is NULL");
+    SelectParams p{links, bs, adj_rowptr, adj_col, ppr_rowptr, ppr_col, ppr_val, th_cn, th_1hop, th_non1hop,
+                   mode, nullptr, ptr, node, src_ppr, tgt_ppr, link};
+    return launch_select(true, p, (cudaStream_t)stream);
+}
+
+extern "C" int64_t lpf_scan_scratch_bytes(int64_t n) {
+    const int64_t tiles = (n + kScanTile - 1) / kScanTile;
+    return (tiles > 0 ? tiles : 1) * (int64_t)sizeof(int64_t);
+}
+
+extern "C" int lpf_scan_counts(const int32_t* counts, int64_t n, int64_t* ptr, void* scratch, void* stream) {
+    LPF_REQUIRE(n >= 0, "negative length");
+    LPF_REQUIRE(ptr && scratch, "ptr/scratch is NULL");
+    LPF_REQUIRE(n == 0 || counts, "counts is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t tiles = (n + kScanTile - 1) / kScanTile;
+    if (tiles == 0) {
+        scan_tiles<<<1, kScanThreads, 0, st>>>(counts, 0, (const int64_t*)scratch, ptr);
+        return check_launch("lpf_scan_counts");
+    }
+    scan_tile_sums<<<(unsigned)tiles, kScanThreads, 0, st>>>(counts, n, (int64_t*)scratch);
+    scan_tiles<<<(unsigned)tiles, kScanThreads, 0, st>>>(counts, n, (const int64_t*)scratch, ptr);
+    return check_launch("lpf_scan_counts");
+}

@@ -1,0 +1,163 @@
+"""Tensor-level wrappers over the C-ABI (one function per entry point).
+
+All tensors must live on the CUDA device; outputs are allocated with torch (device memory
+plumbing) and every launch goes to torch's current stream.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import EPI_NONE, EPI_RELU, EPI_SIGMOID, MODE, call, ptr, require_cuda, stream
+from .graph import CSR
+
+TYPE_NAMES = ("cn", "1hop", "non1hop")
+
+
+def _rowmajor(x: torch.Tensor) -> torch.Tensor:
+    """fp32 2-D tensor with unit stride in the last dimension (row stride arbitrary)."""
+    if x.dtype != torch.float32:
+        x = x.float()
+    if x.dim() != 2:
+        raise ValueError("expected a 2-D tensor")
+    if x.stride(1) != 1 or x.stride(0) < x.shape[1]:
+        x = x.contiguous()
+    return x
+
+
+def gemm(A, W, bias=None, bias_scale=1.0, out=None, epilogue=EPI_NONE):
+    """out[M,N] = epi(A[M,K] @ W[N,K]^T + bias_scale * bias)."""
+    require_cuda(A, W, bias, out)
+    A, W = _rowmajor(A), _rowmajor(W)
+    M, K = A.shape
+    N = W.shape[0]
+    if W.shape[1] != K:
+        raise ValueError(f"gemm: A is [{M},{K}] but W is {list(W.shape)}")
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    elif out.shape != (M, N) or out.stride(1) != 1 or out.dtype != torch.float32:
+        raise ValueError("gemm: bad `out`")
+    if bias is not None:
+        bias = bias.float().contiguous()
+    call("lpf_gemm", ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(bias), float(bias_scale), ptr(out),
+         out.stride(0) if M > 0 else N, M, N, K, epilogue, stream())
+    return out
+
+
+def layernorm_act(x, weight, bias, relu=False, residual=None, out=None, n=None):
+    """out = residual + act(LayerNorm(x[:, :n])) row-wise; weight=None skips the norm."""
+    require_cuda(x, weight, bias, residual, out)
+    x = _rowmajor(x)
+    rows = x.shape[0]
+    n = x.shape[1] if n is None else n
+    if out is None:
+        out = torch.empty((rows, n), dtype=torch.float32, device=x.device)
+    if residual is not None:
+        residual = _rowmajor(residual)
+    call("lpf_layernorm_act", ptr(x), x.stride(0), ptr(weight), ptr(bias), ptr(residual),
+         residual.stride(0) if residual is not None else 0, ptr(out), out.stride(0), rows, n, int(relu), stream())
+    return out
+
+
+def gather_links(links, X, want_sum=True, want_prod=True, out_sum=None, out_prod=None):
+    require_cuda(links, X)
+    X = _rowmajor(X)
+    bs, d = links.shape[1], X.shape[1]
+    if want_sum and out_sum is None:
+        out_sum = torch.empty((bs, d), dtype=torch.float32, device=X.device)
+    if want_prod and out_prod is None:
+        out_prod = torch.empty((bs, d), dtype=torch.float32, device=X.device)
+    call("lpf_gather_links", ptr(links), bs, ptr(X), X.stride(0), d, ptr(out_sum),
+         out_sum.stride(0) if out_sum is not None else 0, ptr(out_prod),
+         out_prod.stride(0) if out_prod is not None else 0, stream())
+    return out_sum, out_prod
+
+
+@dataclass
+class Selection:
+    """Selected (link, node) pairs of one batch, type-major (CN | 1-hop | >1-hop), each type
+    sorted by (link, node): the concatenation order of reference link_transformer.py:161."""
+    mode: str
+    bs: int
+    ptr: torch.Tensor            # int64 [3*bs+1]
+    node: torch.Tensor           # int32 [S]
+    src_ppr: torch.Tensor        # fp32 [S]
+    tgt_ppr: torch.Tensor        # fp32 [S]
+    link: Optional[torch.Tensor]  # int32 [S] or None
+    bounds: tuple                # (0, S_cn, S_cn+S_1hop, S) python ints
+
+    @property
+    def total(self) -> int:
+        return self.bounds[3]
+
+    def type_range(self, t: int):
+        return self.bounds[t], self.bounds[t + 1]
+
+    def counts(self) -> torch.Tensor:
+        """int64 [3, bs] set sizes."""
+        p = self.ptr
+        return (p[1:] - p[:-1]).view(3, self.bs)
+
+
+def links_tensor(batch, device) -> torch.Tensor:
+    """int64 [2,BS] contiguous on `device` (reference forward() moves the batch, :98)."""
+    b = torch.as_tensor(batch)
+    if b.dim() != 2 or b.shape[0] != 2:
+        raise ValueError("batch must be a [2, BS] tensor of (source, target) node ids")
+    return b.to(device=device, dtype=torch.int64).contiguous()
+
+
+def select(links, adj: CSR, ppr: CSR, th_cn, th_1hop, th_non1hop, mode: str, want_link=False) -> Selection:
+    """K1: count -> scan -> fill.  One host sync (reading the three totals) sizes the outputs."""
+    require_cuda(links, adj.rowptr, ppr.rowptr)
+    dev = links.device
+    bs = links.shape[1]
+    m = MODE[mode]
+    st = stream()
+    counts = torch.empty(3 * bs, dtype=torch.int32, device=dev)
+    args = (ptr(links), bs, ptr(adj.rowptr), ptr(adj.col), ptr(ppr.rowptr), ptr(ppr.col), ptr(ppr.val),
+            float(th_cn), float(th_1hop), float(th_non1hop), m)
+    call("lpf_select_count", *args, ptr(counts), st)
+    p = torch.empty(3 * bs + 1, dtype=torch.int64, device=dev)
+    scratch = torch.empty(max(1, _lib.load().lpf_scan_scratch_bytes(3 * bs) // 8), dtype=torch.int64, device=dev)
+    call("lpf_scan_counts", ptr(counts), 3 * bs, ptr(p), ptr(scratch), st)
+    b = p[[bs, 2 * bs, 3 * bs]].tolist() if bs > 0 else [0, 0, 0]
+    S = b[2]
+    node = torch.empty(S, dtype=torch.int32, device=dev)
+    pa = torch.empty(S, dtype=torch.float32, device=dev)
+    pb = torch.empty(S, dtype=torch.float32, device=dev)
+    link = torch.empty(S, dtype=torch.int32, device=dev) if want_link else None
+    if S > 0:
+        call("lpf_select_fill", *args, ptr(p), ptr(node), ptr(pa), ptr(pb), ptr(link), st)
+    return Selection(mode, bs, p, node, pa, pb, link, (0, b[0], b[1], b[2]))
+
+
+def rpe_hidden(sel: Selection, t: int, w1, b1, ln_w, ln_b, hsum):
+    r0, r1 = sel.type_range(t)
+    if r1 > r0:
+        call("lpf_rpe_hidden", ptr(sel.src_ppr), ptr(sel.tgt_ppr), r0, r1 - r0, ptr(w1), ptr(b1), ptr(ln_w),
+             ptr(ln_b), hsum.shape[1], ptr(hsum), hsum.stride(0), stream())
+
+
+def attend(sel: Selection, KV, R, Q, att, bias, ln_w, ln_b, heads, ch, write_counts, out, alpha_out=None):
+    require_cuda(KV, R, Q, out)
+    call("lpf_attend_fused", ptr(sel.ptr), sel.bs, ptr(sel.node), ptr(KV), KV.stride(0),
+         ptr(R) if sel.total > 0 else None, R.stride(0) if R is not None and R.dim() == 2 else heads * ch,
+         ptr(Q), Q.stride(0), ptr(att), ptr(bias), ptr(ln_w), ptr(ln_b), heads, ch, MODE[sel.mode],
+         int(write_counts), ptr(out), out.stride(0), ptr(alpha_out), stream())
+    return out
+
+
+def gcn_spmm(adj: CSR, XW, bias, out=None, row0=0, rows=None):
+    require_cuda(adj.rowptr, XW, bias, out)
+    XW = _rowmajor(XW)
+    n, d = adj.n, XW.shape[1]
+    rows = n - row0 if rows is None else rows
+    if out is None:
+        out = torch.empty((n, d), dtype=torch.float32, device=XW.device)
+    call("lpf_gcn_spmm", ptr(adj.rowptr), ptr(adj.col), ptr(adj.val), row0, rows, ptr(XW), XW.stride(0), ptr(bias), d,
+         ptr(out), out.stride(0), stream())
+    return out

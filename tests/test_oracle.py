@@ -7,14 +7,7 @@ from oracle import lpformer_oracle as O
 
 
 def graph_of(g):
-    e, n = g["edges"], g.n
-    row = np.concatenate([e[0], e[1]])
-    col = np.concatenate([e[1], e[0]])
-    w = np.concatenate([g["edge_weight"], g["edge_weight"]])
-    adj = O.CSR.from_coo(row, col, None, n)
-    adj_w = O.CSR.from_coo(row, col, w, n)
-    ppr = O.CSR.from_coo(g["ppr_row"], g["ppr_col"], g["ppr_val"], n)
-    return adj, adj_w, ppr
+    return g.oracle_graph()
 
 
 def test_selection_bit_exact(golden):
