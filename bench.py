@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py — scored links/s of the per-link pairwise-encoding path (BASELINE.json metric).
+
+A "step" = one pass of the hot path (selection -> RPE -> attention -> heads -> mlp_score) over one
+batch of synthetic citation2-style queries (1 held-out positive + 1,000 random negatives sharing the
+source; reference train/testing.py:14-47) on a precomputed X_node, i.e. the body of the reference's
+eval loop.  Workload: the ogbl-citation2-shaped synthetic graph (2.93M nodes, 30.6M edges, dim 64,
+hyper-parameters of reference scripts/replicate_heart.sh:22).
+
+  python bench.py [--gpus N --steps K --warmup W]          this repo's CUDA path, one JSON line
+  python bench.py --impl reference [...]                   the reference's CPU algorithm (oracle port)
+
+Under torchrun (N > 1) queries are sharded over the ranks (weak scaling: --queries per rank per
+step), node tables are replicated by one NCCL all-gather before the timed region, and the timed
+region has no collective.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="citation2", choices=["citation2", "ppa", "collab", "ddi", "cora"])
+    ap.add_argument("--scale", type=float, default=1.0, help="graph size multiplier (1.0 = the named shape)")
+    ap.add_argument("--queries", type=int, default=256, help="queries per step per GPU (x (1+negs) links)")
+    ap.add_argument("--negs", type=int, default=None)
+    ap.add_argument("--cpu-sample-links", type=int, default=32768)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=0)
+    return ap.parse_args()
+
+
+def env_rank():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def load_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def make_workload(args, rank):
+    from lpformer_b200 import synthetic as S
+    cfg = S.CONFIGS[args.workload]
+    negs = cfg["negs"] if args.negs is None else args.negs
+    t0 = time.time()
+    g = S.make_graph(args.workload, seed=args.seed, scale=args.scale, heldout=8192)
+    gen_s = time.time() - t0
+    return g, negs, gen_s
+
+
+def batch_bytes(g, links, negs, S_total, d, hc):
+    """Algorithmic bytes of one batch: per link 4(deg a+deg b) [adj col ids] +
+    8(nP a + nP b) [PPR col+val] + 32 [4 rowptr pairs] + 16 [link ids]; `select` is what one selection
+    pass reads, dedup'd = the shared source's rows counted once per query instead of once per link."""
+    deg = np.diff(g.indptr)
+    npp = np.diff(g.ppr[0])
+    a, b = links[0], links[1]
+    row_a = 4 * deg[a] + 8 * npp[a]
+    row_b = 4 * deg[b] + 8 * npp[b]
+    per_link_fixed = 32 + 16
+    select_full = float(row_a.sum() + row_b.sum() + per_link_fixed * links.shape[1])
+    q = links.shape[1] // (1 + negs)
+    row_a_dedup = row_a.reshape(q, 1 + negs)[:, 0].sum() if q * (1 + negs) == links.shape[1] else row_a.sum()
+    select_dedup = float(row_a_dedup + row_b.sum() + (32 / 2 + 8) * links.shape[1] + 24 * q)
+    e = 4
+    path_extra = float(links.shape[1] * (2 * d * e + 4) + S_total * hc * e)
+    return {"select_full": select_full, "select_dedup": select_dedup, "path_full": select_full + path_extra,
+            "path_dedup": select_dedup + path_extra - float((links.shape[1] - q) * d * e)}
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle/ref_port.py, torch sparse-COO algebra on the
+    host cores) on a bounded sample of the same workload per step."""
+    rank, _, world = env_rank()
+    if rank != 0:
+        return
+    from oracle import ref_port as R
+    import lpformer_b200 as L
+    from lpformer_b200 import synthetic as S
+    torch.set_num_threads(os.cpu_count())
+    g, negs, gen_s = make_workload(args, 0)
+    cfg = g.cfg
+    targs = S.train_args_of(cfg)
+    torch.manual_seed(args.seed)
+    model = L.LinkTransformer(targs, {"x": torch.from_numpy(g.x)}, device="cpu").eval()   # seeded weights only
+    score = L.mlp_score(model.out_dim, model.out_dim, 1, 2).eval()
+    P = {k: v.detach() for k, v in model.state_dict().items()}
+    Sd = {k: v.detach() for k, v in score.state_dict().items()}
+    X = torch.randn(g.n, cfg["dim"], generator=torch.Generator().manual_seed(args.seed + 5))
+    A = R.coo_from_csr(g.indptr, g.indices, None, g.n)
+    Pm = R.coo_from_csr(*g.ppr, g.n)
+    nq = max(1, args.cpu_sample_links // (1 + negs))
+    cfgd = dict(targs)
+    times = []
+    for step in range(args.warmup + args.steps):
+        links = torch.from_numpy(S.citation2_queries(g, nq, negs, seed=1000 + step))
+        t0 = time.perf_counter()
+        R.score_links(links, X, A, Pm, P, Sd, cfgd, model.mask)
+        if step >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    nlinks = nq * (1 + negs)
+    total = sum(times)
+    val = nlinks * len(times) / total
+    line = {"impl": "reference", "metric": "scored links/sec", "value": val, "unit": "links/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"ogbl-{args.workload}-shaped synthetic eval, 1 positive + {negs} negatives per query",
+                       "scale": args.scale, "graph": g.stats(), "links_per_step": nlinks},
+            "cpu_baseline": {"value": val, "unit": "links/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"{nq} queries x {1 + negs} links per step (oracle/ref_port.py, torch sparse-COO "
+                                       f"algebra of the reference, X_node seeded N(0,1))"},
+            "e2e": {"value": val, "unit": "links/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    import lpformer_b200 as L
+    from lpformer_b200 import _lib, synthetic as S
+    from lpformer_b200.evaluate import propagate_replicated
+
+    rank, local_rank, world = env_rank()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: lpformer_b200 has no CPU fallback (use --impl reference "
+                         "for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    g, negs, gen_s = make_workload(args, rank)
+    cfg = g.cfg
+    targs = S.train_args_of(cfg)
+    torch.manual_seed(args.seed)
+    model = L.LinkTransformer(targs, g.data_dict(dev), device=dev).to(dev).eval()
+    score = L.mlp_score(model.out_dim, model.out_dim, 1, 2).to(dev).eval()
+    d, hc = cfg["dim"], cfg["dim"]
+
+    # ---- per-eval work (not in the timed region): GCN + gnn_norm + K/V projection (+ one all-gather)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    X = propagate_replicated(model)          # first call builds the normalised CSR
+    torch.cuda.synchronize()
+    e0.record()
+    X = propagate_replicated(model)
+    e1.record()
+    torch.cuda.synchronize()
+    propagate_ms = e0.elapsed_time(e1)
+
+    nq = args.queries
+    total_steps = args.warmup + args.steps
+    host_links = [S.citation2_queries(g, nq, negs, seed=1000 + rank * 100003 + s) for s in range(total_steps)]
+    dev_links = [torch.from_numpy(l).to(dev) for l in host_links]
+    pinned = [torch.from_numpy(l).pin_memory() for l in host_links]
+    nlinks = nq * (1 + negs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`)
+    for s in range(args.warmup):
+        model.score_links(dev_links[s], X, score)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    trace = _lib.Trace(events=True)
+    _lib.TRACE = trace
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for s in range(args.warmup, total_steps):
+        out = model.score_links(dev_links[s], X, score)
+    t_end.record()
+    barrier()
+    _lib.TRACE = None
+    clocks = sampler.stop() if sampler else None
+    dev_ms = t_start.elapsed_time(t_end)
+
+    # ---- end-to-end through the public API with host buffers (H2D of links, D2H of scores, per step)
+    for s in range(min(args.warmup, 2)):
+        model.score_links(pinned[s], X, score).cpu()
+    barrier()
+    w0 = time.perf_counter()
+    for s in range(args.warmup, total_steps):
+        res = model.score_links(pinned[s], X, score).cpu()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - w0
+    barrier()
+
+    times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = times.tolist()
+
+    if rank == 0:
+        summ = trace.summary()
+        launches_per_step = trace.launches / args.steps
+        # set statistics + algorithmic bytes of the timed batches
+        sel_stats = {"pairs_per_link": 0.0, "empty_frac": 0.0}
+        tot_pairs, tot_empty, byt = 0, 0, {"select_full": 0.0, "select_dedup": 0.0, "path_full": 0.0, "path_dedup": 0.0}
+        from lpformer_b200 import ops
+        for s in range(args.warmup, total_steps):
+            sel = model._select(dev_links[s], False)
+            c = sel.counts().sum(0)
+            tot_pairs += int(c.sum())
+            tot_empty += int((c == 0).sum())
+            bb = batch_bytes(g, host_links[s], negs, sel.total, d, hc)
+            for k in byt:
+                byt[k] += bb[k]
+        sel_stats["pairs_per_link"] = tot_pairs / (nlinks * args.steps)
+        sel_stats["empty_frac"] = tot_empty / (nlinks * args.steps)
+
+        kern = sorted(((n, c, t) for n, (c, t) in summ.items()), key=lambda r: -r[2])
+        top_name, top_calls, top_ms = kern[0]
+        peak, peak_src = load_peaks()
+        if top_name in ("lpf_select_count", "lpf_select_fill"):
+            alg = byt["select_dedup"] / args.steps          # per launch (one launch per step)
+            alg_full = byt["select_full"] / args.steps
+        else:
+            alg = alg_full = None
+        avg_ms = top_ms / top_calls
+        roof = {"bound": "hbm", "kernel": top_name, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
+                "traffic": None, "peak_source": peak_src, "avg_launch_ms": avg_ms,
+                "share_of_kernel_time": top_ms / sum(t for _, _, t in kern)}
+        if alg is not None:
+            roof["achieved"] = alg / (avg_ms * 1e-3) / 1e9
+            roof["frac"] = roof["achieved"] / peak
+            roof["achieved_undeduped"] = alg_full / (avg_ms * 1e-3) / 1e9
+            roof["algorithmic_bytes_per_launch"] = alg
+        path_gbs = byt["path_dedup"] / (dev_ms * 1e-3) / 1e9
+        value = world * nlinks * args.steps / (dev_ms * 1e-3)
+        e2e_val = world * nlinks * args.steps / (e2e_ms * 1e-3)
+
+        cpu_base = None
+        if not args.no_cpu_baseline:
+            cpu_base = cpu_baseline(args, g, negs, model, score, X, targs)
+
+        line = {"metric": "scored links/sec", "value": value, "unit": "links/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"ogbl-{args.workload}-shaped synthetic eval, 1 positive + {negs} negatives per query",
+                           "scale": args.scale, "graph": g.stats(), "queries_per_step_per_gpu": nq,
+                           "links_per_step_per_gpu": nlinks, "dim": d, "mode": model.mask,
+                           "thresholds": [cfg["thresh_cn"], cfg["thresh_1hop"], cfg["thresh_non1hop"]],
+                           "l2_policy": "distinct link batch every step; node/graph tables (%.2f GB) exceed the 126 MB L2"
+                                        % ((g.indices.nbytes + g.ppr[1].nbytes * 2 + 2 * g.n * d * 4) / 1e9),
+                           "set_stats": sel_stats, "parallelism": f"links sharded over {world} GPU(s), tables replicated"},
+                "e2e": {"value": e2e_val, "unit": "links/s", "h2d_bytes_per_step": int(host_links[0].nbytes),
+                        "d2h_bytes_per_step": int(nlinks * 4), "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": int(trace.launches),
+                "gpu_launches_per_step": launches_per_step,
+                "roofline": roof,
+                "path_algorithmic_gbs": path_gbs,
+                "path_frac_of_peak": path_gbs / peak,
+                "kernels": [{"name": n, "calls": c, "total_ms": t} for n, c, t in kern],
+                "per_eval": {"propagate_ms": propagate_ms, "graph_gen_s": gen_s},
+                "cpu_baseline": cpu_base,
+                "clocks": clocks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, g, negs, model, score, X, targs):
+    """The reference's CPU algorithm (oracle/ref_port.py) on a bounded sample of the same workload, same
+    weights and the same X_node, on this box's host cores; also cross-checks the GPU scores."""
+    from oracle import ref_port as R
+    from lpformer_b200 import synthetic as S
+    torch.set_num_threads(os.cpu_count())
+    P = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    Sd = {k: v.detach().cpu() for k, v in score.state_dict().items()}
+    Xc = X.detach().cpu().contiguous()
+    A = R.coo_from_csr(g.indptr, g.indices, None, g.n)
+    Pm = R.coo_from_csr(*g.ppr, g.n)
+    nq = max(1, args.cpu_sample_links // (1 + negs))
+    spent, done, first, max_diff = 0.0, 0, None, None
+    for it in range(4):
+        links_np = S.citation2_queries(g, nq, negs, seed=5000 + it)
+        links = torch.from_numpy(links_np)
+        t0 = time.perf_counter()
+        prob, _ = R.score_links(links, Xc, A, Pm, P, Sd, dict(targs), model.mask)
+        dt = time.perf_counter() - t0
+        if it == 0:
+            first = dt
+            gpu = model.score_links(links.to(X.device), X, score).cpu()
+            max_diff = float((gpu - prob).abs().max())
+        else:
+            spent += dt
+            done += 1
+        if spent + first > 20.0:
+            break
+    if done == 0:
+        spent, done = first, 1
+    return {"value": nq * (1 + negs) * done / spent, "unit": "links/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{done} timed batch(es) of {nq} queries x {1 + negs} links after 1 warm-up batch "
+                      f"(oracle/ref_port.py: the reference's torch sparse-COO algorithm)",
+            "max_abs_prob_diff_vs_gpu": max_diff}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -154,6 +154,18 @@ int lpf_gcn_spmm(const int64_t* rowptr, const int32_t* col, const float* val,
                  int64_t row0, int64_t rows, const float* XW, int64_t ld_xw, const float* bias,
                  int32_t d, float* Y, int64_t ldy, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Host-side PPR precompute (data preparation, not on the per-link path) — the
+ * Andersen push of util/calc_ppr_scores.py:137-192 + the fp32 sorted matrix of
+ * :221-241, multi-threaded over sources, bit-identical values.  HOST pointers.
+ * lpf_ppr_push_host returns an opaque handle (NULL on error) and the entry count;
+ * lpf_ppr_push_host_fetch copies the CSR out (rowptr [n+1], col/val [nnz]) and
+ * releases the handle.
+ * ------------------------------------------------------------------------- */
+void* lpf_ppr_push_host(const int64_t* indptr_host, const int32_t* indices_host, int64_t n,
+                        double alpha, double eps, int nthreads, int64_t* nnz);
+int lpf_ppr_push_host_fetch(void* handle, int64_t* rowptr_host, int32_t* col_host, float* val_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,8 @@ SIGNATURES = {
     "lpf_gather_links": (_int, [_p, _i64, _p, _i64, _i32, _p, _i64, _p, _i64, _p]),
     "lpf_attend_fused": (_int, [_p, _i64, _p, _p, _i64, _p, _i64, _p, _i64, _p, _p, _p, _p, _i32, _i32, _int, _int,
                                 _p, _i64, _p, _p]),
+    "lpf_ppr_push_host": (_p, [_p, _p, _i64, C.c_double, C.c_double, _int, _p]),
+    "lpf_ppr_push_host_fetch": (_int, [_p, _p, _p, _p]),
     "lpf_gcn_spmm": (_int, [_p, _p, _p, _i64, _i64, _p, _i64, _p, _i32, _p, _i64, _p]),
 }
 
@@ -60,10 +62,50 @@ def load():
     return lib
 
 
-def call(name, *args):
+# kernels launched per entry point (for bench.py's gpu_launches and per-kernel CUDA-event timing)
+KERNEL_LAUNCHES = {"lpf_select_count": 1, "lpf_scan_counts": 2, "lpf_select_fill": 1, "lpf_rpe_hidden": 1,
+                   "lpf_gemm": 1, "lpf_layernorm_act": 1, "lpf_gather_links": 1, "lpf_attend_fused": 1,
+                   "lpf_gcn_spmm": 1}
+
+
+class Trace:
+    """Optional per-call instrumentation: counts launches and brackets every entry point with CUDA
+    events on the launching stream.  Enabled by bench.py; off by default."""
+
+    def __init__(self, events=True):
+        self.events = events
+        self.launches = 0
+        self.records = []   # (name, meta, start_event, end_event)
+
+    def summary(self):
+        """name -> (calls, total_ms); call after torch.cuda.synchronize()."""
+        out = {}
+        for name, _, a, b in self.records:
+            c, t = out.get(name, (0, 0.0))
+            out[name] = (c + 1, t + a.elapsed_time(b))
+        return out
+
+
+TRACE = None
+
+
+def call(name, *args, meta=None):
     """Invoke an int-returning entry point; raise LpfError with lpf_last_error() on failure."""
     lib = load()
-    rc = getattr(lib, name)(*args)
+    tr = TRACE
+    if tr is not None:
+        tr.launches += KERNEL_LAUNCHES.get(name, 0)
+        if tr.events:
+            a = torch.cuda.Event(enable_timing=True)
+            b = torch.cuda.Event(enable_timing=True)
+            a.record()
+            rc = getattr(lib, name)(*args)
+            b.record()
+            tr.records.append((name, meta, a, b))
+        else:
+            rc = getattr(lib, name)(*args)
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise LpfError(f"{name} failed ({rc}): {lib.lpf_last_error().decode()}")
 

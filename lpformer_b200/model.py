@@ -407,6 +407,12 @@ class LinkTransformer(nn.Module):
         self._kv_cache = (key, kvs, X_node)   # keep X_node alive so the pointer key stays valid
         return kvs
 
+    def _prime_kv(self, X_node, kvs):
+        """Install externally built K/V tables for X_node (multi-GPU all-gather path)."""
+        key = (X_node.data_ptr(), X_node._version, tuple(X_node.shape),
+               tuple(layer.att.lin_r.weight._version for layer in self.att_layers))
+        self._kv_cache = (key, kvs, X_node)
+
     # ------------------------------------------------------------------ reference API
     @torch.no_grad()
     def forward(self, batch, adj_prop=None, adj_mask=None, test_set=False, return_weights=False):

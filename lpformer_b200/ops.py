@@ -43,7 +43,7 @@ def gemm(A, W, bias=None, bias_scale=1.0, out=None, epilogue=EPI_NONE):
     if bias is not None:
         bias = bias.float().contiguous()
     call("lpf_gemm", ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(bias), float(bias_scale), ptr(out),
-         out.stride(0) if M > 0 else N, M, N, K, epilogue, stream())
+         out.stride(0) if M > 0 else N, M, N, K, epilogue, stream(), meta=(M, N, K))
     return out
 
 
@@ -120,7 +120,7 @@ def select(links, adj: CSR, ppr: CSR, th_cn, th_1hop, th_non1hop, mode: str, wan
     counts = torch.empty(3 * bs, dtype=torch.int32, device=dev)
     args = (ptr(links), bs, ptr(adj.rowptr), ptr(adj.col), ptr(ppr.rowptr), ptr(ppr.col), ptr(ppr.val),
             float(th_cn), float(th_1hop), float(th_non1hop), m)
-    call("lpf_select_count", *args, ptr(counts), st)
+    call("lpf_select_count", *args, ptr(counts), st, meta=(bs,))
     p = torch.empty(3 * bs + 1, dtype=torch.int64, device=dev)
     scratch = torch.empty(max(1, _lib.load().lpf_scan_scratch_bytes(3 * bs) // 8), dtype=torch.int64, device=dev)
     call("lpf_scan_counts", ptr(counts), 3 * bs, ptr(p), ptr(scratch), st)
@@ -131,7 +131,7 @@ def select(links, adj: CSR, ppr: CSR, th_cn, th_1hop, th_non1hop, mode: str, wan
     pb = torch.empty(S, dtype=torch.float32, device=dev)
     link = torch.empty(S, dtype=torch.int32, device=dev) if want_link else None
     if S > 0:
-        call("lpf_select_fill", *args, ptr(p), ptr(node), ptr(pa), ptr(pb), ptr(link), st)
+        call("lpf_select_fill", *args, ptr(p), ptr(node), ptr(pa), ptr(pb), ptr(link), st, meta=(bs, S))
     return Selection(mode, bs, p, node, pa, pb, link, (0, b[0], b[1], b[2]))
 
 
@@ -147,7 +147,7 @@ def attend(sel: Selection, KV, R, Q, att, bias, ln_w, ln_b, heads, ch, write_cou
     call("lpf_attend_fused", ptr(sel.ptr), sel.bs, ptr(sel.node), ptr(KV), KV.stride(0),
          ptr(R) if sel.total > 0 else None, R.stride(0) if R is not None and R.dim() == 2 else heads * ch,
          ptr(Q), Q.stride(0), ptr(att), ptr(bias), ptr(ln_w), ptr(ln_b), heads, ch, MODE[sel.mode],
-         int(write_counts), ptr(out), out.stride(0), ptr(alpha_out), stream())
+         int(write_counts), ptr(out), out.stride(0), ptr(alpha_out), stream(), meta=(sel.bs, sel.total, heads * ch))
     return out
 
 

@@ -56,3 +56,40 @@ def test_ppr_push_matches_reference_kernel(golden):
     ppr = O.ppr_push(adj.indptr, adj.indices, g.cfg["alpha"], g.cfg["eps"])
     assert np.array_equal(ppr.indices, g["ppr_col"])
     assert np.array_equal(ppr.val.view(np.uint32), g["ppr_val"].view(np.uint32))
+
+
+# --------------------------------------------------------------------------- #
+# oracle/ref_port.py: the torch sparse-COO restatement of the reference's algorithm
+# --------------------------------------------------------------------------- #
+def _port_inputs(g):
+    import torch
+    from oracle import ref_port as R
+    adj, _, ppr = g.oracle_graph()
+    A = R.coo_from_csr(adj.indptr, adj.indices, None, g.n)
+    Pm = R.coo_from_csr(ppr.indptr, ppr.indices, ppr.val, g.n)
+    P = {k: torch.from_numpy(v) for k, v in g.model_params.items()}
+    S = {k: torch.from_numpy(v) for k, v in g.score_params.items()}
+    return R, A, Pm, P, S
+
+
+def test_ref_port_selection_bit_exact(golden):
+    import torch
+    g = golden
+    R, A, Pm, _, _ = _port_inputs(g)
+    sets = R.select_pairs(A, Pm, torch.from_numpy(g["links"]), g.cfg["thresh_cn"], g.cfg["thresh_1hop"],
+                          g.cfg["thresh_non1hop"], g.cfg["mask"])
+    ref = g.sets()
+    assert set(ref) == set(sets)
+    for t, (ix, src, tgt) in ref.items():
+        assert np.array_equal(sets[t][0].numpy(), ix), t
+        assert np.array_equal(sets[t][1].numpy().view(np.uint32), src.view(np.uint32)), t
+        assert np.array_equal(sets[t][2].numpy().view(np.uint32), tgt.view(np.uint32)), t
+
+
+def test_ref_port_scores(golden):
+    import torch
+    g = golden
+    R, A, Pm, P, S = _port_inputs(g)
+    prob, _ = R.score_links(torch.from_numpy(g["links"]), torch.from_numpy(g["X_node"]), A, Pm, P, S, g.cfg,
+                            g.cfg["mask"])
+    np.testing.assert_allclose(prob.numpy(), g["prob"], rtol=1e-4, atol=1e-6)
