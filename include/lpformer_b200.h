@@ -39,6 +39,17 @@ extern "C" {
 #define LPF_MODE_1HOP 1
 #define LPF_MODE_ALL 2
 
+/* selection algorithms (same results, different work shapes):
+ *   GENERIC    warp-per-link merge-path over both rows; valid for any thresholds / values.
+ *   INTERSECT8 / INTERSECT32
+ *              group-of-8 / warp-per-link walk of the shorter row with binary search into the
+ *              longer one.  Requires th_1hop > 0 (modes 1HOP, ALL), th_non1hop > 0 (mode ALL) and
+ *              every stored PPR value in (0, 1] (the caller asserts this for its table);
+ *              otherwise LPF_ERR_UNSUPPORTED / undefined sets. */
+#define LPF_ALGO_GENERIC 0
+#define LPF_ALGO_INTERSECT8 1
+#define LPF_ALGO_INTERSECT32 2
+
 /* node-set types, concatenation order of models/link_transformer.py:161 */
 #define LPF_T_CN 0
 #define LPF_T_1HOP 1
@@ -73,7 +84,7 @@ int lpf_device_ok(void);
 int lpf_select_count(const int64_t* links, int64_t bs,
                      const int64_t* adj_rowptr, const int32_t* adj_col,
                      const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val,
-                     float th_cn, float th_1hop, float th_non1hop, int mode,
+                     float th_cn, float th_1hop, float th_non1hop, int mode, int algo,
                      int32_t* counts, void* stream);
 
 /* Exclusive scan of n int32 counts into n+1 int64 offsets (single launch).
@@ -84,7 +95,7 @@ int lpf_scan_counts(const int32_t* counts, int64_t n, int64_t* ptr, void* scratc
 int lpf_select_fill(const int64_t* links, int64_t bs,
                     const int64_t* adj_rowptr, const int32_t* adj_col,
                     const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val,
-                    float th_cn, float th_1hop, float th_non1hop, int mode,
+                    float th_cn, float th_1hop, float th_non1hop, int mode, int algo,
                     const int64_t* ptr,
                     int32_t* node, float* src_ppr, float* tgt_ppr, int32_t* link /* may be NULL */,
                     void* stream);

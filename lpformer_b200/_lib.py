@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "_C", "liblpformer_b200.so")
 
 MODE = {"cn": 0, "1-hop": 1, "all": 2}
 EPI_NONE, EPI_RELU, EPI_SIGMOID = 0, 1, 2
+ALGO_GENERIC, ALGO_INTERSECT8, ALGO_INTERSECT32 = 0, 1, 2
 
 _p, _i64, _i32, _f32, _int = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_int
 
@@ -23,10 +24,10 @@ SIGNATURES = {
     "lpf_abi_version": (_int, []),
     "lpf_last_error": (C.c_char_p, []),
     "lpf_device_ok": (_int, []),
-    "lpf_select_count": (_int, [_p, _i64, _p, _p, _p, _p, _p, _f32, _f32, _f32, _int, _p, _p]),
+    "lpf_select_count": (_int, [_p, _i64, _p, _p, _p, _p, _p, _f32, _f32, _f32, _int, _int, _p, _p]),
     "lpf_scan_scratch_bytes": (_i64, [_i64]),
     "lpf_scan_counts": (_int, [_p, _i64, _p, _p, _p]),
-    "lpf_select_fill": (_int, [_p, _i64, _p, _p, _p, _p, _p, _f32, _f32, _f32, _int, _p, _p, _p, _p, _p, _p]),
+    "lpf_select_fill": (_int, [_p, _i64, _p, _p, _p, _p, _p, _f32, _f32, _f32, _int, _int, _p, _p, _p, _p, _p, _p]),
     "lpf_rpe_hidden": (_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _i32, _p, _i64, _p]),
     "lpf_gemm": (_int, [_p, _i64, _p, _i64, _p, _f32, _p, _i64, _i64, _i32, _i32, _int, _p]),
     "lpf_layernorm_act": (_int, [_p, _i64, _p, _p, _p, _i64, _p, _i64, _i64, _i32, _int, _p]),

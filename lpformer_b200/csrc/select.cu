@@ -278,6 +278,25 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles(const int32_t* __rest
 
 using namespace lpf;
 
+namespace lpf {
+int select_fast(bool fill, int group, const int64_t* links, int64_t bs, const int64_t* adj_rowptr,
+                const int32_t* adj_col, const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val,
+                float th_cn, float th_1hop, float th_non1hop, int mode, int32_t* counts, const int64_t* ptr,
+                int32_t* node, float* pa, float* pb, int32_t* link, cudaStream_t st);
+}
+
+static int check_algo(int algo, int mode, float th_1hop, float th_non1hop) {
+    LPF_REQUIRE(algo == LPF_ALGO_GENERIC || algo == LPF_ALGO_INTERSECT8 || algo == LPF_ALGO_INTERSECT32, "bad algo");
+    if (algo != LPF_ALGO_GENERIC) {
+        const bool ok = (mode == LPF_MODE_CN) || (th_1hop > 0.0f && (mode != LPF_MODE_ALL || th_non1hop > 0.0f));
+        if (!ok) {
+            lpf::set_error("intersection algorithm needs th_1hop > 0 (and th_non1hop > 0 in mode ALL)");
+            return LPF_ERR_UNSUPPORTED;
+        }
+    }
+    return LPF_OK;
+}
+
 static int check_select_args(const int64_t* links, int64_t bs, const void* arp, const void* ac, const void* prp,
                              const void* pc, const void* pv, int mode) {
     LPF_REQUIRE(bs >= 0, "negative batch size");
@@ -290,10 +309,18 @@ static int check_select_args(const int64_t* links, int64_t bs, const void* arp, 
 
 extern "C" int lpf_select_count(const int64_t* links, int64_t bs, const int64_t* adj_rowptr, const int32_t* adj_col,
                                 const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val, float th_cn,
-                                float th_1hop, float th_non1hop, int mode, int32_t* counts, void* stream) {
+                                float th_1hop, float th_non1hop, int mode, int algo, int32_t* counts, void* stream) {
     int rc = check_select_args(links, bs, adj_rowptr, adj_col, ppr_rowptr, ppr_col, ppr_val, mode);
     if (rc) return rc;
+    rc = check_algo(algo, mode, th_1hop, th_non1hop);
+    if (rc) return rc;
     LPF_REQUIRE(bs == 0 || counts, "counts is NULL");
+    if (algo != LPF_ALGO_GENERIC) {
+        if (bs == 0) return LPF_OK;
+        return select_fast(false, algo == LPF_ALGO_INTERSECT32 ? 32 : 8, links, bs, adj_rowptr, adj_col, ppr_rowptr,
+                           ppr_col, ppr_val, th_cn, th_1hop, th_non1hop, mode, counts, nullptr, nullptr, nullptr,
+                           nullptr, nullptr, (cudaStream_t)stream);
+    }
     SelectParams p{links, bs, adj_rowptr, adj_col, ppr_rowptr, ppr_col, ppr_val, th_cn, th_1hop, th_non1hop,
                    mode, counts, nullptr, nullptr, nullptr, nullptr, nullptr};
     return launch_select(false, p, (cudaStream_t)stream);
@@ -301,11 +328,19 @@ extern "C" int lpf_select_count(const int64_t* links, int64_t bs, const int64_t*
 
 extern "C" int lpf_select_fill(const int64_t* links, int64_t bs, const int64_t* adj_rowptr, const int32_t* adj_col,
                                const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val, float th_cn,
-                               float th_1hop, float th_non1hop, int mode, const int64_t* ptr, int32_t* node,
+                               float th_1hop, float th_non1hop, int mode, int algo, const int64_t* ptr, int32_t* node,
                                float* src_ppr, float* tgt_ppr, int32_t* link, void* stream) {
     int rc = check_select_args(links, bs, adj_rowptr, adj_col, ppr_rowptr, ppr_col, ppr_val, mode);
     if (rc) return rc;
+    rc = check_algo(algo, mode, th_1hop, th_non1hop);
+    if (rc) return rc;
     LPF_REQUIRE(bs == 0 || ptr, "ptr is NULL");
+    if (algo != LPF_ALGO_GENERIC) {
+        if (bs == 0) return LPF_OK;
+        return select_fast(true, algo == LPF_ALGO_INTERSECT32 ? 32 : 8, links, bs, adj_rowptr, adj_col, ppr_rowptr,
+                           ppr_col, ppr_val, th_cn, th_1hop, th_non1hop, mode, nullptr, ptr, node, src_ppr, tgt_ppr,
+                           link, (cudaStream_t)stream);
+    }
     SelectParams p{links, bs, adj_rowptr, adj_col, ppr_rowptr, ppr_col, ppr_val, th_cn, th_1hop, th_non1hop,
                    mode, nullptr, ptr, node, src_ppr, tgt_ppr, link};
     return launch_select(true, p, (cudaStream_t)stream);

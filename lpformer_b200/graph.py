@@ -20,6 +20,7 @@ class CSR:
     col: torch.Tensor               # int32 [nnz]
     val: Optional[torch.Tensor]     # fp32 [nnz] or None (0/1 mask)
     n: int
+    unit_range: Optional[bool] = None   # cached: all values in (0, 1] (lets K1 use its intersection algorithm)
 
     @property
     def nnz(self) -> int:

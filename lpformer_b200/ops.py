@@ -110,7 +110,21 @@ def links_tensor(batch, device) -> torch.Tensor:
     return b.to(device=device, dtype=torch.int64).contiguous()
 
 
-def select(links, adj: CSR, ppr: CSR, th_cn, th_1hop, th_non1hop, mode: str, want_link=False) -> Selection:
+def pick_select_algo(adj: CSR, ppr: CSR, th_1hop, th_non1hop, mode: str) -> int:
+    """Intersection-driven kernel when its preconditions hold (thresholds gating PPR-derived sets > 0 and
+    all PPR values in (0,1], checked once per table), group width by mean row length; else the generic one."""
+    ok = mode == "cn" or (th_1hop > 0 and (mode != "all" or th_non1hop > 0))
+    if not ok:
+        return _lib.ALGO_GENERIC
+    if ppr.unit_range is None:
+        ppr.unit_range = bool(ppr.val.numel() == 0 or (float(ppr.val.min()) > 0.0 and float(ppr.val.max()) <= 1.0))
+    if not ppr.unit_range:
+        return _lib.ALGO_GENERIC
+    mean_deg = adj.nnz / max(1, adj.n)
+    return _lib.ALGO_INTERSECT32 if mean_deg >= 96 else _lib.ALGO_INTERSECT8
+
+
+def select(links, adj: CSR, ppr: CSR, th_cn, th_1hop, th_non1hop, mode: str, want_link=False, algo=None) -> Selection:
     """K1: count -> scan -> fill.  One host sync (reading the three totals) sizes the outputs."""
     require_cuda(links, adj.rowptr, ppr.rowptr)
     dev = links.device
@@ -119,7 +133,8 @@ def select(links, adj: CSR, ppr: CSR, th_cn, th_1hop, th_non1hop, mode: str, wan
     st = stream()
     counts = torch.empty(3 * bs, dtype=torch.int32, device=dev)
     args = (ptr(links), bs, ptr(adj.rowptr), ptr(adj.col), ptr(ppr.rowptr), ptr(ppr.col), ptr(ppr.val),
-            float(th_cn), float(th_1hop), float(th_non1hop), m)
+            float(th_cn), float(th_1hop), float(th_non1hop), m,
+            pick_select_algo(adj, ppr, th_1hop, th_non1hop, mode) if algo is None else algo)
     call("lpf_select_count", *args, ptr(counts), st, meta=(bs,))
     p = torch.empty(3 * bs + 1, dtype=torch.int64, device=dev)
     scratch = torch.empty(max(1, _lib.load().lpf_scan_scratch_bytes(3 * bs) // 8), dtype=torch.int64, device=dev)

@@ -120,3 +120,66 @@ def test_cn_mode_vs_oracle():
     pw, _ = model.calc_pairwise(torch.from_numpy(g["links"]), X)
     ref_pw, _, _, _ = O.calc_pairwise(g["links"], g["X_node"], adj, ppr, P, args)
     np.testing.assert_allclose(pw.cpu().numpy(), ref_pw, rtol=FP32_RTOL, atol=2e-5)
+
+
+@pytest.mark.parametrize("algo", [0, 1, 2])
+def test_selection_algorithms_agree_with_golden(golden, algo):
+    """K1 has a generic merge kernel and an intersection-driven one (sub-warp groups of 8 / 32);
+    every algorithm that accepts the case's thresholds must give the reference's sets bit-exactly."""
+    from lpformer_b200 import ops, _lib
+    g = golden
+    model, _ = build(g)
+    links = ops.links_tensor(torch.from_numpy(g["links"]), "cuda:0")
+    adj, ppr = model.get_adj(False, mask=True), model.get_ppr(False)
+    if algo != 0 and ops.pick_select_algo(adj, ppr, model.thresh_1hop, model.thresh_non1hop, model.mask) == 0:
+        with pytest.raises(_lib.LpfError):
+            ops.select(links, adj, ppr, model.thresh_cn, model.thresh_1hop, model.thresh_non1hop, model.mask,
+                       want_link=True, algo=algo)
+        return
+    sel = ops.select(links, adj, ppr, model.thresh_cn, model.thresh_1hop, model.thresh_non1hop, model.mask,
+                     want_link=True, algo=algo)
+    ref = g.sets()
+    for t, name in enumerate(("cn", "1hop", "non1hop")):
+        r0, r1 = sel.type_range(t)
+        if name not in ref:
+            assert r1 == r0
+            continue
+        ix, src, tgt = ref[name]
+        assert np.array_equal(sel.link[r0:r1].cpu().numpy(), ix[0]), name
+        assert np.array_equal(sel.node[r0:r1].cpu().numpy(), ix[1]), name
+        assert np.array_equal(sel.src_ppr[r0:r1].cpu().numpy().view(np.uint32), src.view(np.uint32)), name
+        assert np.array_equal(sel.tgt_ppr[r0:r1].cpu().numpy().view(np.uint32), tgt.view(np.uint32)), name
+
+
+@pytest.mark.parametrize("workload,scale", [("citation2", 0.02), ("ddi", 0.25), ("collab", 0.05)])
+def test_selection_synthetic_vs_oracle(workload, scale):
+    """Seeded synthetic graphs of the BASELINE shapes (scaled so the numpy oracle finishes in seconds):
+    all three K1 algorithms against oracle.select_sets, on in-graph positives, held-out positives,
+    random negatives, self pairs and shared-source query groups."""
+    from lpformer_b200 import ops, synthetic as S
+    g = S.make_graph(workload, seed=3, scale=scale, heldout=256)
+    cfg = g.cfg
+    rng = np.random.default_rng(7)
+    pos = g.edges[:, rng.integers(0, g.edges.shape[1], 300)]
+    q = S.citation2_queries(g, 4, 100, seed=5)
+    selfp = np.tile(rng.integers(0, g.n, 8), (2, 1))
+    links_np = np.concatenate([pos, pos[::-1, :50], g.heldout[:, :100], q, selfp], axis=1).astype(np.int64)
+    adj_o = O.CSR(g.indptr, g.indices, None, g.n)
+    ppr_o = O.CSR(g.ppr[0], g.ppr[1], g.ppr[2], g.n)
+    th = (cfg["thresh_cn"], cfg["thresh_1hop"], cfg["thresh_non1hop"])
+    mode, sets = O.select_sets(adj_o, ppr_o, links_np, *th)
+    dev = torch.device("cuda:0")
+    d = g.data_dict(dev)
+    links = torch.from_numpy(links_np).to(dev)
+    for algo in (0, 1, 2):
+        sel = ops.select(links, d["adj_mask"], d["ppr"], *th, mode, want_link=True, algo=algo)
+        for t, name in enumerate(("cn", "1hop", "non1hop")):
+            r0, r1 = sel.type_range(t)
+            if name not in sets:
+                assert r1 == r0
+                continue
+            li, nd, qa, qb = sets[name]
+            assert np.array_equal(sel.link[r0:r1].cpu().numpy(), li), (algo, name)
+            assert np.array_equal(sel.node[r0:r1].cpu().numpy(), nd), (algo, name)
+            assert np.array_equal(sel.src_ppr[r0:r1].cpu().numpy().view(np.uint32), qa.view(np.uint32)), (algo, name)
+            assert np.array_equal(sel.tgt_ppr[r0:r1].cpu().numpy().view(np.uint32), qb.view(np.uint32)), (algo, name)
