@@ -43,7 +43,8 @@ extern "C" {
  *   GENERIC    warp-per-link merge-path over both rows; valid for any thresholds / values.
  *   INTERSECT8 / INTERSECT32
  *              group-of-8 / warp-per-link walk of the shorter row with binary search into the
- *              longer one.  Requires th_1hop > 0 (modes 1HOP, ALL), th_non1hop > 0 (mode ALL) and
+ *              longer one; links whose shorter row exceeds 16 elements per lane are deferred to a
+ *              second launch in which a whole CTA walks each of them.  Requires th_1hop > 0 (modes 1HOP, ALL), th_non1hop > 0 (mode ALL) and
  *              every stored PPR value in (0, 1] (the caller asserts this for its table);
  *              otherwise LPF_ERR_UNSUPPORTED / undefined sets. */
 #define LPF_ALGO_GENERIC 0
@@ -85,7 +86,12 @@ int lpf_select_count(const int64_t* links, int64_t bs,
                      const int64_t* adj_rowptr, const int32_t* adj_col,
                      const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val,
                      float th_cn, float th_1hop, float th_non1hop, int mode, int algo,
-                     int32_t* counts, void* stream);
+                     int32_t* counts, void* workspace, void* stream);
+
+/* Bytes of device workspace the INTERSECT algorithms need for a batch of bs links (the count pass records
+ * the links it defers to the CTA-wide kernel there; the fill pass of the SAME batch must get the same
+ * buffer, untouched in between).  GENERIC ignores the workspace (may be NULL). */
+int64_t lpf_select_workspace_bytes(int64_t bs);
 
 /* Exclusive scan of n int32 counts into n+1 int64 offsets (single launch).
  * `scratch` must hold lpf_scan_scratch_bytes(n) bytes. */
@@ -98,7 +104,7 @@ int lpf_select_fill(const int64_t* links, int64_t bs,
                     float th_cn, float th_1hop, float th_non1hop, int mode, int algo,
                     const int64_t* ptr,
                     int32_t* node, float* src_ppr, float* tgt_ppr, int32_t* link /* may be NULL */,
-                    void* stream);
+                    void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * RPE hidden vector — first half of get_pos_encodings (models/link_transformer.py
@@ -121,6 +127,15 @@ int lpf_rpe_hidden(const float* src_ppr, const float* tgt_ppr, int64_t row0, int
 int lpf_gemm(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
              float bias_scale, float* C, int64_t ldc, int64_t M, int32_t N, int32_t K,
              int epilogue, void* stream);
+
+/* The same contraction on the tcgen05 tensor cores (kind::tf32 with the 3xTF32 split, fp32-level accuracy;
+ * accumulators in TMEM, weights staged by bulk TMA copies).  `Wpacked` is the pre-split, pre-swizzled image of
+ * the nn.Linear weight W[N,K] built once per weight by lpf_pack_weight into lpf_pack_weight_bytes(N,K) bytes
+ * of device memory (16-byte aligned).  N <= 256 per call (split larger weights by rows). */
+int64_t lpf_pack_weight_bytes(int32_t N, int32_t K);
+int lpf_pack_weight(const float* W, int64_t ldw, int32_t N, int32_t K, float* packed, void* stream);
+int lpf_gemm_tc(const float* A, int64_t lda, const float* Wpacked, const float* bias, float bias_scale,
+                float* C, int64_t ldc, int64_t M, int32_t N, int32_t K, int epilogue, void* stream);
 
 /* Row-wise LayerNorm (eps 1e-5) over the first `n` columns, optional ReLU, in place
  * or out of place (X may equal Y).  nn.LayerNorm + F.relu of MLP/GCN/gnn_norm.

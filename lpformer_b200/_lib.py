@@ -24,12 +24,17 @@ SIGNATURES = {
     "lpf_abi_version": (_int, []),
     "lpf_last_error": (C.c_char_p, []),
     "lpf_device_ok": (_int, []),
-    "lpf_select_count": (_int, [_p, _i64, _p, _p, _p, _p, _p, _f32, _f32, _f32, _int, _int, _p, _p]),
+    "lpf_select_count": (_int, [_p, _i64, _p, _p, _p, _p, _p, _f32, _f32, _f32, _int, _int, _p, _p, _p]),
+    "lpf_select_workspace_bytes": (_i64, [_i64]),
     "lpf_scan_scratch_bytes": (_i64, [_i64]),
     "lpf_scan_counts": (_int, [_p, _i64, _p, _p, _p]),
-    "lpf_select_fill": (_int, [_p, _i64, _p, _p, _p, _p, _p, _f32, _f32, _f32, _int, _int, _p, _p, _p, _p, _p, _p]),
+    "lpf_select_fill": (_int, [_p, _i64, _p, _p, _p, _p, _p, _f32, _f32, _f32, _int, _int, _p, _p, _p, _p, _p, _p,
+                                _p]),
     "lpf_rpe_hidden": (_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _i32, _p, _i64, _p]),
     "lpf_gemm": (_int, [_p, _i64, _p, _i64, _p, _f32, _p, _i64, _i64, _i32, _i32, _int, _p]),
+    "lpf_pack_weight_bytes": (_i64, [_i32, _i32]),
+    "lpf_pack_weight": (_int, [_p, _i64, _i32, _i32, _p, _p]),
+    "lpf_gemm_tc": (_int, [_p, _i64, _p, _p, _f32, _p, _i64, _i64, _i32, _i32, _int, _p]),
     "lpf_layernorm_act": (_int, [_p, _i64, _p, _p, _p, _i64, _p, _i64, _i64, _i32, _int, _p]),
     "lpf_gather_links": (_int, [_p, _i64, _p, _i64, _i32, _p, _i64, _p, _i64, _p]),
     "lpf_attend_fused": (_int, [_p, _i64, _p, _p, _i64, _p, _i64, _p, _i64, _p, _p, _p, _p, _i32, _i32, _int, _int,
@@ -64,8 +69,8 @@ def load():
 
 
 # kernels launched per entry point (for bench.py's gpu_launches and per-kernel CUDA-event timing)
-KERNEL_LAUNCHES = {"lpf_select_count": 1, "lpf_scan_counts": 2, "lpf_select_fill": 1, "lpf_rpe_hidden": 1,
-                   "lpf_gemm": 1, "lpf_layernorm_act": 1, "lpf_gather_links": 1, "lpf_attend_fused": 1,
+KERNEL_LAUNCHES = {"lpf_select_count": 3, "lpf_scan_counts": 2, "lpf_select_fill": 2, "lpf_rpe_hidden": 1,
+                   "lpf_gemm": 1, "lpf_gemm_tc": 1, "lpf_pack_weight": 1, "lpf_layernorm_act": 1, "lpf_gather_links": 1, "lpf_attend_fused": 1,
                    "lpf_gcn_spmm": 1}
 
 

@@ -1,0 +1,227 @@
+// K3 — dense contraction C = epi(A W^T + bias) on the 5th-generation tensor cores (tcgen05.mma, kind::tf32,
+// accumulator in TMEM), with fp32-level accuracy by the 3xTF32 split (tc.cuh).
+//
+// Every nn.Linear of the path whose weight is reused across many rows goes through here: GCNConv.lin and the
+// per-node K/V projection (N rows per eval), the RPE contraction (S rows), lin_l and the MLP heads (BS rows)
+// (reference modules/layers.py:130-131,208-214; models/other_models.py:61-76,125-138,173-179).
+//
+// Work shape: one CTA = one 128-row tile of A and the whole (padded) N <= 256; the k-blocks (32 fp32 = one
+// 128-byte swizzled row) stream through a 2-stage shared-memory ring:
+//   * the weight's pre-split, pre-swizzled image (lpf_pack_weight, built once per weight) arrives by one bulk
+//     TMA copy (cp.async.bulk) per k-block, completion on an mbarrier;
+//   * the A tile is loaded with coalesced 128-bit global loads, split into hi/lo in registers and stored in
+//     the UMMA canonical layout;
+//   * thread 0 issues the 12 MMAs of the k-block (4 K-slices x 3 split products) and commits them to the
+//     stage's "free" barrier, so loading k-block i+1 overlaps the tensor pipe working on k-block i;
+//   * epilogue: tcgen05.ld of the thread's own row (TMEM lane = row), bias / ReLU / sigmoid, 128-bit stores.
+// Several CTAs are resident per SM (<= 96 KB smem, <= 256 TMEM columns each), which overlaps one CTA's
+// epilogue with another's loads and MMAs.
+#include "tc.cuh"
+
+namespace lpf {
+
+using namespace tc;
+
+constexpr int kGemmThreads = 128;
+
+// Packed weight image: [KB][2 (hi, lo)][NP rows][128 B swizzled];  KB = ceil(K/32), NP = round_up(N,16).
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ W, int64_t ldw, int N, int K,
+                                                          int NP, int KB, float* __restrict__ out) {
+    const int64_t total = (int64_t)KB * NP * 32;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int kk = (int)(e % 32);
+        const int n = (int)((e / 32) % NP);
+        const int kb = (int)(e / (32 * (int64_t)NP));
+        const int k = kb * 32 + kk;
+        const float w = (n < N && k < K) ? W[(int64_t)n * ldw + k] : 0.f;
+        const float hi = tf32_hi(w), lo = w - hi;
+        const uint32_t off = swz_chunk_off(n, kk >> 2) + (uint32_t)((kk & 3) << 2);
+        char* base = reinterpret_cast<char*>(out) + (size_t)kb * 2 * NP * 128;
+        *reinterpret_cast<float*>(base + off) = hi;
+        *reinterpret_cast<float*>(base + (size_t)NP * 128 + off) = lo;
+    }
+}
+
+struct GemmTcParams {
+    const float* A;
+    int64_t lda;
+    const float* Wp;   // packed image
+    const float* bias;
+    float bias_scale;
+    float* C;
+    int64_t ldc;
+    int64_t M;
+    int N, K, NP, KB, epi;
+    uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(GemmTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_w[2], bar_free[2], bar_acc;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t w_tile = (uint32_t)p.NP * 128;                 // bytes of one W part (hi or lo) per k-block
+    const uint32_t stage_bytes = 2 * kATileBytes + 2 * w_tile;
+    const int64_t m0 = (int64_t)blockIdx.x * kTileM;
+
+    if (tid == 0) {
+        mbar_init(&bar_w[0], 1);
+        mbar_init(&bar_w[1], 1);
+        mbar_init(&bar_free[0], 1);
+        mbar_init(&bar_free[1], 1);
+        mbar_init(&bar_acc, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc(&tmem_slot, p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_slot;
+    const uint32_t idesc = make_idesc_tf32(kTileM, p.NP);
+
+    const bool vec_a = ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) && (p.lda % 4 == 0);
+    const int chunk = tid & 7;          // 16-byte chunk of the 128-byte row
+    const int row_in_pass = tid >> 3;   // 16 rows per pass
+
+    for (int kb = 0; kb < p.KB; ++kb) {
+        const int s = kb & 1;
+        const uint32_t use = (uint32_t)(kb >> 1);
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        if (kb >= 2) mbar_wait(&bar_free[s], (use - 1) & 1);      // MMAs that read this stage have completed
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&bar_w[s], 2 * w_tile);
+            bulk_g2s(st + 2 * kATileBytes, reinterpret_cast<const uint8_t*>(p.Wp) + (size_t)kb * 2 * w_tile, 2 * w_tile,
+                     &bar_w[s]);
+        }
+        __syncwarp();
+        // A k-block: rows m0..m0+127, columns kb*32 .. +31
+        const int k0 = kb * 32 + chunk * 4;
+#pragma unroll
+        for (int pass = 0; pass < 8; ++pass) {
+            const int r = pass * 16 + row_in_pass;
+            const int64_t m = m0 + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < p.M) {
+                const float* src = p.A + m * p.lda + k0;
+                if (vec_a && k0 + 3 < p.K) {
+                    v = __ldg(reinterpret_cast<const float4*>(src));
+                } else {
+                    if (k0 + 0 < p.K) v.x = __ldg(src + 0);
+                    if (k0 + 1 < p.K) v.y = __ldg(src + 1);
+                    if (k0 + 2 < p.K) v.z = __ldg(src + 2);
+                    if (k0 + 3 < p.K) v.w = __ldg(src + 3);
+                }
+            }
+            const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+            const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+            const uint32_t off = swz_chunk_off(r, chunk);
+            *reinterpret_cast<float4*>(st + off) = hi;
+            *reinterpret_cast<float4*>(st + kATileBytes + off) = lo;
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            mbar_wait(&bar_w[s], use & 1);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(st), a_lo = a_hi + kATileBytes;
+            const uint32_t b_hi = a_hi + 2 * kATileBytes, b_lo = b_hi + w_tile;
+            issue_kblock_3x(tmem_d, a_hi, a_lo, b_hi, b_lo, idesc, kb == 0);
+            umma_commit(&bar_free[s]);
+            if (kb == p.KB - 1) umma_commit(&bar_acc);
+        }
+        __syncwarp();
+    }
+
+    mbar_wait(&bar_acc, 0);
+    tc_fence_after();
+
+    // epilogue: thread t owns row m0 + t (TMEM lane t)
+    const int64_t m = m0 + tid;
+    const bool vec_c = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.ldc % 4 == 0);
+    const uint32_t lane_base = tmem_d + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < p.NP; c0 += 16) {
+        float v[16];
+        tmem_ld16(lane_base + (uint32_t)c0, v);    // warp-collective: every lane executes it
+        if (m < p.M) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int n = c0 + j;
+                float x = v[j];
+                if (p.bias && n < p.N) x += p.bias_scale * __ldg(p.bias + n);
+                if (p.epi == LPF_EPI_RELU) x = fmaxf(x, 0.f);
+                else if (p.epi == LPF_EPI_SIGMOID) x = 1.0f / (1.0f + expf(-x));
+                v[j] = x;
+            }
+            float* dst = p.C + m * p.ldc + c0;
+            if (vec_c && c0 + 16 <= p.N) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < p.N) dst[j] = v[j];
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, p.tmem_cols);
+}
+
+}  // namespace lpf
+
+using namespace lpf;
+
+extern "C" int64_t lpf_pack_weight_bytes(int32_t N, int32_t K) {
+    if (N < 1 || K < 1) return 0;
+    const int64_t KB = (K + 31) / 32, NP = tc::round_up(N, 16);
+    return KB * 2 * NP * 128;
+}
+
+extern "C" int lpf_pack_weight(const float* W, int64_t ldw, int32_t N, int32_t K, float* packed, void* stream) {
+    LPF_REQUIRE(W && packed, "NULL argument");
+    LPF_REQUIRE(N >= 1 && K >= 1 && ldw >= K, "bad shape");
+    LPF_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "packed image must be 16-byte aligned");
+    const int KB = (K + 31) / 32, NP = tc::round_up(N, 16);
+    const int64_t total = (int64_t)KB * NP * 32;
+    const unsigned grid = (unsigned)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256);
+    pack_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(W, ldw, N, K, NP, KB, packed);
+    return check_launch("lpf_pack_weight");
+}
+
+extern "C" int lpf_gemm_tc(const float* A, int64_t lda, const float* Wpacked, const float* bias, float bias_scale,
+                           float* C, int64_t ldc, int64_t M, int32_t N, int32_t K, int epilogue, void* stream) {
+    LPF_REQUIRE(M >= 0 && N >= 1 && K >= 1, "bad shape");
+    if (M == 0) return LPF_OK;
+    LPF_REQUIRE(A && Wpacked && C, "NULL argument");
+    LPF_REQUIRE(lda >= K && ldc >= N, "leading dimension too small");
+    LPF_REQUIRE(epilogue >= LPF_EPI_NONE && epilogue <= LPF_EPI_SIGMOID, "bad epilogue");
+    LPF_REQUIRE((reinterpret_cast<uintptr_t>(Wpacked) & 15) == 0, "packed image must be 16-byte aligned");
+    if (N > 256) {
+        set_error("lpf_gemm_tc: N = %d exceeds one UMMA tile (256); split the weight by rows", N);
+        return LPF_ERR_UNSUPPORTED;
+    }
+    GemmTcParams p;
+    p.A = A; p.lda = lda; p.Wp = Wpacked; p.bias = bias; p.bias_scale = bias_scale; p.C = C; p.ldc = ldc;
+    p.M = M; p.N = N; p.K = K; p.NP = tc::round_up(N, 16); p.KB = (K + 31) / 32; p.epi = epilogue;
+    p.tmem_cols = tc::tmem_cols_for(p.NP);
+    const int stages = p.KB < 2 ? 1 : 2;
+    const size_t smem = (size_t)stages * (2 * tc::kATileBytes + 2 * (size_t)p.NP * 128) + 1024;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("lpf_gemm_tc: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+            return LPF_ERR_CUDA;
+        }
+        configured = smem;
+    }
+    const unsigned grid = (unsigned)((M + tc::kTileM - 1) / tc::kTileM);
+    gemm_tc_kernel<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(p);
+    return check_launch("lpf_gemm_tc");
+}

@@ -282,7 +282,7 @@ namespace lpf {
 int select_fast(bool fill, int group, const int64_t* links, int64_t bs, const int64_t* adj_rowptr,
                 const int32_t* adj_col, const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val,
                 float th_cn, float th_1hop, float th_non1hop, int mode, int32_t* counts, const int64_t* ptr,
-                int32_t* node, float* pa, float* pb, int32_t* link, cudaStream_t st);
+                int32_t* node, float* pa, float* pb, int32_t* link, int32_t* heavy, cudaStream_t st);
 }
 
 static int check_algo(int algo, int mode, float th_1hop, float th_non1hop) {
@@ -309,7 +309,8 @@ static int check_select_args(const int64_t* links, int64_t bs, const void* arp, 
 
 extern "C" int lpf_select_count(const int64_t* links, int64_t bs, const int64_t* adj_rowptr, const int32_t* adj_col,
                                 const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val, float th_cn,
-                                float th_1hop, float th_non1hop, int mode, int algo, int32_t* counts, void* stream) {
+                                float th_1hop, float th_non1hop, int mode, int algo, int32_t* counts, void* workspace,
+                                void* stream) {
     int rc = check_select_args(links, bs, adj_rowptr, adj_col, ppr_rowptr, ppr_col, ppr_val, mode);
     if (rc) return rc;
     rc = check_algo(algo, mode, th_1hop, th_non1hop);
@@ -317,9 +318,10 @@ extern "C" int lpf_select_count(const int64_t* links, int64_t bs, const int64_t*
     LPF_REQUIRE(bs == 0 || counts, "counts is NULL");
     if (algo != LPF_ALGO_GENERIC) {
         if (bs == 0) return LPF_OK;
+        LPF_REQUIRE(workspace, "workspace is NULL (lpf_select_workspace_bytes)");
         return select_fast(false, algo == LPF_ALGO_INTERSECT32 ? 32 : 8, links, bs, adj_rowptr, adj_col, ppr_rowptr,
                            ppr_col, ppr_val, th_cn, th_1hop, th_non1hop, mode, counts, nullptr, nullptr, nullptr,
-                           nullptr, nullptr, (cudaStream_t)stream);
+                           nullptr, nullptr, (int32_t*)workspace, (cudaStream_t)stream);
     }
     SelectParams p{links, bs, adj_rowptr, adj_col, ppr_rowptr, ppr_col, ppr_val, th_cn, th_1hop, th_non1hop,
                    mode, counts, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -329,7 +331,7 @@ extern "C" int lpf_select_count(const int64_t* links, int64_t bs, const int64_t*
 extern "C" int lpf_select_fill(const int64_t* links, int64_t bs, const int64_t* adj_rowptr, const int32_t* adj_col,
                                const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val, float th_cn,
                                float th_1hop, float th_non1hop, int mode, int algo, const int64_t* ptr, int32_t* node,
-                               float* src_ppr, float* tgt_ppr, int32_t* link, void* stream) {
+                               float* src_ppr, float* tgt_ppr, int32_t* link, void* workspace, void* stream) {
     int rc = check_select_args(links, bs, adj_rowptr, adj_col, ppr_rowptr, ppr_col, ppr_val, mode);
     if (rc) return rc;
     rc = check_algo(algo, mode, th_1hop, th_non1hop);
@@ -337,14 +339,17 @@ extern "C" int lpf_select_fill(const int64_t* links, int64_t bs, const int64_t* 
     LPF_REQUIRE(bs == 0 || ptr, "ptr is NULL");
     if (algo != LPF_ALGO_GENERIC) {
         if (bs == 0) return LPF_OK;
+        LPF_REQUIRE(workspace, "workspace is NULL (lpf_select_workspace_bytes)");
         return select_fast(true, algo == LPF_ALGO_INTERSECT32 ? 32 : 8, links, bs, adj_rowptr, adj_col, ppr_rowptr,
                            ppr_col, ppr_val, th_cn, th_1hop, th_non1hop, mode, nullptr, ptr, node, src_ppr, tgt_ppr,
-                           link, (cudaStream_t)stream);
+                           link, (int32_t*)workspace, (cudaStream_t)stream);
     }
     SelectParams p{links, bs, adj_rowptr, adj_col, ppr_rowptr, ppr_col, ppr_val, th_cn, th_1hop, th_non1hop,
                    mode, nullptr, ptr, node, src_ppr, tgt_ppr, link};
     return launch_select(true, p, (cudaStream_t)stream);
 }
+
+extern "C" int64_t lpf_select_workspace_bytes(int64_t bs) { return (bs + 4) * (int64_t)sizeof(int32_t); }
 
 extern "C" int64_t lpf_scan_scratch_bytes(int64_t n) {
     const int64_t tiles = (n + kScanTile - 1) / kScanTile;

@@ -37,7 +37,14 @@ struct SelectParams2 {
     float* pa;
     float* pb;
     int32_t* link;
+    int32_t* heavy;   // workspace: [0] = number of heavy links, [4..] their batch positions (written by the count pass)
 };
+
+// A link whose shorter adjacency (or PPR) row exceeds kHeavyPerLane elements per lane of its group is deferred
+// to select_heavy_kernel, where a whole CTA walks it: a few such links (hub-hub positives) would otherwise
+// serialise thousands of dependent searches behind 8 lanes and set the duration of the whole launch.
+constexpr int kHeavyPerLane = 16;
+constexpr int kHeavyThreads = 256;
 
 // lower_bound restricted to [lo, n)
 __device__ __forceinline__ int lower_bound_from(const int32_t* __restrict__ a, int lo, int n, int32_t key) {
@@ -85,6 +92,10 @@ __global__ void __launch_bounds__(256) select_fast_kernel(SelectParams2 p) {
         const int64_t pb0 = __ldg(p.ppr_rowptr + b), pb1 = __ldg(p.ppr_rowptr + b + 1);
         const int na = (int)(a1 - a0), nb = (int)(b1 - b0);
         const int npa = (int)(pa1 - pa0), npb = (int)(pb1 - pb0);
+        if (max(min(na, nb), want_pi ? min(npa, npb) : 0) > kHeavyPerLane * G) {
+            if (!FILL && gl == 0) p.heavy[4 + atomicAdd(p.heavy, 1)] = (int32_t)i;
+            continue;
+        }
         const int32_t* Aa = p.adj_col + a0;
         const int32_t* Ab = p.adj_col + b0;
         const int32_t* Pac = p.ppr_col + pa0;
@@ -186,23 +197,165 @@ __global__ void __launch_bounds__(256) select_fast_kernel(SelectParams2 p) {
     }
 }
 
+
+// Ordered block-wide compaction step: every thread passes its flag; returns this thread's rank among the
+// flagged threads (thread order) and adds the block total to `running`.  Two __syncthreads per call.
+__device__ __forceinline__ int block_rank(bool flag, int* warp_tot, int& running) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(kFull, flag);
+    if (lane == 0) warp_tot[warp] = __popc(m);
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kHeavyThreads / 32; ++w) {
+        const int t = warp_tot[w];
+        before += (w < warp) ? t : 0;
+        total += t;
+    }
+    const int rank = running + before + __popc(m & ((1u << lane) - 1u));
+    running += total;
+    __syncthreads();
+    return rank;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(kHeavyThreads) select_heavy_kernel(SelectParams2 p) {
+    __shared__ int wt[kHeavyThreads / 32];
+    const int nheavy = p.heavy[0];
+    const bool want_pi = p.mode != LPF_MODE_CN;
+    const bool want_n1 = p.mode == LPF_MODE_ALL;
+    const bool cn_needs_ppr = FILL || p.th_cn > 0.0f;
+    const float th_pre = want_n1 ? fminf(p.th_1hop, p.th_non1hop) : p.th_1hop;
+    for (int q = blockIdx.x; q < nheavy; q += gridDim.x) {
+        const int64_t i = p.heavy[4 + q];
+        int64_t o_cn = 0, o_1h = 0, o_n1 = 0;
+        if (FILL) {
+            o_cn = __ldg(p.ptr + i);
+            o_1h = __ldg(p.ptr + p.bs + i);
+            o_n1 = __ldg(p.ptr + 2 * p.bs + i);
+            if (o_cn == __ldg(p.ptr + i + 1) && o_1h == __ldg(p.ptr + p.bs + i + 1) &&
+                o_n1 == __ldg(p.ptr + 2 * p.bs + i + 1))
+                continue;   // nothing selected for this link
+        }
+        const int64_t a = __ldg(p.links + i), b = __ldg(p.links + p.bs + i);
+        const int64_t a0 = __ldg(p.adj_rowptr + a), b0 = __ldg(p.adj_rowptr + b);
+        const int na = (int)(__ldg(p.adj_rowptr + a + 1) - a0), nb = (int)(__ldg(p.adj_rowptr + b + 1) - b0);
+        const int64_t pa0 = __ldg(p.ppr_rowptr + a), pb0 = __ldg(p.ppr_rowptr + b);
+        const int npa = (int)(__ldg(p.ppr_rowptr + a + 1) - pa0), npb = (int)(__ldg(p.ppr_rowptr + b + 1) - pb0);
+        const int32_t* Aa = p.adj_col + a0;
+        const int32_t* Ab = p.adj_col + b0;
+        const int32_t* Pac = p.ppr_col + pa0;
+        const int32_t* Pbc = p.ppr_col + pb0;
+        const float* Pav = p.ppr_val + pa0;
+        const float* Pbv = p.ppr_val + pb0;
+
+        int c_cn = 0, c_1h = 0, c_n1 = 0;
+        {   // CN: every thread probes one element of the shorter adjacency row per step
+            const bool a_short = na <= nb;
+            const int32_t* S = a_short ? Aa : Ab;
+            const int32_t* Lg = a_short ? Ab : Aa;
+            const int ns = a_short ? na : nb, nl = a_short ? nb : na;
+            int lo = 0;   // this thread's elements ascend, so its search window only moves right
+            for (int k = 0; k < ns; k += kHeavyThreads) {
+                const bool act = k + (int)threadIdx.x < ns;
+                const int32_t u = act ? __ldg(S + k + threadIdx.x) : 0x7fffffff;
+                bool hit = false;
+                float qa = 0.f, qb = 0.f;
+                if (act) {
+                    lo = lower_bound_from(Lg, lo, nl, u);
+                    hit = lo < nl && __ldg(Lg + lo) == u;
+                    if (hit && cn_needs_ppr) {
+                        int t = lower_bound_from(Pac, 0, npa, u);
+                        if (t < npa && __ldg(Pac + t) == u) qa = quantise(__ldg(Pav + t));
+                        t = lower_bound_from(Pbc, 0, npb, u);
+                        if (t < npb && __ldg(Pbc + t) == u) qb = quantise(__ldg(Pbv + t));
+                        hit = qa >= p.th_cn && qb >= p.th_cn;
+                    }
+                }
+                const int r = block_rank(hit, wt, c_cn);
+                if (FILL && hit) {
+                    const int64_t s = o_cn + r;
+                    p.node[s] = u;
+                    p.pa[s] = qa;
+                    p.pb[s] = qb;
+                    if (p.link) p.link[s] = (int32_t)i;
+                }
+            }
+        }
+        if (want_pi) {   // 1-hop / >1-hop from the intersection of the two PPR rows
+            const bool a_short = npa <= npb;
+            const int32_t* Sc = a_short ? Pac : Pbc;
+            const float* Sv = a_short ? Pav : Pbv;
+            const int32_t* Lc = a_short ? Pbc : Pac;
+            const float* Lv = a_short ? Pbv : Pav;
+            const int ns = a_short ? npa : npb, nl = a_short ? npb : npa;
+            int lo = 0;
+            for (int k = 0; k < ns; k += kHeavyThreads) {
+                const bool act = k + (int)threadIdx.x < ns;
+                const int32_t u = act ? __ldg(Sc + k + threadIdx.x) : 0x7fffffff;
+                bool k1 = false, kn = false;
+                float qa = 0.f, qb = 0.f;
+                if (act) {
+                    lo = lower_bound_from(Lc, lo, nl, u);
+                    if (lo < nl && __ldg(Lc + lo) == u) {
+                        const float qs = quantise(__ldg(Sv + k + threadIdx.x)), ql = quantise(__ldg(Lv + lo));
+                        qa = a_short ? qs : ql;
+                        qb = a_short ? ql : qs;
+                        if (qa >= th_pre && qb >= th_pre) {
+                            int t = lower_bound_from(Aa, 0, na, u);
+                            const bool in_a = t < na && __ldg(Aa + t) == u;
+                            t = lower_bound_from(Ab, 0, nb, u);
+                            const bool in_b = t < nb && __ldg(Ab + t) == u;
+                            k1 = (in_a != in_b) && qa >= p.th_1hop && qb >= p.th_1hop;
+                            kn = want_n1 && !in_a && !in_b && qa >= p.th_non1hop && qb >= p.th_non1hop;
+                        }
+                    }
+                }
+                const int r1 = block_rank(k1, wt, c_1h);
+                const int rn = block_rank(kn, wt, c_n1);
+                if (FILL && (k1 || kn)) {
+                    const int64_t s = k1 ? o_1h + r1 : o_n1 + rn;
+                    p.node[s] = u;
+                    p.pa[s] = qa;
+                    p.pb[s] = qb;
+                    if (p.link) p.link[s] = (int32_t)i;
+                }
+            }
+        }
+        if (!FILL && threadIdx.x == 0) {
+            p.counts[i] = c_cn;
+            p.counts[p.bs + i] = c_1h;
+            p.counts[2 * p.bs + i] = c_n1;
+        }
+    }
+}
+
+__global__ void select_reset_heavy(int32_t* heavy) { heavy[0] = 0; }
+
 template <int G>
 static int launch_fast(bool fill, const SelectParams2& p, cudaStream_t st) {
     const int64_t groups_per_block = 256 / G;
     int64_t blocks = (p.bs + groups_per_block - 1) / groups_per_block;
     const int64_t cap = (int64_t)kNumSMs * 8 * 8;
     if (blocks > cap) blocks = cap;
-    if (fill) select_fast_kernel<G, true><<<(unsigned)blocks, 256, 0, st>>>(p);
-    else select_fast_kernel<G, false><<<(unsigned)blocks, 256, 0, st>>>(p);
+    const unsigned hgrid = kNumSMs * 2;
+    if (fill) {
+        select_fast_kernel<G, true><<<(unsigned)blocks, 256, 0, st>>>(p);
+        select_heavy_kernel<true><<<hgrid, kHeavyThreads, 0, st>>>(p);
+    } else {
+        select_reset_heavy<<<1, 1, 0, st>>>(p.heavy);
+        select_fast_kernel<G, false><<<(unsigned)blocks, 256, 0, st>>>(p);
+        select_heavy_kernel<false><<<hgrid, kHeavyThreads, 0, st>>>(p);
+    }
     return check_launch(fill ? "lpf_select_fill" : "lpf_select_count");
 }
 
 int select_fast(bool fill, int group, const int64_t* links, int64_t bs, const int64_t* adj_rowptr,
                 const int32_t* adj_col, const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val,
                 float th_cn, float th_1hop, float th_non1hop, int mode, int32_t* counts, const int64_t* ptr,
-                int32_t* node, float* pa, float* pb, int32_t* link, cudaStream_t st) {
+                int32_t* node, float* pa, float* pb, int32_t* link, int32_t* heavy, cudaStream_t st) {
     SelectParams2 p{links, bs, adj_rowptr, adj_col, ppr_rowptr, ppr_col, ppr_val, th_cn, th_1hop, th_non1hop,
-                    mode, counts, ptr, node, pa, pb, link};
+                    mode, counts, ptr, node, pa, pb, link, heavy};
     if (group == 32) return launch_fast<32>(fill, p, st);
     return launch_fast<8>(fill, p, st);
 }

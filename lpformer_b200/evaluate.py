@@ -61,7 +61,7 @@ def propagate_replicated(model, test_set=False, group=None):
                 ops.layernorm_act(sh, model.gnn_norm.weight, model.gnn_norm.bias, relu=False, out=xs)
                 c0 = d
                 for layer, w in zip(model.att_layers, widths[1:]):
-                    ops.gemm(xs, layer.att.lin_r.weight[:, :d], out=packed[:rows, c0:c0 + w])
+                    ops.linear(xs, layer.att.lin_r.weight[:, :d], out=packed[:rows, c0:c0 + w])
                     c0 += w
             full = torch.empty((per * world, sum(widths)), dtype=torch.float32, device=dev)
             dist.all_gather_into_tensor(full, packed, group=group)          # the one collective of the eval

@@ -49,7 +49,7 @@ class _GlorotLinear(nn.Module):
             self.bias.data.fill_(0)
 
     def forward(self, x):
-        return ops.gemm(x, self.weight, self.bias)
+        return ops.linear(x, self.weight, self.bias)
 
 
 class MLP(nn.Module):
@@ -85,12 +85,12 @@ class MLP(nn.Module):
         x = x.reshape(-1, x.shape[-1])
         for lin in list(self.linears)[:-1]:
             if self.norm is not None:
-                x = ops.gemm(x, lin.weight, lin.bias)
+                x = ops.linear(x, lin.weight, lin.bias)
                 x = ops.layernorm_act(x, self.norm.weight, self.norm.bias, relu=True, out=x)
             else:
-                x = ops.gemm(x, lin.weight, lin.bias, epilogue=EPI_RELU)
+                x = ops.linear(x, lin.weight, lin.bias, epilogue=EPI_RELU)
         last = self.linears[-1]
-        x = ops.gemm(x, last.weight, last.bias, out=out, epilogue=EPI_SIGMOID if self.sigmoid else EPI_NONE)
+        x = ops.linear(x, last.weight, last.bias, out=out, epilogue=EPI_SIGMOID if self.sigmoid else EPI_NONE)
         x = x.reshape(*lead, x.shape[-1])
         return x.squeeze(-1)
 
@@ -119,9 +119,9 @@ class mlp_score(nn.Module):
         _no_training(self, "dropout" if self.dropout > 0 else "")
         x = x.reshape(-1, x.shape[-1])
         for lin in list(self.lins)[:-1]:
-            x = ops.gemm(x, lin.weight, lin.bias, epilogue=EPI_RELU)
+            x = ops.linear(x, lin.weight, lin.bias, epilogue=EPI_RELU)
         last = self.lins[-1]
-        x = ops.gemm(x, last.weight, last.bias, epilogue=EPI_NONE if return_logits else EPI_SIGMOID)
+        x = ops.linear(x, last.weight, last.bias, epilogue=EPI_NONE if return_logits else EPI_SIGMOID)
         return x.squeeze(-1)
 
 
@@ -144,7 +144,7 @@ class GCNConv(nn.Module):
     @torch.no_grad()
     def forward(self, x, adj_norm: CSR, out=None, row0=0, rows=None):
         """A_hat @ (x W^T) + bias on an already gcn-normalised CSR (rows [row0,row0+rows))."""
-        xw = ops.gemm(x, self.lin.weight)
+        xw = ops.linear(x, self.lin.weight)
         return ops.gcn_spmm(adj_norm, xw, self.bias, out=out, row0=row0, rows=rows)
 
 
@@ -403,7 +403,7 @@ class LinkTransformer(nn.Module):
         if self._kv_cache is not None and self._kv_cache[0] == key:
             return self._kv_cache[1]
         d = self.dim
-        kvs = [ops.gemm(X_node, layer.att.lin_r.weight[:, :d]) for layer in self.att_layers]
+        kvs = [ops.linear(X_node, layer.att.lin_r.weight[:, :d]) for layer in self.att_layers]
         self._kv_cache = (key, kvs, X_node)   # keep X_node alive so the pointer key stays valid
         return kvs
 
@@ -491,14 +491,14 @@ class LinkTransformer(nn.Module):
             HC = H * C
             last = l == self.num_layers - 1
             if l == 0:
-                Q = ops.gemm(xsum, att.lin_l.weight, att.lin_l.bias, bias_scale=2.0)
+                Q = ops.linear(xsum, att.lin_l.weight, att.lin_l.bias, bias_scale=2.0)
             else:   # e1, e2 = chunk(2) of the previous layer's output (reference modules/layers.py:211)
-                Q = ops.gemm(feats, derived[l]["w_l_cat"], att.lin_l.bias, bias_scale=2.0)
+                Q = ops.linear(feats, derived[l]["w_l_cat"], att.lin_l.bias, bias_scale=2.0)
             R = torch.empty((S, HC), dtype=torch.float32, device=dev)
             for t, (m, c) in enumerate(derived[l]["rpe"]):
                 r0, r1 = sel.type_range(t)
                 if r1 > r0:
-                    ops.gemm(hsum[r0:r1], m, c, out=R[r0:r1])
+                    ops.linear(hsum[r0:r1], m, c, out=R[r0:r1])
             width = HC + (self.count_dim if last else 0)
             feats = torch.empty((bs, width), dtype=torch.float32, device=dev)
             ops.attend(sel, kvs[l], R, Q, att.att, att.bias, layer.post_att_norm.weight, layer.post_att_norm.bias,

@@ -5,6 +5,7 @@ plumbing) and every launch goes to torch's current stream.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -44,6 +45,55 @@ def gemm(A, W, bias=None, bias_scale=1.0, out=None, epilogue=EPI_NONE):
         bias = bias.float().contiguous()
     call("lpf_gemm", ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(bias), float(bias_scale), ptr(out),
          out.stride(0) if M > 0 else N, M, N, K, epilogue, stream(), meta=(M, N, K))
+    return out
+
+
+_PACKED = {}          # (data_ptr, version, shape, stride) -> (packed image, weight kept alive)
+GEMM_BACKEND = os.environ.get("LPF_GEMM_BACKEND", "simt")   # "tc": tcgen05 3xTF32 kernel (lpf_gemm_tc);  "simt": fp32 FFMA kernel (lpf_gemm)
+
+
+def pack_weight(W):
+    """Pre-split (hi/lo tf32) pre-swizzled image of an nn.Linear weight [N,K] for lpf_gemm_tc; cached per
+    (storage, version) so it is built once per weight."""
+    key = (W.data_ptr(), W._version, tuple(W.shape), W.stride(0), W.device.index)
+    hit = _PACKED.get(key)
+    if hit is not None:
+        return hit[0]
+    require_cuda(W)
+    Wc = _rowmajor(W.detach())
+    N, K = Wc.shape
+    nbytes = _lib.load().lpf_pack_weight_bytes(N, K)
+    packed = torch.empty(nbytes // 4, dtype=torch.float32, device=W.device)
+    call("lpf_pack_weight", ptr(Wc), Wc.stride(0), N, K, ptr(packed), stream())
+    if len(_PACKED) > 512:
+        _PACKED.clear()
+    _PACKED[key] = (packed, W)
+    return packed
+
+
+def linear(A, W, bias=None, bias_scale=1.0, out=None, epilogue=EPI_NONE):
+    """out[M,N] = epi(A @ W^T + bias_scale*bias) on the tensor cores (rows of W in chunks of <= 256)."""
+    if GEMM_BACKEND != "tc":
+        return gemm(A, W, bias, bias_scale, out, epilogue)
+    require_cuda(A, W, bias, out)
+    A = _rowmajor(A)
+    M, K = A.shape
+    N = W.shape[0]
+    if W.shape[1] != K:
+        raise ValueError(f"linear: A is [{M},{K}] but W is {list(W.shape)}")
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    elif out.shape != (M, N) or out.stride(1) != 1 or out.dtype != torch.float32:
+        raise ValueError("linear: bad `out`")
+    if bias is not None:
+        bias = bias.detach().float().contiguous()
+    for n0 in range(0, N, 256):
+        n1 = min(N, n0 + 256)
+        Wc = W if (n0 == 0 and n1 == N) else W[n0:n1]
+        o = out if (n0 == 0 and n1 == N) else out[:, n0:n1]
+        b = None if bias is None else (bias if (n0 == 0 and n1 == N) else bias[n0:n1])
+        call("lpf_gemm_tc", ptr(A), A.stride(0), ptr(pack_weight(Wc)), ptr(b), float(bias_scale), ptr(o),
+             o.stride(0) if M > 0 else N, M, n1 - n0, K, epilogue, stream(), meta=(M, n1 - n0, K))
     return out
 
 
@@ -135,7 +185,8 @@ def select(links, adj: CSR, ppr: CSR, th_cn, th_1hop, th_non1hop, mode: str, wan
     args = (ptr(links), bs, ptr(adj.rowptr), ptr(adj.col), ptr(ppr.rowptr), ptr(ppr.col), ptr(ppr.val),
             float(th_cn), float(th_1hop), float(th_non1hop), m,
             pick_select_algo(adj, ppr, th_1hop, th_non1hop, mode) if algo is None else algo)
-    call("lpf_select_count", *args, ptr(counts), st, meta=(bs,))
+    ws = torch.empty(bs + 4, dtype=torch.int32, device=dev)
+    call("lpf_select_count", *args, ptr(counts), ptr(ws), st, meta=(bs,))
     p = torch.empty(3 * bs + 1, dtype=torch.int64, device=dev)
     scratch = torch.empty(max(1, _lib.load().lpf_scan_scratch_bytes(3 * bs) // 8), dtype=torch.int64, device=dev)
     call("lpf_scan_counts", ptr(counts), 3 * bs, ptr(p), ptr(scratch), st)
@@ -146,7 +197,7 @@ def select(links, adj: CSR, ppr: CSR, th_cn, th_1hop, th_non1hop, mode: str, wan
     pb = torch.empty(S, dtype=torch.float32, device=dev)
     link = torch.empty(S, dtype=torch.int32, device=dev) if want_link else None
     if S > 0:
-        call("lpf_select_fill", *args, ptr(p), ptr(node), ptr(pa), ptr(pb), ptr(link), st, meta=(bs, S))
+        call("lpf_select_fill", *args, ptr(p), ptr(node), ptr(pa), ptr(pb), ptr(link), ptr(ws), st, meta=(bs, S))
     return Selection(mode, bs, p, node, pa, pb, link, (0, b[0], b[1], b[2]))
 
 

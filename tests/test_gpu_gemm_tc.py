@@ -1,0 +1,44 @@
+"""-m gpu: the tcgen05 (3xTF32, TMEM accumulator) contraction against a float64 reference of the same op."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [  # (M, N, K)
+    (128, 64, 64), (1000, 64, 64), (257, 68, 68), (129, 1, 128), (5, 64, 2), (4096, 128, 128), (300, 256, 256),
+    (100, 512, 512), (777, 64, 1433), (1, 16, 32), (3000, 80, 40),
+]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("epi", [0, 1, 2])
+def test_gemm_tc_matches_fp64(M, N, K, epi):
+    from lpformer_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / np.sqrt(K)
+    b = torch.randn(N, generator=g)
+    ref = A.double() @ W.double().T + 2.0 * b.double()
+    if epi == 1:
+        ref = ref.clamp_min(0)
+    elif epi == 2:
+        ref = torch.sigmoid(ref)
+    old = ops.GEMM_BACKEND
+    ops.GEMM_BACKEND = "tc"
+    try:
+        out = ops.linear(A.to(dev), W.to(dev), b.to(dev), bias_scale=2.0, epilogue=epi)
+        # strided views: A with a wider leading dimension, output into a column slice
+        Abig = torch.zeros(M, K + 5, device=dev)
+        Abig[:, :K] = A.to(dev)
+        Cbig = torch.full((M, N + 3), -7.0, device=dev)
+        ops.linear(Abig[:, :K], W.to(dev), b.to(dev), bias_scale=2.0, out=Cbig[:, 1:N + 1], epilogue=epi)
+    finally:
+        ops.GEMM_BACKEND = old
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max()) + 1e-6
+    err = float((out.cpu().double() - ref).abs().max()) / scale
+    assert err < 2e-6, f"max scaled error {err:.3g}"      # fp32-level: plain TF32 would be ~5e-4
+    assert torch.equal(Cbig[:, 1:N + 1], out)
+    assert bool((Cbig[:, 0] == -7.0).all()) and bool((Cbig[:, N + 1:] == -7.0).all())

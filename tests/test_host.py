@@ -49,7 +49,7 @@ def test_no_cpu_fallback():
 
 def test_argument_validation(lib):
     # bad mode / NULL pointers are rejected before any launch (no GPU needed)
-    rc = lib.lpf_select_count(None, 4, None, None, None, None, None, 0.0, 0.0, 0.0, 2, 0, None, None)
+    rc = lib.lpf_select_count(None, 4, None, None, None, None, None, 0.0, 0.0, 0.0, 2, 0, None, None, None)
     assert rc == -1 and b"NULL" in lib.lpf_last_error()
     rc = lib.lpf_gemm(None, 4, None, 4, None, 1.0, None, 4, 4, 4, 4, 0, None)
     assert rc == -1
