@@ -98,6 +98,11 @@ int64_t lpf_select_workspace_bytes(int64_t bs);
 int64_t lpf_scan_scratch_bytes(int64_t n);
 int lpf_scan_counts(const int32_t* counts, int64_t n, int64_t* ptr, void* scratch, void* stream);
 
+/* After the scan: batch positions of the links with at least one selected node (nz_list int32 [<= BS], any
+ * order) and header int64[4] = (S_cn, S_cn + S_1hop, S, number of non-empty links) — the one small read-back
+ * the host needs to size the pair arrays and the compacted attention batch. */
+int lpf_select_compact(const int64_t* ptr, int64_t bs, int32_t* nz_list, int64_t* header, void* stream);
+
 int lpf_select_fill(const int64_t* links, int64_t bs,
                     const int64_t* adj_rowptr, const int32_t* adj_col,
                     const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val,
@@ -148,8 +153,15 @@ int lpf_layernorm_act(const float* X, int64_t ldx, const float* gamma, const flo
 /* Link-level gathers (models/link_transformer.py:101-102,143-144; train/testing.py:29,113):
  * xsum[i,:] = X[a_i,:] + X[b_i,:]   (input of lin_l, since lin_l(e1)+lin_l(e2) = W_l(e1+e2)+2b)
  * xprod[i,:] = X[a_i,:] * X[b_i,:]  (input of elementwise_lin).  Either output may be NULL. */
-int lpf_gather_links(const int64_t* links, int64_t bs, const float* X, int64_t ldx, int32_t d,
+int lpf_gather_links(const int64_t* links, int64_t bs, const int32_t* idx /* NULL or [n] batch positions */,
+                     int64_t n, const float* X, int64_t ldx, int32_t d,
                      float* xsum, int64_t ld_sum, float* xprod, int64_t ld_prod, void* stream);
+
+/* dst[r,:] = fill_row[:] for all `rows` rows (skipped when fill_row is NULL), then dst[idx[j],:] = src[j,:]
+ * for j < n: puts the pairwise rows of the compacted non-empty links back in batch order, every other link
+ * getting the constant empty-set row. */
+int lpf_scatter_rows(const float* src, int64_t ld_src, const int32_t* idx, int64_t n,
+                     float* dst, int64_t ld_dst, int64_t rows, int32_t d, const float* fill_row, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * K4  fused per-link attention — replaces LinkTransformerLayer.forward +
@@ -163,13 +175,32 @@ int lpf_gather_links(const int64_t* links, int64_t bs, const float* X, int64_t l
  * outputs: mode ALL -> (cn, 1hop, non1hop, cn+1hop); 1HOP -> (cn, 1hop, cn+1hop);
  * CN -> (cn); pass write_counts=0 for inner layers of a multi-layer stack.
  * alpha_out (may be NULL) receives the head-mean attention weight per pair.
+ * With idx != NULL only the n listed links are processed and rows j of Q / out belong to link idx[j]
+ * (the compacted list of lpf_select_compact); otherwise n == bs and row j is link j.
  * ------------------------------------------------------------------------- */
-int lpf_attend_fused(const int64_t* ptr, int64_t bs, const int32_t* node,
+int lpf_attend_fused(const int64_t* ptr, int64_t bs, const int32_t* idx /* NULL or [n] batch positions */,
+                     int64_t n, const int32_t* node,
                      const float* KV, int64_t ld_kv, const float* R, int64_t ld_r,
                      const float* Q, int64_t ld_q,
                      const float* att, const float* bias, const float* ln_w, const float* ln_b,
                      int32_t heads, int32_t ch, int mode, int write_counts,
                      float* out, int64_t ld_out, float* alpha_out, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Fused per-link heads on the tensor cores (d in {32, 64}) — the rest of the eval-loop body
+ * (train/testing.py:29-31,113-115) for links whose pairwise vector pw is known:
+ *     prob = mlp_score([ elementwise_lin(X[a]*X[b]) | pw ])          (models/other_models.py:125-138,173-179)
+ * with mlp_score = Linear(2d,2d) -> ReLU -> Linear(2d,1) -> sigmoid.  The pairwise half enters through
+ * zb = bs1 + Ws1[:, d:] pw: either the constant c3 [2d] (links whose selected sets are all empty share one pw)
+ * or per-row zb [n, 2d].  w1/w2 (elementwise_lin.linears.{0,1}.weight, [d,d]) and ws1 = Ws1[:, :d] ([2d,d])
+ * are lpf_pack_weight images.  idx (optional) lists the batch positions to score; prob[pos] is written.
+ * ------------------------------------------------------------------------- */
+int lpf_link_heads_tc(const int64_t* links, int64_t bs, const int32_t* idx, int64_t n,
+                      const float* X, int64_t ldx, int32_t d,
+                      const float* w1_packed, const float* b1, const float* ln_w, const float* ln_b,
+                      const float* w2_packed, const float* b2,
+                      const float* ws1_packed, const float* c3, const float* zb, int64_t ld_zb,
+                      const float* ws2, const float* bs2, float* prob, int logits, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * K2  GCN message passing — GCNConv's SpMM (models/other_models.py:66 via

@@ -16,6 +16,8 @@ namespace lpf {
 struct AttendParams {
     const int64_t* ptr;
     int64_t bs;
+    const int32_t* idx;   // optional: batch positions of the links to process (rows of Q / out follow the list)
+    int64_t n;            // number of links to process (== bs when idx is NULL)
     const int32_t* node;
     const float* KV;
     int64_t ld_kv;
@@ -48,7 +50,8 @@ __global__ void __launch_bounds__(kAttWarps * 32) attend_kernel(AttendParams p) 
             att[h][k] = (c < C) ? __ldg(p.att + h * C + c) : 0.f;
         }
 
-    for (int64_t i = (int64_t)blockIdx.x * kAttWarps + warp; i < p.bs; i += (int64_t)gridDim.x * kAttWarps) {
+    for (int64_t j = (int64_t)blockIdx.x * kAttWarps + warp; j < p.n; j += (int64_t)gridDim.x * kAttWarps) {
+        const int64_t i = p.idx ? (int64_t)__ldg(p.idx + j) : j;   // position in the batch (indexes ptr)
         float q[H][KC], acc[H][KC], mx[H], den[H];
 #pragma unroll
         for (int h = 0; h < H; ++h) {
@@ -57,7 +60,7 @@ __global__ void __launch_bounds__(kAttWarps * 32) attend_kernel(AttendParams p) 
 #pragma unroll
             for (int k = 0; k < KC; ++k) {
                 const int c = lane + 32 * k;
-                q[h][k] = (c < C) ? __ldg(p.Q + i * p.ld_q + h * C + c) : 0.f;
+                q[h][k] = (c < C) ? __ldg(p.Q + j * p.ld_q + h * C + c) : 0.f;
                 acc[h][k] = 0.f;
             }
         }
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(kAttWarps * 32) attend_kernel(AttendParams p) 
                 var = fmaf(dlt, dlt, var);
             }
         const float rstd = rsqrtf(warp_sum(var) / (float)HC + 1e-5f);
-        float* out = p.out + i * p.ld_out;
+        float* out = p.out + j * p.ld_out;
 #pragma unroll
         for (int h = 0; h < H; ++h)
 #pragma unroll
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(kAttWarps * 32) attend_kernel(AttendParams p) 
 
 template <int H>
 static int launch_attend_h(const AttendParams& p, cudaStream_t st) {
-    int64_t blocks = (p.bs + kAttWarps - 1) / kAttWarps;
+    int64_t blocks = (p.n + kAttWarps - 1) / kAttWarps;
     const int64_t cap = (int64_t)kNumSMs * 8 * 4;
     if (blocks > cap) blocks = cap;
     const unsigned g = (unsigned)blocks;
@@ -212,13 +215,15 @@ static int launch_attend_h(const AttendParams& p, cudaStream_t st) {
 
 using namespace lpf;
 
-extern "C" int lpf_attend_fused(const int64_t* ptr, int64_t bs, const int32_t* node, const float* KV, int64_t ld_kv,
+extern "C" int lpf_attend_fused(const int64_t* ptr, int64_t bs, const int32_t* idx, int64_t n, const int32_t* node,
+                                const float* KV, int64_t ld_kv,
                                 const float* R, int64_t ld_r, const float* Q, int64_t ld_q, const float* att,
                                 const float* bias, const float* ln_w, const float* ln_b, int32_t heads, int32_t ch,
                                 int mode, int write_counts, float* out, int64_t ld_out, float* alpha_out,
                                 void* stream) {
-    LPF_REQUIRE(bs >= 0, "negative batch size");
-    if (bs == 0) return LPF_OK;
+    LPF_REQUIRE(bs >= 0 && n >= 0, "negative batch size");
+    LPF_REQUIRE(idx || n == bs, "n must equal bs when idx is NULL");
+    if (n == 0) return LPF_OK;
     LPF_REQUIRE(ptr && KV && Q && att && bias && ln_w && ln_b && out, "NULL argument");
     LPF_REQUIRE(heads >= 1 && ch >= 1, "bad heads/ch");
     LPF_REQUIRE(mode == LPF_MODE_CN || mode == LPF_MODE_1HOP || mode == LPF_MODE_ALL, "bad mode");
@@ -227,7 +232,7 @@ extern "C" int lpf_attend_fused(const int64_t* ptr, int64_t bs, const int32_t* n
     LPF_REQUIRE(ld_kv >= hc && ld_q >= hc && ld_out >= hc + cd, "leading dimension too small");
     LPF_REQUIRE(R == nullptr || ld_r >= hc, "ld_r too small");
     // node / R may be NULL only if every set is empty; the kernel never dereferences them then.
-    AttendParams p{ptr, bs, node, KV, ld_kv, R, ld_r, Q, ld_q, att, bias, ln_w, ln_b,
+    AttendParams p{ptr, bs, idx, n, node, KV, ld_kv, R, ld_r, Q, ld_q, att, bias, ln_w, ln_b,
                    heads, ch, mode, write_counts, out, ld_out, alpha_out};
     cudaStream_t st = (cudaStream_t)stream;
     switch (heads) {

@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(256) layernorm_act_kernel(const float* X, int6
 // Link gathers: xsum = X[a]+X[b], xprod = X[a]*X[b]
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gather_links_kernel(const int64_t* __restrict__ links, int64_t bs,
+                                                           const int32_t* __restrict__ idx, int64_t n,
                                                            const float* __restrict__ X, int64_t ldx, int d,
                                                            float* __restrict__ xsum, int64_t lds,
                                                            float* __restrict__ xprod, int64_t ldp) {
@@ -175,8 +176,9 @@ __global__ void __launch_bounds__(256) gather_links_kernel(const int64_t* __rest
     const bool vec = (d % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) &&
                      (!xsum || ((lds % 4 == 0) && (reinterpret_cast<uintptr_t>(xsum) & 15) == 0)) &&
                      (!xprod || ((ldp % 4 == 0) && (reinterpret_cast<uintptr_t>(xprod) & 15) == 0));
-    for (int64_t i = warp; i < bs; i += nwarps) {
-        const int64_t a = __ldg(links + i), b = __ldg(links + bs + i);
+    for (int64_t i = warp; i < n; i += nwarps) {
+        const int64_t pos = idx ? (int64_t)__ldg(idx + i) : i;
+        const int64_t a = __ldg(links + pos), b = __ldg(links + bs + pos);
         const float* xa = X + a * ldx;
         const float* xb = X + b * ldx;
         if (vec) {
@@ -193,6 +195,27 @@ __global__ void __launch_bounds__(256) gather_links_kernel(const int64_t* __rest
                 if (xprod) xprod[i * ldp + c] = u * w;
             }
         }
+    }
+}
+
+// dst[r,:] = fill[:] for every row / dst[idx[j],:] = src[j,:]
+__global__ void __launch_bounds__(256) fill_rows_kernel(float* __restrict__ dst, int64_t ldd, int64_t rows, int d,
+                                                        const float* __restrict__ fill) {
+    const int64_t total = rows * d;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / d;
+        const int c = (int)(e - r * d);
+        dst[r * ldd + c] = __ldg(fill + c);
+    }
+}
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const float* __restrict__ src, int64_t lds,
+                                                           const int32_t* __restrict__ idx, int64_t n,
+                                                           float* __restrict__ dst, int64_t ldd, int d) {
+    const int64_t total = n * d;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = e / d;
+        const int c = (int)(e - j * d);
+        dst[(int64_t)__ldg(idx + j) * ldd + c] = src[j * lds + c];
     }
 }
 
@@ -261,14 +284,35 @@ extern "C" int lpf_layernorm_act(const float* X, int64_t ldx, const float* gamma
     return check_launch("lpf_layernorm_act");
 }
 
-extern "C" int lpf_gather_links(const int64_t* links, int64_t bs, const float* X, int64_t ldx, int32_t d, float* xsum,
-                                int64_t ld_sum, float* xprod, int64_t ld_prod, void* stream) {
-    LPF_REQUIRE(bs >= 0 && d >= 1, "bad shape");
-    if (bs == 0) return LPF_OK;
+extern "C" int lpf_gather_links(const int64_t* links, int64_t bs, const int32_t* idx, int64_t n, const float* X,
+                                int64_t ldx, int32_t d, float* xsum, int64_t ld_sum, float* xprod, int64_t ld_prod,
+                                void* stream) {
+    LPF_REQUIRE(bs >= 0 && n >= 0 && d >= 1, "bad shape");
+    LPF_REQUIRE(idx || n == bs, "n must equal bs when idx is NULL");
+    if (n == 0) return LPF_OK;
     LPF_REQUIRE(links && X, "NULL argument");
     LPF_REQUIRE(xsum || xprod, "no output requested");
     LPF_REQUIRE(ldx >= d && (!xsum || ld_sum >= d) && (!xprod || ld_prod >= d), "leading dimension too small");
-    gather_links_kernel<<<warp_grid(bs, 256), 256, 0, (cudaStream_t)stream>>>(links, bs, X, ldx, d, xsum, ld_sum, xprod,
-                                                                              ld_prod);
+    gather_links_kernel<<<warp_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(links, bs, idx, n, X, ldx, d, xsum, ld_sum,
+                                                                             xprod, ld_prod);
     return check_launch("lpf_gather_links");
+}
+
+extern "C" int lpf_scatter_rows(const float* src, int64_t ld_src, const int32_t* idx, int64_t n, float* dst,
+                                int64_t ld_dst, int64_t rows, int32_t d, const float* fill_row, void* stream) {
+    LPF_REQUIRE(n >= 0 && rows >= 0 && d >= 1, "bad shape");
+    LPF_REQUIRE(rows == 0 || dst, "dst is NULL");
+    LPF_REQUIRE(n == 0 || (src && idx), "src/idx is NULL");
+    LPF_REQUIRE(ld_dst >= d && (n == 0 || ld_src >= d), "leading dimension too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t cap = (int64_t)kNumSMs * 16;
+    if (fill_row && rows > 0) {
+        int64_t blocks = (rows * d + 255) / 256;
+        fill_rows_kernel<<<(unsigned)(blocks > cap ? cap : blocks), 256, 0, st>>>(dst, ld_dst, rows, d, fill_row);
+    }
+    if (n > 0) {
+        int64_t blocks = (n * d + 255) / 256;
+        scatter_rows_kernel<<<(unsigned)(blocks > cap ? cap : blocks), 256, 0, st>>>(src, ld_src, idx, n, dst, ld_dst, d);
+    }
+    return check_launch("lpf_scatter_rows");
 }

@@ -188,6 +188,34 @@ __global__ void __launch_bounds__(kSelWarps * 32) select_kernel(SelectParams p) 
     }
 }
 
+// Batch positions of the links with at least one selected node (any order) and the totals the host needs to
+// size the pair arrays: header = (S_cn, S_cn + S_1hop, S, number of non-empty links).
+__global__ void __launch_bounds__(256) compact_nonempty_kernel(const int64_t* __restrict__ ptr, int64_t bs,
+                                                               int32_t* __restrict__ nz_list,
+                                                               int64_t* __restrict__ header) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane; base < bs;
+         base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = base + lane;
+        bool nz = false;
+        if (i < bs)
+            nz = (ptr[i + 1] != ptr[i]) || (ptr[bs + i + 1] != ptr[bs + i]) || (ptr[2 * bs + i + 1] != ptr[2 * bs + i]);
+        const unsigned m = __ballot_sync(kFull, nz);
+        if (m) {
+            unsigned long long start = 0;
+            if (lane == 0) start = atomicAdd(reinterpret_cast<unsigned long long*>(header + 3), (unsigned long long)__popc(m));
+            start = __shfl_sync(kFull, start, 0);
+            if (nz) nz_list[start + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        header[0] = ptr[bs];
+        header[1] = ptr[2 * bs];
+        header[2] = ptr[3 * bs];
+    }
+}
+__global__ void zero_header_kernel(int64_t* header) { header[3] = 0; }
+
 static int launch_select(bool fill, const SelectParams& p, cudaStream_t st) {
     if (p.bs == 0) return LPF_OK;
     int64_t blocks = (p.bs + kSelWarps - 1) / kSelWarps;
@@ -354,6 +382,18 @@ extern "C" int64_t lpf_select_workspace_bytes(int64_t bs) { return (bs + 4) * (i
 extern "C" int64_t lpf_scan_scratch_bytes(int64_t n) {
     const int64_t tiles = (n + kScanTile - 1) / kScanTile;
     return (tiles > 0 ? tiles : 1) * (int64_t)sizeof(int64_t);
+}
+
+extern "C" int lpf_select_compact(const int64_t* ptr, int64_t bs, int32_t* nz_list, int64_t* header, void* stream) {
+    LPF_REQUIRE(bs >= 0, "negative batch size");
+    LPF_REQUIRE(ptr && header && (bs == 0 || nz_list), "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    zero_header_kernel<<<1, 1, 0, st>>>(header);
+    int64_t blocks = (bs + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+    compact_nonempty_kernel<<<(unsigned)blocks, 256, 0, st>>>(ptr, bs, nz_list, header);
+    return check_launch("lpf_select_compact");
 }
 
 extern "C" int lpf_scan_counts(const int32_t* counts, int64_t n, int64_t* ptr, void* scratch, void* stream) {

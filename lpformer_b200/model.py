@@ -326,6 +326,8 @@ class LinkTransformer(nn.Module):
         self._tables = {False: _Tables(), True: _Tables()}
         self._derived = None        # folded weights, keyed by parameter versions
         self._kv_cache = None       # per-layer KV tables, keyed by the X_node they were built from
+        self._pw_const_cache = None  # pairwise vector of a link with empty sets, keyed by parameter versions
+        self._head_cache = None     # operands of the fused heads kernel
 
     # ------------------------------------------------------------------ graph tables
     def _dev(self):
@@ -463,16 +465,43 @@ class LinkTransformer(nn.Module):
 
     @torch.no_grad()
     def calc_pairwise(self, batch, X_node, test_set=False, adj_mask=None, return_weights=False, out=None):
-        """reference :132-178.  Returns (pairwise feats [BS, dim], att_weights [2,S] or None)."""
+        """reference :132-178.  Returns (pairwise feats [BS, dim], att_weights [2,S] or None).
+
+        Links whose three node sets are all empty share one pairwise vector (attention output = LayerNorm(bias),
+        counts = 0), so the attention + pairwise_lin stack runs only on the compacted list of non-empty links
+        and the constant row is broadcast to the rest."""
         dev = self._dev()
         batch = ops.links_tensor(batch, dev)
+        X_node = self._check_x(X_node)
+        bs = batch.shape[1]
+        sel = self._select(batch, test_set, adj_mask, want_link=return_weights)
+        nnz = sel.nz.numel()
+        if return_weights or nnz == bs or bs == 0:
+            pw, alpha = self._pairwise_rows(batch, X_node, sel, None, out=out, want_alpha=return_weights)
+        else:
+            alpha = None
+            pw = out if out is not None else torch.empty((bs, self.dim), dtype=torch.float32, device=dev)
+            rows = self._pairwise_rows(batch, X_node, sel, sel.nz)[0] if nnz > 0 else None
+            ops.scatter_rows(rows, sel.nz, pw, fill_row=self._pw_const(X_node))
+        att_weights = None
+        if return_weights:
+            att_weights = torch.stack((sel.link.float(), alpha))
+        return pw, att_weights
+
+    def _check_x(self, X_node):
         if not X_node.is_cuda:
             raise LpfError("X_node must be a CUDA tensor")
         X_node = X_node.detach()
         if X_node.dtype != torch.float32 or X_node.stride(-1) != 1:
             X_node = X_node.float().contiguous()
-        bs, d, H = batch.shape[1], self.dim, self.num_heads
-        sel = self._select(batch, test_set, adj_mask, want_link=return_weights)
+        return X_node
+
+    def _pairwise_rows(self, batch, X_node, sel, idx, out=None, want_alpha=False):
+        """RPE -> attention layers -> counts -> pairwise_lin for the batch positions in idx (all links when None).
+        Returns ([n, dim] rows in idx order, per-pair attention weights or None)."""
+        dev = self._dev()
+        d, H = self.dim, self.num_heads
+        n = sel.bs if idx is None else idx.numel()
         S = sel.total
         derived = self._get_derived()
         kvs = self._get_kv(X_node)
@@ -482,8 +511,8 @@ class LinkTransformer(nn.Module):
         for t, enc in enumerate(self._encoders()):
             ops.rpe_hidden(sel, t, enc.linears[0].weight, enc.linears[0].bias, enc.norm.weight, enc.norm.bias, hsum)
 
-        xsum, _ = ops.gather_links(batch, X_node, want_sum=True, want_prod=False)   # e1 + e2 of layer 0
-        alpha = torch.empty(S, dtype=torch.float32, device=dev) if return_weights else None
+        xsum, _ = ops.gather_links(batch, X_node, want_sum=True, want_prod=False, idx=idx)   # e1 + e2 of layer 0
+        alpha = torch.empty(S, dtype=torch.float32, device=dev) if want_alpha else None
         feats = None
         for l, layer in enumerate(self.att_layers):
             att = layer.att
@@ -500,23 +529,77 @@ class LinkTransformer(nn.Module):
                 if r1 > r0:
                     ops.linear(hsum[r0:r1], m, c, out=R[r0:r1])
             width = HC + (self.count_dim if last else 0)
-            feats = torch.empty((bs, width), dtype=torch.float32, device=dev)
+            feats = torch.empty((n, width), dtype=torch.float32, device=dev)
             ops.attend(sel, kvs[l], R, Q, att.att, att.bias, layer.post_att_norm.weight, layer.post_att_norm.bias,
-                       H, C, write_counts=last, out=feats, alpha_out=alpha if last else None)
-        pw = self.pairwise_lin(feats, out=out)
-        att_weights = None
-        if return_weights:
-            att_weights = torch.stack((sel.link.float(), alpha))
-        return pw, att_weights
+                       H, C, write_counts=last, out=feats, alpha_out=alpha if last else None, idx=idx)
+        return self.pairwise_lin(feats, out=out), alpha
+
+    def _pw_const(self, X_node):
+        """[1, dim] pairwise vector of a link with empty node sets; depends on the weights only (cached)."""
+        key = tuple(p._version for p in self.parameters()) + (self._dev(),)
+        if self._pw_const_cache is not None and self._pw_const_cache[0] == key:
+            return self._pw_const_cache[1]
+        dev = self._dev()
+        empty = ops.Selection(self.mask, 1, torch.zeros(4, dtype=torch.int64, device=dev),
+                              torch.empty(0, dtype=torch.int32, device=dev), torch.empty(0, device=dev),
+                              torch.empty(0, device=dev), None, (0, 0, 0, 0),
+                              torch.empty(0, dtype=torch.int32, device=dev))
+        row = self._pairwise_rows(torch.zeros((2, 1), dtype=torch.int64, device=dev), X_node, empty, None)[0]
+        self._pw_const_cache = (key, row)
+        return row
 
     # ------------------------------------------------------------------ fused eval body
+    def _head_consts(self, score_func, X_node):
+        """Operands of lpf_link_heads_tc (packed weights, folded pairwise constant), or None when the fused
+        kernel does not cover this configuration."""
+        d = self.dim
+        if ops.GEMM_BACKEND != "tc" or d not in (32, 64) or self.num_layers != 1:
+            return None
+        lins = getattr(score_func, "lins", None)
+        el = self.elementwise_lin
+        if lins is None or len(lins) != 2 or tuple(lins[0].weight.shape) != (2 * d, 2 * d) or \
+                tuple(lins[1].weight.shape) != (1, 2 * d) or len(el.linears) != 2 or el.norm is None:
+            return None
+        key = tuple(p._version for p in self.parameters()) + tuple(p._version for p in score_func.parameters()) + \
+            (self._dev(), id(score_func))
+        if self._head_cache is not None and self._head_cache[0] == key:
+            return self._head_cache[1]
+        ws1 = lins[0].weight.detach()
+        consts = {
+            "w1p": ops.pack_weight(el.linears[0].weight), "b1": el.linears[0].bias.detach().contiguous(),
+            "ln_w": el.norm.weight.detach().contiguous(), "ln_b": el.norm.bias.detach().contiguous(),
+            "w2p": ops.pack_weight(el.linears[1].weight), "b2": el.linears[1].bias.detach().contiguous(),
+            "ws1p": ops.pack_weight(ws1[:, :d]), "ws1_pw": ws1[:, d:], "bs1": lins[0].bias.detach().contiguous(),
+            "ws2": lins[1].weight.detach().reshape(-1).contiguous(), "bs2": lins[1].bias.detach().contiguous(),
+        }
+        consts["c3"] = ops.linear(self._pw_const(X_node), consts["ws1_pw"], consts["bs1"]).reshape(-1).contiguous()
+        self._head_cache = (key, consts)
+        return consts
+
     @torch.no_grad()
     def score_links(self, batch, X_node, score_func, test_set=False, return_logits=False):
         """Body of the reference eval loops (train/testing.py:29-31, :113-115):
-        score_func(cat(elementwise_lin(h[src]*h[dst]), calc_pairwise(...)))."""
-        batch = ops.links_tensor(batch, self._dev())
-        feats = torch.empty((batch.shape[1], 2 * self.dim), dtype=torch.float32, device=self._dev())
-        _, xprod = ops.gather_links(batch, X_node, want_sum=False, want_prod=True)
-        self.elementwise_lin(xprod, out=feats[:, : self.dim])
-        self.calc_pairwise(batch, X_node, test_set, out=feats[:, self.dim:])
-        return score_func(feats, return_logits=return_logits) if return_logits else score_func(feats)
+        score_func(cat(elementwise_lin(h[src]*h[dst]), calc_pairwise(...))).
+
+        dim in {32, 64}: one fused tensor-core launch scores every link with the empty-set pairwise constant,
+        then the (few) links with non-empty sets go through selection fill -> RPE -> attention -> pairwise_lin
+        and are re-scored with their own pairwise vector."""
+        dev = self._dev()
+        batch = ops.links_tensor(batch, dev)
+        X_node = self._check_x(X_node)
+        consts = self._head_consts(score_func, X_node)
+        if consts is None:
+            feats = torch.empty((batch.shape[1], 2 * self.dim), dtype=torch.float32, device=dev)
+            _, xprod = ops.gather_links(batch, X_node, want_sum=False, want_prod=True)
+            self.elementwise_lin(xprod, out=feats[:, : self.dim])
+            self.calc_pairwise(batch, X_node, test_set, out=feats[:, self.dim:])
+            return score_func(feats, return_logits=return_logits) if return_logits else score_func(feats)
+        bs = batch.shape[1]
+        prob = torch.empty(bs, dtype=torch.float32, device=dev)
+        ops.link_heads(batch, X_node, consts, prob, logits=return_logits)
+        sel = self._select(batch, test_set)
+        if sel.nz.numel() > 0:
+            rows = self._pairwise_rows(batch, X_node, sel, sel.nz)[0]
+            zb = ops.linear(rows, consts["ws1_pw"], consts["bs1"])
+            ops.link_heads(batch, X_node, consts, prob, idx=sel.nz, zb=zb, logits=return_logits)
+        return prob

@@ -49,7 +49,7 @@ def gemm(A, W, bias=None, bias_scale=1.0, out=None, epilogue=EPI_NONE):
 
 
 _PACKED = {}          # (data_ptr, version, shape, stride) -> (packed image, weight kept alive)
-GEMM_BACKEND = os.environ.get("LPF_GEMM_BACKEND", "simt")   # "tc": tcgen05 3xTF32 kernel (lpf_gemm_tc);  "simt": fp32 FFMA kernel (lpf_gemm)
+GEMM_BACKEND = os.environ.get("LPF_GEMM_BACKEND", "tc")   # "tc": tcgen05 3xTF32 kernel (lpf_gemm_tc);  "simt": fp32 FFMA kernel (lpf_gemm)
 
 
 def pack_weight(W):
@@ -112,18 +112,30 @@ def layernorm_act(x, weight, bias, relu=False, residual=None, out=None, n=None):
     return out
 
 
-def gather_links(links, X, want_sum=True, want_prod=True, out_sum=None, out_prod=None):
-    require_cuda(links, X)
+def gather_links(links, X, want_sum=True, want_prod=True, out_sum=None, out_prod=None, idx=None):
+    """xsum = X[a]+X[b], xprod = X[a]*X[b] for every link, or for the batch positions listed in idx."""
+    require_cuda(links, X, idx)
     X = _rowmajor(X)
     bs, d = links.shape[1], X.shape[1]
+    n = bs if idx is None else idx.numel()
     if want_sum and out_sum is None:
-        out_sum = torch.empty((bs, d), dtype=torch.float32, device=X.device)
+        out_sum = torch.empty((n, d), dtype=torch.float32, device=X.device)
     if want_prod and out_prod is None:
-        out_prod = torch.empty((bs, d), dtype=torch.float32, device=X.device)
-    call("lpf_gather_links", ptr(links), bs, ptr(X), X.stride(0), d, ptr(out_sum),
+        out_prod = torch.empty((n, d), dtype=torch.float32, device=X.device)
+    call("lpf_gather_links", ptr(links), bs, ptr(idx), n, ptr(X), X.stride(0), d, ptr(out_sum),
          out_sum.stride(0) if out_sum is not None else 0, ptr(out_prod),
          out_prod.stride(0) if out_prod is not None else 0, stream())
     return out_sum, out_prod
+
+
+def scatter_rows(src, idx, dst, fill_row=None):
+    """dst[:, :] = fill_row (if given), then dst[idx[j], :] = src[j, :]."""
+    require_cuda(src, idx, dst, fill_row)
+    n = 0 if idx is None or src is None else idx.numel()
+    d = dst.shape[1]
+    call("lpf_scatter_rows", ptr(src), src.stride(0) if n > 0 else d, ptr(idx), n, ptr(dst), dst.stride(0), dst.shape[0], d,
+         ptr(fill_row), stream())
+    return dst
 
 
 @dataclass
@@ -138,6 +150,7 @@ class Selection:
     tgt_ppr: torch.Tensor        # fp32 [S]
     link: Optional[torch.Tensor]  # int32 [S] or None
     bounds: tuple                # (0, S_cn, S_cn+S_1hop, S) python ints
+    nz: Optional[torch.Tensor] = None   # int32 [M']: batch positions of the links with a non-empty set (any order)
 
     @property
     def total(self) -> int:
@@ -190,7 +203,10 @@ def select(links, adj: CSR, ppr: CSR, th_cn, th_1hop, th_non1hop, mode: str, wan
     p = torch.empty(3 * bs + 1, dtype=torch.int64, device=dev)
     scratch = torch.empty(max(1, _lib.load().lpf_scan_scratch_bytes(3 * bs) // 8), dtype=torch.int64, device=dev)
     call("lpf_scan_counts", ptr(counts), 3 * bs, ptr(p), ptr(scratch), st)
-    b = p[[bs, 2 * bs, 3 * bs]].tolist() if bs > 0 else [0, 0, 0]
+    nz = torch.empty(bs, dtype=torch.int32, device=dev)
+    header = torch.empty(4, dtype=torch.int64, device=dev)
+    call("lpf_select_compact", ptr(p), bs, ptr(nz), ptr(header), st)
+    b = header.tolist()          # the one host sync of the batch: (S_cn, S_cn+S_1hop, S, #non-empty links)
     S = b[2]
     node = torch.empty(S, dtype=torch.int32, device=dev)
     pa = torch.empty(S, dtype=torch.float32, device=dev)
@@ -198,7 +214,7 @@ def select(links, adj: CSR, ppr: CSR, th_cn, th_1hop, th_non1hop, mode: str, wan
     link = torch.empty(S, dtype=torch.int32, device=dev) if want_link else None
     if S > 0:
         call("lpf_select_fill", *args, ptr(p), ptr(node), ptr(pa), ptr(pb), ptr(link), ptr(ws), st, meta=(bs, S))
-    return Selection(mode, bs, p, node, pa, pb, link, (0, b[0], b[1], b[2]))
+    return Selection(mode, bs, p, node, pa, pb, link, (0, b[0], b[1], b[2]), nz[:b[3]])
 
 
 def rpe_hidden(sel: Selection, t: int, w1, b1, ln_w, ln_b, hsum):
@@ -208,13 +224,29 @@ def rpe_hidden(sel: Selection, t: int, w1, b1, ln_w, ln_b, hsum):
              ptr(ln_b), hsum.shape[1], ptr(hsum), hsum.stride(0), stream())
 
 
-def attend(sel: Selection, KV, R, Q, att, bias, ln_w, ln_b, heads, ch, write_counts, out, alpha_out=None):
-    require_cuda(KV, R, Q, out)
-    call("lpf_attend_fused", ptr(sel.ptr), sel.bs, ptr(sel.node), ptr(KV), KV.stride(0),
+def attend(sel: Selection, KV, R, Q, att, bias, ln_w, ln_b, heads, ch, write_counts, out, alpha_out=None, idx=None):
+    """K4 over every link of the batch, or over the batch positions in idx (rows of Q / out follow idx)."""
+    require_cuda(KV, R, Q, out, idx)
+    n = sel.bs if idx is None else idx.numel()
+    call("lpf_attend_fused", ptr(sel.ptr), sel.bs, ptr(idx), n, ptr(sel.node), ptr(KV), KV.stride(0),
          ptr(R) if sel.total > 0 else None, R.stride(0) if R is not None and R.dim() == 2 else heads * ch,
          ptr(Q), Q.stride(0), ptr(att), ptr(bias), ptr(ln_w), ptr(ln_b), heads, ch, MODE[sel.mode],
-         int(write_counts), ptr(out), out.stride(0), ptr(alpha_out), stream(), meta=(sel.bs, sel.total, heads * ch))
+         int(write_counts), ptr(out), out.stride(0), ptr(alpha_out), stream(), meta=(n, sel.total, heads * ch))
     return out
+
+
+def link_heads(links, X, consts, prob, idx=None, zb=None, logits=False):
+    """Fused tensor-core heads (lpf_link_heads_tc): prob[pos] for every link (constant pairwise half `c3`) or for the
+    positions in idx with per-row zb."""
+    require_cuda(links, X, prob, idx, zb)
+    X = _rowmajor(X)
+    bs = links.shape[1]
+    n = bs if idx is None else idx.numel()
+    call("lpf_link_heads_tc", ptr(links), bs, ptr(idx), n, ptr(X), X.stride(0), X.shape[1], ptr(consts["w1p"]),
+         ptr(consts["b1"]), ptr(consts["ln_w"]), ptr(consts["ln_b"]), ptr(consts["w2p"]), ptr(consts["b2"]),
+         ptr(consts["ws1p"]), ptr(consts["c3"]) if zb is None else None, ptr(zb), zb.stride(0) if zb is not None else 0,
+         ptr(consts["ws2"]), ptr(consts["bs2"]), ptr(prob), int(logits), stream(), meta=(n,))
+    return prob
 
 
 def gcn_spmm(adj: CSR, XW, bias, out=None, row0=0, rows=None):

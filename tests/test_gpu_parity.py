@@ -183,3 +183,54 @@ def test_selection_synthetic_vs_oracle(workload, scale):
             assert np.array_equal(sel.node[r0:r1].cpu().numpy(), nd), (algo, name)
             assert np.array_equal(sel.src_ppr[r0:r1].cpu().numpy().view(np.uint32), qa.view(np.uint32)), (algo, name)
             assert np.array_equal(sel.tgt_ppr[r0:r1].cpu().numpy().view(np.uint32), qb.view(np.uint32)), (algo, name)
+
+
+@pytest.mark.parametrize("workload,scale,nq,negs", [("citation2", 0.02, 6, 150), ("ppa", 0.004, 4, 100)])
+def test_score_links_synthetic_vs_oracle(workload, scale, nq, negs):
+    """The whole eval-loop body on seeded synthetic graphs of the BASELINE shapes (d = 64: the fused tensor-core
+    heads + compacted attention path) against the float64 numpy oracle, and against the unfused fp32 SIMT path."""
+    import lpformer_b200 as L
+    from lpformer_b200 import ops, synthetic as S
+    g = S.make_graph(workload, seed=11, scale=scale, heldout=128)
+    cfg = g.cfg
+    targs = S.train_args_of(cfg)
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    model = L.LinkTransformer(targs, g.data_dict(dev), device=dev).to(dev).eval()
+    score = L.mlp_score(model.out_dim, model.out_dim, 1, 2).to(dev).eval()
+    with torch.no_grad():   # non-trivial biases / norms so that every folded constant matters
+        for p in list(model.parameters()) + list(score.parameters()):
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    rng = np.random.default_rng(3)
+    pos = g.edges[:, rng.integers(0, g.edges.shape[1], 200)]
+    links_np = np.concatenate([S.citation2_queries(g, nq, negs, seed=2), pos, pos[::-1, :40]], axis=1).astype(np.int64)
+    links = torch.from_numpy(links_np).to(dev)
+    X = torch.randn(g.n, cfg["dim"], generator=torch.Generator().manual_seed(1)).to(dev)
+
+    assert model._head_consts(score, X) is not None          # the fused kernel covers this configuration
+    prob = model.score_links(links, X, score).cpu().numpy()
+    logit = model.score_links(links, X, score, return_logits=True).cpu().numpy()
+
+    P = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in model.state_dict().items()}
+    Sd = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in score.state_dict().items()}
+    adj_o = O.CSR(g.indptr, g.indices, None, g.n)
+    ppr_o = O.CSR(g.ppr[0], g.ppr[1], g.ppr[2], g.n)
+    feats, (mode, sets), counts, _ = O.link_features(links_np, X.cpu().numpy(), adj_o, ppr_o, P, dict(targs))
+    ref_logit, ref_prob = O.mlp_score(feats, Sd)
+    assert (counts.sum(1) > 0).sum() > 20 and (counts.sum(1) == 0).sum() > 20      # both kinds of link present
+    np.testing.assert_allclose(prob, ref_prob, rtol=FP32_RTOL, atol=1e-6)
+    np.testing.assert_allclose(logit, ref_logit, rtol=FP32_RTOL, atol=1e-5)
+
+    old = ops.GEMM_BACKEND
+    ops.GEMM_BACKEND = "simt"
+    try:
+        assert model._head_consts(score, X) is None
+        prob_simt = model.score_links(links, X, score).cpu().numpy()
+        pw_simt, _ = model.calc_pairwise(links, X)
+    finally:
+        ops.GEMM_BACKEND = old
+    np.testing.assert_allclose(prob_simt, ref_prob, rtol=FP32_RTOL, atol=1e-6)
+    np.testing.assert_allclose(pw_simt.cpu().numpy(), feats[:, cfg["dim"]:], rtol=FP32_RTOL, atol=2e-5)
+    pw_tc, _ = model.calc_pairwise(links, X)
+    np.testing.assert_allclose(pw_tc.cpu().numpy(), feats[:, cfg["dim"]:], rtol=FP32_RTOL, atol=2e-5)
