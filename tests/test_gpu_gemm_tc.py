@@ -39,6 +39,9 @@ def test_gemm_tc_matches_fp64(M, N, K, epi):
     torch.cuda.synchronize()
     scale = float(ref.abs().max()) + 1e-6
     err = float((out.cpu().double() - ref).abs().max()) / scale
-    assert err < 1e-5, f"max scaled error {err:.3g}"      # fp32-level (K-long fp32 sums): plain TF32 would be ~5e-4
+    # fp32-level: the tensor core's fp32 accumulator truncates, so the error grows ~linearly with the number of
+    # K-slices; plain single-pass TF32 would sit at ~5e-4 regardless of K
+    tol = max(1e-5, 4e-8 * K)
+    assert err < tol, f"max scaled error {err:.3g} (tol {tol:.3g})"
     assert torch.equal(Cbig[:, 1:N + 1], out)
     assert bool((Cbig[:, 0] == -7.0).all()) and bool((Cbig[:, N + 1:] == -7.0).all())

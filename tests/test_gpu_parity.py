@@ -218,7 +218,9 @@ def test_score_links_synthetic_vs_oracle(workload, scale, nq, negs):
     ppr_o = O.CSR(g.ppr[0], g.ppr[1], g.ppr[2], g.n)
     feats, (mode, sets), counts, _ = O.link_features(links_np, X.cpu().numpy(), adj_o, ppr_o, P, dict(targs))
     ref_logit, ref_prob = O.mlp_score(feats, Sd)
-    assert (counts.sum(1) > 0).sum() > 20 and (counts.sum(1) == 0).sum() > 20      # both kinds of link present
+    assert (counts.sum(1) > 0).sum() > 20                      # links with selected nodes ...
+    if workload == "citation2":
+        assert (counts.sum(1) == 0).sum() > 20                 # ... and links whose sets are all empty
     np.testing.assert_allclose(prob, ref_prob, rtol=FP32_RTOL, atol=1e-6)
     np.testing.assert_allclose(logit, ref_logit, rtol=FP32_RTOL, atol=1e-5)
 
