@@ -190,16 +190,18 @@ int lpf_attend_fused(const int64_t* ptr, int64_t bs, const int32_t* idx /* NULL 
  * Fused per-link heads on the tensor cores (d in {32, 64}) — the rest of the eval-loop body
  * (train/testing.py:29-31,113-115) for links whose pairwise vector pw is known:
  *     prob = mlp_score([ elementwise_lin(X[a]*X[b]) | pw ])          (models/other_models.py:125-138,173-179)
- * with mlp_score = Linear(2d,2d) -> ReLU -> Linear(2d,1) -> sigmoid.  The pairwise half enters through
- * zb = bs1 + Ws1[:, d:] pw: either the constant c3 [2d] (links whose selected sets are all empty share one pw)
- * or per-row zb [n, 2d].  w1/w2 (elementwise_lin.linears.{0,1}.weight, [d,d]) and ws1 = Ws1[:, :d] ([2d,d])
- * are lpf_pack_weight images.  idx (optional) lists the batch positions to score; prob[pos] is written.
+ * with elementwise_lin = Linear(W1,b1) -> LayerNorm -> ReLU -> Linear(W2,b2) and mlp_score = Linear(Ws1,bs1) ->
+ * ReLU -> Linear(ws2,bs2) -> sigmoid.  W2 and Ws1[:, :d] are adjacent linear maps and are folded by the caller:
+ *     w23 = Ws1[:, :d] W2  [2d, d],   offset = Ws1[:, :d] b2 + bs1 + Ws1[:, d:] pw  [2d]
+ *     prob = sigmoid(ws2 . ReLU(w23 ReLU(LN(W1 (X[a]*X[b]) + b1)) + offset) + bs2).
+ * offset is either the constant c3 (links whose selected sets are all empty share one pw) or per-row zb [n, 2d].
+ * w1_packed / w23_packed are lpf_pack_weight images.  idx (optional) lists the batch positions to score;
+ * prob[pos] is written (the pre-sigmoid logit when logits != 0).
  * ------------------------------------------------------------------------- */
 int lpf_link_heads_tc(const int64_t* links, int64_t bs, const int32_t* idx, int64_t n,
                       const float* X, int64_t ldx, int32_t d,
                       const float* w1_packed, const float* b1, const float* ln_w, const float* ln_b,
-                      const float* w2_packed, const float* b2,
-                      const float* ws1_packed, const float* c3, const float* zb, int64_t ld_zb,
+                      const float* w23_packed, const float* c3, const float* zb, int64_t ld_zb,
                       const float* ws2, const float* bs2, float* prob, int logits, void* stream);
 
 /* ------------------------------------------------------------------------- *

@@ -2,26 +2,33 @@
 //     xprod = X[a] * X[b]                                   (gather, reference train/testing.py:29,113)
 //     h     = ReLU(LayerNorm(W1 xprod + b1))                (elementwise_lin, models/other_models.py:125-133)
 //     el    = W2 h + b2                                     (                 :135)
-//     z     = ReLU(Ws1[:, :d] el + zb)                      (mlp_score layer 0, :173-177; zb = bs1 + Ws1[:, d:] pw)
+//     z     = ReLU(Ws1[:, :d] el + bs1 + Ws1[:, d:] pw)     (mlp_score layer 0 on [el | pw], :173-177)
 //     prob  = sigmoid(ws2 . z + bs2)                        (:178-179)
-// never leaving the SM: the three contractions run as tcgen05.mma (kind::tf32, 3xTF32 split, accumulators in
+// never leaving the SM.  There is no non-linearity between el and mlp_score's first Linear, so the two are
+// folded once per weight set: z = ReLU(W23 h + offset), W23 = Ws1[:, :d] W2, offset = Ws1[:, :d] b2 + bs1 +
+// Ws1[:, d:] pw.  The two remaining contractions run as tcgen05.mma (kind::tf32, 3xTF32 split, accumulators in
 // TMEM); their weights (pre-split, pre-swizzled images from lpf_pack_weight) are brought into shared memory
 // ONCE per CTA by bulk TMA copies and stay resident while the CTA walks its tiles; each thread owns one link
 // (= one TMEM lane), so LayerNorm and the final dot product are thread-local.
 //
-// `zb` carries the pairwise half of the concatenated feature vector [el | pw] (models/link_transformer.py:105,
-// train/testing.py:31): for a link whose selected node sets are all empty, pw is the same vector for every link
-// (pairwise_lin(LayerNorm(att.bias) | 0...)), so its contribution is the constant c3; links with non-empty sets
-// are scored by a second call over the compacted list (`idx`) with per-row zb.
+// Warps 4-7 gather the NEXT tile's X[a]*X[b] rows into a staging buffer while warps 0-3 run the current
+// tile's MMAs and epilogues (mbarrier full/empty hand-off), so HBM latency is off the critical path.
 //
-// Supported: d in {32, 64} (weights 40 / 128 KB resident); other widths use the unfused kernels.
+// `offset` carries the pairwise half of the concatenated feature vector [el | pw] (models/link_transformer.py:105,
+// train/testing.py:31): for a link whose selected node sets are all empty, pw is the same vector for every link
+// (pairwise_lin(LayerNorm(att.bias) | 0...)), so the offset is the constant c3; links with non-empty sets
+// are scored by a second call over the compacted list (`idx`) with per-row offsets zb.
+//
+// Supported: d in {32, 64} (weights 24 / 96 KB resident); other widths use the unfused kernels.
 #include "tc.cuh"
 
 namespace lpf {
 
 using namespace tc;
 
-constexpr int kHeadThreads = 128;
+constexpr int kHeadConsumers = 128;   // warps 0-3: one link (= TMEM lane) per thread; thread 0 issues the MMAs
+constexpr int kHeadProducers = 128;   // warps 4-7: gather X[a]*X[b] of the NEXT tile while this one is computed
+constexpr int kHeadThreads = kHeadConsumers + kHeadProducers;
 
 struct HeadsParams {
     const int64_t* links;
@@ -30,15 +37,13 @@ struct HeadsParams {
     int64_t n;
     const float* X;
     int64_t ldx;
-    const float* w1p;
+    const float* w1p;    // packed elementwise_lin.linears[0].weight            [d, d]
     const float* b1;
     const float* ln_g;
     const float* ln_b;
-    const float* w2p;
-    const float* b2;
-    const float* ws1p;
-    const float* c3;
-    const float* zb;
+    const float* w23p;   // packed Ws1[:, :d] . elementwise_lin.linears[1].weight [2d, d]
+    const float* c3;     // [2d] constant pre-activation offset (see header) or NULL
+    const float* zb;     // [n, 2d] per-row offset or NULL
     int64_t ld_zb;
     const float* ws2;
     const float* bs2;
@@ -46,36 +51,44 @@ struct HeadsParams {
     int logits;
 };
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 template <int D>
 __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsParams p) {
-    constexpr int KB = D / 32;                       // k-blocks of every contraction (K = D)
+    constexpr int KB = D / 32;                       // k-blocks of both contractions (K = D)
     constexpr int N3 = 2 * D;                        // width of mlp_score's hidden layer
     constexpr uint32_t W1_BYTES = KB * 2 * D * 128;  // packed [D, D]
     constexpr uint32_t W3_BYTES = KB * 2 * N3 * 128; // packed [2D, D]
-    constexpr uint32_t A_BYTES = KB * 2 * kATileBytes;
-    constexpr uint32_t TMEM_COLS = (2 * D + N3) <= 128 ? 128 : 256;   // D1 | D2 | D3
+    constexpr uint32_t STG_BYTES = KB * kATileBytes; // raw fp32 xprod tile, same swizzle as an operand
+    constexpr uint32_t TMEM_COLS = (D + N3) <= 128 ? 128 : 256;   // D1 | D3
 
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar_w, bar_mma;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t bar_w, bar_mma, bar_full, bar_empty;
     __shared__ uint32_t tmem_slot;
-    __shared__ int64_t tile_a[kTileM], tile_b[kTileM];
-    __shared__ float s_b1[D], s_g[D], s_bt[D], s_b2[D], s_c3[N3], s_ws2[N3];
+    __shared__ int32_t ids[2][2][kTileM];            // [tile parity][a, b][row]
+    __shared__ float s_b1[D], s_g[D], s_bt[D], s_c3[N3], s_ws2[N3];
 
     const int tid = threadIdx.x, warp = tid >> 5;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sW1 = smem;
-    uint8_t* sW2 = sW1 + W1_BYTES;
-    uint8_t* sW3 = sW2 + W1_BYTES;
+    uint8_t* sW3 = sW1 + W1_BYTES;
     uint8_t* sA = sW3 + W3_BYTES;                    // [kb][hi, lo][128 rows][128 B]
+    uint8_t* sStg = sA + KB * 2 * kATileBytes;       // [kb][128 rows][128 B]
 
     if (tid == 0) {
         mbar_init(&bar_w, 1);
         mbar_init(&bar_mma, 1);
+        mbar_init(&bar_full, kHeadProducers);
+        mbar_init(&bar_empty, kHeadConsumers);
         fence_mbar_init();
-        mbar_arrive_expect_tx(&bar_w, 2 * W1_BYTES + W3_BYTES);
+        mbar_arrive_expect_tx(&bar_w, W1_BYTES + W3_BYTES);
         bulk_g2s(sW1, p.w1p, W1_BYTES, &bar_w);
-        bulk_g2s(sW2, p.w2p, W1_BYTES, &bar_w);
-        bulk_g2s(sW3, p.ws1p, W3_BYTES, &bar_w);
+        bulk_g2s(sW3, p.w23p, W3_BYTES, &bar_w);
     }
     __syncwarp();
     if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
@@ -83,74 +96,91 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
         s_b1[c] = p.b1[c];
         s_g[c] = p.ln_g[c];
         s_bt[c] = p.ln_b[c];
-        s_b2[c] = p.b2[c];
     }
     for (int c = tid; c < N3; c += kHeadThreads) {
         s_c3[c] = p.c3 ? p.c3[c] : 0.f;
         s_ws2[c] = p.ws2[c];
     }
-    const float bs2 = p.bs2[0];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_d = tmem_slot;
-    const uint32_t d1 = tmem_d, d2 = tmem_d + D, d3 = tmem_d + 2 * D;
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-    const uint32_t idesc_d = make_idesc_tf32(kTileM, D), idesc_3 = make_idesc_tf32(kTileM, N3);
-    const uint32_t aA = smem_u32(sA), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
-
-    const int chunk = tid & 7, row_in_pass = tid >> 3;
-    const bool vec_x = ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0) && (p.ldx % 4 == 0);
-    uint32_t mma_phase = 0;
-    bool weights_ready = false;
 
     const int64_t ntiles = (p.n + kTileM - 1) / kTileM;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t j0 = tile * kTileM;
-        // ---- link ids of the tile
-        {
-            const int64_t j = j0 + tid;
-            int64_t a = 0, b = 0;
+
+    if (warp >= kHeadConsumers / 32) {
+        // =========================== producers: gather the next tile into the staging buffer
+        const int ptid = tid - kHeadConsumers;
+        const int chunk = ptid & 7, row_in_pass = ptid >> 3;
+        const bool vec_x = ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0) && (p.ldx % 4 == 0);
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int64_t j = tile * kTileM + ptid;
+            int32_t a = 0, b = 0;
             if (j < p.n) {
                 const int64_t pos = p.idx ? (int64_t)__ldg(p.idx + j) : j;
-                a = __ldg(p.links + pos);
-                b = __ldg(p.links + p.bs + pos);
+                a = (int32_t)__ldg(p.links + pos);
+                b = (int32_t)__ldg(p.links + p.bs + pos);
             }
-            tile_a[tid] = a;
-            tile_b[tid] = b;
-        }
-        __syncthreads();
-        // ---- gather: xprod tile, split, canonical layout
+            ids[it & 1][0][ptid] = a;
+            ids[it & 1][1][ptid] = b;
+            named_bar_sync(2, kHeadProducers);
+            float4 v[KB][8];
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb) {
-            float4 xa[8], xb[8];
+            for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
-            for (int pass = 0; pass < 8; ++pass) {
-                const int r = pass * 16 + row_in_pass;
-                const float* pa = p.X + tile_a[r] * p.ldx + kb * 32 + chunk * 4;
-                const float* pb = p.X + tile_b[r] * p.ldx + kb * 32 + chunk * 4;
-                if (vec_x) {
-                    xa[pass] = __ldg(reinterpret_cast<const float4*>(pa));
-                    xb[pass] = __ldg(reinterpret_cast<const float4*>(pb));
-                } else {
-                    xa[pass] = make_float4(__ldg(pa), __ldg(pa + 1), __ldg(pa + 2), __ldg(pa + 3));
-                    xb[pass] = make_float4(__ldg(pb), __ldg(pb + 1), __ldg(pb + 2), __ldg(pb + 3));
+                for (int pass = 0; pass < 8; ++pass) {
+                    const int r = pass * 16 + row_in_pass;
+                    const float* pa = p.X + (int64_t)ids[it & 1][0][r] * p.ldx + kb * 32 + chunk * 4;
+                    const float* pb = p.X + (int64_t)ids[it & 1][1][r] * p.ldx + kb * 32 + chunk * 4;
+                    float4 xa, xb;
+                    if (vec_x) {
+                        xa = __ldg(reinterpret_cast<const float4*>(pa));
+                        xb = __ldg(reinterpret_cast<const float4*>(pb));
+                    } else {
+                        xa = make_float4(__ldg(pa), __ldg(pa + 1), __ldg(pa + 2), __ldg(pa + 3));
+                        xb = make_float4(__ldg(pb), __ldg(pb + 1), __ldg(pb + 2), __ldg(pb + 3));
+                    }
+                    v[kb][pass] = make_float4(xa.x * xb.x, xa.y * xb.y, xa.z * xb.z, xa.w * xb.w);
                 }
             }
+            if (it > 0) mbar_wait(&bar_empty, (it - 1) & 1);      // consumers have drained the previous tile
 #pragma unroll
-            for (int pass = 0; pass < 8; ++pass) {
-                const int r = pass * 16 + row_in_pass;
-                const float4 v = make_float4(xa[pass].x * xb[pass].x, xa[pass].y * xb[pass].y, xa[pass].z * xb[pass].z,
-                                             xa[pass].w * xb[pass].w);
-                const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-                const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-                const uint32_t off = (uint32_t)kb * 2 * kATileBytes + swz_chunk_off(r, chunk);
-                *reinterpret_cast<float4*>(sA + off) = hi;
-                *reinterpret_cast<float4*>(sA + off + kATileBytes) = lo;
-            }
+            for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                for (int pass = 0; pass < 8; ++pass)
+                    *reinterpret_cast<float4*>(sStg + kb * kATileBytes + swz_chunk_off(pass * 16 + row_in_pass, chunk)) =
+                        v[kb][pass];
+            mbar_arrive(&bar_full);
         }
+        return;
+    }
+
+    // =============================== consumers
+    const float bs2 = p.bs2[0];
+    const uint32_t tmem_d = tmem_slot;
+    const uint32_t d1 = tmem_d, d3 = tmem_d + D;
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    const uint32_t idesc_d = make_idesc_tf32(kTileM, D), idesc_3 = make_idesc_tf32(kTileM, N3);
+    const uint32_t aA = smem_u32(sA), aW1 = smem_u32(sW1), aW3 = smem_u32(sW3);
+    uint32_t mma_phase = 0, it = 0;
+    bool weights_ready = false;
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int64_t j = tile * kTileM + tid;
+        // ---- staged xprod row of this thread -> hi / lo operand tile
+        mbar_wait(&bar_full, it & 1);
+#pragma unroll
+        for (int c = 0; c < D / 4; ++c) {
+            const uint32_t off = swz_chunk_off(tid, c & 7);
+            const float4 v = *reinterpret_cast<const float4*>(sStg + (c >> 3) * kATileBytes + off);
+            const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+            const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+            *reinterpret_cast<float4*>(sA + (c >> 3) * 2 * kATileBytes + off) = hi;
+            *reinterpret_cast<float4*>(sA + (c >> 3) * 2 * kATileBytes + kATileBytes + off) = lo;
+        }
+        mbar_arrive(&bar_empty);
         fence_async_smem();
-        __syncthreads();
+        named_bar_sync(1, kHeadConsumers);
 
         // ---- contraction 1: D1 = xprod . W1^T
         if (tid == 0) {
@@ -173,20 +203,20 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
             float v[D];
 #pragma unroll
             for (int c0 = 0; c0 < D; c0 += 16) tmem_ld16(d1 + lane_sel + c0, v + c0);
-            float s = 0.f;
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int c = 0; c < D; ++c) {
                 v[c] += s_b1[c];
-                s += v[c];
+                s4[c & 3] += v[c];
             }
-            const float mean = s * (1.0f / D);
-            float var = 0.f;
+            const float mean = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.0f / D);
+            float q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int c = 0; c < D; ++c) {
                 const float dlt = v[c] - mean;
-                var = fmaf(dlt, dlt, var);
+                q4[c & 3] = fmaf(dlt, dlt, q4[c & 3]);
             }
-            const float rstd = rsqrtf(var * (1.0f / D) + 1e-5f);
+            const float rstd = rsqrtf(((q4[0] + q4[1]) + (q4[2] + q4[3])) * (1.0f / D) + 1e-5f);
 #pragma unroll
             for (int c = 0; c < D; c += 4) {
                 float h[4];
@@ -201,47 +231,9 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
         }
         tc_fence_before();
         fence_async_smem();
-        __syncthreads();
+        named_bar_sync(1, kHeadConsumers);
 
-        // ---- contraction 2: D2 = h . W2^T
-        if (tid == 0) {
-            tc_fence_after();
-#pragma unroll
-            for (int kb = 0; kb < KB; ++kb)
-                issue_kblock_3x(d2, aA + kb * 2 * kATileBytes, aA + kb * 2 * kATileBytes + kATileBytes,
-                                aW2 + kb * 2 * D * 128, aW2 + kb * 2 * D * 128 + D * 128, idesc_d, kb == 0);
-            umma_commit(&bar_mma);
-        }
-        __syncwarp();
-        mbar_wait(&bar_mma, mma_phase);
-        mma_phase ^= 1;
-        tc_fence_after();
-
-        // ---- epilogue 2: el = D2 + b2
-        {
-#pragma unroll
-            for (int c0 = 0; c0 < D; c0 += 16) {
-                float v[16];
-                tmem_ld16(d2 + lane_sel + c0, v);
-#pragma unroll
-                for (int c = 0; c < 16; c += 4) {
-                    float h[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) h[e] = v[c + e] + s_b2[c0 + c + e];
-                    const float4 hi = make_float4(tf32_hi(h[0]), tf32_hi(h[1]), tf32_hi(h[2]), tf32_hi(h[3]));
-                    const float4 lo = make_float4(h[0] - hi.x, h[1] - hi.y, h[2] - hi.z, h[3] - hi.w);
-                    const int cc = c0 + c;
-                    const uint32_t off = (uint32_t)(cc / 32) * 2 * kATileBytes + swz_chunk_off(tid, (cc % 32) / 4);
-                    *reinterpret_cast<float4*>(sA + off) = hi;
-                    *reinterpret_cast<float4*>(sA + off + kATileBytes) = lo;
-                }
-            }
-        }
-        tc_fence_before();
-        fence_async_smem();
-        __syncthreads();
-
-        // ---- contraction 3: D3 = el . Ws1[:, :d]^T
+        // ---- contraction 2: D3 = h . (Ws1[:, :d] W2)^T
         if (tid == 0) {
             tc_fence_after();
 #pragma unroll
@@ -255,11 +247,10 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
         mma_phase ^= 1;
         tc_fence_after();
 
-        // ---- epilogue 3: prob = sigmoid(ws2 . ReLU(D3 + zb) + bs2)
+        // ---- epilogue 2: prob = sigmoid(ws2 . ReLU(D3 + offset) + bs2)
         {
-            const int64_t j = j0 + tid;
             const float* zrow = (p.zb && j < p.n) ? p.zb + j * p.ld_zb : nullptr;
-            float acc = 0.f;
+            float acc4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int c0 = 0; c0 < N3; c0 += 16) {
                 float v[16];
@@ -267,29 +258,30 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                     const float z = v[c] + (zrow ? __ldg(zrow + c0 + c) : s_c3[c0 + c]);
-                    acc = fmaf(fmaxf(z, 0.f), s_ws2[c0 + c], acc);
+                    acc4[c & 3] = fmaf(fmaxf(z, 0.f), s_ws2[c0 + c], acc4[c & 3]);
                 }
             }
             if (j < p.n) {
-                const float logit = acc + bs2;
+                const float logit = ((acc4[0] + acc4[1]) + (acc4[2] + acc4[3])) + bs2;
                 const int64_t pos = p.idx ? (int64_t)__ldg(p.idx + j) : j;
                 p.prob[pos] = p.logits ? logit : 1.0f / (1.0f + expf(-logit));
             }
         }
         tc_fence_before();
-        __syncthreads();   // TMEM columns, the A tile and tile_a/b are reused by the next tile
+        named_bar_sync(1, kHeadConsumers);   // TMEM columns and the operand tile are reused by the next tile
     }
 
     if (!weights_ready && tid == 0) mbar_wait(&bar_w, 0);   // never exit with a bulk copy in flight
     tc_fence_before();
-    __syncthreads();
+    named_bar_sync(1, kHeadConsumers);
     if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
 }
 
 template <int D>
 static int launch_heads(const HeadsParams& p, cudaStream_t st) {
-    constexpr size_t smem = (size_t)(D / 32) * 2 * D * 128 * 2 + (size_t)(D / 32) * 2 * 2 * D * 128 +
-                            (size_t)(D / 32) * 2 * tc::kATileBytes + 1024;
+    constexpr int KB = D / 32;
+    constexpr size_t smem = (size_t)KB * 2 * D * 128 + (size_t)KB * 2 * 2 * D * 128 + (size_t)KB * 2 * tc::kATileBytes +
+                            (size_t)KB * tc::kATileBytes + 1024;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(link_heads_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -312,18 +304,16 @@ using namespace lpf;
 
 extern "C" int lpf_link_heads_tc(const int64_t* links, int64_t bs, const int32_t* idx, int64_t n, const float* X,
                                  int64_t ldx, int32_t d, const float* w1_packed, const float* b1, const float* ln_w,
-                                 const float* ln_b, const float* w2_packed, const float* b2, const float* ws1_packed,
-                                 const float* c3, const float* zb, int64_t ld_zb, const float* ws2, const float* bs2,
-                                 float* prob, int logits, void* stream) {
+                                 const float* ln_b, const float* w23_packed, const float* c3, const float* zb,
+                                 int64_t ld_zb, const float* ws2, const float* bs2, float* prob, int logits,
+                                 void* stream) {
     LPF_REQUIRE(bs >= 0 && n >= 0, "negative size");
     if (n == 0) return LPF_OK;
-    LPF_REQUIRE(links && X && w1_packed && b1 && ln_w && ln_b && w2_packed && b2 && ws1_packed && ws2 && bs2 && prob,
-                "NULL argument");
+    LPF_REQUIRE(links && X && w1_packed && b1 && ln_w && ln_b && w23_packed && ws2 && bs2 && prob, "NULL argument");
     LPF_REQUIRE(c3 || zb, "either the constant c3 or per-row zb must be given");
     LPF_REQUIRE(idx || n == bs, "n must equal bs when idx is NULL");
     LPF_REQUIRE(ldx >= d && (!zb || ld_zb >= 2 * d), "leading dimension too small");
-    HeadsParams p{links, bs, idx, n, X, ldx, w1_packed, b1, ln_w, ln_b, w2_packed, b2, ws1_packed, c3, zb, ld_zb,
-                  ws2, bs2, prob, logits};
+    HeadsParams p{links, bs, idx, n, X, ldx, w1_packed, b1, ln_w, ln_b, w23_packed, c3, zb, ld_zb, ws2, bs2, prob, logits};
     cudaStream_t st = (cudaStream_t)stream;
     if (d == 64) return launch_heads<64>(p, st);
     if (d == 32) return launch_heads<32>(p, st);

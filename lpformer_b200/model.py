@@ -564,15 +564,18 @@ class LinkTransformer(nn.Module):
             (self._dev(), id(score_func))
         if self._head_cache is not None and self._head_cache[0] == key:
             return self._head_cache[1]
-        ws1 = lins[0].weight.detach()
+        # no non-linearity between elementwise_lin's last Linear and mlp_score's first: fold them (fp64, once)
+        ws1 = lins[0].weight.detach().double()
+        w2, b2 = el.linears[1].weight.detach().double(), el.linears[1].bias.detach().double()
+        w23 = (ws1[:, :d] @ w2).float().contiguous()
         consts = {
             "w1p": ops.pack_weight(el.linears[0].weight), "b1": el.linears[0].bias.detach().contiguous(),
             "ln_w": el.norm.weight.detach().contiguous(), "ln_b": el.norm.bias.detach().contiguous(),
-            "w2p": ops.pack_weight(el.linears[1].weight), "b2": el.linears[1].bias.detach().contiguous(),
-            "ws1p": ops.pack_weight(ws1[:, :d]), "ws1_pw": ws1[:, d:], "bs1": lins[0].bias.detach().contiguous(),
+            "w23": w23, "w23p": ops.pack_weight(w23), "ws1_pw": lins[0].weight.detach()[:, d:],
+            "off": (ws1[:, :d] @ b2 + lins[0].bias.detach().double()).float().contiguous(),
             "ws2": lins[1].weight.detach().reshape(-1).contiguous(), "bs2": lins[1].bias.detach().contiguous(),
         }
-        consts["c3"] = ops.linear(self._pw_const(X_node), consts["ws1_pw"], consts["bs1"]).reshape(-1).contiguous()
+        consts["c3"] = ops.linear(self._pw_const(X_node), consts["ws1_pw"], consts["off"]).reshape(-1).contiguous()
         self._head_cache = (key, consts)
         return consts
 
@@ -600,6 +603,6 @@ class LinkTransformer(nn.Module):
         sel = self._select(batch, test_set)
         if sel.nz.numel() > 0:
             rows = self._pairwise_rows(batch, X_node, sel, sel.nz)[0]
-            zb = ops.linear(rows, consts["ws1_pw"], consts["bs1"])
+            zb = ops.linear(rows, consts["ws1_pw"], consts["off"])
             ops.link_heads(batch, X_node, consts, prob, idx=sel.nz, zb=zb, logits=return_logits)
         return prob

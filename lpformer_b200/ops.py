@@ -243,8 +243,8 @@ def link_heads(links, X, consts, prob, idx=None, zb=None, logits=False):
     bs = links.shape[1]
     n = bs if idx is None else idx.numel()
     call("lpf_link_heads_tc", ptr(links), bs, ptr(idx), n, ptr(X), X.stride(0), X.shape[1], ptr(consts["w1p"]),
-         ptr(consts["b1"]), ptr(consts["ln_w"]), ptr(consts["ln_b"]), ptr(consts["w2p"]), ptr(consts["b2"]),
-         ptr(consts["ws1p"]), ptr(consts["c3"]) if zb is None else None, ptr(zb), zb.stride(0) if zb is not None else 0,
+         ptr(consts["b1"]), ptr(consts["ln_w"]), ptr(consts["ln_b"]), ptr(consts["w23p"]),
+         ptr(consts["c3"]) if zb is None else None, ptr(zb), zb.stride(0) if zb is not None else 0,
          ptr(consts["ws2"]), ptr(consts["bs2"]), ptr(prob), int(logits), stream(), meta=(n,))
     return prob
 
