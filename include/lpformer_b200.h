@@ -98,6 +98,27 @@ int64_t lpf_select_workspace_bytes(int64_t bs);
 int64_t lpf_scan_scratch_bytes(int64_t n);
 int lpf_scan_counts(const int32_t* counts, int64_t n, int64_t* ptr, void* scratch, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Device-side sizes.  Entry points with a trailing `const int64_t* *_dev` argument accept a DEVICE pointer to
+ * the actual row / link count; the host-side count is then only the capacity the grid and the buffers were
+ * sized for (actual = min(capacity, *dev)).  With them a whole batch runs without a host round trip and can be
+ * captured in a CUDA graph.  Pass NULL for the plain host-sized behaviour.
+ *
+ * One-pass selection (INTERSECT algorithms only): counts, allocates and writes in a single launch sequence.
+ * Pairs of type t go to rows [t*cap, t*cap + header[t]) of node / src_ppr / tgt_ppr (arrays of 3*cap rows);
+ * within a type a link's pairs are contiguous and ascending, links appear in arbitrary order.  Outputs:
+ * counts[t*BS+i], seg_start[t*BS+i] (first row relative to t*cap), nz_list (batch positions of the links with
+ * a non-empty set), header int64[8] = (pairs of type 0, 1, 2, non-empty links, overflow flag, ...).  If a pool
+ * overflows, header[4] = 1, header[0..3] = 0 and the pair arrays are undefined: re-run the batch through
+ * count / scan / fill.
+ * ------------------------------------------------------------------------- */
+int lpf_select_onepass(const int64_t* links, int64_t bs,
+                       const int64_t* adj_rowptr, const int32_t* adj_col,
+                       const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val,
+                       float th_cn, float th_1hop, float th_non1hop, int mode, int algo, int64_t cap,
+                       int32_t* counts, int32_t* seg_start, int32_t* nz_list, int64_t* header,
+                       int32_t* node, float* src_ppr, float* tgt_ppr, void* workspace, void* stream);
+
 /* After the scan: batch positions of the links with at least one selected node (nz_list int32 [<= BS], any
  * order) and header int64[4] = (S_cn, S_cn + S_1hop, S, number of non-empty links) — the one small read-back
  * the host needs to size the pair arrays and the compacted attention batch. */
@@ -121,7 +142,7 @@ int lpf_select_fill(const int64_t* links, int64_t bs,
  * ------------------------------------------------------------------------- */
 int lpf_rpe_hidden(const float* src_ppr, const float* tgt_ppr, int64_t row0, int64_t rows,
                    const float* w1, const float* b1, const float* ln_w, const float* ln_b,
-                   int32_t d, float* hsum, int64_t ld_hsum, void* stream);
+                   int32_t d, float* hsum, int64_t ld_hsum, const int64_t* rows_dev, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Dense contraction  C[M,N] = epi( A[M,K] . W[N,K]^T + bias[N] )  — every
@@ -140,7 +161,8 @@ int lpf_gemm(const float* A, int64_t lda, const float* W, int64_t ldw, const flo
 int64_t lpf_pack_weight_bytes(int32_t N, int32_t K);
 int lpf_pack_weight(const float* W, int64_t ldw, int32_t N, int32_t K, float* packed, void* stream);
 int lpf_gemm_tc(const float* A, int64_t lda, const float* Wpacked, const float* bias, float bias_scale,
-                float* C, int64_t ldc, int64_t M, int32_t N, int32_t K, int epilogue, void* stream);
+                float* C, int64_t ldc, int64_t M, int32_t N, int32_t K, int epilogue, const int64_t* m_dev,
+                void* stream);
 
 /* Row-wise LayerNorm (eps 1e-5) over the first `n` columns, optional ReLU, in place
  * or out of place (X may equal Y).  nn.LayerNorm + F.relu of MLP/GCN/gnn_norm.
@@ -148,14 +170,15 @@ int lpf_gemm_tc(const float* A, int64_t lda, const float* Wpacked, const float* 
  * gamma == beta == NULL skips the normalisation (GCN with layer_norm=False). */
 int lpf_layernorm_act(const float* X, int64_t ldx, const float* gamma, const float* beta,
                       const float* residual, int64_t ldr, float* Y, int64_t ldy,
-                      int64_t rows, int32_t n, int relu, void* stream);
+                      int64_t rows, int32_t n, int relu, const int64_t* rows_dev, void* stream);
 
 /* Link-level gathers (models/link_transformer.py:101-102,143-144; train/testing.py:29,113):
  * xsum[i,:] = X[a_i,:] + X[b_i,:]   (input of lin_l, since lin_l(e1)+lin_l(e2) = W_l(e1+e2)+2b)
  * xprod[i,:] = X[a_i,:] * X[b_i,:]  (input of elementwise_lin).  Either output may be NULL. */
 int lpf_gather_links(const int64_t* links, int64_t bs, const int32_t* idx /* NULL or [n] batch positions */,
                      int64_t n, const float* X, int64_t ldx, int32_t d,
-                     float* xsum, int64_t ld_sum, float* xprod, int64_t ld_prod, void* stream);
+                     float* xsum, int64_t ld_sum, float* xprod, int64_t ld_prod, const int64_t* n_dev,
+                     void* stream);
 
 /* dst[r,:] = fill_row[:] for all `rows` rows (skipped when fill_row is NULL), then dst[idx[j],:] = src[j,:]
  * for j < n: puts the pairwise rows of the compacted non-empty links back in batch order, every other link
@@ -177,6 +200,8 @@ int lpf_scatter_rows(const float* src, int64_t ld_src, const int32_t* idx, int64
  * alpha_out (may be NULL) receives the head-mean attention weight per pair.
  * With idx != NULL only the n listed links are processed and rows j of Q / out belong to link idx[j]
  * (the compacted list of lpf_select_compact); otherwise n == bs and row j is link j.
+ * With seg_start != NULL (one-pass selection) type t of link i owns pair rows [t*type_stride + seg_start[t*bs+i],
+ * + seg_cnt[t*bs+i]) and ptr is ignored.
  * ------------------------------------------------------------------------- */
 int lpf_attend_fused(const int64_t* ptr, int64_t bs, const int32_t* idx /* NULL or [n] batch positions */,
                      int64_t n, const int32_t* node,
@@ -184,7 +209,9 @@ int lpf_attend_fused(const int64_t* ptr, int64_t bs, const int32_t* idx /* NULL 
                      const float* Q, int64_t ld_q,
                      const float* att, const float* bias, const float* ln_w, const float* ln_b,
                      int32_t heads, int32_t ch, int mode, int write_counts,
-                     float* out, int64_t ld_out, float* alpha_out, void* stream);
+                     float* out, int64_t ld_out, float* alpha_out,
+                     const int64_t* n_dev, const int32_t* seg_start, const int32_t* seg_cnt, int64_t type_stride,
+                     void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Fused per-link heads on the tensor cores (d in {32, 64}) — the rest of the eval-loop body
@@ -202,7 +229,8 @@ int lpf_link_heads_tc(const int64_t* links, int64_t bs, const int32_t* idx, int6
                       const float* X, int64_t ldx, int32_t d,
                       const float* w1_packed, const float* b1, const float* ln_w, const float* ln_b,
                       const float* w23_packed, const float* c3, const float* zb, int64_t ld_zb,
-                      const float* ws2, const float* bs2, float* prob, int logits, void* stream);
+                      const float* ws2, const float* bs2, float* prob, int logits, const int64_t* n_dev,
+                      void* stream);
 
 /* ------------------------------------------------------------------------- *
  * K2  GCN message passing — GCNConv's SpMM (models/other_models.py:66 via

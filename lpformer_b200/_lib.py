@@ -30,19 +30,21 @@ SIGNATURES = {
     "lpf_scan_counts": (_int, [_p, _i64, _p, _p, _p]),
     "lpf_select_fill": (_int, [_p, _i64, _p, _p, _p, _p, _p, _f32, _f32, _f32, _int, _int, _p, _p, _p, _p, _p, _p,
                                 _p]),
-    "lpf_rpe_hidden": (_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _i32, _p, _i64, _p]),
+    "lpf_rpe_hidden": (_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _i32, _p, _i64, _p, _p]),
+    "lpf_select_onepass": (_int, [_p, _i64, _p, _p, _p, _p, _p, _f32, _f32, _f32, _int, _int, _i64, _p, _p, _p, _p, _p,
+                                  _p, _p, _p, _p]),
     "lpf_gemm": (_int, [_p, _i64, _p, _i64, _p, _f32, _p, _i64, _i64, _i32, _i32, _int, _p]),
     "lpf_pack_weight_bytes": (_i64, [_i32, _i32]),
     "lpf_pack_weight": (_int, [_p, _i64, _i32, _i32, _p, _p]),
-    "lpf_gemm_tc": (_int, [_p, _i64, _p, _p, _f32, _p, _i64, _i64, _i32, _i32, _int, _p]),
-    "lpf_layernorm_act": (_int, [_p, _i64, _p, _p, _p, _i64, _p, _i64, _i64, _i32, _int, _p]),
-    "lpf_gather_links": (_int, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _i64, _p, _i64, _p]),
+    "lpf_gemm_tc": (_int, [_p, _i64, _p, _p, _f32, _p, _i64, _i64, _i32, _i32, _int, _p, _p]),
+    "lpf_layernorm_act": (_int, [_p, _i64, _p, _p, _p, _i64, _p, _i64, _i64, _i32, _int, _p, _p]),
+    "lpf_gather_links": (_int, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _i64, _p, _i64, _p, _p]),
     "lpf_scatter_rows": (_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _i32, _p, _p]),
     "lpf_select_compact": (_int, [_p, _i64, _p, _p, _p]),
     "lpf_link_heads_tc": (_int, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p,
-                                 _p, _int, _p]),
+                                 _p, _int, _p, _p]),
     "lpf_attend_fused": (_int, [_p, _i64, _p, _i64, _p, _p, _i64, _p, _i64, _p, _i64, _p, _p, _p, _p, _i32, _i32, _int, _int,
-                                _p, _i64, _p, _p]),
+                                _p, _i64, _p, _p, _p, _p, _i64, _p]),
     "lpf_ppr_push_host": (_p, [_p, _p, _i64, C.c_double, C.c_double, _int, _p]),
     "lpf_ppr_push_host_fetch": (_int, [_p, _p, _p, _p]),
     "lpf_gcn_spmm": (_int, [_p, _p, _p, _i64, _i64, _p, _i64, _p, _i32, _p, _i64, _p]),
@@ -75,7 +77,7 @@ def load():
 # kernels launched per entry point (for bench.py's gpu_launches and per-kernel CUDA-event timing)
 KERNEL_LAUNCHES = {"lpf_select_count": 3, "lpf_scan_counts": 2, "lpf_select_fill": 2, "lpf_rpe_hidden": 1,
                    "lpf_gemm": 1, "lpf_gemm_tc": 1, "lpf_pack_weight": 1, "lpf_layernorm_act": 1, "lpf_gather_links": 1, "lpf_attend_fused": 1,
-                   "lpf_gcn_spmm": 1, "lpf_select_compact": 2, "lpf_scatter_rows": 2, "lpf_link_heads_tc": 1}
+                   "lpf_gcn_spmm": 1, "lpf_select_compact": 2, "lpf_select_onepass": 4, "lpf_scatter_rows": 2, "lpf_link_heads_tc": 1}
 
 
 class Trace:
@@ -97,6 +99,7 @@ class Trace:
 
 
 TRACE = None
+COUNTERS = None   # optional dict: bench.py counts CUDA-graph launches here
 
 
 def call(name, *args, meta=None):

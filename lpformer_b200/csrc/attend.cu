@@ -18,6 +18,12 @@ struct AttendParams {
     int64_t bs;
     const int32_t* idx;   // optional: batch positions of the links to process (rows of Q / out follow the list)
     int64_t n;            // number of links to process (== bs when idx is NULL)
+    const int64_t* n_dev; // optional device-side n (n is then an upper bound)
+    // optional one-pass addressing (lpf_select_onepass): type t of link i owns rows
+    // [t*type_stride + seg_start[t*bs+i], ... + seg_cnt[t*bs+i]) instead of [ptr[t*bs+i], ptr[t*bs+i+1])
+    const int32_t* seg_start;
+    const int32_t* seg_cnt;
+    int64_t type_stride;
     const int32_t* node;
     const float* KV;
     int64_t ld_kv;
@@ -50,7 +56,8 @@ __global__ void __launch_bounds__(kAttWarps * 32) attend_kernel(AttendParams p) 
             att[h][k] = (c < C) ? __ldg(p.att + h * C + c) : 0.f;
         }
 
-    for (int64_t j = (int64_t)blockIdx.x * kAttWarps + warp; j < p.n; j += (int64_t)gridDim.x * kAttWarps) {
+    const int64_t n_links = p.n_dev ? min(p.n, *p.n_dev) : p.n;
+    for (int64_t j = (int64_t)blockIdx.x * kAttWarps + warp; j < n_links; j += (int64_t)gridDim.x * kAttWarps) {
         const int64_t i = p.idx ? (int64_t)__ldg(p.idx + j) : j;   // position in the batch (indexes ptr)
         float q[H][KC], acc[H][KC], mx[H], den[H];
 #pragma unroll
@@ -67,8 +74,13 @@ __global__ void __launch_bounds__(kAttWarps * 32) attend_kernel(AttendParams p) 
         int64_t seg_lo[3], seg_hi[3];
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
-            seg_lo[t] = __ldg(p.ptr + t * p.bs + i);
-            seg_hi[t] = __ldg(p.ptr + t * p.bs + i + 1);
+            if (p.seg_start) {
+                seg_lo[t] = t * p.type_stride + __ldg(p.seg_start + t * p.bs + i);
+                seg_hi[t] = seg_lo[t] + __ldg(p.seg_cnt + t * p.bs + i);
+            } else {
+                seg_lo[t] = __ldg(p.ptr + t * p.bs + i);
+                seg_hi[t] = __ldg(p.ptr + t * p.bs + i + 1);
+            }
         }
 
 #pragma unroll
@@ -220,11 +232,12 @@ extern "C" int lpf_attend_fused(const int64_t* ptr, int64_t bs, const int32_t* i
                                 const float* R, int64_t ld_r, const float* Q, int64_t ld_q, const float* att,
                                 const float* bias, const float* ln_w, const float* ln_b, int32_t heads, int32_t ch,
                                 int mode, int write_counts, float* out, int64_t ld_out, float* alpha_out,
-                                void* stream) {
+                                const int64_t* n_dev, const int32_t* seg_start, const int32_t* seg_cnt,
+                                int64_t type_stride, void* stream) {
     LPF_REQUIRE(bs >= 0 && n >= 0, "negative batch size");
     LPF_REQUIRE(idx || n == bs, "n must equal bs when idx is NULL");
     if (n == 0) return LPF_OK;
-    LPF_REQUIRE(ptr && KV && Q && att && bias && ln_w && ln_b && out, "NULL argument");
+    LPF_REQUIRE((ptr || (seg_start && seg_cnt)) && KV && Q && att && bias && ln_w && ln_b && out, "NULL argument");
     LPF_REQUIRE(heads >= 1 && ch >= 1, "bad heads/ch");
     LPF_REQUIRE(mode == LPF_MODE_CN || mode == LPF_MODE_1HOP || mode == LPF_MODE_ALL, "bad mode");
     const int hc = heads * ch;
@@ -232,7 +245,7 @@ extern "C" int lpf_attend_fused(const int64_t* ptr, int64_t bs, const int32_t* i
     LPF_REQUIRE(ld_kv >= hc && ld_q >= hc && ld_out >= hc + cd, "leading dimension too small");
     LPF_REQUIRE(R == nullptr || ld_r >= hc, "ld_r too small");
     // node / R may be NULL only if every set is empty; the kernel never dereferences them then.
-    AttendParams p{ptr, bs, idx, n, node, KV, ld_kv, R, ld_r, Q, ld_q, att, bias, ln_w, ln_b,
+    AttendParams p{ptr, bs, idx, n, n_dev, seg_start, seg_cnt, type_stride, node, KV, ld_kv, R, ld_r, Q, ld_q, att, bias, ln_w, ln_b,
                    heads, ch, mode, write_counts, out, ld_out, alpha_out};
     cudaStream_t st = (cudaStream_t)stream;
     switch (heads) {

@@ -15,7 +15,8 @@ __global__ void __launch_bounds__(256) rpe_hidden_kernel(const float* __restrict
                                                          int64_t row0, int64_t rows, const float* __restrict__ w1,
                                                          const float* __restrict__ b1, const float* __restrict__ g,
                                                          const float* __restrict__ be, int d, float* __restrict__ hsum,
-                                                         int64_t ld) {
+                                                         int64_t ld, const int64_t* __restrict__ rows_dev) {
+    if (rows_dev) rows = min(rows, *rows_dev);
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -134,7 +135,8 @@ __global__ void __launch_bounds__(256) layernorm_act_kernel(const float* X, int6
                                                             const float* __restrict__ g, const float* __restrict__ b,
                                                             const float* R, int64_t ldr,
                                                             float* Y, int64_t ldy, int64_t rows, int n,
-                                                            int relu) {
+                                                            int relu, const int64_t* __restrict__ rows_dev) {
+    if (rows_dev) rows = min(rows, *rows_dev);
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -169,7 +171,9 @@ __global__ void __launch_bounds__(256) gather_links_kernel(const int64_t* __rest
                                                            const int32_t* __restrict__ idx, int64_t n,
                                                            const float* __restrict__ X, int64_t ldx, int d,
                                                            float* __restrict__ xsum, int64_t lds,
-                                                           float* __restrict__ xprod, int64_t ldp) {
+                                                           float* __restrict__ xprod, int64_t ldp,
+                                                           const int64_t* __restrict__ n_dev) {
+    if (n_dev) n = min(n, *n_dev);
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -234,7 +238,7 @@ using namespace lpf;
 
 extern "C" int lpf_rpe_hidden(const float* src_ppr, const float* tgt_ppr, int64_t row0, int64_t rows, const float* w1,
                               const float* b1, const float* ln_w, const float* ln_b, int32_t d, float* hsum,
-                              int64_t ld_hsum, void* stream) {
+                              int64_t ld_hsum, const int64_t* rows_dev, void* stream) {
     LPF_REQUIRE(rows >= 0 && row0 >= 0, "negative row range");
     if (rows == 0) return LPF_OK;
     LPF_REQUIRE(src_ppr && tgt_ppr && w1 && b1 && ln_w && ln_b && hsum, "NULL argument");
@@ -243,7 +247,7 @@ extern "C" int lpf_rpe_hidden(const float* src_ppr, const float* tgt_ppr, int64_
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = warp_grid(rows, 256);
     const int kc = (d + 31) / 32;
-#define LPF_RPE(KC) rpe_hidden_kernel<KC><<<grid, 256, 0, st>>>(src_ppr, tgt_ppr, row0, rows, w1, b1, ln_w, ln_b, d, hsum, ld_hsum)
+#define LPF_RPE(KC) rpe_hidden_kernel<KC><<<grid, 256, 0, st>>>(src_ppr, tgt_ppr, row0, rows, w1, b1, ln_w, ln_b, d, hsum, ld_hsum, rows_dev)
     if (kc <= 1) LPF_RPE(1);
     else if (kc <= 2) LPF_RPE(2);
     else if (kc <= 4) LPF_RPE(4);
@@ -273,20 +277,20 @@ extern "C" int lpf_gemm(const float* A, int64_t lda, const float* W, int64_t ldw
 
 extern "C" int lpf_layernorm_act(const float* X, int64_t ldx, const float* gamma, const float* beta,
                                  const float* residual, int64_t ldr, float* Y, int64_t ldy, int64_t rows, int32_t n,
-                                 int relu, void* stream) {
+                                 int relu, const int64_t* rows_dev, void* stream) {
     LPF_REQUIRE(rows >= 0 && n >= 1, "bad shape");
     if (rows == 0) return LPF_OK;
     LPF_REQUIRE(X && Y, "NULL argument");
     LPF_REQUIRE((gamma == nullptr) == (beta == nullptr), "gamma and beta must both be given or both NULL");
     LPF_REQUIRE(ldx >= n && ldy >= n && (!residual || ldr >= n), "leading dimension too small");
     layernorm_act_kernel<<<warp_grid(rows, 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, gamma, beta, residual, ldr, Y,
-                                                                                 ldy, rows, n, relu);
+                                                                                 ldy, rows, n, relu, rows_dev);
     return check_launch("lpf_layernorm_act");
 }
 
 extern "C" int lpf_gather_links(const int64_t* links, int64_t bs, const int32_t* idx, int64_t n, const float* X,
                                 int64_t ldx, int32_t d, float* xsum, int64_t ld_sum, float* xprod, int64_t ld_prod,
-                                void* stream) {
+                                const int64_t* n_dev, void* stream) {
     LPF_REQUIRE(bs >= 0 && n >= 0 && d >= 1, "bad shape");
     LPF_REQUIRE(idx || n == bs, "n must equal bs when idx is NULL");
     if (n == 0) return LPF_OK;
@@ -294,7 +298,7 @@ extern "C" int lpf_gather_links(const int64_t* links, int64_t bs, const int32_t*
     LPF_REQUIRE(xsum || xprod, "no output requested");
     LPF_REQUIRE(ldx >= d && (!xsum || ld_sum >= d) && (!xprod || ld_prod >= d), "leading dimension too small");
     gather_links_kernel<<<warp_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(links, bs, idx, n, X, ldx, d, xsum, ld_sum,
-                                                                             xprod, ld_prod);
+                                                                             xprod, ld_prod, n_dev);
     return check_launch("lpf_gather_links");
 }
 

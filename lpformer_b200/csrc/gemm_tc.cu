@@ -53,6 +53,7 @@ struct GemmTcParams {
     int64_t M;
     int N, K, NP, KB, epi;
     uint32_t tmem_cols;
+    const int64_t* m_dev;   // optional device-side row count (M is then the capacity the grid was sized for)
 };
 
 __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(GemmTcParams p) {
@@ -61,6 +62,10 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(GemmTcParams p) {
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    if (p.m_dev) {
+        p.M = min(p.M, *p.m_dev);
+        if ((int64_t)blockIdx.x * kTileM >= p.M) return;   // whole CTA, before any barrier / TMEM state exists
+    }
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t w_tile = (uint32_t)p.NP * 128;                 // bytes of one W part (hi or lo) per k-block
     const uint32_t stage_bytes = 2 * kATileBytes + 2 * w_tile;
@@ -195,7 +200,8 @@ extern "C" int lpf_pack_weight(const float* W, int64_t ldw, int32_t N, int32_t K
 }
 
 extern "C" int lpf_gemm_tc(const float* A, int64_t lda, const float* Wpacked, const float* bias, float bias_scale,
-                           float* C, int64_t ldc, int64_t M, int32_t N, int32_t K, int epilogue, void* stream) {
+                           float* C, int64_t ldc, int64_t M, int32_t N, int32_t K, int epilogue, const int64_t* m_dev,
+                           void* stream) {
     LPF_REQUIRE(M >= 0 && N >= 1 && K >= 1, "bad shape");
     if (M == 0) return LPF_OK;
     LPF_REQUIRE(A && Wpacked && C, "NULL argument");
@@ -210,6 +216,7 @@ extern "C" int lpf_gemm_tc(const float* A, int64_t lda, const float* Wpacked, co
     p.A = A; p.lda = lda; p.Wp = Wpacked; p.bias = bias; p.bias_scale = bias_scale; p.C = C; p.ldc = ldc;
     p.M = M; p.N = N; p.K = K; p.NP = tc::round_up(N, 16); p.KB = (K + 31) / 32; p.epi = epilogue;
     p.tmem_cols = tc::tmem_cols_for(p.NP);
+    p.m_dev = m_dev;
     const int stages = p.KB < 2 ? 1 : 2;
     const size_t smem = (size_t)stages * (2 * tc::kATileBytes + 2 * (size_t)p.NP * 128) + 1024;
     static size_t configured = 0;

@@ -49,6 +49,7 @@ struct HeadsParams {
     const float* bs2;
     float* prob;
     int logits;
+    const int64_t* n_dev;   // optional device-side n
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
     __syncthreads();
     tc_fence_after();
 
+    if (p.n_dev) p.n = min(p.n, *p.n_dev);
     const int64_t ntiles = (p.n + kTileM - 1) / kTileM;
 
     if (warp >= kHeadConsumers / 32) {
@@ -306,14 +308,14 @@ extern "C" int lpf_link_heads_tc(const int64_t* links, int64_t bs, const int32_t
                                  int64_t ldx, int32_t d, const float* w1_packed, const float* b1, const float* ln_w,
                                  const float* ln_b, const float* w23_packed, const float* c3, const float* zb,
                                  int64_t ld_zb, const float* ws2, const float* bs2, float* prob, int logits,
-                                 void* stream) {
+                                 const int64_t* n_dev, void* stream) {
     LPF_REQUIRE(bs >= 0 && n >= 0, "negative size");
     if (n == 0) return LPF_OK;
     LPF_REQUIRE(links && X && w1_packed && b1 && ln_w && ln_b && w23_packed && ws2 && bs2 && prob, "NULL argument");
     LPF_REQUIRE(c3 || zb, "either the constant c3 or per-row zb must be given");
     LPF_REQUIRE(idx || n == bs, "n must equal bs when idx is NULL");
     LPF_REQUIRE(ldx >= d && (!zb || ld_zb >= 2 * d), "leading dimension too small");
-    HeadsParams p{links, bs, idx, n, X, ldx, w1_packed, b1, ln_w, ln_b, w23_packed, c3, zb, ld_zb, ws2, bs2, prob, logits};
+    HeadsParams p{links, bs, idx, n, X, ldx, w1_packed, b1, ln_w, ln_b, w23_packed, c3, zb, ld_zb, ws2, bs2, prob, logits, n_dev};
     cudaStream_t st = (cudaStream_t)stream;
     if (d == 64) return launch_heads<64>(p, st);
     if (d == 32) return launch_heads<32>(p, st);

@@ -313,6 +313,13 @@ int select_fast(bool fill, int group, const int64_t* links, int64_t bs, const in
                 int32_t* node, float* pa, float* pb, int32_t* link, int32_t* heavy, cudaStream_t st);
 }
 
+namespace lpf {
+int select_onepass(int group, const int64_t* links, int64_t bs, const int64_t* adj_rowptr, const int32_t* adj_col,
+                   const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val, float th_cn, float th_1hop,
+                   float th_non1hop, int mode, int64_t cap, int32_t* counts, int32_t* seg_start, int32_t* nz_list,
+                   int64_t* hdr, int32_t* node, float* pa, float* pb, int32_t* heavy, cudaStream_t st);
+}
+
 static int check_algo(int algo, int mode, float th_1hop, float th_non1hop) {
     LPF_REQUIRE(algo == LPF_ALGO_GENERIC || algo == LPF_ALGO_INTERSECT8 || algo == LPF_ALGO_INTERSECT32, "bad algo");
     if (algo != LPF_ALGO_GENERIC) {
@@ -375,6 +382,28 @@ extern "C" int lpf_select_fill(const int64_t* links, int64_t bs, const int64_t* 
     SelectParams p{links, bs, adj_rowptr, adj_col, ppr_rowptr, ppr_col, ppr_val, th_cn, th_1hop, th_non1hop,
                    mode, nullptr, ptr, node, src_ppr, tgt_ppr, link};
     return launch_select(true, p, (cudaStream_t)stream);
+}
+
+extern "C" int lpf_select_onepass(const int64_t* links, int64_t bs, const int64_t* adj_rowptr, const int32_t* adj_col,
+                                  const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val, float th_cn,
+                                  float th_1hop, float th_non1hop, int mode, int algo, int64_t cap, int32_t* counts,
+                                  int32_t* seg_start, int32_t* nz_list, int64_t* header, int32_t* node, float* src_ppr,
+                                  float* tgt_ppr, void* workspace, void* stream) {
+    int rc = check_select_args(links, bs, adj_rowptr, adj_col, ppr_rowptr, ppr_col, ppr_val, mode);
+    if (rc) return rc;
+    rc = check_algo(algo, mode, th_1hop, th_non1hop);
+    if (rc) return rc;
+    if (algo == LPF_ALGO_GENERIC) {
+        lpf::set_error("lpf_select_onepass needs an INTERSECT algorithm (thresholds > 0)");
+        return LPF_ERR_UNSUPPORTED;
+    }
+    LPF_REQUIRE(cap >= 0 && 3 * cap < ((int64_t)1 << 31), "bad pair capacity");
+    LPF_REQUIRE(header && workspace, "header/workspace is NULL");
+    LPF_REQUIRE(bs == 0 || (counts && seg_start && nz_list), "NULL output");
+    LPF_REQUIRE(cap == 0 || (node && src_ppr && tgt_ppr), "NULL pair arrays");
+    return select_onepass(algo == LPF_ALGO_INTERSECT32 ? 32 : 8, links, bs, adj_rowptr, adj_col, ppr_rowptr, ppr_col,
+                          ppr_val, th_cn, th_1hop, th_non1hop, mode, cap, counts, seg_start, nz_list, header, node,
+                          src_ppr, tgt_ppr, (int32_t*)workspace, (cudaStream_t)stream);
 }
 
 extern "C" int64_t lpf_select_workspace_bytes(int64_t bs) { return (bs + 4) * (int64_t)sizeof(int32_t); }

@@ -38,6 +38,11 @@ struct SelectParams2 {
     float* pb;
     int32_t* link;
     int32_t* heavy;   // workspace: [0] = number of heavy links, [4..] their batch positions (written by the count pass)
+    // one-pass mode (select_onepass_kernel): pairs of type t go to rows [t*cap, t*cap + hdr[t]) of the pair arrays
+    int64_t cap;       // rows reserved per type
+    int64_t* hdr;      // [0..2] pairs per type, [3] non-empty links, [4] overflow flag
+    int32_t* seg_start;  // [3*bs] first row of link i's type-t segment, relative to t*cap
+    int32_t* nz_list;    // [bs] batch positions of the non-empty links (any order)
 };
 
 // A link whose shorter adjacency (or PPR) row exceeds kHeavyPerLane elements per lane of its group is deferred
@@ -62,19 +67,131 @@ __device__ __forceinline__ unsigned group_mask(int lane) {
     else return ((1u << G) - 1u) << (lane & ~(G - 1));
 }
 
+
+// Rows of one link.
+struct LinkRows {
+    const int32_t* Aa; const int32_t* Ab; const int32_t* Pac; const int32_t* Pbc; const float* Pav; const float* Pbv;
+    int na, nb, npa, npb;
+};
+__device__ __forceinline__ LinkRows load_rows(const SelectParams2& p, int64_t i) {
+    const int64_t a = __ldg(p.links + i), b = __ldg(p.links + p.bs + i);
+    const int64_t a0 = __ldg(p.adj_rowptr + a), a1 = __ldg(p.adj_rowptr + a + 1);
+    const int64_t b0 = __ldg(p.adj_rowptr + b), b1 = __ldg(p.adj_rowptr + b + 1);
+    const int64_t pa0 = __ldg(p.ppr_rowptr + a), pa1 = __ldg(p.ppr_rowptr + a + 1);
+    const int64_t pb0 = __ldg(p.ppr_rowptr + b), pb1 = __ldg(p.ppr_rowptr + b + 1);
+    LinkRows r;
+    r.na = (int)(a1 - a0); r.nb = (int)(b1 - b0); r.npa = (int)(pa1 - pa0); r.npb = (int)(pb1 - pb0);
+    r.Aa = p.adj_col + a0; r.Ab = p.adj_col + b0;
+    r.Pac = p.ppr_col + pa0; r.Pbc = p.ppr_col + pb0; r.Pav = p.ppr_val + pa0; r.Pbv = p.ppr_val + pb0;
+    return r;
+}
+__device__ __forceinline__ bool is_heavy(const LinkRows& r, bool want_pi, int lanes) {
+    return max(min(r.na, r.nb), want_pi ? min(r.npa, r.npb) : 0) > kHeavyPerLane * lanes;
+}
+
+// One group of G lanes walks one link: counts its three sets and, with WRITE, stores the pairs at rows
+// o_cn / o_1h / o_n1 (ascending node id within each set).
+template <int G, bool WRITE>
+__device__ __forceinline__ void walk_link(const SelectParams2& p, const LinkRows& r, int64_t i, int lane, int64_t o_cn,
+                                          int64_t o_1h, int64_t o_n1, int& c_cn, int& c_1h, int& c_n1) {
+    const int gl = lane & (G - 1);
+    const unsigned gmask = group_mask<G>(lane);
+    const unsigned lt = gmask & ((1u << lane) - 1u);
+    const int last = (lane & ~(G - 1)) + G - 1;
+    const bool want_pi = p.mode != LPF_MODE_CN;
+    const bool want_n1 = p.mode == LPF_MODE_ALL;
+    const bool cn_needs_ppr = WRITE || p.th_cn > 0.0f;
+    const float th_pre = want_n1 ? fminf(p.th_1hop, p.th_non1hop) : p.th_1hop;
+    c_cn = c_1h = c_n1 = 0;
+    {   // ---- CN: walk the shorter adjacency row, search the longer
+        const bool a_short = r.na <= r.nb;
+        const int32_t* S = a_short ? r.Aa : r.Ab;
+        const int32_t* Lg = a_short ? r.Ab : r.Aa;
+        const int ns = a_short ? r.na : r.nb, nl = a_short ? r.nb : r.na;
+        int lo = 0;
+        for (int k = 0; k < ns && lo < nl; k += G) {
+            const bool act = k + gl < ns;
+            const int32_t u = act ? __ldg(S + k + gl) : 0x7fffffff;
+            int pos = nl;
+            bool hit = false;
+            if (act) {
+                pos = lower_bound_from(Lg, lo, nl, u);
+                hit = pos < nl && __ldg(Lg + pos) == u;
+            }
+            float qa = 0.f, qb = 0.f;
+            if (hit && cn_needs_ppr) {
+                int t = lower_bound_from(r.Pac, 0, r.npa, u);
+                if (t < r.npa && __ldg(r.Pac + t) == u) qa = quantise(__ldg(r.Pav + t));
+                t = lower_bound_from(r.Pbc, 0, r.npb, u);
+                if (t < r.npb && __ldg(r.Pbc + t) == u) qb = quantise(__ldg(r.Pbv + t));
+                hit = qa >= p.th_cn && qb >= p.th_cn;
+            }
+            const unsigned m = __ballot_sync(gmask, hit);
+            if (WRITE && hit) {
+                const int64_t s = o_cn + c_cn + __popc(m & lt);
+                p.node[s] = u;
+                p.pa[s] = qa;
+                p.pb[s] = qb;
+                if (p.link) p.link[s] = (int32_t)i;
+            }
+            c_cn += __popc(m);
+            // galloping: later elements are larger, so they cannot sit before the last lane's position
+            lo = __shfl_sync(gmask, pos, last);
+        }
+    }
+    if (want_pi) {   // ---- 1-hop / >1-hop from the intersection of the two PPR rows
+        const bool a_short = r.npa <= r.npb;
+        const int32_t* Sc = a_short ? r.Pac : r.Pbc;
+        const float* Sv = a_short ? r.Pav : r.Pbv;
+        const int32_t* Lc = a_short ? r.Pbc : r.Pac;
+        const float* Lv = a_short ? r.Pbv : r.Pav;
+        const int ns = a_short ? r.npa : r.npb, nl = a_short ? r.npb : r.npa;
+        int lo = 0;
+        for (int k = 0; k < ns && lo < nl; k += G) {
+            const bool act = k + gl < ns;
+            const int32_t u = act ? __ldg(Sc + k + gl) : 0x7fffffff;
+            int pos = nl;
+            bool k1 = false, kn = false;
+            float qa = 0.f, qb = 0.f;
+            if (act) {
+                pos = lower_bound_from(Lc, lo, nl, u);
+                if (pos < nl && __ldg(Lc + pos) == u) {
+                    const float qs = quantise(__ldg(Sv + k + gl)), ql = quantise(__ldg(Lv + pos));
+                    qa = a_short ? qs : ql;
+                    qb = a_short ? ql : qs;
+                    if (qa >= th_pre && qb >= th_pre) {
+                        int t = lower_bound_from(r.Aa, 0, r.na, u);
+                        const bool in_a = t < r.na && __ldg(r.Aa + t) == u;
+                        t = lower_bound_from(r.Ab, 0, r.nb, u);
+                        const bool in_b = t < r.nb && __ldg(r.Ab + t) == u;
+                        k1 = (in_a != in_b) && qa >= p.th_1hop && qb >= p.th_1hop;
+                        kn = want_n1 && !in_a && !in_b && qa >= p.th_non1hop && qb >= p.th_non1hop;
+                    }
+                }
+            }
+            const unsigned m1 = __ballot_sync(gmask, k1);
+            const unsigned mn = __ballot_sync(gmask, kn);
+            if (WRITE && (k1 || kn)) {
+                const int64_t s = k1 ? o_1h + c_1h + __popc(m1 & lt) : o_n1 + c_n1 + __popc(mn & lt);
+                p.node[s] = u;
+                p.pa[s] = qa;
+                p.pb[s] = qb;
+                if (p.link) p.link[s] = (int32_t)i;
+            }
+            c_1h += __popc(m1);
+            c_n1 += __popc(mn);
+            lo = __shfl_sync(gmask, pos, last);
+        }
+    }
+}
+
+// ---- two-pass interface (count / fill with caller-side scan): output ordered by (type, link, node)
 template <int G, bool FILL>
 __global__ void __launch_bounds__(256) select_fast_kernel(SelectParams2 p) {
     const int lane = threadIdx.x & 31;
-    const int gl = lane & (G - 1);                 // lane within the group
-    const unsigned gmask = group_mask<G>(lane);
-    const unsigned lt = gmask & ((1u << lane) - 1u);   // group lanes below me
     const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / G;
     const bool want_pi = p.mode != LPF_MODE_CN;
-    const bool want_n1 = p.mode == LPF_MODE_ALL;
-    const bool cn_needs_ppr = FILL || p.th_cn > 0.0f;
-    const float th_pre = want_n1 ? fminf(p.th_1hop, p.th_non1hop) : p.th_1hop;
-
     for (int64_t i = group; i < p.bs; i += ngroups) {
         int64_t o_cn = 0, o_1h = 0, o_n1 = 0;
         if (FILL) {
@@ -85,111 +202,14 @@ __global__ void __launch_bounds__(256) select_fast_kernel(SelectParams2 p) {
             if (p0 == p0e && p1 == p1e && p2 == p2e) continue;
             o_cn = p0; o_1h = p1; o_n1 = p2;
         }
-        const int64_t a = __ldg(p.links + i), b = __ldg(p.links + p.bs + i);
-        const int64_t a0 = __ldg(p.adj_rowptr + a), a1 = __ldg(p.adj_rowptr + a + 1);
-        const int64_t b0 = __ldg(p.adj_rowptr + b), b1 = __ldg(p.adj_rowptr + b + 1);
-        const int64_t pa0 = __ldg(p.ppr_rowptr + a), pa1 = __ldg(p.ppr_rowptr + a + 1);
-        const int64_t pb0 = __ldg(p.ppr_rowptr + b), pb1 = __ldg(p.ppr_rowptr + b + 1);
-        const int na = (int)(a1 - a0), nb = (int)(b1 - b0);
-        const int npa = (int)(pa1 - pa0), npb = (int)(pb1 - pb0);
-        if (max(min(na, nb), want_pi ? min(npa, npb) : 0) > kHeavyPerLane * G) {
-            if (!FILL && gl == 0) p.heavy[4 + atomicAdd(p.heavy, 1)] = (int32_t)i;
+        const LinkRows r = load_rows(p, i);
+        if (is_heavy(r, want_pi, G)) {
+            if (!FILL && (lane & (G - 1)) == 0) p.heavy[4 + atomicAdd(p.heavy, 1)] = (int32_t)i;
             continue;
         }
-        const int32_t* Aa = p.adj_col + a0;
-        const int32_t* Ab = p.adj_col + b0;
-        const int32_t* Pac = p.ppr_col + pa0;
-        const int32_t* Pbc = p.ppr_col + pb0;
-        const float* Pav = p.ppr_val + pa0;
-        const float* Pbv = p.ppr_val + pb0;
-
-        // ---- CN: walk the shorter adjacency row, search the longer
-        int c_cn = 0;
-        {
-            const bool a_short = na <= nb;
-            const int32_t* S = a_short ? Aa : Ab;
-            const int32_t* Lg = a_short ? Ab : Aa;
-            const int ns = a_short ? na : nb, nl = a_short ? nb : na;
-            int lo = 0;
-            for (int k = 0; k < ns && lo < nl; k += G) {
-                const bool act = k + gl < ns;
-                const int32_t u = act ? __ldg(S + k + gl) : 0x7fffffff;
-                int pos = nl;
-                bool hit = false;
-                if (act) {
-                    pos = lower_bound_from(Lg, lo, nl, u);
-                    hit = pos < nl && __ldg(Lg + pos) == u;
-                }
-                float qa = 0.f, qb = 0.f;
-                if (hit && cn_needs_ppr) {
-                    int t = lower_bound_from(Pac, 0, npa, u);
-                    if (t < npa && __ldg(Pac + t) == u) qa = quantise(__ldg(Pav + t));
-                    t = lower_bound_from(Pbc, 0, npb, u);
-                    if (t < npb && __ldg(Pbc + t) == u) qb = quantise(__ldg(Pbv + t));
-                    hit = qa >= p.th_cn && qb >= p.th_cn;
-                }
-                const unsigned m = __ballot_sync(gmask, hit);
-                if (FILL && hit) {
-                    const int64_t s = o_cn + c_cn + __popc(m & lt);
-                    p.node[s] = u;
-                    p.pa[s] = qa;
-                    p.pb[s] = qb;
-                    if (p.link) p.link[s] = (int32_t)i;
-                }
-                c_cn += __popc(m);
-                // galloping: later elements are larger, so they cannot sit before the last lane's position
-                lo = __shfl_sync(gmask, pos, (lane & ~(G - 1)) + G - 1);
-            }
-        }
-
-        // ---- 1-hop / >1-hop from the intersection of the two PPR rows
-        int c_1h = 0, c_n1 = 0;
-        if (want_pi) {
-            const bool a_short = npa <= npb;
-            const int32_t* Sc = a_short ? Pac : Pbc;
-            const float* Sv = a_short ? Pav : Pbv;
-            const int32_t* Lc = a_short ? Pbc : Pac;
-            const float* Lv = a_short ? Pbv : Pav;
-            const int ns = a_short ? npa : npb, nl = a_short ? npb : npa;
-            int lo = 0;
-            for (int k = 0; k < ns && lo < nl; k += G) {
-                const bool act = k + gl < ns;
-                const int32_t u = act ? __ldg(Sc + k + gl) : 0x7fffffff;
-                int pos = nl;
-                bool k1 = false, kn = false;
-                float qa = 0.f, qb = 0.f;
-                if (act) {
-                    pos = lower_bound_from(Lc, lo, nl, u);
-                    if (pos < nl && __ldg(Lc + pos) == u) {
-                        const float qs = quantise(__ldg(Sv + k + gl)), ql = quantise(__ldg(Lv + pos));
-                        qa = a_short ? qs : ql;
-                        qb = a_short ? ql : qs;
-                        if (qa >= th_pre && qb >= th_pre) {
-                            int t = lower_bound_from(Aa, 0, na, u);
-                            const bool in_a = t < na && __ldg(Aa + t) == u;
-                            t = lower_bound_from(Ab, 0, nb, u);
-                            const bool in_b = t < nb && __ldg(Ab + t) == u;
-                            k1 = (in_a != in_b) && qa >= p.th_1hop && qb >= p.th_1hop;
-                            kn = want_n1 && !in_a && !in_b && qa >= p.th_non1hop && qb >= p.th_non1hop;
-                        }
-                    }
-                }
-                const unsigned m1 = __ballot_sync(gmask, k1);
-                const unsigned mn = __ballot_sync(gmask, kn);
-                if (FILL && (k1 || kn)) {
-                    const int64_t s = k1 ? o_1h + c_1h + __popc(m1 & lt) : o_n1 + c_n1 + __popc(mn & lt);
-                    p.node[s] = u;
-                    p.pa[s] = qa;
-                    p.pb[s] = qb;
-                    if (p.link) p.link[s] = (int32_t)i;
-                }
-                c_1h += __popc(m1);
-                c_n1 += __popc(mn);
-                lo = __shfl_sync(gmask, pos, (lane & ~(G - 1)) + G - 1);
-            }
-        }
-
-        if (!FILL && gl == 0) {
+        int c_cn, c_1h, c_n1;
+        walk_link<G, FILL>(p, r, i, lane, o_cn, o_1h, o_n1, c_cn, c_1h, c_n1);
+        if (!FILL && (lane & (G - 1)) == 0) {
             p.counts[i] = c_cn;
             p.counts[p.bs + i] = c_1h;
             p.counts[2 * p.bs + i] = c_n1;
@@ -197,6 +217,62 @@ __global__ void __launch_bounds__(256) select_fast_kernel(SelectParams2 p) {
     }
 }
 
+// Segment allocation of the one-pass mode: rows for (c_cn, c_1h, c_n1) pairs in the three per-type pools.
+// Called by ONE thread; returns false (and raises the overflow flag) if a pool is full.
+__device__ __forceinline__ bool alloc_segments(const SelectParams2& p, int64_t i, int c_cn, int c_1h, int c_n1,
+                                               int64_t& s_cn, int64_t& s_1h, int64_t& s_n1) {
+    auto take = [&](int t, int c) -> int64_t {
+        return c > 0 ? (int64_t)atomicAdd(reinterpret_cast<unsigned long long*>(p.hdr + t), (unsigned long long)c) : 0;
+    };
+    s_cn = take(0, c_cn);
+    s_1h = take(1, c_1h);
+    s_n1 = take(2, c_n1);
+    p.counts[i] = c_cn;
+    p.counts[p.bs + i] = c_1h;
+    p.counts[2 * p.bs + i] = c_n1;
+    p.seg_start[i] = (int32_t)s_cn;
+    p.seg_start[p.bs + i] = (int32_t)s_1h;
+    p.seg_start[2 * p.bs + i] = (int32_t)s_n1;
+    if (c_cn + c_1h + c_n1 == 0) return true;
+    const bool fits = s_cn + c_cn <= p.cap && s_1h + c_1h <= p.cap && s_n1 + c_n1 <= p.cap;
+    if (!fits) {
+        p.hdr[4] = 1;
+        return false;
+    }
+    p.nz_list[atomicAdd(reinterpret_cast<unsigned long long*>(p.hdr + 3), 1ull)] = (int32_t)i;
+    return true;
+}
+
+// ---- one-pass interface: count, allocate, write in the same launch; a link's pairs are contiguous and
+// ascending within each type pool, links appear in arbitrary order.  No scan, no second launch, no host sync.
+template <int G>
+__global__ void __launch_bounds__(256) select_onepass_kernel(SelectParams2 p) {
+    const int lane = threadIdx.x & 31;
+    const int leader = lane & ~(G - 1);
+    const unsigned gmask = group_mask<G>(lane);
+    const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / G;
+    const bool want_pi = p.mode != LPF_MODE_CN;
+    for (int64_t i = group; i < p.bs; i += ngroups) {
+        const LinkRows r = load_rows(p, i);
+        if (is_heavy(r, want_pi, G)) {
+            if (lane == leader) p.heavy[4 + atomicAdd(p.heavy, 1)] = (int32_t)i;
+            continue;
+        }
+        int c_cn, c_1h, c_n1;
+        walk_link<G, false>(p, r, i, lane, 0, 0, 0, c_cn, c_1h, c_n1);
+        int64_t s_cn = 0, s_1h = 0, s_n1 = 0;
+        int ok = 1;
+        if (lane == leader) ok = alloc_segments(p, i, c_cn, c_1h, c_n1, s_cn, s_1h, s_n1) ? 1 : 0;
+        if (c_cn + c_1h + c_n1 == 0) continue;       // uniform within the group
+        ok = __shfl_sync(gmask, ok, leader);
+        if (!ok) continue;
+        s_cn = __shfl_sync(gmask, s_cn, leader);
+        s_1h = __shfl_sync(gmask, s_1h, leader);
+        s_n1 = __shfl_sync(gmask, s_n1, leader);
+        walk_link<G, true>(p, r, i, lane, s_cn, p.cap + s_1h, 2 * p.cap + s_n1, c_cn, c_1h, c_n1);
+    }
+}
 
 // Ordered block-wide compaction step: every thread passes its flag; returns this thread's rank among the
 // flagged threads (thread order) and adds the block total to `running`.  Two __syncthreads per call.
@@ -218,14 +294,93 @@ __device__ __forceinline__ int block_rank(bool flag, int* warp_tot, int& running
     return rank;
 }
 
+// A whole CTA walks one (heavy) link.
+template <bool WRITE>
+__device__ __forceinline__ void walk_link_cta(const SelectParams2& p, const LinkRows& r, int64_t i, int* wt, int64_t o_cn,
+                                              int64_t o_1h, int64_t o_n1, int& c_cn, int& c_1h, int& c_n1) {
+    const bool want_pi = p.mode != LPF_MODE_CN;
+    const bool want_n1 = p.mode == LPF_MODE_ALL;
+    const bool cn_needs_ppr = WRITE || p.th_cn > 0.0f;
+    const float th_pre = want_n1 ? fminf(p.th_1hop, p.th_non1hop) : p.th_1hop;
+    c_cn = c_1h = c_n1 = 0;
+    {   // CN: every thread probes one element of the shorter adjacency row per step
+        const bool a_short = r.na <= r.nb;
+        const int32_t* S = a_short ? r.Aa : r.Ab;
+        const int32_t* Lg = a_short ? r.Ab : r.Aa;
+        const int ns = a_short ? r.na : r.nb, nl = a_short ? r.nb : r.na;
+        int lo = 0;   // this thread's elements ascend, so its search window only moves right
+        for (int k = 0; k < ns; k += kHeavyThreads) {
+            const bool act = k + (int)threadIdx.x < ns;
+            const int32_t u = act ? __ldg(S + k + threadIdx.x) : 0x7fffffff;
+            bool hit = false;
+            float qa = 0.f, qb = 0.f;
+            if (act) {
+                lo = lower_bound_from(Lg, lo, nl, u);
+                hit = lo < nl && __ldg(Lg + lo) == u;
+                if (hit && cn_needs_ppr) {
+                    int t = lower_bound_from(r.Pac, 0, r.npa, u);
+                    if (t < r.npa && __ldg(r.Pac + t) == u) qa = quantise(__ldg(r.Pav + t));
+                    t = lower_bound_from(r.Pbc, 0, r.npb, u);
+                    if (t < r.npb && __ldg(r.Pbc + t) == u) qb = quantise(__ldg(r.Pbv + t));
+                    hit = qa >= p.th_cn && qb >= p.th_cn;
+                }
+            }
+            const int rk = block_rank(hit, wt, c_cn);
+            if (WRITE && hit) {
+                const int64_t s = o_cn + rk;
+                p.node[s] = u;
+                p.pa[s] = qa;
+                p.pb[s] = qb;
+                if (p.link) p.link[s] = (int32_t)i;
+            }
+        }
+    }
+    if (want_pi) {   // 1-hop / >1-hop from the intersection of the two PPR rows
+        const bool a_short = r.npa <= r.npb;
+        const int32_t* Sc = a_short ? r.Pac : r.Pbc;
+        const float* Sv = a_short ? r.Pav : r.Pbv;
+        const int32_t* Lc = a_short ? r.Pbc : r.Pac;
+        const float* Lv = a_short ? r.Pbv : r.Pav;
+        const int ns = a_short ? r.npa : r.npb, nl = a_short ? r.npb : r.npa;
+        int lo = 0;
+        for (int k = 0; k < ns; k += kHeavyThreads) {
+            const bool act = k + (int)threadIdx.x < ns;
+            const int32_t u = act ? __ldg(Sc + k + threadIdx.x) : 0x7fffffff;
+            bool k1 = false, kn = false;
+            float qa = 0.f, qb = 0.f;
+            if (act) {
+                lo = lower_bound_from(Lc, lo, nl, u);
+                if (lo < nl && __ldg(Lc + lo) == u) {
+                    const float qs = quantise(__ldg(Sv + k + threadIdx.x)), ql = quantise(__ldg(Lv + lo));
+                    qa = a_short ? qs : ql;
+                    qb = a_short ? ql : qs;
+                    if (qa >= th_pre && qb >= th_pre) {
+                        int t = lower_bound_from(r.Aa, 0, r.na, u);
+                        const bool in_a = t < r.na && __ldg(r.Aa + t) == u;
+                        t = lower_bound_from(r.Ab, 0, r.nb, u);
+                        const bool in_b = t < r.nb && __ldg(r.Ab + t) == u;
+                        k1 = (in_a != in_b) && qa >= p.th_1hop && qb >= p.th_1hop;
+                        kn = want_n1 && !in_a && !in_b && qa >= p.th_non1hop && qb >= p.th_non1hop;
+                    }
+                }
+            }
+            const int r1 = block_rank(k1, wt, c_1h);
+            const int rn = block_rank(kn, wt, c_n1);
+            if (WRITE && (k1 || kn)) {
+                const int64_t s = k1 ? o_1h + r1 : o_n1 + rn;
+                p.node[s] = u;
+                p.pa[s] = qa;
+                p.pb[s] = qb;
+                if (p.link) p.link[s] = (int32_t)i;
+            }
+        }
+    }
+}
+
 template <bool FILL>
 __global__ void __launch_bounds__(kHeavyThreads) select_heavy_kernel(SelectParams2 p) {
     __shared__ int wt[kHeavyThreads / 32];
     const int nheavy = p.heavy[0];
-    const bool want_pi = p.mode != LPF_MODE_CN;
-    const bool want_n1 = p.mode == LPF_MODE_ALL;
-    const bool cn_needs_ppr = FILL || p.th_cn > 0.0f;
-    const float th_pre = want_n1 ? fminf(p.th_1hop, p.th_non1hop) : p.th_1hop;
     for (int q = blockIdx.x; q < nheavy; q += gridDim.x) {
         const int64_t i = p.heavy[4 + q];
         int64_t o_cn = 0, o_1h = 0, o_n1 = 0;
@@ -237,91 +392,9 @@ __global__ void __launch_bounds__(kHeavyThreads) select_heavy_kernel(SelectParam
                 o_n1 == __ldg(p.ptr + 2 * p.bs + i + 1))
                 continue;   // nothing selected for this link
         }
-        const int64_t a = __ldg(p.links + i), b = __ldg(p.links + p.bs + i);
-        const int64_t a0 = __ldg(p.adj_rowptr + a), b0 = __ldg(p.adj_rowptr + b);
-        const int na = (int)(__ldg(p.adj_rowptr + a + 1) - a0), nb = (int)(__ldg(p.adj_rowptr + b + 1) - b0);
-        const int64_t pa0 = __ldg(p.ppr_rowptr + a), pb0 = __ldg(p.ppr_rowptr + b);
-        const int npa = (int)(__ldg(p.ppr_rowptr + a + 1) - pa0), npb = (int)(__ldg(p.ppr_rowptr + b + 1) - pb0);
-        const int32_t* Aa = p.adj_col + a0;
-        const int32_t* Ab = p.adj_col + b0;
-        const int32_t* Pac = p.ppr_col + pa0;
-        const int32_t* Pbc = p.ppr_col + pb0;
-        const float* Pav = p.ppr_val + pa0;
-        const float* Pbv = p.ppr_val + pb0;
-
-        int c_cn = 0, c_1h = 0, c_n1 = 0;
-        {   // CN: every thread probes one element of the shorter adjacency row per step
-            const bool a_short = na <= nb;
-            const int32_t* S = a_short ? Aa : Ab;
-            const int32_t* Lg = a_short ? Ab : Aa;
-            const int ns = a_short ? na : nb, nl = a_short ? nb : na;
-            int lo = 0;   // this thread's elements ascend, so its search window only moves right
-            for (int k = 0; k < ns; k += kHeavyThreads) {
-                const bool act = k + (int)threadIdx.x < ns;
-                const int32_t u = act ? __ldg(S + k + threadIdx.x) : 0x7fffffff;
-                bool hit = false;
-                float qa = 0.f, qb = 0.f;
-                if (act) {
-                    lo = lower_bound_from(Lg, lo, nl, u);
-                    hit = lo < nl && __ldg(Lg + lo) == u;
-                    if (hit && cn_needs_ppr) {
-                        int t = lower_bound_from(Pac, 0, npa, u);
-                        if (t < npa && __ldg(Pac + t) == u) qa = quantise(__ldg(Pav + t));
-                        t = lower_bound_from(Pbc, 0, npb, u);
-                        if (t < npb && __ldg(Pbc + t) == u) qb = quantise(__ldg(Pbv + t));
-                        hit = qa >= p.th_cn && qb >= p.th_cn;
-                    }
-                }
-                const int r = block_rank(hit, wt, c_cn);
-                if (FILL && hit) {
-                    const int64_t s = o_cn + r;
-                    p.node[s] = u;
-                    p.pa[s] = qa;
-                    p.pb[s] = qb;
-                    if (p.link) p.link[s] = (int32_t)i;
-                }
-            }
-        }
-        if (want_pi) {   // 1-hop / >1-hop from the intersection of the two PPR rows
-            const bool a_short = npa <= npb;
-            const int32_t* Sc = a_short ? Pac : Pbc;
-            const float* Sv = a_short ? Pav : Pbv;
-            const int32_t* Lc = a_short ? Pbc : Pac;
-            const float* Lv = a_short ? Pbv : Pav;
-            const int ns = a_short ? npa : npb, nl = a_short ? npb : npa;
-            int lo = 0;
-            for (int k = 0; k < ns; k += kHeavyThreads) {
-                const bool act = k + (int)threadIdx.x < ns;
-                const int32_t u = act ? __ldg(Sc + k + threadIdx.x) : 0x7fffffff;
-                bool k1 = false, kn = false;
-                float qa = 0.f, qb = 0.f;
-                if (act) {
-                    lo = lower_bound_from(Lc, lo, nl, u);
-                    if (lo < nl && __ldg(Lc + lo) == u) {
-                        const float qs = quantise(__ldg(Sv + k + threadIdx.x)), ql = quantise(__ldg(Lv + lo));
-                        qa = a_short ? qs : ql;
-                        qb = a_short ? ql : qs;
-                        if (qa >= th_pre && qb >= th_pre) {
-                            int t = lower_bound_from(Aa, 0, na, u);
-                            const bool in_a = t < na && __ldg(Aa + t) == u;
-                            t = lower_bound_from(Ab, 0, nb, u);
-                            const bool in_b = t < nb && __ldg(Ab + t) == u;
-                            k1 = (in_a != in_b) && qa >= p.th_1hop && qb >= p.th_1hop;
-                            kn = want_n1 && !in_a && !in_b && qa >= p.th_non1hop && qb >= p.th_non1hop;
-                        }
-                    }
-                }
-                const int r1 = block_rank(k1, wt, c_1h);
-                const int rn = block_rank(kn, wt, c_n1);
-                if (FILL && (k1 || kn)) {
-                    const int64_t s = k1 ? o_1h + r1 : o_n1 + rn;
-                    p.node[s] = u;
-                    p.pa[s] = qa;
-                    p.pb[s] = qb;
-                    if (p.link) p.link[s] = (int32_t)i;
-                }
-            }
-        }
+        const LinkRows r = load_rows(p, i);
+        int c_cn, c_1h, c_n1;
+        walk_link_cta<FILL>(p, r, i, wt, o_cn, o_1h, o_n1, c_cn, c_1h, c_n1);
         if (!FILL && threadIdx.x == 0) {
             p.counts[i] = c_cn;
             p.counts[p.bs + i] = c_1h;
@@ -330,7 +403,39 @@ __global__ void __launch_bounds__(kHeavyThreads) select_heavy_kernel(SelectParam
     }
 }
 
+__global__ void __launch_bounds__(kHeavyThreads) select_heavy_onepass_kernel(SelectParams2 p) {
+    __shared__ int wt[kHeavyThreads / 32];
+    __shared__ int64_t seg[3];
+    __shared__ int ok_s;
+    const int nheavy = p.heavy[0];
+    for (int q = blockIdx.x; q < nheavy; q += gridDim.x) {
+        const int64_t i = p.heavy[4 + q];
+        const LinkRows r = load_rows(p, i);
+        int c_cn, c_1h, c_n1;
+        walk_link_cta<false>(p, r, i, wt, 0, 0, 0, c_cn, c_1h, c_n1);
+        if (threadIdx.x == 0) {
+            int64_t s0, s1, s2;
+            ok_s = alloc_segments(p, i, c_cn, c_1h, c_n1, s0, s1, s2) ? 1 : 0;
+            seg[0] = s0; seg[1] = s1; seg[2] = s2;
+        }
+        __syncthreads();
+        const bool go = ok_s && (c_cn + c_1h + c_n1 > 0);
+        const int64_t s0 = seg[0], s1 = seg[1], s2 = seg[2];
+        __syncthreads();
+        if (go) walk_link_cta<true>(p, r, i, wt, s0, p.cap + s1, 2 * p.cap + s2, c_cn, c_1h, c_n1);
+    }
+}
+
 __global__ void select_reset_heavy(int32_t* heavy) { heavy[0] = 0; }
+// a full pool invalidates the batch: later launches of the same stream / graph see empty sizes and do nothing,
+// the host finds header[4] != 0 and re-runs the batch through the two-pass interface
+__global__ void select_finalize_onepass(int64_t* hdr) {
+    if (hdr[4]) hdr[0] = hdr[1] = hdr[2] = hdr[3] = 0;
+}
+__global__ void select_reset_onepass(int32_t* heavy, int64_t* hdr) {
+    heavy[0] = 0;
+    hdr[0] = hdr[1] = hdr[2] = hdr[3] = hdr[4] = 0;
+}
 
 template <int G>
 static int launch_fast(bool fill, const SelectParams2& p, cudaStream_t st) {
@@ -339,6 +444,13 @@ static int launch_fast(bool fill, const SelectParams2& p, cudaStream_t st) {
     const int64_t cap = (int64_t)kNumSMs * 8 * 8;
     if (blocks > cap) blocks = cap;
     const unsigned hgrid = kNumSMs * 2;
+    if (p.hdr) {
+        select_reset_onepass<<<1, 1, 0, st>>>(p.heavy, p.hdr);
+        select_onepass_kernel<G><<<(unsigned)blocks, 256, 0, st>>>(p);
+        select_heavy_onepass_kernel<<<hgrid, kHeavyThreads, 0, st>>>(p);
+        select_finalize_onepass<<<1, 1, 0, st>>>(p.hdr);
+        return check_launch("lpf_select_onepass");
+    }
     if (fill) {
         select_fast_kernel<G, true><<<(unsigned)blocks, 256, 0, st>>>(p);
         select_heavy_kernel<true><<<hgrid, kHeavyThreads, 0, st>>>(p);
@@ -355,9 +467,19 @@ int select_fast(bool fill, int group, const int64_t* links, int64_t bs, const in
                 float th_cn, float th_1hop, float th_non1hop, int mode, int32_t* counts, const int64_t* ptr,
                 int32_t* node, float* pa, float* pb, int32_t* link, int32_t* heavy, cudaStream_t st) {
     SelectParams2 p{links, bs, adj_rowptr, adj_col, ppr_rowptr, ppr_col, ppr_val, th_cn, th_1hop, th_non1hop,
-                    mode, counts, ptr, node, pa, pb, link, heavy};
+                    mode, counts, ptr, node, pa, pb, link, heavy, 0, nullptr, nullptr, nullptr};
     if (group == 32) return launch_fast<32>(fill, p, st);
     return launch_fast<8>(fill, p, st);
+}
+
+int select_onepass(int group, const int64_t* links, int64_t bs, const int64_t* adj_rowptr, const int32_t* adj_col,
+                   const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val, float th_cn, float th_1hop,
+                   float th_non1hop, int mode, int64_t cap, int32_t* counts, int32_t* seg_start, int32_t* nz_list,
+                   int64_t* hdr, int32_t* node, float* pa, float* pb, int32_t* heavy, cudaStream_t st) {
+    SelectParams2 p{links, bs, adj_rowptr, adj_col, ppr_rowptr, ppr_col, ppr_val, th_cn, th_1hop, th_non1hop,
+                    mode, counts, nullptr, node, pa, pb, nullptr, heavy, cap, hdr, seg_start, nz_list};
+    if (group == 32) return launch_fast<32>(false, p, st);
+    return launch_fast<8>(false, p, st);
 }
 
 }  // namespace lpf

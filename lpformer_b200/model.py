@@ -328,6 +328,10 @@ class LinkTransformer(nn.Module):
         self._kv_cache = None       # per-layer KV tables, keyed by the X_node they were built from
         self._pw_const_cache = None  # pairwise vector of a link with empty sets, keyed by parameter versions
         self._head_cache = None     # operands of the fused heads kernel
+        self._plans = {}            # sync-free execution plans of score_links, keyed by batch size / X_node
+        self._plan_cap = {}
+        self.use_plans = True       # one-pass selection + device-side sizes (plan.py)
+        self.use_graphs = True      # ... replayed as a CUDA graph
 
     # ------------------------------------------------------------------ graph tables
     def _dev(self):
@@ -588,21 +592,51 @@ class LinkTransformer(nn.Module):
         then the (few) links with non-empty sets go through selection fill -> RPE -> attention -> pairwise_lin
         and are re-scored with their own pairwise vector."""
         dev = self._dev()
-        batch = ops.links_tensor(batch, dev)
         X_node = self._check_x(X_node)
         consts = self._head_consts(score_func, X_node)
         if consts is None:
+            batch = ops.links_tensor(batch, dev)
             feats = torch.empty((batch.shape[1], 2 * self.dim), dtype=torch.float32, device=dev)
             _, xprod = ops.gather_links(batch, X_node, want_sum=False, want_prod=True)
             self.elementwise_lin(xprod, out=feats[:, : self.dim])
             self.calc_pairwise(batch, X_node, test_set, out=feats[:, self.dim:])
             return score_func(feats, return_logits=return_logits) if return_logits else score_func(feats)
+        plan = self._get_plan(score_func, consts, X_node, batch, test_set, return_logits)
+        if plan is not None:
+            prob, overflow = plan.run(batch)
+            if not overflow:
+                return prob.clone()
+            self._plans.pop(plan.key, None)          # a pair pool was too small: host-sized path now, bigger pools next time
+        batch = ops.links_tensor(batch, dev)
         bs = batch.shape[1]
         prob = torch.empty(bs, dtype=torch.float32, device=dev)
         ops.link_heads(batch, X_node, consts, prob, logits=return_logits)
         sel = self._select(batch, test_set)
+        if plan is not None:
+            self._plan_cap[plan.key] = 2 * max(b - a for a, b in zip(sel.bounds[:-1], sel.bounds[1:]))
         if sel.nz.numel() > 0:
             rows = self._pairwise_rows(batch, X_node, sel, sel.nz)[0]
             zb = ops.linear(rows, consts["ws1_pw"], consts["off"])
             ops.link_heads(batch, X_node, consts, prob, idx=sel.nz, zb=zb, logits=return_logits)
         return prob
+
+    def _get_plan(self, score_func, consts, X_node, batch, test_set, logits):
+        """The sync-free CUDA-graph plan for this batch size (plan.py), or None when the configuration needs the
+        host-sized path (generic selection algorithm, i.e. a threshold of 0)."""
+        if not self.use_plans or not torch.is_tensor(batch) or batch.dim() != 2 or batch.shape[0] != 2 or \
+                batch.dtype != torch.int64 or batch.shape[1] == 0:
+            return None
+        adj, ppr = self.get_adj(test_set, mask=True), self.get_ppr(test_set)
+        if ops.pick_select_algo(adj, ppr, self.thresh_1hop, self.thresh_non1hop, self.mask) == 0:
+            return None
+        key = (batch.shape[1], X_node.data_ptr(), X_node._version, bool(test_set), bool(logits), id(consts))
+        plan = self._plans.get(key)
+        if plan is None:
+            from .plan import ScorePlan
+            while len(self._plans) >= 2:                       # plans own capacity-sized buffers: keep two
+                self._plans.pop(next(iter(self._plans)))
+            plan = ScorePlan(self, score_func, consts, X_node, self._get_kv(X_node)[0], batch.shape[1], test_set, logits,
+                             cap=self._plan_cap.get(key), use_graph=self.use_graphs)
+            plan.key = key
+            self._plans[key] = plan
+        return plan

@@ -93,7 +93,7 @@ def linear(A, W, bias=None, bias_scale=1.0, out=None, epilogue=EPI_NONE):
         o = out if (n0 == 0 and n1 == N) else out[:, n0:n1]
         b = None if bias is None else (bias if (n0 == 0 and n1 == N) else bias[n0:n1])
         call("lpf_gemm_tc", ptr(A), A.stride(0), ptr(pack_weight(Wc)), ptr(b), float(bias_scale), ptr(o),
-             o.stride(0) if M > 0 else N, M, n1 - n0, K, epilogue, stream(), meta=(M, n1 - n0, K))
+             o.stride(0) if M > 0 else N, M, n1 - n0, K, epilogue, None, stream(), meta=(M, n1 - n0, K))
     return out
 
 
@@ -108,7 +108,7 @@ def layernorm_act(x, weight, bias, relu=False, residual=None, out=None, n=None):
     if residual is not None:
         residual = _rowmajor(residual)
     call("lpf_layernorm_act", ptr(x), x.stride(0), ptr(weight), ptr(bias), ptr(residual),
-         residual.stride(0) if residual is not None else 0, ptr(out), out.stride(0), rows, n, int(relu), stream())
+         residual.stride(0) if residual is not None else 0, ptr(out), out.stride(0), rows, n, int(relu), None, stream())
     return out
 
 
@@ -124,7 +124,7 @@ def gather_links(links, X, want_sum=True, want_prod=True, out_sum=None, out_prod
         out_prod = torch.empty((n, d), dtype=torch.float32, device=X.device)
     call("lpf_gather_links", ptr(links), bs, ptr(idx), n, ptr(X), X.stride(0), d, ptr(out_sum),
          out_sum.stride(0) if out_sum is not None else 0, ptr(out_prod),
-         out_prod.stride(0) if out_prod is not None else 0, stream())
+         out_prod.stride(0) if out_prod is not None else 0, None, stream())
     return out_sum, out_prod
 
 
@@ -221,7 +221,7 @@ def rpe_hidden(sel: Selection, t: int, w1, b1, ln_w, ln_b, hsum):
     r0, r1 = sel.type_range(t)
     if r1 > r0:
         call("lpf_rpe_hidden", ptr(sel.src_ppr), ptr(sel.tgt_ppr), r0, r1 - r0, ptr(w1), ptr(b1), ptr(ln_w),
-             ptr(ln_b), hsum.shape[1], ptr(hsum), hsum.stride(0), stream())
+             ptr(ln_b), hsum.shape[1], ptr(hsum), hsum.stride(0), None, stream())
 
 
 def attend(sel: Selection, KV, R, Q, att, bias, ln_w, ln_b, heads, ch, write_counts, out, alpha_out=None, idx=None):
@@ -231,7 +231,8 @@ def attend(sel: Selection, KV, R, Q, att, bias, ln_w, ln_b, heads, ch, write_cou
     call("lpf_attend_fused", ptr(sel.ptr), sel.bs, ptr(idx), n, ptr(sel.node), ptr(KV), KV.stride(0),
          ptr(R) if sel.total > 0 else None, R.stride(0) if R is not None and R.dim() == 2 else heads * ch,
          ptr(Q), Q.stride(0), ptr(att), ptr(bias), ptr(ln_w), ptr(ln_b), heads, ch, MODE[sel.mode],
-         int(write_counts), ptr(out), out.stride(0), ptr(alpha_out), stream(), meta=(n, sel.total, heads * ch))
+         int(write_counts), ptr(out), out.stride(0), ptr(alpha_out), None, None, None, 0, stream(),
+         meta=(n, sel.total, heads * ch))
     return out
 
 
@@ -245,7 +246,7 @@ def link_heads(links, X, consts, prob, idx=None, zb=None, logits=False):
     call("lpf_link_heads_tc", ptr(links), bs, ptr(idx), n, ptr(X), X.stride(0), X.shape[1], ptr(consts["w1p"]),
          ptr(consts["b1"]), ptr(consts["ln_w"]), ptr(consts["ln_b"]), ptr(consts["w23p"]),
          ptr(consts["c3"]) if zb is None else None, ptr(zb), zb.stride(0) if zb is not None else 0,
-         ptr(consts["ws2"]), ptr(consts["bs2"]), ptr(prob), int(logits), stream(), meta=(n,))
+         ptr(consts["ws2"]), ptr(consts["bs2"]), ptr(prob), int(logits), None, stream(), meta=(n,))
     return prob
 
 

@@ -1,0 +1,140 @@
+"""Sync-free execution plan of the eval-loop body for one batch size.
+
+`LinkTransformer.score_links` (the body of reference train/testing.py:29-31 / :113-115) is a fixed sequence of
+C-ABI launches whose row counts (selected pairs per type, links with a non-empty set) are produced ON the
+device by the one-pass selection kernel.  A ScorePlan owns capacity-sized buffers for one batch size, passes the
+device-side counts to every later launch (`*_dev` arguments of include/lpformer_b200.h), and records the whole
+sequence once in a CUDA graph; a batch is then one H2D/D2D copy of the links, one graph launch and one
+read-back of the overflow flag.  If a pair pool overflows the plan reports it and the caller re-runs the batch
+through the host-sized two-pass path (and the plan is rebuilt with larger pools).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import EPI_NONE, MODE, call, ptr, stream
+
+
+class ScorePlan:
+    def __init__(self, model, score_func, consts, X_node, kv, bs, test_set, logits, cap=None, use_graph=True):
+        dev = X_node.device
+        self.model, self.bs, self.logits, self.dev = model, bs, bool(logits), dev
+        self.X, self.kv, self.consts = X_node, kv, consts
+        self.adj = model.get_adj(test_set, mask=True)
+        self.ppr = model.get_ppr(test_set)
+        from . import ops
+        self.algo = ops.pick_select_algo(self.adj, self.ppr, model.thresh_1hop, model.thresh_non1hop, model.mask)
+        if self.algo == _lib.ALGO_GENERIC:
+            raise _lib.LpfError("the one-pass plan needs an INTERSECT selection algorithm")
+        d, H = model.dim, model.num_heads
+        layer = model.att_layers[0]
+        self.layer = layer
+        self.C = layer.att.out_channels
+        HC = H * self.C
+        self.HC, self.d, self.H = HC, d, H
+        self.cap = int(cap if cap is not None else max(1 << 16, 2 * bs))
+        cap, f32, i32, i64 = self.cap, torch.float32, torch.int32, torch.int64
+        e = lambda *shape, dtype=f32: torch.empty(shape, dtype=dtype, device=dev)   # noqa: E731
+        self.links = e(2, bs, dtype=i64)
+        self.prob = e(bs)
+        self.counts, self.seg_start, self.nz = e(3 * bs, dtype=i32), e(3 * bs, dtype=i32), e(bs, dtype=i32)
+        self.hdr = torch.zeros(8, dtype=i64, device=dev)
+        self.ws = e(bs + 4, dtype=i32)
+        self.node, self.pa, self.pb = e(3 * cap, dtype=i32), e(3 * cap), e(3 * cap)
+        self.hsum, self.R = e(3 * cap, d), e(3 * cap, HC)
+        pd = HC + model.count_dim
+        self.pd = pd
+        self.xsum, self.Q, self.feats, self.hid, self.pw, self.zb = e(bs, d), e(bs, HC), e(bs, pd), e(bs, pd), e(bs, d), e(bs, 2 * d)
+        derived = model._get_derived()[0]
+        self.rpe = []
+        for enc, (m, c) in zip(model._encoders(), derived["rpe"]):
+            self.rpe.append((enc.linears[0].weight.detach(), enc.linears[0].bias.detach(), enc.norm.weight.detach(),
+                             enc.norm.bias.detach(), ops.pack_weight(m), c))
+        att = layer.att
+        pl = model.pairwise_lin
+        self.w = {
+            "wl": ops.pack_weight(att.lin_l.weight), "bl": att.lin_l.bias.detach(),
+            "att": att.att.detach(), "abias": att.bias.detach(),
+            "pn_w": layer.post_att_norm.weight.detach(), "pn_b": layer.post_att_norm.bias.detach(),
+            "p1": ops.pack_weight(pl.linears[0].weight), "pb1": pl.linears[0].bias.detach(),
+            "pln_w": pl.norm.weight.detach(), "pln_b": pl.norm.bias.detach(),
+            "p2": ops.pack_weight(pl.linears[1].weight), "pb2": pl.linears[1].bias.detach(),
+            "wz": ops.pack_weight(consts["ws1_pw"]),
+        }
+        self.th = (float(model.thresh_cn), float(model.thresh_1hop), float(model.thresh_non1hop))
+        self.mode = MODE[model.mask]
+        self.graph = None
+        self.use_graph = use_graph
+        self.runs = 0
+
+    # ------------------------------------------------------------------
+    def _launch(self):
+        """Every launch of one batch on the current stream; no host synchronisation, no allocation."""
+        st = stream()
+        bs, cap, d, HC, pd = self.bs, self.cap, self.d, self.HC, self.pd
+        c, w, hdr = self.consts, self.w, self.hdr
+        links, X = self.links, self.X
+        hp = hdr.data_ptr()
+        n_dev = hp + 3 * 8                      # &header[3]: links with a non-empty set
+
+        def heads(idx, n, zb, ndev):
+            call("lpf_link_heads_tc", ptr(links), bs, idx, n, ptr(X), X.stride(0), d, ptr(c["w1p"]), ptr(c["b1"]),
+                 ptr(c["ln_w"]), ptr(c["ln_b"]), ptr(c["w23p"]), ptr(c["c3"]) if zb is None else None,
+                 ptr(zb), self.zb.stride(0) if zb is not None else 0, ptr(c["ws2"]), ptr(c["bs2"]), ptr(self.prob),
+                 int(self.logits), ndev, st, meta=(n,))
+
+        def gemm(A, Wp, bias, scale, C, M, N, K, mdev):
+            call("lpf_gemm_tc", ptr(A), A.stride(0), ptr(Wp), ptr(bias), float(scale), ptr(C), C.stride(0), M, N, K,
+                 EPI_NONE, mdev, st, meta=(M, N, K))
+
+        # every link with the empty-set pairwise constant (independent of the selection)
+        heads(None, bs, None, None)
+        # K1: one-pass selection into the per-type pools
+        call("lpf_select_onepass", ptr(links), bs, ptr(self.adj.rowptr), ptr(self.adj.col), ptr(self.ppr.rowptr),
+             ptr(self.ppr.col), ptr(self.ppr.val), *self.th, self.mode, self.algo, cap, ptr(self.counts),
+             ptr(self.seg_start), ptr(self.nz), hp, ptr(self.node), ptr(self.pa), ptr(self.pb), ptr(self.ws), st,
+             meta=(bs,))
+        # RPE hidden vectors and their contraction, per type pool
+        for t, (w1, b1, g, b, mp, cvec) in enumerate(self.rpe):
+            call("lpf_rpe_hidden", ptr(self.pa), ptr(self.pb), t * cap, cap, ptr(w1), ptr(b1), ptr(g), ptr(b), d,
+                 ptr(self.hsum), self.hsum.stride(0), hp + t * 8, st)
+            gemm(self.hsum[t * cap:], mp, cvec, 1.0, self.R[t * cap:], cap, HC, d, hp + t * 8)
+        # compacted non-empty links: query vectors, attention, pairwise_lin, offset of mlp_score's first layer
+        call("lpf_gather_links", ptr(links), bs, ptr(self.nz), bs, ptr(X), X.stride(0), d, ptr(self.xsum),
+             self.xsum.stride(0), None, 0, n_dev, st)
+        gemm(self.xsum, w["wl"], w["bl"], 2.0, self.Q, bs, HC, d, n_dev)
+        call("lpf_attend_fused", None, bs, ptr(self.nz), bs, ptr(self.node), ptr(self.kv), self.kv.stride(0),
+             ptr(self.R), self.R.stride(0), ptr(self.Q), self.Q.stride(0), ptr(w["att"]), ptr(w["abias"]),
+             ptr(w["pn_w"]), ptr(w["pn_b"]), self.H, self.C, self.mode, 1, ptr(self.feats), self.feats.stride(0), None,
+             n_dev, ptr(self.seg_start), ptr(self.counts), cap, st, meta=(bs, 0, HC))
+        gemm(self.feats, w["p1"], w["pb1"], 1.0, self.hid, bs, pd, pd, n_dev)
+        call("lpf_layernorm_act", ptr(self.hid), self.hid.stride(0), ptr(w["pln_w"]), ptr(w["pln_b"]), None, 0,
+             ptr(self.hid), self.hid.stride(0), bs, pd, 1, n_dev, st)
+        gemm(self.hid, w["p2"], w["pb2"], 1.0, self.pw, bs, d, pd, n_dev)
+        gemm(self.pw, w["wz"], c["off"], 1.0, self.zb, bs, 2 * d, d, n_dev)
+        heads(ptr(self.nz), bs, self.zb, n_dev)
+
+    def run(self, links):
+        """Scores `links` (int64 [2, bs], host-pinned or device).  Returns (prob [bs] — a buffer owned by the plan,
+        valid until the next run — and overflow: bool)."""
+        self.links.copy_(links, non_blocking=True)
+        tracing = _lib.TRACE is not None
+        if self.use_graph and not tracing and self.runs >= 1:
+            if self.graph is None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch()
+                self.graph = g
+            self.graph.replay()
+            if _lib.COUNTERS is not None:
+                _lib.COUNTERS["graph_launches"] = _lib.COUNTERS.get("graph_launches", 0) + 1
+        else:
+            self._launch()
+        self.runs += 1
+        overflow = bool(self.hdr[4].item())          # the batch's only host round trip
+        return self.prob, overflow
+
+    def stats(self):
+        h = self.hdr.tolist()
+        return {"pairs": h[:3], "nonempty_links": h[3], "overflow": h[4], "cap": self.cap}

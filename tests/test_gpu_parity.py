@@ -236,3 +236,47 @@ def test_score_links_synthetic_vs_oracle(workload, scale, nq, negs):
     np.testing.assert_allclose(pw_simt.cpu().numpy(), feats[:, cfg["dim"]:], rtol=FP32_RTOL, atol=2e-5)
     pw_tc, _ = model.calc_pairwise(links, X)
     np.testing.assert_allclose(pw_tc.cpu().numpy(), feats[:, cfg["dim"]:], rtol=FP32_RTOL, atol=2e-5)
+
+
+def test_plan_graph_replay_and_overflow():
+    """The sync-free plan (one-pass selection, device-side sizes, CUDA-graph replay) gives the same scores as the
+    host-sized two-pass path on consecutive different batches, and a too-small pair pool is detected and handled."""
+    import lpformer_b200 as L
+    from lpformer_b200 import synthetic as S
+    g = S.make_graph("citation2", seed=4, scale=0.02, heldout=256)
+    targs = S.train_args_of(g.cfg)
+    dev = torch.device("cuda:0")
+    torch.manual_seed(2)
+    model = L.LinkTransformer(targs, g.data_dict(dev), device=dev).to(dev).eval()
+    score = L.mlp_score(model.out_dim, model.out_dim, 1, 2).to(dev).eval()
+    X = torch.randn(g.n, g.cfg["dim"], generator=torch.Generator().manual_seed(1)).to(dev)
+    rng = np.random.default_rng(0)
+
+    def batch(seed):
+        q = S.citation2_queries(g, 3, 300, seed=seed)
+        pos = g.edges[:, rng.integers(0, g.edges.shape[1], 97)]
+        return torch.from_numpy(np.concatenate([q, pos], 1).astype(np.int64)).to(dev)
+
+    batches = [batch(s) for s in range(5)]
+    model.use_plans = False
+    ref = [model.score_links(b, X, score).cpu().numpy() for b in batches]
+    model.use_plans = True
+    for rep in range(2):                                   # eager run, capture + replay, replays
+        for b, r in zip(batches, ref):
+            out = model.score_links(b, X, score).cpu().numpy()
+            np.testing.assert_allclose(out, r, rtol=1e-5, atol=1e-7)
+    plan = next(iter(model._plans.values()))
+    assert plan.graph is not None and plan.stats()["nonempty_links"] > 0
+    # host-pinned input goes through the same plan
+    out = model.score_links(batches[2].cpu().pin_memory(), X, score).cpu().numpy()
+    np.testing.assert_allclose(out, ref[2], rtol=1e-5, atol=1e-7)
+    # overflow: pools of 4 rows per type cannot hold this batch
+    model._plans.clear()
+    key = (batches[0].shape[1], X.data_ptr(), X._version, False, False, id(model._head_consts(score, X)))
+    model._plan_cap[key] = 4
+    out = model.score_links(batches[0], X, score).cpu().numpy()
+    np.testing.assert_allclose(out, ref[0], rtol=1e-5, atol=1e-7)
+    assert model._plan_cap[key] > 4 and key not in model._plans
+    out = model.score_links(batches[1], X, score).cpu().numpy()      # rebuilt with larger pools
+    np.testing.assert_allclose(out, ref[1], rtol=1e-5, atol=1e-7)
+    assert model._plans[key].stats()["overflow"] == 0
