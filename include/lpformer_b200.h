@@ -232,6 +232,10 @@ int lpf_link_heads_tc(const int64_t* links, int64_t bs, const int32_t* idx, int6
                       const float* ws2, const float* bs2, float* prob, int logits, const int64_t* n_dev,
                       void* stream);
 
+/* Profiling hook: CTA 0 of later lpf_link_heads_tc launches writes clock64() stamps of its pipeline phases for
+ * its first 8 tiles into device_buffer (int64 [8][16]); NULL disables. */
+int lpf_debug_heads_clocks(void* device_buffer);
+
 /* ------------------------------------------------------------------------- *
  * K2  GCN message passing — GCNConv's SpMM (models/other_models.py:66 via
  * torch_sparse.matmul): Y[r,:] = sum_k val[k] * XW[col[k],:] + bias over CSR row r,

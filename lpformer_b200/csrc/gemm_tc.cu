@@ -15,7 +15,8 @@
 //     stage's "free" barrier, so loading k-block i+1 overlaps the tensor pipe working on k-block i;
 //   * epilogue: tcgen05.ld of the thread's own row (TMEM lane = row), bias / ReLU / sigmoid, 128-bit stores.
 // Several CTAs are resident per SM (<= 96 KB smem, <= 256 TMEM columns each), which overlaps one CTA's
-// epilogue with another's loads and MMAs.
+// epilogue with another's loads and MMAs.  A CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (one tile
+// each when the grid covers M; a persistent grid when M is a capacity and the real count lives on the device).
 #include "tc.cuh"
 
 namespace lpf {
@@ -62,14 +63,12 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(GemmTcParams p) {
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5;
-    if (p.m_dev) {
-        p.M = min(p.M, *p.m_dev);
-        if ((int64_t)blockIdx.x * kTileM >= p.M) return;   // whole CTA, before any barrier / TMEM state exists
-    }
+    if (p.m_dev) p.M = min(p.M, *p.m_dev);
+    const int64_t ntiles = (p.M + kTileM - 1) / kTileM;
+    if ((int64_t)blockIdx.x >= ntiles) return;   // whole CTA, before any barrier / TMEM state exists
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t w_tile = (uint32_t)p.NP * 128;                 // bytes of one W part (hi or lo) per k-block
     const uint32_t stage_bytes = 2 * kATileBytes + 2 * w_tile;
-    const int64_t m0 = (int64_t)blockIdx.x * kTileM;
 
     if (tid == 0) {
         mbar_init(&bar_w[0], 1);
@@ -88,93 +87,99 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(GemmTcParams p) {
     const uint32_t idesc = make_idesc_tf32(kTileM, p.NP);
 
     const bool vec_a = ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) && (p.lda % 4 == 0);
+    const bool vec_c = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.ldc % 4 == 0);
     const int chunk = tid & 7;          // 16-byte chunk of the 128-byte row
     const int row_in_pass = tid >> 3;   // 16 rows per pass
+    const uint32_t lane_base = tmem_d + ((uint32_t)(warp * 32) << 16);
 
-    for (int kb = 0; kb < p.KB; ++kb) {
-        const int s = kb & 1;
-        const uint32_t use = (uint32_t)(kb >> 1);
-        uint8_t* st = smem + (size_t)s * stage_bytes;
-        if (kb >= 2) mbar_wait(&bar_free[s], (use - 1) & 1);      // MMAs that read this stage have completed
-        if (tid == 0) {
-            mbar_arrive_expect_tx(&bar_w[s], 2 * w_tile);
-            bulk_g2s(st + 2 * kATileBytes, reinterpret_cast<const uint8_t*>(p.Wp) + (size_t)kb * 2 * w_tile, 2 * w_tile,
-                     &bar_w[s]);
-        }
-        __syncwarp();
-        // A k-block: rows m0..m0+127, columns kb*32 .. +31
-        const int k0 = kb * 32 + chunk * 4;
+    uint32_t it = 0;        // k-blocks issued by this CTA so far (ring position / barrier phases)
+    uint32_t tile_it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
+        const int64_t m0 = tile * kTileM;
+        for (int kb = 0; kb < p.KB; ++kb, ++it) {
+            const int s = it & 1;
+            const uint32_t use = it >> 1;
+            uint8_t* st = smem + (size_t)s * stage_bytes;
+            if (it >= 2) mbar_wait(&bar_free[s], (use - 1) & 1);      // MMAs that read this stage have completed
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&bar_w[s], 2 * w_tile);
+                bulk_g2s(st + 2 * kATileBytes, reinterpret_cast<const uint8_t*>(p.Wp) + (size_t)kb * 2 * w_tile,
+                         2 * w_tile, &bar_w[s]);
+            }
+            __syncwarp();
+            // A k-block: rows m0..m0+127, columns kb*32 .. +31
+            const int k0 = kb * 32 + chunk * 4;
 #pragma unroll
-        for (int pass = 0; pass < 8; ++pass) {
-            const int r = pass * 16 + row_in_pass;
-            const int64_t m = m0 + r;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int pass = 0; pass < 8; ++pass) {
+                const int r = pass * 16 + row_in_pass;
+                const int64_t m = m0 + r;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m < p.M) {
+                    const float* src = p.A + m * p.lda + k0;
+                    if (vec_a && k0 + 3 < p.K) {
+                        v = __ldg(reinterpret_cast<const float4*>(src));
+                    } else {
+                        if (k0 + 0 < p.K) v.x = __ldg(src + 0);
+                        if (k0 + 1 < p.K) v.y = __ldg(src + 1);
+                        if (k0 + 2 < p.K) v.z = __ldg(src + 2);
+                        if (k0 + 3 < p.K) v.w = __ldg(src + 3);
+                    }
+                }
+                const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+                const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+                const uint32_t off = swz_chunk_off(r, chunk);
+                *reinterpret_cast<float4*>(st + off) = hi;
+                *reinterpret_cast<float4*>(st + kATileBytes + off) = lo;
+            }
+            fence_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                mbar_wait(&bar_w[s], use & 1);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(st), a_lo = a_hi + kATileBytes;
+                const uint32_t b_hi = a_hi + 2 * kATileBytes, b_lo = b_hi + w_tile;
+                issue_kblock_3x(tmem_d, a_hi, a_lo, b_hi, b_lo, idesc, kb == 0);
+                umma_commit(&bar_free[s]);
+                if (kb == p.KB - 1) umma_commit(&bar_acc);
+            }
+            __syncwarp();
+        }
+
+        mbar_wait(&bar_acc, tile_it & 1);
+        tc_fence_after();
+
+        // epilogue: thread t owns row m0 + t (TMEM lane t)
+        const int64_t m = m0 + tid;
+        for (int c0 = 0; c0 < p.NP; c0 += 16) {
+            float v[16];
+            tmem_ld16(lane_base + (uint32_t)c0, v);    // warp-collective: every lane executes it
             if (m < p.M) {
-                const float* src = p.A + m * p.lda + k0;
-                if (vec_a && k0 + 3 < p.K) {
-                    v = __ldg(reinterpret_cast<const float4*>(src));
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = c0 + j;
+                    float x = v[j];
+                    if (p.bias && n < p.N) x += p.bias_scale * __ldg(p.bias + n);
+                    if (p.epi == LPF_EPI_RELU) x = fmaxf(x, 0.f);
+                    else if (p.epi == LPF_EPI_SIGMOID) x = 1.0f / (1.0f + expf(-x));
+                    v[j] = x;
+                }
+                float* dst = p.C + m * p.ldc + c0;
+                if (vec_c && c0 + 16 <= p.N) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 } else {
-                    if (k0 + 0 < p.K) v.x = __ldg(src + 0);
-                    if (k0 + 1 < p.K) v.y = __ldg(src + 1);
-                    if (k0 + 2 < p.K) v.z = __ldg(src + 2);
-                    if (k0 + 3 < p.K) v.w = __ldg(src + 3);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < p.N) dst[j] = v[j];
                 }
             }
-            const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-            const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-            const uint32_t off = swz_chunk_off(r, chunk);
-            *reinterpret_cast<float4*>(st + off) = hi;
-            *reinterpret_cast<float4*>(st + kATileBytes + off) = lo;
         }
-        fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            mbar_wait(&bar_w[s], use & 1);
-            tc_fence_after();
-            const uint32_t a_hi = smem_u32(st), a_lo = a_hi + kATileBytes;
-            const uint32_t b_hi = a_hi + 2 * kATileBytes, b_lo = b_hi + w_tile;
-            issue_kblock_3x(tmem_d, a_hi, a_lo, b_hi, b_lo, idesc, kb == 0);
-            umma_commit(&bar_free[s]);
-            if (kb == p.KB - 1) umma_commit(&bar_acc);
-        }
-        __syncwarp();
+        tc_fence_before();
+        __syncthreads();   // the accumulator columns are overwritten by the next tile's first MMA
+        tc_fence_after();
     }
 
-    mbar_wait(&bar_acc, 0);
-    tc_fence_after();
-
-    // epilogue: thread t owns row m0 + t (TMEM lane t)
-    const int64_t m = m0 + tid;
-    const bool vec_c = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.ldc % 4 == 0);
-    const uint32_t lane_base = tmem_d + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < p.NP; c0 += 16) {
-        float v[16];
-        tmem_ld16(lane_base + (uint32_t)c0, v);    // warp-collective: every lane executes it
-        if (m < p.M) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int n = c0 + j;
-                float x = v[j];
-                if (p.bias && n < p.N) x += p.bias_scale * __ldg(p.bias + n);
-                if (p.epi == LPF_EPI_RELU) x = fmaxf(x, 0.f);
-                else if (p.epi == LPF_EPI_SIGMOID) x = 1.0f / (1.0f + expf(-x));
-                v[j] = x;
-            }
-            float* dst = p.C + m * p.ldc + c0;
-            if (vec_c && c0 + 16 <= p.N) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (c0 + j < p.N) dst[j] = v[j];
-            }
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_d, p.tmem_cols);
 }
 
@@ -228,7 +233,12 @@ extern "C" int lpf_gemm_tc(const float* A, int64_t lda, const float* Wpacked, co
         }
         configured = smem;
     }
-    const unsigned grid = (unsigned)((M + tc::kTileM - 1) / tc::kTileM);
-    gemm_tc_kernel<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(p);
+    // one CTA per tile; with a device-side row count the host M is only a capacity, so cap the grid at a few
+    // CTAs per SM and let them walk the tiles that really exist
+    int64_t grid = (M + tc::kTileM - 1) / tc::kTileM;
+    const int64_t per_sm = (int64_t)(227 * 1024) / (int64_t)(smem + 1024);
+    const int64_t persistent = (int64_t)kNumSMs * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
+    if (m_dev && grid > persistent) grid = persistent;
+    gemm_tc_kernel<<<(unsigned)grid, kGemmThreads, smem, (cudaStream_t)stream>>>(p);
     return check_launch("lpf_gemm_tc");
 }

@@ -50,6 +50,7 @@ struct HeadsParams {
     float* prob;
     int logits;
     const int64_t* n_dev;   // optional device-side n
+    long long* dbg;         // optional: per-phase clock64 stamps of CTA 0 / thread 0 (lpf_debug_heads_clocks)
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -75,6 +76,9 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
     __shared__ float s_b1[D], s_g[D], s_bt[D], s_c3[N3], s_ws2[N3];
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    if (p.n_dev) p.n = min(p.n, *p.n_dev);
+    const int64_t ntiles = (p.n + kTileM - 1) / kTileM;
+    if ((int64_t)blockIdx.x >= ntiles) return;       // nothing to do: before any barrier / TMEM / bulk-copy state
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sW1 = smem;
     uint8_t* sW3 = sW1 + W1_BYTES;
@@ -105,9 +109,6 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-
-    if (p.n_dev) p.n = min(p.n, *p.n_dev);
-    const int64_t ntiles = (p.n + kTileM - 1) / kTileM;
 
     if (warp >= kHeadConsumers / 32) {
         // =========================== producers: gather the next tile into the staging buffer
@@ -167,10 +168,14 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
     uint32_t mma_phase = 0, it = 0;
     bool weights_ready = false;
 
+    const bool stamp = p.dbg && blockIdx.x == 0 && tid == 0;
+#define LPF_STAMP(k) do { if (stamp && it < 8) p.dbg[it * 16 + (k)] = clock64(); } while (0)
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int64_t j = tile * kTileM + tid;
+        LPF_STAMP(0);
         // ---- staged xprod row of this thread -> hi / lo operand tile
         mbar_wait(&bar_full, it & 1);
+        LPF_STAMP(1);
 #pragma unroll
         for (int c = 0; c < D / 4; ++c) {
             const uint32_t off = swz_chunk_off(tid, c & 7);
@@ -183,6 +188,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
         mbar_arrive(&bar_empty);
         fence_async_smem();
         named_bar_sync(1, kHeadConsumers);
+        LPF_STAMP(2);
 
         // ---- contraction 1: D1 = xprod . W1^T
         if (tid == 0) {
@@ -196,9 +202,11 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
         }
         weights_ready = true;
         __syncwarp();
+        LPF_STAMP(3);
         mbar_wait(&bar_mma, mma_phase);
         mma_phase ^= 1;
         tc_fence_after();
+        LPF_STAMP(4);
 
         // ---- epilogue 1: h = ReLU(LN(D1 + b1)), thread-local over the link's row; becomes the next A operand
         {
@@ -234,6 +242,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
         tc_fence_before();
         fence_async_smem();
         named_bar_sync(1, kHeadConsumers);
+        LPF_STAMP(5);
 
         // ---- contraction 2: D3 = h . (Ws1[:, :d] W2)^T
         if (tid == 0) {
@@ -245,9 +254,11 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
             umma_commit(&bar_mma);
         }
         __syncwarp();
+        LPF_STAMP(6);
         mbar_wait(&bar_mma, mma_phase);
         mma_phase ^= 1;
         tc_fence_after();
+        LPF_STAMP(7);
 
         // ---- epilogue 2: prob = sigmoid(ws2 . ReLU(D3 + offset) + bs2)
         {
@@ -271,7 +282,9 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
         }
         tc_fence_before();
         named_bar_sync(1, kHeadConsumers);   // TMEM columns and the operand tile are reused by the next tile
+        LPF_STAMP(8);
     }
+#undef LPF_STAMP
 
     if (!weights_ready && tid == 0) mbar_wait(&bar_w, 0);   // never exit with a bulk copy in flight
     tc_fence_before();
@@ -304,6 +317,14 @@ static int launch_heads(const HeadsParams& p, cudaStream_t st) {
 
 using namespace lpf;
 
+static long long* g_heads_dbg = nullptr;
+// Debug hook (not part of the data path): device buffer of 8 x 16 int64 that CTA 0 of every later
+// lpf_link_heads_tc launch fills with per-phase clock64() stamps of its first 8 tiles; NULL switches it off.
+extern "C" int lpf_debug_heads_clocks(void* device_buffer) {
+    g_heads_dbg = (long long*)device_buffer;
+    return LPF_OK;
+}
+
 extern "C" int lpf_link_heads_tc(const int64_t* links, int64_t bs, const int32_t* idx, int64_t n, const float* X,
                                  int64_t ldx, int32_t d, const float* w1_packed, const float* b1, const float* ln_w,
                                  const float* ln_b, const float* w23_packed, const float* c3, const float* zb,
@@ -315,7 +336,7 @@ extern "C" int lpf_link_heads_tc(const int64_t* links, int64_t bs, const int32_t
     LPF_REQUIRE(c3 || zb, "either the constant c3 or per-row zb must be given");
     LPF_REQUIRE(idx || n == bs, "n must equal bs when idx is NULL");
     LPF_REQUIRE(ldx >= d && (!zb || ld_zb >= 2 * d), "leading dimension too small");
-    HeadsParams p{links, bs, idx, n, X, ldx, w1_packed, b1, ln_w, ln_b, w23_packed, c3, zb, ld_zb, ws2, bs2, prob, logits, n_dev};
+    HeadsParams p{links, bs, idx, n, X, ldx, w1_packed, b1, ln_w, ln_b, w23_packed, c3, zb, ld_zb, ws2, bs2, prob, logits, n_dev, g_heads_dbg};
     cudaStream_t st = (cudaStream_t)stream;
     if (d == 64) return launch_heads<64>(p, st);
     if (d == 32) return launch_heads<32>(p, st);
