@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--negs", type=int, default=None)
     ap.add_argument("--cpu-sample-links", type=int, default=32768)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sampler", action="store_true", help="debug: do not poll nvidia-smi during the timed region")
     ap.add_argument("--seed", type=int, default=0)
     return ap.parse_args()
 
@@ -66,20 +67,28 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period_ms=100):
+        """Started BEFORE the warm-up (nvidia-smi's own start-up takes tens of ms and would otherwise land inside a
+        short timed region); mark() / stop() bracket the timed region and only samples between them are used."""
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.t0 = self.t1 = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "200", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu=timestamp,{self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", str(period_ms), "-i", str(gpu_index)], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
         except OSError:
             pass
+
+    def mark(self):
+        self.t0 = time.time()
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
-        time.sleep(0.25)
+        self.t1 = time.time()
+        time.sleep(0.15)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -88,20 +97,28 @@ class ClockSampler:
         self.f.flush()
         rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
+        import datetime
+        parsed = []
         for r in rows:
-            if len(r) < 9:
+            if len(r) < 10:
                 continue
             try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
+                ts = datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                parsed.append((ts, float(r[2]), float(r[3]), [v.strip().lower() == "active" for v in r[6:10]]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.strip().lower() == "active":
+        inside = [q for q in parsed if self.t0 is not None and self.t0 - 0.02 <= q[0] <= self.t1 + 0.12]
+        if not inside and parsed:       # region shorter than the sampling period: the sample nearest to it
+            mid = 0.5 * ((self.t0 or self.t1) + self.t1)
+            inside = [min(parsed, key=lambda q: abs(q[0] - mid))]
+        reasons = set()
+        for q in inside:
+            for name, on in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), q[3]):
+                if on:
                     reasons.add(name)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        if inside:
+            out.update(sm_mhz=float(np.median([q[1] for q in inside])), sm_max_mhz=float(max(q[2] for q in inside)),
+                       reasons=sorted(reasons), samples=len(inside))
         return out
 
 
@@ -231,10 +248,14 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput (`value`): K untimed-instrumentation-free steps between two events
+    sampler = ClockSampler(local_rank) if (rank == 0 and not args.no_sampler) else None
     for s in range(args.warmup):
         model.score_links(dev_links[s], X, score)
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        time.sleep(0.3)          # let nvidia-smi finish starting up before the timed region
+        sampler.mark()
+    _lib.COUNTERS = {}
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     for s in range(args.warmup, total_steps):
@@ -243,6 +264,8 @@ def run_b200(args):
     barrier()
     clocks = sampler.stop() if sampler else None
     dev_ms = t_start.elapsed_time(t_end)
+    graph_launches = _lib.COUNTERS.get("graph_launches", 0)
+    _lib.COUNTERS = None
 
     # ---- the same K steps again with every C-ABI call bracketed by CUDA events (per-kernel breakdown)
     trace = _lib.Trace(events=True)
@@ -293,7 +316,7 @@ def run_b200(args):
             os.path.join(REPO, "MEASURED_PEAKS.json")) else {}
         avg_ms = top_ms / top_calls
         alg = alg_full = alg_flops = None
-        if top_name in ("lpf_select_count", "lpf_select_fill"):
+        if top_name in ("lpf_select_count", "lpf_select_fill", "lpf_select_onepass"):
             alg = byt["select_dedup"] / args.steps          # per launch (one launch per step)
             alg_full = byt["select_full"] / args.steps
         elif top_name == "lpf_link_heads_tc":
@@ -338,6 +361,7 @@ def run_b200(args):
                         "d2h_bytes_per_step": int(nlinks * 4), "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": int(trace.launches),
                 "gpu_launches_per_step": launches_per_step,
+                "cuda_graph_launches_per_step": graph_launches / args.steps,
                 "roofline": roof,
                 "path_algorithmic_gbs": path_gbs,
                 "path_frac_of_peak": path_gbs / peak,
