@@ -1,0 +1,266 @@
+// K1, run-aware one-pass selection: the shape citation2-style evaluation produces — long runs of links that
+// share their source (reference train/testing.py:20-23: source.repeat(1000) against 1000 negative targets).
+//
+// A CTA takes 256 consecutive links.  If they form at most kMaxRuns runs of equal source, each run is processed
+// with the source's tables staged in shared memory ONCE:
+//   * A(a), the source's sorted adjacency row, becomes an open-addressing hash set (<= 4096 neighbours), so the
+//     membership test of every element of every target row is one multiply-shift and ~1.3 shared-memory probes
+//     instead of a ~log2(deg a)-step binary search through L1/L2;
+//   * P(a), the source's PPR row (cols + values), is copied to shared memory (<= 128 entries).
+// Groups of 8 lanes then walk the TARGET rows only (coalesced 32-byte reads of A(b), P(b)), with the next link's
+// row pointers prefetched while the current link is processed.  Everything else (count -> allocate -> write into
+// the per-type pools, the deferral of heavy links to the CTA-wide kernel) is the one-pass protocol of
+// select_fast.cu, and a chunk that is not run-shaped falls back to its generic group walk.  The selected sets,
+// their order inside a link and the fp32 values are identical (tests compare all paths with the oracle).
+#include "select_walk.cuh"
+
+namespace lpf {
+
+constexpr int kRunThreads = 256;
+constexpr int kRunChunk = 256;       // links per CTA iteration
+constexpr int kMaxRuns = 3;
+constexpr int kHashSlots = 8192;     // int32 slots: rows of up to 4096 neighbours at load <= 0.5
+constexpr int kMaxHashRow = kHashSlots / 2;
+constexpr int kMaxPprRow = 128;
+constexpr int kMaxTargetRow = kHeavyPerLane * 8;   // longer target rows take the generic / heavy route
+
+__device__ __forceinline__ uint32_t hash_slot(int32_t u, int shift) { return ((uint32_t)u * 0x9E3779B1u) >> shift; }
+
+__device__ __forceinline__ bool hash_contains(const int32_t* tab, uint32_t mask, int shift, int32_t u) {
+    uint32_t s = hash_slot(u, shift);
+    while (true) {
+        const int32_t v = tab[s];
+        if (v == u) return true;
+        if (v < 0) return false;
+        s = (s + 1) & mask;
+    }
+}
+
+// (present, q) of node u in the shared-memory copy of the source's PPR row (ascending cols)
+__device__ __forceinline__ bool smem_ppr_lookup(const int32_t* pc, const float* pv, int n, int32_t u, float& q) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (pc[mid] < u) lo = mid + 1; else hi = mid;
+    }
+    if (lo < n && pc[lo] == u) {
+        q = quantise(pv[lo]);
+        return true;
+    }
+    q = 0.f;
+    return false;
+}
+
+struct RunCtx {
+    const int32_t* tab;
+    uint32_t mask;
+    int shift;
+    const int32_t* pac;   // smem copy of P(a)
+    const float* pav;
+    int npa;
+};
+
+// One group of 8 lanes, one link of a hashed run: walks A(b) and P(b) only.
+template <bool WRITE>
+__device__ __forceinline__ void walk_link_hashed(const SelectParams2& p, const RunCtx& h, const LinkRows& r, int64_t i,
+                                                 int lane, int64_t o_cn, int64_t o_1h, int64_t o_n1, int& c_cn,
+                                                 int& c_1h, int& c_n1) {
+    constexpr int G = 8;
+    const int gl = lane & (G - 1);
+    const unsigned gmask = group_mask<G>(lane);
+    const unsigned lt = gmask & ((1u << lane) - 1u);
+    const bool want_pi = p.mode != LPF_MODE_CN;
+    const bool want_n1 = p.mode == LPF_MODE_ALL;
+    const bool cn_needs_ppr = WRITE || p.th_cn > 0.0f;
+    const float th_pre = want_n1 ? fminf(p.th_1hop, p.th_non1hop) : p.th_1hop;
+    c_cn = c_1h = c_n1 = 0;
+    for (int k = 0; k < r.nb; k += G) {          // CN = elements of A(b) found in the hash set of A(a)
+        const bool act = k + gl < r.nb;
+        const int32_t u = act ? __ldg(r.Ab + k + gl) : -1;
+        bool hit = act && hash_contains(h.tab, h.mask, h.shift, u);
+        float qa = 0.f, qb = 0.f;
+        if (hit && cn_needs_ppr) {
+            smem_ppr_lookup(h.pac, h.pav, h.npa, u, qa);
+            const int t = lower_bound_from(r.Pbc, 0, r.npb, u);
+            if (t < r.npb && __ldg(r.Pbc + t) == u) qb = quantise(__ldg(r.Pbv + t));
+            hit = qa >= p.th_cn && qb >= p.th_cn;
+        }
+        const unsigned m = __ballot_sync(gmask, hit);
+        if (WRITE && hit) {
+            const int64_t s = o_cn + c_cn + __popc(m & lt);
+            p.node[s] = u;
+            p.pa[s] = qa;
+            p.pb[s] = qb;
+        }
+        c_cn += __popc(m);
+    }
+    if (want_pi) {                               // 1-hop / >1-hop = elements of P(b) present in P(a)
+        for (int k = 0; k < r.npb; k += G) {
+            const bool act = k + gl < r.npb;
+            const int32_t u = act ? __ldg(r.Pbc + k + gl) : -1;
+            bool k1 = false, kn = false;
+            float qa = 0.f, qb = 0.f;
+            if (act && smem_ppr_lookup(h.pac, h.pav, h.npa, u, qa)) {
+                qb = quantise(__ldg(r.Pbv + k + gl));
+                if (qa >= th_pre && qb >= th_pre) {
+                    const bool in_a = hash_contains(h.tab, h.mask, h.shift, u);
+                    const int t = lower_bound_from(r.Ab, 0, r.nb, u);
+                    const bool in_b = t < r.nb && __ldg(r.Ab + t) == u;
+                    k1 = (in_a != in_b) && qa >= p.th_1hop && qb >= p.th_1hop;
+                    kn = want_n1 && !in_a && !in_b && qa >= p.th_non1hop && qb >= p.th_non1hop;
+                }
+            }
+            const unsigned m1 = __ballot_sync(gmask, k1);
+            const unsigned mn = __ballot_sync(gmask, kn);
+            if (WRITE && (k1 || kn)) {
+                const int64_t s = k1 ? o_1h + c_1h + __popc(m1 & lt) : o_n1 + c_n1 + __popc(mn & lt);
+                p.node[s] = u;
+                p.pa[s] = qa;
+                p.pb[s] = qb;
+            }
+            c_1h += __popc(m1);
+            c_n1 += __popc(mn);
+        }
+    }
+}
+
+// count -> allocate -> write for one link, by one group of 8 lanes; `hashed` selects the walk
+__device__ __forceinline__ void onepass_link(const SelectParams2& p, const RunCtx* h, const LinkRows& r, int64_t i,
+                                             int lane) {
+    constexpr int G = 8;
+    const int leader = lane & ~(G - 1);
+    const unsigned gmask = group_mask<G>(lane);
+    int c_cn, c_1h, c_n1;
+    if (h) walk_link_hashed<false>(p, *h, r, i, lane, 0, 0, 0, c_cn, c_1h, c_n1);
+    else walk_link<G, false>(p, r, i, lane, 0, 0, 0, c_cn, c_1h, c_n1);
+    int64_t s_cn = 0, s_1h = 0, s_n1 = 0;
+    int ok = 1;
+    if (lane == leader) ok = alloc_segments(p, i, c_cn, c_1h, c_n1, s_cn, s_1h, s_n1) ? 1 : 0;
+    if (c_cn + c_1h + c_n1 == 0) return;       // uniform within the group
+    ok = __shfl_sync(gmask, ok, leader);
+    if (!ok) return;
+    s_cn = __shfl_sync(gmask, s_cn, leader);
+    s_1h = __shfl_sync(gmask, s_1h, leader);
+    s_n1 = __shfl_sync(gmask, s_n1, leader);
+    if (h) walk_link_hashed<true>(p, *h, r, i, lane, s_cn, p.cap + s_1h, 2 * p.cap + s_n1, c_cn, c_1h, c_n1);
+    else walk_link<G, true>(p, r, i, lane, s_cn, p.cap + s_1h, 2 * p.cap + s_n1, c_cn, c_1h, c_n1);
+}
+
+__global__ void __launch_bounds__(kRunThreads) select_onepass_runs_kernel(SelectParams2 p) {
+    __shared__ int32_t tab[kHashSlots];
+    __shared__ int32_t s_pac[kMaxPprRow];
+    __shared__ float s_pav[kMaxPprRow];
+    __shared__ int run_start[kMaxRuns + 1];
+    __shared__ int n_runs_s;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int group = tid >> 3;                    // 32 groups of 8 lanes
+    const bool want_pi = p.mode != LPF_MODE_CN;
+    const int64_t nchunks = (p.bs + kRunChunk - 1) / kRunChunk;
+
+    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const int64_t i0 = chunk * kRunChunk;
+        const int len = (int)min((int64_t)kRunChunk, p.bs - i0);
+        // ---- run structure of the chunk: boundaries where the source changes
+        const int64_t a_me = (tid < len) ? __ldg(p.links + i0 + tid) : -1;
+        const int64_t a_prev = (tid > 0 && tid < len) ? __ldg(p.links + i0 + tid - 1) : -2;
+        const bool boundary = tid < len && (tid == 0 || a_me != a_prev);
+        if (tid == 0) n_runs_s = 0;
+        __syncthreads();
+        if (boundary) {
+            const int k = atomicAdd(&n_runs_s, 1);
+            if (k < kMaxRuns) run_start[k] = tid;
+        }
+        __syncthreads();
+        const int n_runs = n_runs_s;
+        if (n_runs > kMaxRuns) {
+            // not run-shaped: generic one-pass walk, 8 links per group
+            for (int t = group; t < len; t += kRunThreads / 8) {
+                const int64_t i = i0 + t;
+                const LinkRows r = load_rows(p, i);
+                if (is_heavy(r, want_pi, 8)) {
+                    if ((lane & 7) == 0) p.heavy[4 + atomicAdd(p.heavy, 1)] = (int32_t)i;
+                    continue;
+                }
+                onepass_link(p, nullptr, r, i, lane);
+            }
+            __syncthreads();
+            continue;
+        }
+        if (tid == 0) {      // sort the (at most kMaxRuns) boundaries, close the list
+            for (int x = 1; x < n_runs; ++x)
+                for (int y = x; y > 0 && run_start[y] < run_start[y - 1]; --y) {
+                    const int tmp = run_start[y]; run_start[y] = run_start[y - 1]; run_start[y - 1] = tmp;
+                }
+            run_start[n_runs] = len;
+        }
+        __syncthreads();
+        for (int rn = 0; rn < n_runs; ++rn) {
+            const int t0 = run_start[rn], t1 = run_start[rn + 1];
+            const int64_t a = __ldg(p.links + i0 + t0);
+            const int64_t a0 = __ldg(p.adj_rowptr + a), pa0 = __ldg(p.ppr_rowptr + a);
+            const int na = (int)(__ldg(p.adj_rowptr + a + 1) - a0), npa = (int)(__ldg(p.ppr_rowptr + a + 1) - pa0);
+            const bool hashed = (t1 - t0) >= 16 && na <= kMaxHashRow && npa <= kMaxPprRow;
+            RunCtx h;
+            if (hashed) {
+                // table size: power of two >= 2*na (>= 64), so short rows cost little to clear
+                int lg = 6;
+                while ((1 << lg) < 2 * na) ++lg;
+                const int size = 1 << lg;
+                h.tab = tab; h.mask = (uint32_t)(size - 1); h.shift = 32 - lg;
+                h.pac = s_pac; h.pav = s_pav; h.npa = npa;
+                for (int s = tid; s < size; s += kRunThreads) tab[s] = -1;
+                for (int s = tid; s < npa; s += kRunThreads) {
+                    s_pac[s] = __ldg(p.ppr_col + pa0 + s);
+                    s_pav[s] = __ldg(p.ppr_val + pa0 + s);
+                }
+                __syncthreads();
+                for (int s = tid; s < na; s += kRunThreads) {
+                    const int32_t u = __ldg(p.adj_col + a0 + s);
+                    uint32_t slot = hash_slot(u, h.shift);
+                    while (atomicCAS(&tab[slot], -1, u) != -1) slot = (slot + 1) & h.mask;
+                }
+                __syncthreads();
+            }
+            // links of the run, one per group of 8 lanes; the next link's target pointers are prefetched
+            int t = t0 + group;
+            int64_t b_n = 0, b0_n = 0, b1_n = 0, pb0_n = 0, pb1_n = 0;
+            auto fetch = [&](int tt) {
+                if (tt < t1) {
+                    b_n = __ldg(p.links + p.bs + i0 + tt);
+                    b0_n = __ldg(p.adj_rowptr + b_n);
+                    b1_n = __ldg(p.adj_rowptr + b_n + 1);
+                    pb0_n = __ldg(p.ppr_rowptr + b_n);
+                    pb1_n = __ldg(p.ppr_rowptr + b_n + 1);
+                }
+            };
+            fetch(t);
+            for (; t < t1; t += kRunThreads / 8) {
+                const int64_t i = i0 + t;
+                LinkRows r;
+                r.na = na; r.npa = npa;
+                r.Aa = p.adj_col + a0; r.Pac = p.ppr_col + pa0; r.Pav = p.ppr_val + pa0;
+                r.nb = (int)(b1_n - b0_n); r.npb = (int)(pb1_n - pb0_n);
+                r.Ab = p.adj_col + b0_n; r.Pbc = p.ppr_col + pb0_n; r.Pbv = p.ppr_val + pb0_n;
+                fetch(t + kRunThreads / 8);
+                const bool use_hash = hashed && r.nb <= kMaxTargetRow && r.npb <= kMaxTargetRow;
+                if (!use_hash && is_heavy(r, want_pi, 8)) {
+                    if ((lane & 7) == 0) p.heavy[4 + atomicAdd(p.heavy, 1)] = (int32_t)i;
+                    continue;
+                }
+                onepass_link(p, use_hash ? &h : nullptr, r, i, lane);
+            }
+            __syncthreads();     // the shared tables are rebuilt for the next run / chunk
+        }
+    }
+}
+
+int launch_select_runs(const SelectParams2& p, cudaStream_t st) {
+    int64_t blocks = (p.bs + kRunChunk - 1) / kRunChunk;
+    const int64_t cap = (int64_t)kNumSMs * 6 * 4;
+    if (blocks > cap) blocks = cap;
+    select_onepass_runs_kernel<<<(unsigned)blocks, kRunThreads, 0, st>>>(p);
+    return check_launch("lpf_select_onepass");
+}
+
+}  // namespace lpf

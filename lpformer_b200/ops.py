@@ -217,6 +217,32 @@ def select(links, adj: CSR, ppr: CSR, th_cn, th_1hop, th_non1hop, mode: str, wan
     return Selection(mode, bs, p, node, pa, pb, link, (0, b[0], b[1], b[2]), nz[:b[3]])
 
 
+def select_onepass(links, adj: CSR, ppr: CSR, th_cn, th_1hop, th_non1hop, mode: str, cap: int, algo=None):
+    """K1, one launch sequence and no host round trip (lpf_select_onepass): pairs of type t land in rows
+    [t*cap, t*cap + header[t]) of the pair arrays, per-link segments in (seg_start, counts).  Returns a dict of the
+    raw device buffers; ScorePlan (plan.py) is the production caller, tests use this wrapper."""
+    require_cuda(links, adj.rowptr, ppr.rowptr)
+    dev = links.device
+    bs = links.shape[1]
+    algo = pick_select_algo(adj, ppr, th_1hop, th_non1hop, mode) if algo is None else algo
+    out = {
+        "counts": torch.empty(3 * bs, dtype=torch.int32, device=dev),
+        "seg_start": torch.empty(3 * bs, dtype=torch.int32, device=dev),
+        "nz": torch.empty(bs, dtype=torch.int32, device=dev),
+        "header": torch.zeros(8, dtype=torch.int64, device=dev),
+        "node": torch.empty(3 * cap, dtype=torch.int32, device=dev),
+        "src_ppr": torch.empty(3 * cap, dtype=torch.float32, device=dev),
+        "tgt_ppr": torch.empty(3 * cap, dtype=torch.float32, device=dev),
+        "cap": cap,
+    }
+    ws = torch.empty(bs + 4, dtype=torch.int32, device=dev)
+    call("lpf_select_onepass", ptr(links), bs, ptr(adj.rowptr), ptr(adj.col), ptr(ppr.rowptr), ptr(ppr.col), ptr(ppr.val),
+         float(th_cn), float(th_1hop), float(th_non1hop), MODE[mode], algo, cap, ptr(out["counts"]),
+         ptr(out["seg_start"]), ptr(out["nz"]), ptr(out["header"]), ptr(out["node"]), ptr(out["src_ppr"]),
+         ptr(out["tgt_ppr"]), ptr(ws), stream(), meta=(bs,))
+    return out
+
+
 def rpe_hidden(sel: Selection, t: int, w1, b1, ln_w, ln_b, hsum):
     r0, r1 = sel.type_range(t)
     if r1 > r0:

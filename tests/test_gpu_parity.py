@@ -280,3 +280,67 @@ def test_plan_graph_replay_and_overflow():
     out = model.score_links(batches[1], X, score).cpu().numpy()      # rebuilt with larger pools
     np.testing.assert_allclose(out, ref[1], rtol=1e-5, atol=1e-7)
     assert model._plans[key].stats()["overflow"] == 0
+
+
+def _onepass_sets(out, bs):
+    """Per type: (link, node, src_ppr bits, tgt_ppr bits) sorted by (link, position) from the one-pass buffers."""
+    cnt = out["counts"].cpu().numpy().reshape(3, bs)
+    st = out["seg_start"].cpu().numpy().reshape(3, bs)
+    node, pa, pb = (out[k].cpu().numpy() for k in ("node", "src_ppr", "tgt_ppr"))
+    cap = out["cap"]
+    res = []
+    for t in range(3):
+        li = np.repeat(np.arange(bs), cnt[t])
+        rows = np.concatenate([t * cap + st[t, i] + np.arange(cnt[t, i]) for i in range(bs)] or [np.zeros(0, np.int64)]).astype(np.int64)
+        res.append((li, node[rows], pa[rows].view(np.uint32), pb[rows].view(np.uint32)))
+    return res
+
+
+@pytest.mark.parametrize("workload,scale,algo", [("citation2", 0.05, 1), ("citation2", 0.05, 2), ("collab", 0.05, 1),
+                                                 ("ppa", 0.004, 2), ("ddi", 0.5, 2)])
+def test_select_onepass_vs_oracle(workload, scale, algo):
+    """One-pass selection (run-aware hashed kernel for algo 1, warp kernel for algo 2, deferred heavy links in both)
+    against the numpy oracle: long shared-source runs, short runs, unsorted links, hub-hub pairs, self pairs."""
+    from lpformer_b200 import ops, synthetic as S
+    g = S.make_graph(workload, seed=9, scale=scale, heldout=512)
+    cfg = g.cfg
+    rng = np.random.default_rng(1)
+    deg = np.diff(g.indptr)
+    hubs = np.argsort(-deg)[:40]
+    q_long = S.citation2_queries(g, 3, 400, seed=1)                       # runs of 401 links
+    hub_q = np.stack([np.repeat(hubs[:2], 300), rng.integers(0, g.n, 600)])  # hub sources (hash or fallback)
+    hub_pairs = np.stack([rng.choice(hubs, 64), rng.choice(hubs, 64)])    # heavy / huge links
+    short_runs = np.stack([np.repeat(rng.integers(0, g.n, 40), 5), rng.integers(0, g.n, 200)])
+    rnd = rng.integers(0, g.n, (2, 300))
+    pos = g.edges[:, rng.integers(0, g.edges.shape[1], 200)]
+    selfp = np.tile(hubs[:4], (2, 1))
+    links_np = np.concatenate([q_long, hub_q, hub_pairs, short_runs, rnd, pos, selfp], axis=1).astype(np.int64)
+    th = (cfg["thresh_cn"], cfg["thresh_1hop"], cfg["thresh_non1hop"])
+    mode, sets = O.select_sets(O.CSR(g.indptr, g.indices, None, g.n), O.CSR(g.ppr[0], g.ppr[1], g.ppr[2], g.n),
+                               links_np, *th)
+    dev = torch.device("cuda:0")
+    d = g.data_dict(dev)
+    bs = links_np.shape[1]
+    total = max(len(v[0]) for v in sets.values())
+    out = ops.select_onepass(torch.from_numpy(links_np).to(dev), d["adj_mask"], d["ppr"], *th, mode, cap=total + 8, algo=algo)
+    hdr = out["header"].tolist()
+    assert hdr[4] == 0
+    got = _onepass_sets(out, bs)
+    nz_ref = np.zeros(bs, bool)
+    for t, name in enumerate(("cn", "1hop", "non1hop")):
+        if name not in sets:
+            assert hdr[t] == 0
+            continue
+        li, nd, qa, qb = sets[name]
+        nz_ref[li] = True
+        assert hdr[t] == len(li), name
+        assert np.array_equal(got[t][0], li), name
+        assert np.array_equal(got[t][1], nd), name
+        assert np.array_equal(got[t][2], qa.view(np.uint32)), name
+        assert np.array_equal(got[t][3], qb.view(np.uint32)), name
+    nz = np.sort(out["nz"][:hdr[3]].cpu().numpy())
+    assert np.array_equal(nz, np.nonzero(nz_ref)[0])
+    # a pool that is too small is reported, never overrun
+    small = ops.select_onepass(torch.from_numpy(links_np).to(dev), d["adj_mask"], d["ppr"], *th, mode, cap=max(1, total // 4), algo=algo)
+    h2 = small["header"].tolist()
+    assert h2[4] == 1 and h2[:4] == [0, 0, 0, 0]
