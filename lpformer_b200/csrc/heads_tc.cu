@@ -11,8 +11,11 @@
 // ONCE per CTA by bulk TMA copies and stay resident while the CTA walks its tiles; each thread owns one link
 // (= one TMEM lane), so LayerNorm and the final dot product are thread-local.
 //
-// Warps 4-7 gather the NEXT tile's X[a]*X[b] rows into a staging buffer while warps 0-3 run the current
-// tile's MMAs and epilogues (mbarrier full/empty hand-off), so HBM latency is off the critical path.
+// Software pipeline across tiles: warps 4-7 (producers) gather tile t+1's X[a]*X[b] rows into registers while
+// tile t is computed; as soon as contraction 2 of tile t has finished reading the operand tile they store the
+// hi/lo split there and issue contraction 1 of tile t+1, which runs on the tensor pipe while warps 0-3
+// (consumers) are still in tile t's final epilogue.  HBM latency, the operand split and half of the MMA time
+// are off the consumers' critical path; hand-offs are mbarriers fed by tcgen05.commit.
 //
 // `offset` carries the pairwise half of the concatenated feature vector [el | pw] (models/link_transformer.py:105,
 // train/testing.py:31): for a link whose selected node sets are all empty, pw is the same vector for every link
@@ -66,11 +69,12 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
     constexpr int N3 = 2 * D;                        // width of mlp_score's hidden layer
     constexpr uint32_t W1_BYTES = KB * 2 * D * 128;  // packed [D, D]
     constexpr uint32_t W3_BYTES = KB * 2 * N3 * 128; // packed [2D, D]
-    constexpr uint32_t STG_BYTES = KB * kATileBytes; // raw fp32 xprod tile, same swizzle as an operand
     constexpr uint32_t TMEM_COLS = (D + N3) <= 128 ? 128 : 256;   // D1 | D3
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ uint64_t bar_w, bar_mma, bar_full, bar_empty;
+    // bar_w: weights landed;  bar_mma1 / bar_mma3: contraction 1 / 2 of the current tile complete;
+    // bar_a_free: contraction 2 has finished reading the operand tile (producers may overwrite it)
+    __shared__ uint64_t bar_w, bar_mma1, bar_mma3, bar_a_free;
     __shared__ uint32_t tmem_slot;
     __shared__ int32_t ids[2][2][kTileM];            // [tile parity][a, b][row]
     __shared__ float s_b1[D], s_g[D], s_bt[D], s_c3[N3], s_ws2[N3];
@@ -83,13 +87,12 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
     uint8_t* sW1 = smem;
     uint8_t* sW3 = sW1 + W1_BYTES;
     uint8_t* sA = sW3 + W3_BYTES;                    // [kb][hi, lo][128 rows][128 B]
-    uint8_t* sStg = sA + KB * 2 * kATileBytes;       // [kb][128 rows][128 B]
 
     if (tid == 0) {
         mbar_init(&bar_w, 1);
-        mbar_init(&bar_mma, 1);
-        mbar_init(&bar_full, kHeadProducers);
-        mbar_init(&bar_empty, kHeadConsumers);
+        mbar_init(&bar_mma1, 1);
+        mbar_init(&bar_mma3, 1);
+        mbar_init(&bar_a_free, 1);
         fence_mbar_init();
         mbar_arrive_expect_tx(&bar_w, W1_BYTES + W3_BYTES);
         bulk_g2s(sW1, p.w1p, W1_BYTES, &bar_w);
@@ -110,8 +113,14 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
     __syncthreads();
     tc_fence_after();
 
+    const uint32_t tmem_d = tmem_slot;
+    const uint32_t d1 = tmem_d, d3 = tmem_d + D;
+    const uint32_t idesc_d = make_idesc_tf32(kTileM, D), idesc_3 = make_idesc_tf32(kTileM, N3);
+    const uint32_t aA = smem_u32(sA), aW1 = smem_u32(sW1), aW3 = smem_u32(sW3);
+
     if (warp >= kHeadConsumers / 32) {
-        // =========================== producers: gather the next tile into the staging buffer
+        // =========================== producers: gather tile t+1 while tile t is computed, then (once the operand
+        // tile is free) split it into hi / lo, store it in the UMMA layout and issue contraction 1
         const int ptid = tid - kHeadConsumers;
         const int chunk = ptid & 7, row_in_pass = ptid >> 3;
         const bool vec_x = ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0) && (p.ldx % 4 == 0);
@@ -146,67 +155,78 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
                     v[kb][pass] = make_float4(xa.x * xb.x, xa.y * xb.y, xa.z * xb.z, xa.w * xb.w);
                 }
             }
-            if (it > 0) mbar_wait(&bar_empty, (it - 1) & 1);      // consumers have drained the previous tile
+            if (it > 0) mbar_wait(&bar_a_free, (it - 1) & 1);     // contraction 2 of the previous tile is done
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
-                for (int pass = 0; pass < 8; ++pass)
-                    *reinterpret_cast<float4*>(sStg + kb * kATileBytes + swz_chunk_off(pass * 16 + row_in_pass, chunk)) =
-                        v[kb][pass];
-            mbar_arrive(&bar_full);
+                for (int pass = 0; pass < 8; ++pass) {
+                    const float4 x = v[kb][pass];
+                    const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
+                    const float4 lo = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+                    const uint32_t off = (uint32_t)kb * 2 * kATileBytes + swz_chunk_off(pass * 16 + row_in_pass, chunk);
+                    *reinterpret_cast<float4*>(sA + off) = hi;
+                    *reinterpret_cast<float4*>(sA + off + kATileBytes) = lo;
+                }
+            fence_async_smem();
+            named_bar_sync(2, kHeadProducers);
+            if (ptid == 0) {
+                if (it == 0) mbar_wait(&bar_w, 0);
+                tc_fence_after();
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb)
+                    issue_kblock_3x(d1, aA + kb * 2 * kATileBytes, aA + kb * 2 * kATileBytes + kATileBytes,
+                                    aW1 + kb * 2 * D * 128, aW1 + kb * 2 * D * 128 + D * 128, idesc_d, kb == 0);
+                umma_commit(&bar_mma1);
+            }
+            __syncwarp();
         }
         return;
     }
 
-    // =============================== consumers
+    // =============================== consumers: one link (= TMEM lane) per thread
     const float bs2 = p.bs2[0];
-    const uint32_t tmem_d = tmem_slot;
-    const uint32_t d1 = tmem_d, d3 = tmem_d + D;
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-    const uint32_t idesc_d = make_idesc_tf32(kTileM, D), idesc_3 = make_idesc_tf32(kTileM, N3);
-    const uint32_t aA = smem_u32(sA), aW1 = smem_u32(sW1), aW3 = smem_u32(sW3);
-    uint32_t mma_phase = 0, it = 0;
-    bool weights_ready = false;
-
+    uint32_t it = 0;
     const bool stamp = p.dbg && blockIdx.x == 0 && tid == 0;
 #define LPF_STAMP(k) do { if (stamp && it < 8) p.dbg[it * 16 + (k)] = clock64(); } while (0)
+
+    // epilogue 2 of a tile: prob = sigmoid(ws2 . ReLU(D3 + offset) + bs2)
+    auto epilogue2 = [&](int64_t j) {
+        const float* zrow = (p.zb && j < p.n) ? p.zb + j * p.ld_zb : nullptr;
+        float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c0 = 0; c0 < N3; c0 += 16) {
+            float v[16];
+            tmem_ld16(d3 + lane_sel + c0, v);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const float z = v[c] + (zrow ? __ldg(zrow + c0 + c) : s_c3[c0 + c]);
+                acc4[c & 3] = fmaf(fmaxf(z, 0.f), s_ws2[c0 + c], acc4[c & 3]);
+            }
+        }
+        if (j < p.n) {
+            const float logit = ((acc4[0] + acc4[1]) + (acc4[2] + acc4[3])) + bs2;
+            const int64_t pos = p.idx ? (int64_t)__ldg(p.idx + j) : j;
+            p.prob[pos] = p.logits ? logit : 1.0f / (1.0f + expf(-logit));
+        }
+    };
+
+    int64_t j_prev = -1;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int64_t j = tile * kTileM + tid;
         LPF_STAMP(0);
-        // ---- staged xprod row of this thread -> hi / lo operand tile
-        mbar_wait(&bar_full, it & 1);
-        LPF_STAMP(1);
-#pragma unroll
-        for (int c = 0; c < D / 4; ++c) {
-            const uint32_t off = swz_chunk_off(tid, c & 7);
-            const float4 v = *reinterpret_cast<const float4*>(sStg + (c >> 3) * kATileBytes + off);
-            const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-            const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-            *reinterpret_cast<float4*>(sA + (c >> 3) * 2 * kATileBytes + off) = hi;
-            *reinterpret_cast<float4*>(sA + (c >> 3) * 2 * kATileBytes + kATileBytes + off) = lo;
-        }
-        mbar_arrive(&bar_empty);
-        fence_async_smem();
-        named_bar_sync(1, kHeadConsumers);
-        LPF_STAMP(2);
-
-        // ---- contraction 1: D1 = xprod . W1^T
-        if (tid == 0) {
-            if (!weights_ready) mbar_wait(&bar_w, 0);
+        // ---- the previous tile's epilogue 2 runs while the producers refill the operand tile and the tensor
+        // pipe works on this tile's contraction 1
+        if (it > 0) {
+            mbar_wait(&bar_mma3, (it - 1) & 1);
             tc_fence_after();
-#pragma unroll
-            for (int kb = 0; kb < KB; ++kb)
-                issue_kblock_3x(d1, aA + kb * 2 * kATileBytes, aA + kb * 2 * kATileBytes + kATileBytes,
-                                aW1 + kb * 2 * D * 128, aW1 + kb * 2 * D * 128 + D * 128, idesc_d, kb == 0);
-            umma_commit(&bar_mma);
+            LPF_STAMP(1);
+            epilogue2(j_prev);
         }
-        weights_ready = true;
-        __syncwarp();
-        LPF_STAMP(3);
-        mbar_wait(&bar_mma, mma_phase);
-        mma_phase ^= 1;
+        LPF_STAMP(2);
+        mbar_wait(&bar_mma1, it & 1);
         tc_fence_after();
-        LPF_STAMP(4);
+        LPF_STAMP(3);
 
         // ---- epilogue 1: h = ReLU(LN(D1 + b1)), thread-local over the link's row; becomes the next A operand
         {
@@ -242,51 +262,29 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
         tc_fence_before();
         fence_async_smem();
         named_bar_sync(1, kHeadConsumers);
-        LPF_STAMP(5);
+        LPF_STAMP(4);
 
-        // ---- contraction 2: D3 = h . (Ws1[:, :d] W2)^T
+        // ---- contraction 2: D3 = h . (Ws1[:, :d] W2)^T; its completion also frees the operand tile
         if (tid == 0) {
+            if (it == 0) mbar_wait(&bar_w, 0);
             tc_fence_after();
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb)
                 issue_kblock_3x(d3, aA + kb * 2 * kATileBytes, aA + kb * 2 * kATileBytes + kATileBytes,
                                 aW3 + kb * 2 * N3 * 128, aW3 + kb * 2 * N3 * 128 + N3 * 128, idesc_3, kb == 0);
-            umma_commit(&bar_mma);
+            umma_commit(&bar_mma3);
+            umma_commit(&bar_a_free);
         }
         __syncwarp();
-        LPF_STAMP(6);
-        mbar_wait(&bar_mma, mma_phase);
-        mma_phase ^= 1;
-        tc_fence_after();
-        LPF_STAMP(7);
-
-        // ---- epilogue 2: prob = sigmoid(ws2 . ReLU(D3 + offset) + bs2)
-        {
-            const float* zrow = (p.zb && j < p.n) ? p.zb + j * p.ld_zb : nullptr;
-            float acc4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int c0 = 0; c0 < N3; c0 += 16) {
-                float v[16];
-                tmem_ld16(d3 + lane_sel + c0, v);
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const float z = v[c] + (zrow ? __ldg(zrow + c0 + c) : s_c3[c0 + c]);
-                    acc4[c & 3] = fmaf(fmaxf(z, 0.f), s_ws2[c0 + c], acc4[c & 3]);
-                }
-            }
-            if (j < p.n) {
-                const float logit = ((acc4[0] + acc4[1]) + (acc4[2] + acc4[3])) + bs2;
-                const int64_t pos = p.idx ? (int64_t)__ldg(p.idx + j) : j;
-                p.prob[pos] = p.logits ? logit : 1.0f / (1.0f + expf(-logit));
-            }
-        }
-        tc_fence_before();
-        named_bar_sync(1, kHeadConsumers);   // TMEM columns and the operand tile are reused by the next tile
-        LPF_STAMP(8);
+        LPF_STAMP(5);
+        j_prev = j;
     }
+    // drain: epilogue 2 of the last tile
+    mbar_wait(&bar_mma3, (it - 1) & 1);
+    tc_fence_after();
+    epilogue2(j_prev);
 #undef LPF_STAMP
 
-    if (!weights_ready && tid == 0) mbar_wait(&bar_w, 0);   // never exit with a bulk copy in flight
     tc_fence_before();
     named_bar_sync(1, kHeadConsumers);
     if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
@@ -295,8 +293,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
 template <int D>
 static int launch_heads(const HeadsParams& p, cudaStream_t st) {
     constexpr int KB = D / 32;
-    constexpr size_t smem = (size_t)KB * 2 * D * 128 + (size_t)KB * 2 * 2 * D * 128 + (size_t)KB * 2 * tc::kATileBytes +
-                            (size_t)KB * tc::kATileBytes + 1024;
+    constexpr size_t smem = (size_t)KB * 2 * D * 128 + (size_t)KB * 2 * 2 * D * 128 + (size_t)KB * 2 * tc::kATileBytes + 1024;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(link_heads_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

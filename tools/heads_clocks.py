@@ -36,9 +36,10 @@ ops.link_heads(links, X, consts, prob)
 e1.record()
 torch.cuda.synchronize()
 lib.lpf_debug_heads_clocks(None)
-t = buf.cpu().numpy().reshape(8, 16)[:, :9]
-names = ["wait_full", "convert+sync", "issue1", "wait_mma1", "epi1+sync", "issue2", "wait_mma2", "epi2+sync"]
+t = buf.cpu().numpy().reshape(8, 16)[:, :6]
+names = ["wait_mma3(prev)", "epi2(prev)", "wait_mma1", "epi1+sync", "issue_mma3"]
 print("kernel %.1f us for %d tiles/CTA" % (1e3 * e0.elapsed_time(e1), bs // 128 // 148))
-for i in range(8):
+for i in range(1, 8):
     dt = np.diff(t[i])
-    print("tile %d: " % i + "  ".join("%s=%d" % (nm, v) for nm, v in zip(names, dt)) + "  total=%d" % (t[i, 8] - t[i, 0]))
+    nxt = (" period=%d" % (t[i + 1, 0] - t[i, 0])) if i < 7 else ""
+    print("tile %d: " % i + "  ".join("%s=%d" % (nm, v) for nm, v in zip(names, dt)) + nxt)
