@@ -210,7 +210,7 @@ __device__ __forceinline__ void onepass_link_generic(const SelectParams2& p, con
 
 // Deferred links, two tiers: a full warp walks a link whose shorter row has up to kHugeRow elements (hundreds per
 // citation2-shaped batch: hub-hub pairs); a whole CTA walks the few that are longer still.
-constexpr int kHugeRow = 1024;
+constexpr int kHugeRow = 256;
 __device__ __forceinline__ bool is_huge(const LinkRows& r, bool want_pi) {
     return max(min(r.na, r.nb), want_pi ? min(r.npa, r.npb) : 0) > kHugeRow;
 }

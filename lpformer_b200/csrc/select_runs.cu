@@ -6,12 +6,16 @@
 //   * A(a), the source's sorted adjacency row, becomes an open-addressing hash set (<= 4096 neighbours), so the
 //     membership test of every element of every target row is one multiply-shift and ~1.3 shared-memory probes
 //     instead of a ~log2(deg a)-step binary search through L1/L2;
-//   * P(a), the source's PPR row (cols + values), is copied to shared memory (<= 128 entries).
-// Groups of 8 lanes then walk the TARGET rows only (coalesced 32-byte reads of A(b), P(b)), with the next link's
-// row pointers prefetched while the current link is processed.  Everything else (count -> allocate -> write into
-// the per-type pools, the deferral of heavy links to the CTA-wide kernel) is the one-pass protocol of
-// select_fast.cu, and a chunk that is not run-shaped falls back to its generic group walk.  The selected sets,
-// their order inside a link and the fp32 values are identical (tests compare all paths with the oracle).
+//   * P(a), the source's PPR row (cols + values), is copied to shared memory (<= 128 entries) with a small hash
+//     from node id to its position.
+// Inside a run ONE LANE owns ONE LINK: 32 links per warp step, so a warp keeps 32 independent pointer fetches and
+// then 32 independent row reads in flight (the kernel is DRAM-latency bound, not instruction bound), and only
+// the target rows A(b), P(b) are read from HBM.  Links whose target rows exceed 32 entries, and the rare links
+// that select anything (which need the ordered write pass), are then handled one at a time by the whole warp.
+// Everything else (count -> allocate -> write into the per-type pools, the deferral of heavy links to the
+// warp / CTA-wide kernel) is the one-pass protocol of select_fast.cu, and a chunk that is not run-shaped falls
+// back to its generic group walk.  The selected sets, their order inside a link and the fp32 values are
+// identical (tests compare all paths with the oracle).
 #include "select_walk.cuh"
 
 namespace lpf {
@@ -22,7 +26,9 @@ constexpr int kMaxRuns = 3;
 constexpr int kHashSlots = 8192;     // int32 slots: rows of up to 4096 neighbours at load <= 0.5
 constexpr int kMaxHashRow = kHashSlots / 2;
 constexpr int kMaxPprRow = 128;
-constexpr int kMaxTargetRow = kHeavyPerLane * 8;   // longer target rows take the generic / heavy route
+constexpr int kMaxTargetRow = 128;   // longer target rows take the generic / heavy route
+constexpr int kLaneRow = 32;         // target rows up to this length are walked by the link's own lane
+constexpr int kPprHashSlots = 256;   // position hash of P(a) (<= 128 entries)
 
 __device__ __forceinline__ uint32_t hash_slot(int32_t u, int shift) { return ((uint32_t)u * 0x9E3779B1u) >> shift; }
 
@@ -36,36 +42,38 @@ __device__ __forceinline__ bool hash_contains(const int32_t* tab, uint32_t mask,
     }
 }
 
-// (present, q) of node u in the shared-memory copy of the source's PPR row (ascending cols)
-__device__ __forceinline__ bool smem_ppr_lookup(const int32_t* pc, const float* pv, int n, int32_t u, float& q) {
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (pc[mid] < u) lo = mid + 1; else hi = mid;
-    }
-    if (lo < n && pc[lo] == u) {
-        q = quantise(pv[lo]);
-        return true;
-    }
-    q = 0.f;
-    return false;
-}
-
 struct RunCtx {
-    const int32_t* tab;
+    const int32_t* tab;      // hash set of A(a)
     uint32_t mask;
     int shift;
-    const int32_t* pac;   // smem copy of P(a)
+    const int32_t* pac;      // smem copy of P(a): cols, values, and a hash col -> position
     const float* pav;
+    const int32_t* ppos;     // kPprHashSlots entries: position in pac or -1
     int npa;
 };
 
-// One group of 8 lanes, one link of a hashed run: walks A(b) and P(b) only.
-template <bool WRITE>
+// (present, q) of node u in the shared-memory copy of the source's PPR row
+__device__ __forceinline__ bool smem_ppr_lookup(const RunCtx& h, int32_t u, float& q) {
+    uint32_t s = hash_slot(u, 32 - 8);
+    while (true) {
+        const int32_t pos = h.ppos[s];
+        if (pos < 0) {
+            q = 0.f;
+            return false;
+        }
+        if (h.pac[pos] == u) {
+            q = quantise(h.pav[pos]);
+            return true;
+        }
+        s = (s + 1) & (kPprHashSlots - 1);
+    }
+}
+
+// One group of G lanes, one link of a hashed run: walks A(b) and P(b) only.
+template <int G, bool WRITE>
 __device__ __forceinline__ void walk_link_hashed(const SelectParams2& p, const RunCtx& h, const LinkRows& r, int64_t i,
                                                  int lane, int64_t o_cn, int64_t o_1h, int64_t o_n1, int& c_cn,
                                                  int& c_1h, int& c_n1) {
-    constexpr int G = 8;
     const int gl = lane & (G - 1);
     const unsigned gmask = group_mask<G>(lane);
     const unsigned lt = gmask & ((1u << lane) - 1u);
@@ -80,7 +88,7 @@ __device__ __forceinline__ void walk_link_hashed(const SelectParams2& p, const R
         bool hit = act && hash_contains(h.tab, h.mask, h.shift, u);
         float qa = 0.f, qb = 0.f;
         if (hit && cn_needs_ppr) {
-            smem_ppr_lookup(h.pac, h.pav, h.npa, u, qa);
+            smem_ppr_lookup(h, u, qa);
             const int t = lower_bound_from(r.Pbc, 0, r.npb, u);
             if (t < r.npb && __ldg(r.Pbc + t) == u) qb = quantise(__ldg(r.Pbv + t));
             hit = qa >= p.th_cn && qb >= p.th_cn;
@@ -100,7 +108,7 @@ __device__ __forceinline__ void walk_link_hashed(const SelectParams2& p, const R
             const int32_t u = act ? __ldg(r.Pbc + k + gl) : -1;
             bool k1 = false, kn = false;
             float qa = 0.f, qb = 0.f;
-            if (act && smem_ppr_lookup(h.pac, h.pav, h.npa, u, qa)) {
+            if (act && smem_ppr_lookup(h, u, qa)) {
                 qb = quantise(__ldg(r.Pbv + k + gl));
                 if (qa >= th_pre && qb >= th_pre) {
                     const bool in_a = hash_contains(h.tab, h.mask, h.shift, u);
@@ -124,14 +132,14 @@ __device__ __forceinline__ void walk_link_hashed(const SelectParams2& p, const R
     }
 }
 
-// count -> allocate -> write for one link, by one group of 8 lanes; `hashed` selects the walk
+// count -> allocate -> write for one link, by one group of G lanes; `h` != NULL selects the hashed walk
+template <int G>
 __device__ __forceinline__ void onepass_link(const SelectParams2& p, const RunCtx* h, const LinkRows& r, int64_t i,
                                              int lane) {
-    constexpr int G = 8;
     const int leader = lane & ~(G - 1);
     const unsigned gmask = group_mask<G>(lane);
     int c_cn, c_1h, c_n1;
-    if (h) walk_link_hashed<false>(p, *h, r, i, lane, 0, 0, 0, c_cn, c_1h, c_n1);
+    if (h) walk_link_hashed<G, false>(p, *h, r, i, lane, 0, 0, 0, c_cn, c_1h, c_n1);
     else walk_link<G, false>(p, r, i, lane, 0, 0, 0, c_cn, c_1h, c_n1);
     int64_t s_cn = 0, s_1h = 0, s_n1 = 0;
     int ok = 1;
@@ -142,14 +150,62 @@ __device__ __forceinline__ void onepass_link(const SelectParams2& p, const RunCt
     s_cn = __shfl_sync(gmask, s_cn, leader);
     s_1h = __shfl_sync(gmask, s_1h, leader);
     s_n1 = __shfl_sync(gmask, s_n1, leader);
-    if (h) walk_link_hashed<true>(p, *h, r, i, lane, s_cn, p.cap + s_1h, 2 * p.cap + s_n1, c_cn, c_1h, c_n1);
+    if (h) walk_link_hashed<G, true>(p, *h, r, i, lane, s_cn, p.cap + s_1h, 2 * p.cap + s_n1, c_cn, c_1h, c_n1);
     else walk_link<G, true>(p, r, i, lane, s_cn, p.cap + s_1h, 2 * p.cap + s_n1, c_cn, c_1h, c_n1);
+}
+
+// Lane-per-link counting of a hashed run: this lane's link has target rows (Ab, nb) / (Pbc, Pbv, npb), both at most
+// kLaneRow long.  Loop bounds are warp-uniform (maxima over the lanes) so the warp stays converged.
+__device__ __forceinline__ void count_link_lane(const SelectParams2& p, const RunCtx& h, const int32_t* Ab, int nb,
+                                                const int32_t* Pbc, const float* Pbv, int npb, int& c_cn, int& c_1h,
+                                                int& c_n1) {
+    const bool want_pi = p.mode != LPF_MODE_CN;
+    const bool want_n1 = p.mode == LPF_MODE_ALL;
+    const float th_pre = want_n1 ? fminf(p.th_1hop, p.th_non1hop) : p.th_1hop;
+    c_cn = c_1h = c_n1 = 0;
+    const int rounds = __reduce_max_sync(kFull, nb);
+#pragma unroll 4
+    for (int k = 0; k < rounds; ++k) {
+        if (k < nb) {
+            const int32_t u = __ldg(Ab + k);
+            bool hit = hash_contains(h.tab, h.mask, h.shift, u);
+            if (hit && p.th_cn > 0.0f) {
+                float qa, qb = 0.f;
+                smem_ppr_lookup(h, u, qa);
+                const int t = lower_bound_from(Pbc, 0, npb, u);
+                if (t < npb && __ldg(Pbc + t) == u) qb = quantise(__ldg(Pbv + t));
+                hit = qa >= p.th_cn && qb >= p.th_cn;
+            }
+            c_cn += hit ? 1 : 0;
+        }
+    }
+    if (want_pi) {
+        const int prounds = __reduce_max_sync(kFull, npb);
+#pragma unroll 2
+        for (int k = 0; k < prounds; ++k) {
+            if (k < npb) {
+                const int32_t u = __ldg(Pbc + k);
+                float qa;
+                if (smem_ppr_lookup(h, u, qa)) {
+                    const float qb = quantise(__ldg(Pbv + k));
+                    if (qa >= th_pre && qb >= th_pre) {
+                        const bool in_a = hash_contains(h.tab, h.mask, h.shift, u);
+                        const int t = lower_bound_from(Ab, 0, nb, u);
+                        const bool in_b = t < nb && __ldg(Ab + t) == u;
+                        if ((in_a != in_b) && qa >= p.th_1hop && qb >= p.th_1hop) ++c_1h;
+                        if (want_n1 && !in_a && !in_b && qa >= p.th_non1hop && qb >= p.th_non1hop) ++c_n1;
+                    }
+                }
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kRunThreads) select_onepass_runs_kernel(SelectParams2 p) {
     __shared__ int32_t tab[kHashSlots];
     __shared__ int32_t s_pac[kMaxPprRow];
     __shared__ float s_pav[kMaxPprRow];
+    __shared__ int32_t s_ppos[kPprHashSlots];
     __shared__ int run_start[kMaxRuns + 1];
     __shared__ int n_runs_s;
 
@@ -182,7 +238,7 @@ __global__ void __launch_bounds__(kRunThreads) select_onepass_runs_kernel(Select
                     if ((lane & 7) == 0) p.heavy[4 + atomicAdd(p.heavy, 1)] = (int32_t)i;
                     continue;
                 }
-                onepass_link(p, nullptr, r, i, lane);
+                onepass_link<8>(p, nullptr, r, i, lane);
             }
             __syncthreads();
             continue;
@@ -208,8 +264,9 @@ __global__ void __launch_bounds__(kRunThreads) select_onepass_runs_kernel(Select
                 while ((1 << lg) < 2 * na) ++lg;
                 const int size = 1 << lg;
                 h.tab = tab; h.mask = (uint32_t)(size - 1); h.shift = 32 - lg;
-                h.pac = s_pac; h.pav = s_pav; h.npa = npa;
+                h.pac = s_pac; h.pav = s_pav; h.ppos = s_ppos; h.npa = npa;
                 for (int s = tid; s < size; s += kRunThreads) tab[s] = -1;
+                for (int s = tid; s < kPprHashSlots; s += kRunThreads) s_ppos[s] = -1;
                 for (int s = tid; s < npa; s += kRunThreads) {
                     s_pac[s] = __ldg(p.ppr_col + pa0 + s);
                     s_pav[s] = __ldg(p.ppr_val + pa0 + s);
@@ -220,35 +277,74 @@ __global__ void __launch_bounds__(kRunThreads) select_onepass_runs_kernel(Select
                     uint32_t slot = hash_slot(u, h.shift);
                     while (atomicCAS(&tab[slot], -1, u) != -1) slot = (slot + 1) & h.mask;
                 }
-                __syncthreads();
-            }
-            // links of the run, one per group of 8 lanes; the next link's target pointers are prefetched
-            int t = t0 + group;
-            int64_t b_n = 0, b0_n = 0, b1_n = 0, pb0_n = 0, pb1_n = 0;
-            auto fetch = [&](int tt) {
-                if (tt < t1) {
-                    b_n = __ldg(p.links + p.bs + i0 + tt);
-                    b0_n = __ldg(p.adj_rowptr + b_n);
-                    b1_n = __ldg(p.adj_rowptr + b_n + 1);
-                    pb0_n = __ldg(p.ppr_rowptr + b_n);
-                    pb1_n = __ldg(p.ppr_rowptr + b_n + 1);
+                for (int s = tid; s < npa; s += kRunThreads) {
+                    uint32_t slot = hash_slot(s_pac[s], 32 - 8);
+                    while (atomicCAS(&s_ppos[slot], -1, s) != -1) slot = (slot + 1) & (kPprHashSlots - 1);
                 }
-            };
-            fetch(t);
-            for (; t < t1; t += kRunThreads / 8) {
+                __syncthreads();
+                // ---- lane-per-link: 32 links per warp step
+                const int warp = tid >> 5;
+                for (int base = t0 + warp * 32; base < t1; base += kRunThreads) {
+                    const int t = base + lane;
+                    const bool valid = t < t1;
+                    const int64_t i = i0 + t;
+                    int64_t b0 = 0, pb0 = 0;
+                    int nb = 0, npb = 0;
+                    if (valid) {
+                        const int64_t b = __ldg(p.links + p.bs + i);
+                        b0 = __ldg(p.adj_rowptr + b);
+                        nb = (int)(__ldg(p.adj_rowptr + b + 1) - b0);
+                        pb0 = __ldg(p.ppr_rowptr + b);
+                        npb = (int)(__ldg(p.ppr_rowptr + b + 1) - pb0);
+                    }
+                    const bool slow = valid && (nb > kLaneRow || npb > kLaneRow);
+                    int c_cn, c_1h, c_n1;
+                    count_link_lane(p, h, p.adj_col + b0, slow ? 0 : nb, p.ppr_col + pb0, p.ppr_val + pb0, slow ? 0 : npb,
+                                    c_cn, c_1h, c_n1);
+                    int64_t s_cn = 0, s_1h = 0, s_n1 = 0;
+                    bool need_write = false;
+                    if (valid && !slow)
+                        need_write = alloc_segments(p, i, c_cn, c_1h, c_n1, s_cn, s_1h, s_n1) && (c_cn + c_1h + c_n1 > 0);
+                    // ---- warp-cooperative tail: ordered write of the few non-empty links, and the long target rows
+                    unsigned todo = __ballot_sync(kFull, need_write || slow);
+                    while (todo) {
+                        const int src = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        LinkRows r;
+                        r.na = na; r.npa = npa;
+                        r.Aa = p.adj_col + a0; r.Pac = p.ppr_col + pa0; r.Pav = p.ppr_val + pa0;
+                        const int64_t b0s = __shfl_sync(kFull, b0, src), pb0s = __shfl_sync(kFull, pb0, src);
+                        r.nb = __shfl_sync(kFull, nb, src);
+                        r.npb = __shfl_sync(kFull, npb, src);
+                        r.Ab = p.adj_col + b0s; r.Pbc = p.ppr_col + pb0s; r.Pbv = p.ppr_val + pb0s;
+                        const int64_t is = i0 + base + src;
+                        const bool is_slow = __shfl_sync(kFull, (int)slow, src) != 0;
+                        if (!is_slow) {
+                            const int64_t w_cn = __shfl_sync(kFull, s_cn, src), w_1h = __shfl_sync(kFull, s_1h, src);
+                            const int64_t w_n1 = __shfl_sync(kFull, s_n1, src);
+                            int d0, d1, d2;
+                            walk_link_hashed<32, true>(p, h, r, is, lane, w_cn, p.cap + w_1h, 2 * p.cap + w_n1, d0, d1, d2);
+                        } else if (r.nb <= kMaxTargetRow && r.npb <= kMaxTargetRow) {
+                            onepass_link<32>(p, &h, r, is, lane);
+                        } else if (is_heavy(r, want_pi, 8)) {
+                            if (lane == 0) p.heavy[4 + atomicAdd(p.heavy, 1)] = (int32_t)is;
+                        } else {
+                            onepass_link<32>(p, nullptr, r, is, lane);
+                        }
+                    }
+                }
+                __syncthreads();
+                continue;
+            }
+            // ---- run without a hash (short run, or a source row too long for shared memory): generic group walk
+            for (int t = t0 + group; t < t1; t += kRunThreads / 8) {
                 const int64_t i = i0 + t;
-                LinkRows r;
-                r.na = na; r.npa = npa;
-                r.Aa = p.adj_col + a0; r.Pac = p.ppr_col + pa0; r.Pav = p.ppr_val + pa0;
-                r.nb = (int)(b1_n - b0_n); r.npb = (int)(pb1_n - pb0_n);
-                r.Ab = p.adj_col + b0_n; r.Pbc = p.ppr_col + pb0_n; r.Pbv = p.ppr_val + pb0_n;
-                fetch(t + kRunThreads / 8);
-                const bool use_hash = hashed && r.nb <= kMaxTargetRow && r.npb <= kMaxTargetRow;
-                if (!use_hash && is_heavy(r, want_pi, 8)) {
+                const LinkRows r = load_rows(p, i);
+                if (is_heavy(r, want_pi, 8)) {
                     if ((lane & 7) == 0) p.heavy[4 + atomicAdd(p.heavy, 1)] = (int32_t)i;
                     continue;
                 }
-                onepass_link(p, use_hash ? &h : nullptr, r, i, lane);
+                onepass_link<8>(p, nullptr, r, i, lane);
             }
             __syncthreads();     // the shared tables are rebuilt for the next run / chunk
         }
