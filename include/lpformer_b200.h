@@ -232,6 +232,39 @@ int lpf_link_heads_tc(const int64_t* links, int64_t bs, const int32_t* idx, int6
                       const float* ws2, const float* bs2, float* prob, int logits, const int64_t* n_dev,
                       void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Fused path for links with a non-empty node set, small-batch regime: one warp takes one link of nz_list
+ * (n = min(n_cap, *n_dev)) from its node sets (one-pass selection buffers) to its score — lin_l, the RPE MLP and
+ * its contraction per pair, attention with online segment softmax, bias + LayerNorm + counts, pairwise_lin,
+ * elementwise_lin and mlp_score — in fp32 FFMA, replacing lpf_gather_links / lpf_rpe_hidden / lpf_gemm_tc x7 /
+ * lpf_attend_fused / lpf_layernorm_act / lpf_link_heads_tc on the compacted list when that list is a few
+ * thousand links (where those launches are latency, not work).  d in {32, 64}, heads = 1, one attention layer.
+ * Every `*T` matrix is the TRANSPOSE of the nn.Linear weight (row k = input channel k, contiguous outputs):
+ *   wlT = lin_l.weight^T [d][d];  rpe_mT[t] = (W_pe W2_t)^T [d][d], rpe_c[t] = 2 W_pe b2_t + b_r;
+ *   p1T / p2T = pairwise_lin.linears.{0,1}.weight^T [pd][pd] / [pd][d], pd = d + count_dim;
+ *   wzT = Ws1[:, d:]^T [d][2d], off = Ws1[:, :d] b2 + bs1;  w1T = elementwise_lin.linears.0.weight^T [d][d];
+ *   w23T = (Ws1[:, :d] W2)^T [d][2d]  (the folding of lpf_link_heads_tc).
+ * ------------------------------------------------------------------------- */
+typedef struct lpf_nz_args {
+    const int64_t* links; int64_t bs;
+    const int32_t* nz; int64_t n_cap; const int64_t* n_dev;
+    const float* X; int64_t ldx;
+    const float* KV; int64_t ld_kv;
+    const int32_t* node; const float* src_ppr; const float* tgt_ppr;
+    const int32_t* seg_start; const int32_t* counts; int64_t cap;
+    int32_t d; int32_t mode;
+    const float* wlT; const float* bl;
+    const float* rpe_w1[3]; const float* rpe_b1[3]; const float* rpe_ln_w[3]; const float* rpe_ln_b[3];
+    const float* rpe_mT[3]; const float* rpe_c[3];
+    const float* att; const float* att_bias; const float* post_ln_w; const float* post_ln_b;
+    const float* p1T; const float* pb1; const float* pln_w; const float* pln_b; const float* p2T; const float* pb2;
+    const float* wzT; const float* off;
+    const float* w1T; const float* b1; const float* ln_w; const float* ln_b;
+    const float* w23T; const float* ws2; const float* bs2;
+    float* prob; int32_t logits;
+} lpf_nz_args;
+int lpf_nz_links_fused(const lpf_nz_args* args, void* stream);
+
 /* Profiling hook: CTA 0 of later lpf_link_heads_tc launches writes clock64() stamps of its pipeline phases for
  * its first 8 tiles into device_buffer (int64 [8][16]); NULL disables. */
 int lpf_debug_heads_clocks(void* device_buffer);

@@ -1,0 +1,309 @@
+// Fused path for the links that selected at least one node, small-batch regime (citation2-shaped evaluation: ~1 %
+// of the links of a batch): one warp carries one link from its node sets to its score —
+//     Q = lin_l(X[a]) + lin_l(X[b])                                           (modules/layers.py:208-214)
+//     per selected pair: RPE MLP + its contraction, v = KV[u] + r, score, online segment softmax
+//                                                                             (models/link_transformer.py:182-211,
+//                                                                              modules/layers.py:193-224)
+//     + bias, LayerNorm, counts, pairwise_lin                                 (:340-386, :177)
+//     elementwise_lin(X[a]*X[b]), mlp_score on [el | pw], sigmoid             (models/other_models.py:125-138,173-179)
+// in fp32 FFMA with the vectors distributed over the lanes (channel c = lane + 32k) and every weight read as
+// coalesced 128-byte rows of its TRANSPOSE (W^T[k][n], L1/L2 resident).  It replaces ~14 launches of the batched
+// path (gather, 7 tensor-core contractions on a few thousand rows, 3 RPE launches, attention, LayerNorm, heads)
+// whose cost at this size is launch latency; the batched path remains for batches where most links are
+// non-empty (the plan picks by the fraction observed on the previous batch — both give the same numbers).
+#include "common.cuh"
+
+namespace lpf {
+
+struct NzParams {
+    const int64_t* links;
+    int64_t bs;
+    const int32_t* nz;
+    int64_t n_cap;
+    const int64_t* n_dev;
+    const float* X;
+    int64_t ldx;
+    const float* KV;
+    int64_t ld_kv;
+    const int32_t* node;
+    const float* pa;
+    const float* pb;
+    const int32_t* seg_start;
+    const int32_t* counts;
+    int64_t cap;
+    int mode, ntypes, cd;
+    const float* wlT;
+    const float* bl;
+    const float* rpe_w1[3];
+    const float* rpe_b1[3];
+    const float* rpe_g[3];
+    const float* rpe_b[3];
+    const float* rpe_mT[3];
+    const float* rpe_c[3];
+    const float* att;
+    const float* att_bias;
+    const float* pn_w;
+    const float* pn_b;
+    const float* p1T;
+    const float* pb1;
+    const float* pln_w;
+    const float* pln_b;
+    const float* p2T;
+    const float* pb2;
+    const float* wzT;
+    const float* off;
+    const float* w1T;
+    const float* b1;
+    const float* ln_g;
+    const float* ln_b;
+    const float* w23T;
+    const float* ws2;
+    const float* bs2;
+    float* prob;
+    int logits;
+};
+
+// y[j] += sum_c x[c] * WT[c][lane + 32 j]   for the KIN*32 lane-distributed input channels c = l + 32 kk
+template <int KIN, int KOUT>
+__device__ __forceinline__ void matvec(const float* __restrict__ WT, int ldw, const float (&x)[KIN], float (&y)[KOUT],
+                                       int lane) {
+#pragma unroll
+    for (int kk = 0; kk < KIN; ++kk) {
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) {
+            const float xv = __shfl_sync(kFull, x[kk], l);
+            const float* row = WT + (size_t)(l + 32 * kk) * ldw + lane;
+#pragma unroll
+            for (int j = 0; j < KOUT; ++j) y[j] = fmaf(xv, __ldg(row + 32 * j), y[j]);
+        }
+    }
+}
+
+template <int KC>
+__device__ __forceinline__ void layer_norm(float (&x)[KC], const float* __restrict__ g, const float* __restrict__ b,
+                                           int lane, bool relu) {
+    constexpr float inv = 1.0f / (32 * KC);
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) s += x[k];
+    const float mean = warp_sum(s) * inv;
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        const float dlt = x[k] - mean;
+        v = fmaf(dlt, dlt, v);
+    }
+    const float rstd = rsqrtf(warp_sum(v) * inv + 1e-5f);
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        const int c = lane + 32 * k;
+        const float y = fmaf((x[k] - mean) * rstd, __ldg(g + c), __ldg(b + c));
+        x[k] = relu ? fmaxf(y, 0.f) : y;
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) nz_fused_kernel(NzParams p) {
+    constexpr int KC = D / 32;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n = p.n_dev ? min(p.n_cap, *p.n_dev) : p.n_cap;
+    const int pd = D + p.cd;
+
+    for (int64_t j = warp; j < n; j += nwarps) {
+        const int64_t pos = __ldg(p.nz + j);
+        const int64_t a = __ldg(p.links + pos), b = __ldg(p.links + p.bs + pos);
+        float xsum[KC], xprod[KC], q[KC];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            const int c = lane + 32 * k;
+            const float xa = __ldg(p.X + a * p.ldx + c), xb = __ldg(p.X + b * p.ldx + c);
+            xsum[k] = xa + xb;
+            xprod[k] = xa * xb;
+            q[k] = 2.0f * __ldg(p.bl + c);
+        }
+        matvec<KC, KC>(p.wlT, D, xsum, q, lane);
+
+        // ---- attention over the link's pairs (online softmax), reference modules/layers.py:193-224
+        float att[KC], acc[KC];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            att[k] = __ldg(p.att + lane + 32 * k);
+            acc[k] = 0.f;
+        }
+        float mx = -INFINITY, den = 0.f;
+        int cnt[3] = {0, 0, 0};
+        for (int t = 0; t < p.ntypes; ++t) {
+            const int64_t s0 = t * p.cap + __ldg(p.seg_start + t * p.bs + pos);
+            cnt[t] = __ldg(p.counts + t * p.bs + pos);
+            const float* w1 = p.rpe_w1[t];
+            for (int64_t s = s0; s < s0 + cnt[t]; ++s) {
+                const int64_t u = __ldg(p.node + s);
+                const float pa = __ldg(p.pa + s), pb = __ldg(p.pb + s);
+                float z1[KC], z2[KC];
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    const int c = lane + 32 * k;
+                    const float wx = __ldg(w1 + 2 * c), wy = __ldg(w1 + 2 * c + 1), bb = __ldg(p.rpe_b1[t] + c);
+                    z1[k] = fmaf(wx, pa, fmaf(wy, pb, bb));
+                    z2[k] = fmaf(wx, pb, fmaf(wy, pa, bb));
+                }
+                layer_norm<KC>(z1, p.rpe_g[t], p.rpe_b[t], lane, true);
+                layer_norm<KC>(z2, p.rpe_g[t], p.rpe_b[t], lane, true);
+                float hs[KC], v[KC];
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    hs[k] = z1[k] + z2[k];
+                    v[k] = __ldg(p.rpe_c[t] + lane + 32 * k);
+                }
+                matvec<KC, KC>(p.rpe_mT[t], D, hs, v, lane);
+                float part = 0.f;
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    v[k] += __ldg(p.KV + u * p.ld_kv + lane + 32 * k);
+                    float x = v[k] * q[k];
+                    x = (x > 0.f) ? x : 0.2f * x;
+                    part = fmaf(att[k], x, part);
+                }
+                const float sc = warp_sum(part);
+                const float m_new = fmaxf(mx, sc);
+                const float scale = expf(mx - m_new);
+                const float w = expf(sc - m_new);
+                den = fmaf(den, scale, w);
+#pragma unroll
+                for (int k = 0; k < KC; ++k) acc[k] = fmaf(acc[k], scale, w * v[k]);
+                mx = m_new;
+            }
+        }
+        // out = LN(acc / (den + 1e-16) + bias), then the counts (models/link_transformer.py:340-386)
+        float f[KC];
+        {
+            const float inv = 1.0f / (den + 1e-16f);
+#pragma unroll
+            for (int k = 0; k < KC; ++k) f[k] = fmaf(acc[k], inv, __ldg(p.att_bias + lane + 32 * k));
+            layer_norm<KC>(f, p.pn_w, p.pn_b, lane, false);
+        }
+        float fx = 0.f;     // channel D + lane of the pairwise_lin input, lane < cd
+        if (p.mode == LPF_MODE_CN) {
+            if (lane == 0) fx = (float)cnt[0];
+        } else if (p.mode == LPF_MODE_1HOP) {
+            fx = lane == 0 ? (float)cnt[0] : lane == 1 ? (float)cnt[1] : lane == 2 ? (float)(cnt[0] + cnt[1]) : 0.f;
+        } else {
+            fx = lane == 0 ? (float)cnt[0] : lane == 1 ? (float)cnt[1] : lane == 2 ? (float)cnt[2]
+                 : lane == 3 ? (float)(cnt[0] + cnt[1]) : 0.f;
+        }
+
+        // ---- pairwise_lin: Linear(pd,pd) -> LayerNorm(pd) -> ReLU -> Linear(pd,d)
+        float hid[KC], hx = 0.f;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) hid[k] = __ldg(p.pb1 + lane + 32 * k);
+        if (lane < p.cd) hx = __ldg(p.pb1 + D + lane);
+        {
+            // main channels of the input
+#pragma unroll
+            for (int kk = 0; kk < KC; ++kk) {
+#pragma unroll 8
+                for (int l = 0; l < 32; ++l) {
+                    const float xv = __shfl_sync(kFull, f[kk], l);
+                    const float* row = p.p1T + (size_t)(l + 32 * kk) * pd;
+#pragma unroll
+                    for (int k = 0; k < KC; ++k) hid[k] = fmaf(xv, __ldg(row + lane + 32 * k), hid[k]);
+                    if (lane < p.cd) hx = fmaf(xv, __ldg(row + D + lane), hx);
+                }
+            }
+            for (int e = 0; e < p.cd; ++e) {       // the count channels
+                const float xv = __shfl_sync(kFull, fx, e);
+                const float* row = p.p1T + (size_t)(D + e) * pd;
+#pragma unroll
+                for (int k = 0; k < KC; ++k) hid[k] = fmaf(xv, __ldg(row + lane + 32 * k), hid[k]);
+                if (lane < p.cd) hx = fmaf(xv, __ldg(row + D + lane), hx);
+            }
+            // LayerNorm over the pd channels, ReLU
+            float s = (lane < p.cd) ? hx : 0.f;
+#pragma unroll
+            for (int k = 0; k < KC; ++k) s += hid[k];
+            const float mean = warp_sum(s) / (float)pd;
+            float vv = 0.f;
+            if (lane < p.cd) vv = (hx - mean) * (hx - mean);
+#pragma unroll
+            for (int k = 0; k < KC; ++k) vv = fmaf(hid[k] - mean, hid[k] - mean, vv);
+            const float rstd = rsqrtf(warp_sum(vv) / (float)pd + 1e-5f);
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                const int c = lane + 32 * k;
+                hid[k] = fmaxf(fmaf((hid[k] - mean) * rstd, __ldg(p.pln_w + c), __ldg(p.pln_b + c)), 0.f);
+            }
+            if (lane < p.cd) hx = fmaxf(fmaf((hx - mean) * rstd, __ldg(p.pln_w + D + lane), __ldg(p.pln_b + D + lane)), 0.f);
+        }
+        float pw[KC];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) pw[k] = __ldg(p.pb2 + lane + 32 * k);
+        matvec<KC, KC>(p.p2T, D, hid, pw, lane);
+        for (int e = 0; e < p.cd; ++e) {
+            const float xv = __shfl_sync(kFull, hx, e);
+            const float* row = p.p2T + (size_t)(D + e) * D;
+#pragma unroll
+            for (int k = 0; k < KC; ++k) pw[k] = fmaf(xv, __ldg(row + lane + 32 * k), pw[k]);
+        }
+
+        // ---- mlp_score's first layer: offset from the pairwise half + folded elementwise half
+        float z[2 * KC];
+#pragma unroll
+        for (int k = 0; k < 2 * KC; ++k) z[k] = __ldg(p.off + lane + 32 * k);
+        matvec<KC, 2 * KC>(p.wzT, 2 * D, pw, z, lane);
+        float h[KC];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) h[k] = __ldg(p.b1 + lane + 32 * k);
+        matvec<KC, KC>(p.w1T, D, xprod, h, lane);
+        layer_norm<KC>(h, p.ln_g, p.ln_b, lane, true);
+        matvec<KC, 2 * KC>(p.w23T, 2 * D, h, z, lane);
+        float part = 0.f;
+#pragma unroll
+        for (int k = 0; k < 2 * KC; ++k) part = fmaf(fmaxf(z[k], 0.f), __ldg(p.ws2 + lane + 32 * k), part);
+        const float logit = warp_sum(part) + __ldg(p.bs2);
+        if (lane == 0) p.prob[pos] = p.logits ? logit : 1.0f / (1.0f + expf(-logit));
+    }
+}
+
+}  // namespace lpf
+
+using namespace lpf;
+
+/* Pointer block of lpf_nz_links_fused, mirrored field by field by the ctypes Structure in _lib.py. */
+extern "C" int lpf_nz_links_fused(const lpf_nz_args* a, void* stream) {
+    LPF_REQUIRE(a, "NULL argument block");
+    LPF_REQUIRE(a->d == 32 || a->d == 64, "d must be 32 or 64");
+    LPF_REQUIRE(a->n_cap >= 0 && a->bs >= 0, "negative size");
+    if (a->n_cap == 0) return LPF_OK;
+    LPF_REQUIRE(a->mode == LPF_MODE_CN || a->mode == LPF_MODE_1HOP || a->mode == LPF_MODE_ALL, "bad mode");
+    NzParams p;
+    p.links = a->links; p.bs = a->bs; p.nz = a->nz; p.n_cap = a->n_cap; p.n_dev = a->n_dev;
+    p.X = a->X; p.ldx = a->ldx; p.KV = a->KV; p.ld_kv = a->ld_kv;
+    p.node = a->node; p.pa = a->src_ppr; p.pb = a->tgt_ppr; p.seg_start = a->seg_start; p.counts = a->counts;
+    p.cap = a->cap; p.mode = a->mode;
+    p.ntypes = a->mode == LPF_MODE_CN ? 1 : (a->mode == LPF_MODE_1HOP ? 2 : 3);
+    p.cd = a->mode == LPF_MODE_CN ? 1 : (a->mode == LPF_MODE_1HOP ? 3 : 4);
+    p.wlT = a->wlT; p.bl = a->bl;
+    for (int t = 0; t < 3; ++t) {
+        p.rpe_w1[t] = a->rpe_w1[t]; p.rpe_b1[t] = a->rpe_b1[t]; p.rpe_g[t] = a->rpe_ln_w[t]; p.rpe_b[t] = a->rpe_ln_b[t];
+        p.rpe_mT[t] = a->rpe_mT[t]; p.rpe_c[t] = a->rpe_c[t];
+        LPF_REQUIRE(t >= p.ntypes || (p.rpe_w1[t] && p.rpe_b1[t] && p.rpe_g[t] && p.rpe_b[t] && p.rpe_mT[t] && p.rpe_c[t]),
+                    "NULL RPE parameter");
+    }
+    p.att = a->att; p.att_bias = a->att_bias; p.pn_w = a->post_ln_w; p.pn_b = a->post_ln_b;
+    p.p1T = a->p1T; p.pb1 = a->pb1; p.pln_w = a->pln_w; p.pln_b = a->pln_b; p.p2T = a->p2T; p.pb2 = a->pb2;
+    p.wzT = a->wzT; p.off = a->off; p.w1T = a->w1T; p.b1 = a->b1; p.ln_g = a->ln_w; p.ln_b = a->ln_b;
+    p.w23T = a->w23T; p.ws2 = a->ws2; p.bs2 = a->bs2; p.prob = a->prob; p.logits = a->logits;
+    LPF_REQUIRE(p.links && p.nz && p.X && p.KV && p.seg_start && p.counts && p.wlT && p.bl && p.att && p.att_bias &&
+                    p.pn_w && p.pn_b && p.p1T && p.pb1 && p.pln_w && p.pln_b && p.p2T && p.pb2 && p.wzT && p.off &&
+                    p.w1T && p.b1 && p.ln_g && p.ln_b && p.w23T && p.ws2 && p.bs2 && p.prob,
+                "NULL argument");
+    int64_t blocks = (a->n_cap + 7) / 8;
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->d == 64) nz_fused_kernel<64><<<(unsigned)blocks, 256, 0, st>>>(p);
+    else nz_fused_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(p);
+    return check_launch("lpf_nz_links_fused");
+}

@@ -10,6 +10,8 @@ through the host-sized two-pass path (and the plan is rebuilt with larger pools)
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 
 from . import _lib
@@ -64,6 +66,29 @@ class ScorePlan:
         }
         self.th = (float(model.thresh_cn), float(model.thresh_1hop), float(model.thresh_non1hop))
         self.mode = MODE[model.mask]
+        # small-batch fused path for the non-empty links (lpf_nz_links_fused): transposed fp32 weights
+        T = lambda w: w.detach().float().t().contiguous()   # noqa: E731
+        self.keep = [T(att.lin_l.weight), T(pl.linears[0].weight), T(pl.linears[1].weight), T(consts["ws1_pw"]),
+                     T(model.elementwise_lin.linears[0].weight), T(consts["w23"])] + [T(m) for m, _ in derived["rpe"]]
+        a = _lib.NzArgs()
+        a.links, a.bs, a.nz, a.n_cap, a.n_dev = ptr(self.links), bs, ptr(self.nz), bs, self.hdr.data_ptr() + 3 * 8
+        a.X, a.ldx, a.KV, a.ld_kv = ptr(X_node), X_node.stride(0), ptr(kv), kv.stride(0)
+        a.node, a.src_ppr, a.tgt_ppr = ptr(self.node), ptr(self.pa), ptr(self.pb)
+        a.seg_start, a.counts, a.cap, a.d, a.mode = ptr(self.seg_start), ptr(self.counts), cap, d, self.mode
+        a.wlT, a.bl = ptr(self.keep[0]), ptr(self.w["bl"])
+        for t, (w1, b1, g, b, _, cvec) in enumerate(self.rpe):
+            a.rpe_w1[t], a.rpe_b1[t], a.rpe_ln_w[t], a.rpe_ln_b[t] = ptr(w1), ptr(b1), ptr(g), ptr(b)
+            a.rpe_mT[t], a.rpe_c[t] = ptr(self.keep[6 + t]), ptr(cvec)
+        a.att, a.att_bias, a.post_ln_w, a.post_ln_b = ptr(self.w["att"]), ptr(self.w["abias"]), ptr(self.w["pn_w"]), ptr(self.w["pn_b"])
+        a.p1T, a.pb1, a.pln_w, a.pln_b = ptr(self.keep[1]), ptr(self.w["pb1"]), ptr(self.w["pln_w"]), ptr(self.w["pln_b"])
+        a.p2T, a.pb2, a.wzT, a.off = ptr(self.keep[2]), ptr(self.w["pb2"]), ptr(self.keep[3]), ptr(consts["off"])
+        a.w1T, a.b1, a.ln_w, a.ln_b = ptr(self.keep[4]), ptr(consts["b1"]), ptr(consts["ln_w"]), ptr(consts["ln_b"])
+        a.w23T, a.ws2, a.bs2, a.prob, a.logits = ptr(self.keep[5]), ptr(consts["ws2"]), ptr(consts["bs2"]), ptr(self.prob), int(self.logits)
+        self.nz_args = a
+        self.fused_ok = H == 1 and HC == d and d in (32, 64)
+        self.nz_mode = "batched"        # switched to "fused" when the observed share of non-empty links is small
+        self.graphs = {}
+        self.fused_allowed = True
         self.graph = None
         self.use_graph = use_graph
         self.runs = 0
@@ -95,6 +120,10 @@ class ScorePlan:
              ptr(self.ppr.col), ptr(self.ppr.val), *self.th, self.mode, self.algo, cap, ptr(self.counts),
              ptr(self.seg_start), ptr(self.nz), hp, ptr(self.node), ptr(self.pa), ptr(self.pb), ptr(self.ws), st,
              meta=(bs,))
+        if self.nz_mode == "fused":
+            # few non-empty links: one warp per link, everything from node sets to score in one launch
+            call("lpf_nz_links_fused", C.byref(self.nz_args), st, meta=(bs,))
+            return
         # RPE hidden vectors and their contraction, per type pool
         for t, (w1, b1, g, b, mp, cvec) in enumerate(self.rpe):
             call("lpf_rpe_hidden", ptr(self.pa), ptr(self.pb), t * cap, cap, ptr(w1), ptr(b1), ptr(g), ptr(b), d,
@@ -121,19 +150,24 @@ class ScorePlan:
         self.links.copy_(links, non_blocking=True)
         tracing = _lib.TRACE is not None
         if self.use_graph and not tracing and self.runs >= 1:
-            if self.graph is None:
+            g = self.graphs.get(self.nz_mode)
+            if g is None:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._launch()
-                self.graph = g
-            self.graph.replay()
+                self.graphs[self.nz_mode] = g
+            self.graph = g
+            g.replay()
             if _lib.COUNTERS is not None:
                 _lib.COUNTERS["graph_launches"] = _lib.COUNTERS.get("graph_launches", 0) + 1
         else:
             self._launch()
         self.runs += 1
-        overflow = bool(self.hdr[4].item())          # the batch's only host round trip
-        return self.prob, overflow
+        h = self.hdr.tolist()                        # the batch's only host round trip
+        # regime for the NEXT batch (either path is exact; this only picks the cheaper one)
+        if self.fused_ok and self.fused_allowed:
+            self.nz_mode = "fused" if h[3] * 16 < self.bs else "batched"
+        return self.prob, bool(h[4])
 
     def stats(self):
         h = self.hdr.tolist()
