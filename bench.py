@@ -217,6 +217,8 @@ def run_b200(args):
     _lib.load()
 
     g, negs, gen_s = make_workload(args, rank)
+    # started here so that nvidia-smi's own start-up is long over when the timed region begins
+    sampler = ClockSampler(local_rank) if (rank == 0 and not args.no_sampler) else None
     cfg = g.cfg
     targs = S.train_args_of(cfg)
     torch.manual_seed(args.seed)
@@ -248,13 +250,11 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput (`value`): K untimed-instrumentation-free steps between two events
-    sampler = ClockSampler(local_rank) if (rank == 0 and not args.no_sampler) else None
     for s in range(args.warmup):
         model.score_links(dev_links[s], X, score)
     barrier()
     if sampler:
-        time.sleep(0.3)          # let nvidia-smi finish starting up before the timed region
-        sampler.mark()
+        sampler.mark()           # (started long ago; no idle gap here — the GPU would drop its clocks)
     _lib.COUNTERS = {}
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()

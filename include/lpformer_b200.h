@@ -252,6 +252,8 @@ typedef struct lpf_nz_args {
     const float* KV; int64_t ld_kv;
     const int32_t* node; const float* src_ppr; const float* tgt_ppr;
     const int32_t* seg_start; const int32_t* counts; int64_t cap;
+    const int64_t* header;   /* one-pass selection header: [0..2] pairs per type */
+    float* R;                /* scratch [3*cap, d]: RPE contraction per pair */
     int32_t d; int32_t mode;
     const float* wlT; const float* bl;
     const float* rpe_w1[3]; const float* rpe_b1[3]; const float* rpe_ln_w[3]; const float* rpe_ln_b[3];

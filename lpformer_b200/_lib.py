@@ -57,7 +57,7 @@ class NzArgs(C.Structure):
     """lpf_nz_args of include/lpformer_b200.h (field order and types must match)."""
     _fields_ = ([("links", _p), ("bs", _i64), ("nz", _p), ("n_cap", _i64), ("n_dev", _p), ("X", _p), ("ldx", _i64),
                  ("KV", _p), ("ld_kv", _i64), ("node", _p), ("src_ppr", _p), ("tgt_ppr", _p), ("seg_start", _p),
-                 ("counts", _p), ("cap", _i64), ("d", _i32), ("mode", _i32), ("wlT", _p), ("bl", _p)] +
+                 ("counts", _p), ("cap", _i64), ("header", _p), ("R", _p), ("d", _i32), ("mode", _i32), ("wlT", _p), ("bl", _p)] +
                 [(n, _p * 3) for n in ("rpe_w1", "rpe_b1", "rpe_ln_w", "rpe_ln_b", "rpe_mT", "rpe_c")] +
                 [(n, _p) for n in ("att", "att_bias", "post_ln_w", "post_ln_b", "p1T", "pb1", "pln_w", "pln_b", "p2T",
                                    "pb2", "wzT", "off", "w1T", "b1", "ln_w", "ln_b", "w23T", "ws2", "bs2", "prob")] +
@@ -93,7 +93,7 @@ def load():
 # kernels launched per entry point (for bench.py's gpu_launches and per-kernel CUDA-event timing)
 KERNEL_LAUNCHES = {"lpf_select_count": 3, "lpf_scan_counts": 2, "lpf_select_fill": 2, "lpf_rpe_hidden": 1,
                    "lpf_gemm": 1, "lpf_gemm_tc": 1, "lpf_pack_weight": 1, "lpf_layernorm_act": 1, "lpf_gather_links": 1, "lpf_attend_fused": 1,
-                   "lpf_gcn_spmm": 1, "lpf_nz_links_fused": 1, "lpf_select_compact": 2, "lpf_select_onepass": 4, "lpf_scatter_rows": 2, "lpf_link_heads_tc": 1}
+                   "lpf_gcn_spmm": 1, "lpf_nz_links_fused": 2, "lpf_select_compact": 2, "lpf_select_onepass": 4, "lpf_scatter_rows": 2, "lpf_link_heads_tc": 1}
 
 
 class Trace:

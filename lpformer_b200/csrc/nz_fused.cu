@@ -6,7 +6,8 @@
 //                                                                              modules/layers.py:193-224)
 //     + bias, LayerNorm, counts, pairwise_lin                                 (:340-386, :177)
 //     elementwise_lin(X[a]*X[b]), mlp_score on [el | pw], sigmoid             (models/other_models.py:125-138,173-179)
-// in fp32 FFMA with the vectors distributed over the lanes (channel c = lane + 32k) and every weight read as
+// in two launches (one warp per selected pair for the RPE contraction, then one warp per link), in fp32 FFMA
+// with the vectors distributed over the lanes (channel c = lane + 32k) and every weight read as
 // coalesced 128-byte rows of its TRANSPOSE (W^T[k][n], L1/L2 resident).  It replaces ~14 launches of the batched
 // path (gather, 7 tensor-core contractions on a few thousand rows, 3 RPE launches, attention, LayerNorm, heads)
 // whose cost at this size is launch latency; the batched path remains for batches where most links are
@@ -31,6 +32,8 @@ struct NzParams {
     const int32_t* seg_start;
     const int32_t* counts;
     int64_t cap;
+    const int64_t* hdr;   // [0..2] pairs per type (device side)
+    float* R;             // [3*cap, D] RPE contraction per pair (written by nz_pairs_kernel)
     int mode, ntypes, cd;
     const float* wlT;
     const float* bl;
@@ -102,6 +105,45 @@ __device__ __forceinline__ void layer_norm(float (&x)[KC], const float* __restri
     }
 }
 
+// Stage 1: one warp per selected pair — RPE MLP hidden vector and its folded contraction,
+//   R[s] = (h(pa,pb) + h(pb,pa)) (W_pe W2_t)^T + c_t          (models/link_transformer.py:182-211)
+// so that links with hundreds of pairs do not serialise that work behind one warp in stage 2.
+template <int D>
+__global__ void __launch_bounds__(256) nz_pairs_kernel(NzParams p) {
+    constexpr int KC = D / 32;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int t = 0; t < p.ntypes; ++t) {
+        const int64_t rows = min(p.cap, p.hdr[t]);
+        const float* w1 = p.rpe_w1[t];
+        for (int64_t r = warp; r < rows; r += nwarps) {
+            const int64_t s = t * p.cap + r;
+            const float pa = __ldg(p.pa + s), pb = __ldg(p.pb + s);
+            float z1[KC], z2[KC];
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                const int c = lane + 32 * k;
+                const float wx = __ldg(w1 + 2 * c), wy = __ldg(w1 + 2 * c + 1), bb = __ldg(p.rpe_b1[t] + c);
+                z1[k] = fmaf(wx, pa, fmaf(wy, pb, bb));
+                z2[k] = fmaf(wx, pb, fmaf(wy, pa, bb));
+            }
+            layer_norm<KC>(z1, p.rpe_g[t], p.rpe_b[t], lane, true);
+            layer_norm<KC>(z2, p.rpe_g[t], p.rpe_b[t], lane, true);
+            float hs[KC], v[KC];
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                hs[k] = z1[k] + z2[k];
+                v[k] = __ldg(p.rpe_c[t] + lane + 32 * k);
+            }
+            matvec<KC, KC>(p.rpe_mT[t], D, hs, v, lane);
+#pragma unroll
+            for (int k = 0; k < KC; ++k) p.R[s * D + lane + 32 * k] = v[k];
+        }
+    }
+}
+
+// Stage 2: one warp per non-empty link.
 template <int D>
 __global__ void __launch_bounds__(256) nz_fused_kernel(NzParams p) {
     constexpr int KC = D / 32;
@@ -137,31 +179,13 @@ __global__ void __launch_bounds__(256) nz_fused_kernel(NzParams p) {
         for (int t = 0; t < p.ntypes; ++t) {
             const int64_t s0 = t * p.cap + __ldg(p.seg_start + t * p.bs + pos);
             cnt[t] = __ldg(p.counts + t * p.bs + pos);
-            const float* w1 = p.rpe_w1[t];
             for (int64_t s = s0; s < s0 + cnt[t]; ++s) {
                 const int64_t u = __ldg(p.node + s);
-                const float pa = __ldg(p.pa + s), pb = __ldg(p.pb + s);
-                float z1[KC], z2[KC];
-#pragma unroll
-                for (int k = 0; k < KC; ++k) {
-                    const int c = lane + 32 * k;
-                    const float wx = __ldg(w1 + 2 * c), wy = __ldg(w1 + 2 * c + 1), bb = __ldg(p.rpe_b1[t] + c);
-                    z1[k] = fmaf(wx, pa, fmaf(wy, pb, bb));
-                    z2[k] = fmaf(wx, pb, fmaf(wy, pa, bb));
-                }
-                layer_norm<KC>(z1, p.rpe_g[t], p.rpe_b[t], lane, true);
-                layer_norm<KC>(z2, p.rpe_g[t], p.rpe_b[t], lane, true);
-                float hs[KC], v[KC];
-#pragma unroll
-                for (int k = 0; k < KC; ++k) {
-                    hs[k] = z1[k] + z2[k];
-                    v[k] = __ldg(p.rpe_c[t] + lane + 32 * k);
-                }
-                matvec<KC, KC>(p.rpe_mT[t], D, hs, v, lane);
+                float v[KC];
                 float part = 0.f;
 #pragma unroll
                 for (int k = 0; k < KC; ++k) {
-                    v[k] += __ldg(p.KV + u * p.ld_kv + lane + 32 * k);
+                    v[k] = __ldg(p.KV + u * p.ld_kv + lane + 32 * k) + p.R[s * D + lane + 32 * k];
                     float x = v[k] * q[k];
                     x = (x > 0.f) ? x : 0.2f * x;
                     part = fmaf(att[k], x, part);
@@ -281,7 +305,7 @@ extern "C" int lpf_nz_links_fused(const lpf_nz_args* a, void* stream) {
     p.links = a->links; p.bs = a->bs; p.nz = a->nz; p.n_cap = a->n_cap; p.n_dev = a->n_dev;
     p.X = a->X; p.ldx = a->ldx; p.KV = a->KV; p.ld_kv = a->ld_kv;
     p.node = a->node; p.pa = a->src_ppr; p.pb = a->tgt_ppr; p.seg_start = a->seg_start; p.counts = a->counts;
-    p.cap = a->cap; p.mode = a->mode;
+    p.cap = a->cap; p.mode = a->mode; p.hdr = a->header; p.R = a->R;
     p.ntypes = a->mode == LPF_MODE_CN ? 1 : (a->mode == LPF_MODE_1HOP ? 2 : 3);
     p.cd = a->mode == LPF_MODE_CN ? 1 : (a->mode == LPF_MODE_1HOP ? 3 : 4);
     p.wlT = a->wlT; p.bl = a->bl;
@@ -295,6 +319,7 @@ extern "C" int lpf_nz_links_fused(const lpf_nz_args* a, void* stream) {
     p.p1T = a->p1T; p.pb1 = a->pb1; p.pln_w = a->pln_w; p.pln_b = a->pln_b; p.p2T = a->p2T; p.pb2 = a->pb2;
     p.wzT = a->wzT; p.off = a->off; p.w1T = a->w1T; p.b1 = a->b1; p.ln_g = a->ln_w; p.ln_b = a->ln_b;
     p.w23T = a->w23T; p.ws2 = a->ws2; p.bs2 = a->bs2; p.prob = a->prob; p.logits = a->logits;
+    LPF_REQUIRE(p.hdr && (p.cap == 0 || p.R), "NULL header / R");
     LPF_REQUIRE(p.links && p.nz && p.X && p.KV && p.seg_start && p.counts && p.wlT && p.bl && p.att && p.att_bias &&
                     p.pn_w && p.pn_b && p.p1T && p.pb1 && p.pln_w && p.pln_b && p.p2T && p.pb2 && p.wzT && p.off &&
                     p.w1T && p.b1 && p.ln_g && p.ln_b && p.w23T && p.ws2 && p.bs2 && p.prob,
@@ -303,7 +328,15 @@ extern "C" int lpf_nz_links_fused(const lpf_nz_args* a, void* stream) {
     const int64_t cap = (int64_t)kNumSMs * 8;
     if (blocks > cap) blocks = cap;
     cudaStream_t st = (cudaStream_t)stream;
-    if (a->d == 64) nz_fused_kernel<64><<<(unsigned)blocks, 256, 0, st>>>(p);
-    else nz_fused_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(p);
+    int64_t pblocks = (3 * a->cap + 7) / 8;
+    if (pblocks > cap) pblocks = cap;
+    if (pblocks < 1) pblocks = 1;
+    if (a->d == 64) {
+        nz_pairs_kernel<64><<<(unsigned)pblocks, 256, 0, st>>>(p);
+        nz_fused_kernel<64><<<(unsigned)blocks, 256, 0, st>>>(p);
+    } else {
+        nz_pairs_kernel<32><<<(unsigned)pblocks, 256, 0, st>>>(p);
+        nz_fused_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(p);
+    }
     return check_launch("lpf_nz_links_fused");
 }

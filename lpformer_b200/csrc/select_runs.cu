@@ -8,10 +8,14 @@
 //     instead of a ~log2(deg a)-step binary search through L1/L2;
 //   * P(a), the source's PPR row (cols + values), is copied to shared memory (<= 128 entries) with a small hash
 //     from node id to its position.
-// Inside a run ONE LANE owns ONE LINK: 32 links per warp step, so a warp keeps 32 independent pointer fetches and
-// then 32 independent row reads in flight (the kernel is DRAM-latency bound, not instruction bound), and only
-// the target rows A(b), P(b) are read from HBM.  Links whose target rows exceed 32 entries, and the rare links
-// that select anything (which need the ordered write pass), are then handled one at a time by the whole warp.
+// The kernel is DRAM-latency bound, so it is organised around memory-level parallelism, in three phases per run:
+//   A  ONE LANE owns ONE LINK, 32 links per warp step: 32 independent pointer fetches, then the 32 target rows
+//      A(b) (and P(b)) are brought into shared memory by 32 back-to-back coalesced warp loads (one DRAM round
+//      trip for all of them) and each lane probes its own row there;
+//   B  links whose target rows exceed 32 entries are queued and walked element-parallel by the whole CTA (thread
+//      e takes element e of the concatenated rows), counts by shared-memory atomics;
+//   C  the rare links that selected anything get their ordered write pass, one warp per link.
+// Only the target rows are read from HBM; the source's tables are touched once per run.
 // Everything else (count -> allocate -> write into the per-type pools, the deferral of heavy links to the
 // warp / CTA-wide kernel) is the one-pass protocol of select_fast.cu, and a chunk that is not run-shaped falls
 // back to its generic group walk.  The selected sets, their order inside a link and the fp32 values are
@@ -154,64 +158,69 @@ __device__ __forceinline__ void onepass_link(const SelectParams2& p, const RunCt
     else walk_link<G, true>(p, r, i, lane, s_cn, p.cap + s_1h, 2 * p.cap + s_n1, c_cn, c_1h, c_n1);
 }
 
-// Lane-per-link counting of a hashed run: this lane's link has target rows (Ab, nb) / (Pbc, Pbv, npb), both at most
-// kLaneRow long.  Loop bounds are warp-uniform (maxima over the lanes) so the warp stays converged.
-__device__ __forceinline__ void count_link_lane(const SelectParams2& p, const RunCtx& h, const int32_t* Ab, int nb,
-                                                const int32_t* Pbc, const float* Pbv, int npb, int& c_cn, int& c_1h,
-                                                int& c_n1) {
-    const bool want_pi = p.mode != LPF_MODE_CN;
-    const bool want_n1 = p.mode == LPF_MODE_ALL;
-    const float th_pre = want_n1 ? fminf(p.th_1hop, p.th_non1hop) : p.th_1hop;
-    c_cn = c_1h = c_n1 = 0;
-    const int rounds = __reduce_max_sync(kFull, nb);
-#pragma unroll 4
-    for (int k = 0; k < rounds; ++k) {
-        if (k < nb) {
-            const int32_t u = __ldg(Ab + k);
-            bool hit = hash_contains(h.tab, h.mask, h.shift, u);
-            if (hit && p.th_cn > 0.0f) {
-                float qa, qb = 0.f;
-                smem_ppr_lookup(h, u, qa);
-                const int t = lower_bound_from(Pbc, 0, npb, u);
-                if (t < npb && __ldg(Pbc + t) == u) qb = quantise(__ldg(Pbv + t));
-                hit = qa >= p.th_cn && qb >= p.th_cn;
-            }
-            c_cn += hit ? 1 : 0;
-        }
+// ---------------------------------------------------------------------------------------------------------
+// Shared-memory layout of the kernel (dynamic): see RunSmem.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kStageStride = kLaneRow + 1;          // padded: lane i reads stage[i][k] without bank conflicts
+constexpr int kQueueCap = kRunChunk;
+
+struct RunSmem {
+    int32_t tab[kHashSlots];
+    int32_t pac[kMaxPprRow];
+    float pav[kMaxPprRow];
+    int32_t ppos[kPprHashSlots];
+    int32_t stage[kRunThreads / 32][32 * kStageStride];   // per warp: the 32 links' target rows
+    // links of the chunk whose target rows exceed kLaneRow: walked element-parallel by the whole CTA
+    int64_t q_b0[kQueueCap], q_pb0[kQueueCap];
+    int32_t q_t[kQueueCap], q_nb[kQueueCap], q_npb[kQueueCap];
+    int32_t q_off[kQueueCap + 1];                          // prefix sums of the rows being walked
+    int32_t q_cnt[3][kQueueCap];
+    // links that selected something: ordered write pass, one warp per link
+    int64_t w_b0[kQueueCap], w_pb0[kQueueCap];
+    int32_t w_t[kQueueCap], w_nb[kQueueCap], w_npb[kQueueCap], w_seg[3][kQueueCap];
+    int32_t run_start[kMaxRuns + 1];
+    int32_t warp_tot[kRunThreads / 32];
+    int n_runs, n_slow, n_write, next_write;
+};
+
+// exclusive prefix sums of q_val[0..n) into q_off[0..n] (n <= kQueueCap = blockDim), whole CTA
+__device__ __forceinline__ void cta_prefix(RunSmem& sm, const int32_t* q_val, int n) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int v = tid < n ? q_val[tid] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += t;
     }
-    if (want_pi) {
-        const int prounds = __reduce_max_sync(kFull, npb);
-#pragma unroll 2
-        for (int k = 0; k < prounds; ++k) {
-            if (k < npb) {
-                const int32_t u = __ldg(Pbc + k);
-                float qa;
-                if (smem_ppr_lookup(h, u, qa)) {
-                    const float qb = quantise(__ldg(Pbv + k));
-                    if (qa >= th_pre && qb >= th_pre) {
-                        const bool in_a = hash_contains(h.tab, h.mask, h.shift, u);
-                        const int t = lower_bound_from(Ab, 0, nb, u);
-                        const bool in_b = t < nb && __ldg(Ab + t) == u;
-                        if ((in_a != in_b) && qa >= p.th_1hop && qb >= p.th_1hop) ++c_1h;
-                        if (want_n1 && !in_a && !in_b && qa >= p.th_non1hop && qb >= p.th_non1hop) ++c_n1;
-                    }
-                }
-            }
-        }
+    if (lane == 31) sm.warp_tot[warp] = inc;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; ++w) base += sm.warp_tot[w];
+    if (tid < n) sm.q_off[tid] = base + inc - v;
+    if (tid == n - 1 || (n == 0 && tid == 0)) sm.q_off[n] = (n == 0) ? 0 : base + inc;
+    __syncthreads();
+}
+
+// queue entry that owns flattened element e: largest q with q_off[q] <= e
+__device__ __forceinline__ int owner_of(const int32_t* off, int n, int e) {
+    int lo = 0, hi = n;           // invariant: off[lo] <= e < off[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (off[mid] <= e) lo = mid; else hi = mid;
     }
+    return lo;
 }
 
 __global__ void __launch_bounds__(kRunThreads) select_onepass_runs_kernel(SelectParams2 p) {
-    __shared__ int32_t tab[kHashSlots];
-    __shared__ int32_t s_pac[kMaxPprRow];
-    __shared__ float s_pav[kMaxPprRow];
-    __shared__ int32_t s_ppos[kPprHashSlots];
-    __shared__ int run_start[kMaxRuns + 1];
-    __shared__ int n_runs_s;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    RunSmem& sm = *reinterpret_cast<RunSmem*>(smem_raw);
 
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int group = tid >> 3;                    // 32 groups of 8 lanes
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int group = tid >> 3;                    // 32 groups of 8 lanes (generic fallback)
     const bool want_pi = p.mode != LPF_MODE_CN;
+    const bool want_n1 = p.mode == LPF_MODE_ALL;
+    const float th_pre = want_n1 ? fminf(p.th_1hop, p.th_non1hop) : p.th_1hop;
     const int64_t nchunks = (p.bs + kRunChunk - 1) / kRunChunk;
 
     for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
@@ -221,14 +230,14 @@ __global__ void __launch_bounds__(kRunThreads) select_onepass_runs_kernel(Select
         const int64_t a_me = (tid < len) ? __ldg(p.links + i0 + tid) : -1;
         const int64_t a_prev = (tid > 0 && tid < len) ? __ldg(p.links + i0 + tid - 1) : -2;
         const bool boundary = tid < len && (tid == 0 || a_me != a_prev);
-        if (tid == 0) n_runs_s = 0;
+        if (tid == 0) sm.n_runs = 0;
         __syncthreads();
         if (boundary) {
-            const int k = atomicAdd(&n_runs_s, 1);
-            if (k < kMaxRuns) run_start[k] = tid;
+            const int k = atomicAdd(&sm.n_runs, 1);
+            if (k < kMaxRuns) sm.run_start[k] = tid;
         }
         __syncthreads();
-        const int n_runs = n_runs_s;
+        const int n_runs = sm.n_runs;
         if (n_runs > kMaxRuns) {
             // not run-shaped: generic one-pass walk, 8 links per group
             for (int t = group; t < len; t += kRunThreads / 8) {
@@ -245,106 +254,218 @@ __global__ void __launch_bounds__(kRunThreads) select_onepass_runs_kernel(Select
         }
         if (tid == 0) {      // sort the (at most kMaxRuns) boundaries, close the list
             for (int x = 1; x < n_runs; ++x)
-                for (int y = x; y > 0 && run_start[y] < run_start[y - 1]; --y) {
-                    const int tmp = run_start[y]; run_start[y] = run_start[y - 1]; run_start[y - 1] = tmp;
+                for (int y = x; y > 0 && sm.run_start[y] < sm.run_start[y - 1]; --y) {
+                    const int tmp = sm.run_start[y]; sm.run_start[y] = sm.run_start[y - 1]; sm.run_start[y - 1] = tmp;
                 }
-            run_start[n_runs] = len;
+            sm.run_start[n_runs] = len;
         }
         __syncthreads();
         for (int rn = 0; rn < n_runs; ++rn) {
-            const int t0 = run_start[rn], t1 = run_start[rn + 1];
+            const int t0 = sm.run_start[rn], t1 = sm.run_start[rn + 1];
             const int64_t a = __ldg(p.links + i0 + t0);
             const int64_t a0 = __ldg(p.adj_rowptr + a), pa0 = __ldg(p.ppr_rowptr + a);
             const int na = (int)(__ldg(p.adj_rowptr + a + 1) - a0), npa = (int)(__ldg(p.ppr_rowptr + a + 1) - pa0);
             const bool hashed = (t1 - t0) >= 16 && na <= kMaxHashRow && npa <= kMaxPprRow;
-            RunCtx h;
-            if (hashed) {
-                // table size: power of two >= 2*na (>= 64), so short rows cost little to clear
-                int lg = 6;
-                while ((1 << lg) < 2 * na) ++lg;
-                const int size = 1 << lg;
-                h.tab = tab; h.mask = (uint32_t)(size - 1); h.shift = 32 - lg;
-                h.pac = s_pac; h.pav = s_pav; h.ppos = s_ppos; h.npa = npa;
-                for (int s = tid; s < size; s += kRunThreads) tab[s] = -1;
-                for (int s = tid; s < kPprHashSlots; s += kRunThreads) s_ppos[s] = -1;
-                for (int s = tid; s < npa; s += kRunThreads) {
-                    s_pac[s] = __ldg(p.ppr_col + pa0 + s);
-                    s_pav[s] = __ldg(p.ppr_val + pa0 + s);
-                }
-                __syncthreads();
-                for (int s = tid; s < na; s += kRunThreads) {
-                    const int32_t u = __ldg(p.adj_col + a0 + s);
-                    uint32_t slot = hash_slot(u, h.shift);
-                    while (atomicCAS(&tab[slot], -1, u) != -1) slot = (slot + 1) & h.mask;
-                }
-                for (int s = tid; s < npa; s += kRunThreads) {
-                    uint32_t slot = hash_slot(s_pac[s], 32 - 8);
-                    while (atomicCAS(&s_ppos[slot], -1, s) != -1) slot = (slot + 1) & (kPprHashSlots - 1);
-                }
-                __syncthreads();
-                // ---- lane-per-link: 32 links per warp step
-                const int warp = tid >> 5;
-                for (int base = t0 + warp * 32; base < t1; base += kRunThreads) {
-                    const int t = base + lane;
-                    const bool valid = t < t1;
+            if (!hashed) {
+                // short run, or a source row too long for shared memory: generic group walk
+                for (int t = t0 + group; t < t1; t += kRunThreads / 8) {
                     const int64_t i = i0 + t;
-                    int64_t b0 = 0, pb0 = 0;
-                    int nb = 0, npb = 0;
-                    if (valid) {
-                        const int64_t b = __ldg(p.links + p.bs + i);
-                        b0 = __ldg(p.adj_rowptr + b);
-                        nb = (int)(__ldg(p.adj_rowptr + b + 1) - b0);
-                        pb0 = __ldg(p.ppr_rowptr + b);
-                        npb = (int)(__ldg(p.ppr_rowptr + b + 1) - pb0);
+                    const LinkRows r = load_rows(p, i);
+                    if (is_heavy(r, want_pi, 8)) {
+                        if ((lane & 7) == 0) p.heavy[4 + atomicAdd(p.heavy, 1)] = (int32_t)i;
+                        continue;
                     }
-                    const bool slow = valid && (nb > kLaneRow || npb > kLaneRow);
-                    int c_cn, c_1h, c_n1;
-                    count_link_lane(p, h, p.adj_col + b0, slow ? 0 : nb, p.ppr_col + pb0, p.ppr_val + pb0, slow ? 0 : npb,
-                                    c_cn, c_1h, c_n1);
-                    int64_t s_cn = 0, s_1h = 0, s_n1 = 0;
-                    bool need_write = false;
-                    if (valid && !slow)
-                        need_write = alloc_segments(p, i, c_cn, c_1h, c_n1, s_cn, s_1h, s_n1) && (c_cn + c_1h + c_n1 > 0);
-                    // ---- warp-cooperative tail: ordered write of the few non-empty links, and the long target rows
-                    unsigned todo = __ballot_sync(kFull, need_write || slow);
-                    while (todo) {
-                        const int src = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        LinkRows r;
-                        r.na = na; r.npa = npa;
-                        r.Aa = p.adj_col + a0; r.Pac = p.ppr_col + pa0; r.Pav = p.ppr_val + pa0;
-                        const int64_t b0s = __shfl_sync(kFull, b0, src), pb0s = __shfl_sync(kFull, pb0, src);
-                        r.nb = __shfl_sync(kFull, nb, src);
-                        r.npb = __shfl_sync(kFull, npb, src);
-                        r.Ab = p.adj_col + b0s; r.Pbc = p.ppr_col + pb0s; r.Pbv = p.ppr_val + pb0s;
-                        const int64_t is = i0 + base + src;
-                        const bool is_slow = __shfl_sync(kFull, (int)slow, src) != 0;
-                        if (!is_slow) {
-                            const int64_t w_cn = __shfl_sync(kFull, s_cn, src), w_1h = __shfl_sync(kFull, s_1h, src);
-                            const int64_t w_n1 = __shfl_sync(kFull, s_n1, src);
-                            int d0, d1, d2;
-                            walk_link_hashed<32, true>(p, h, r, is, lane, w_cn, p.cap + w_1h, 2 * p.cap + w_n1, d0, d1, d2);
-                        } else if (r.nb <= kMaxTargetRow && r.npb <= kMaxTargetRow) {
-                            onepass_link<32>(p, &h, r, is, lane);
-                        } else if (is_heavy(r, want_pi, 8)) {
-                            if (lane == 0) p.heavy[4 + atomicAdd(p.heavy, 1)] = (int32_t)is;
-                        } else {
-                            onepass_link<32>(p, nullptr, r, is, lane);
-                        }
-                    }
+                    onepass_link<8>(p, nullptr, r, i, lane);
                 }
                 __syncthreads();
                 continue;
             }
-            // ---- run without a hash (short run, or a source row too long for shared memory): generic group walk
-            for (int t = t0 + group; t < t1; t += kRunThreads / 8) {
+            // ---- stage the source: hash set of A(a), P(a) with its position hash
+            RunCtx h;
+            int lg = 6;      // table size: power of two >= 2*na (>= 64), so short rows cost little to clear
+            while ((1 << lg) < 2 * na) ++lg;
+            const int size = 1 << lg;
+            h.tab = sm.tab; h.mask = (uint32_t)(size - 1); h.shift = 32 - lg;
+            h.pac = sm.pac; h.pav = sm.pav; h.ppos = sm.ppos; h.npa = npa;
+            for (int s = tid; s < size; s += kRunThreads) sm.tab[s] = -1;
+            for (int s = tid; s < kPprHashSlots; s += kRunThreads) sm.ppos[s] = -1;
+            for (int s = tid; s < npa; s += kRunThreads) {
+                sm.pac[s] = __ldg(p.ppr_col + pa0 + s);
+                sm.pav[s] = __ldg(p.ppr_val + pa0 + s);
+            }
+            if (tid == 0) sm.n_slow = sm.n_write = sm.next_write = 0;
+            __syncthreads();
+            for (int s = tid; s < na; s += kRunThreads) {
+                const int32_t u = __ldg(p.adj_col + a0 + s);
+                uint32_t slot = hash_slot(u, h.shift);
+                while (atomicCAS(&sm.tab[slot], -1, u) != -1) slot = (slot + 1) & h.mask;
+            }
+            for (int s = tid; s < npa; s += kRunThreads) {
+                uint32_t slot = hash_slot(sm.pac[s], 32 - 8);
+                while (atomicCAS(&sm.ppos[slot], -1, s) != -1) slot = (slot + 1) & (kPprHashSlots - 1);
+            }
+            __syncthreads();
+
+            // ---- phase A: lane-per-link, 32 links per warp step; every target row of the 32 links is fetched by
+            // one coalesced warp-wide load per link, all 32 issued back to back (one DRAM round trip), then each
+            // lane probes its own link's row out of shared memory
+            int32_t* stage = sm.stage[warp];
+            for (int base = t0 + warp * 32; base < t1; base += kRunThreads) {
+                const int t = base + lane;
+                const bool valid = t < t1;
                 const int64_t i = i0 + t;
-                const LinkRows r = load_rows(p, i);
-                if (is_heavy(r, want_pi, 8)) {
-                    if ((lane & 7) == 0) p.heavy[4 + atomicAdd(p.heavy, 1)] = (int32_t)i;
-                    continue;
+                int64_t b0 = 0, pb0 = 0;
+                int nb = 0, npb = 0;
+                if (valid) {
+                    const int64_t b = __ldg(p.links + p.bs + i);
+                    b0 = __ldg(p.adj_rowptr + b);
+                    nb = (int)(__ldg(p.adj_rowptr + b + 1) - b0);
+                    pb0 = __ldg(p.ppr_rowptr + b);
+                    npb = (int)(__ldg(p.ppr_rowptr + b + 1) - pb0);
                 }
-                onepass_link<8>(p, nullptr, r, i, lane);
+                const bool slow = valid && (nb > kLaneRow || npb > kLaneRow);
+                if (slow) {
+                    const int q = atomicAdd(&sm.n_slow, 1);
+                    sm.q_t[q] = t; sm.q_b0[q] = b0; sm.q_nb[q] = nb; sm.q_pb0[q] = pb0; sm.q_npb[q] = npb;
+                }
+                const int nbf = slow ? 0 : nb, npf = slow ? 0 : npb;
+                int c_cn = 0, c_1h = 0, c_n1 = 0;
+                // adjacency rows -> stage
+#pragma unroll 8
+                for (int j = 0; j < 32; ++j) {
+                    const int64_t bj = __shfl_sync(kFull, b0, j);
+                    const int nj = __shfl_sync(kFull, nbf, j);
+                    if (lane < nj) stage[j * kStageStride + lane] = __ldg(p.adj_col + bj + lane);
+                }
+                __syncwarp();
+                const int rounds = __reduce_max_sync(kFull, nbf);
+                for (int k = 0; k < rounds; ++k) {
+                    if (k < nbf) {
+                        const int32_t u = stage[lane * kStageStride + k];
+                        bool hit = hash_contains(h.tab, h.mask, h.shift, u);
+                        if (hit && p.th_cn > 0.0f) {
+                            float qa, qb = 0.f;
+                            smem_ppr_lookup(h, u, qa);
+                            const int x = lower_bound_from(p.ppr_col + pb0, 0, npb, u);
+                            if (x < npb && __ldg(p.ppr_col + pb0 + x) == u) qb = quantise(__ldg(p.ppr_val + pb0 + x));
+                            hit = qa >= p.th_cn && qb >= p.th_cn;
+                        }
+                        c_cn += hit ? 1 : 0;
+                    }
+                }
+                if (want_pi) {
+                    __syncwarp();
+                    // PPR columns -> stage (the adjacency rows stay available in global / L1 for the rare in_b test)
+#pragma unroll 8
+                    for (int j = 0; j < 32; ++j) {
+                        const int64_t pj = __shfl_sync(kFull, pb0, j);
+                        const int nj = __shfl_sync(kFull, npf, j);
+                        if (lane < nj) stage[j * kStageStride + lane] = __ldg(p.ppr_col + pj + lane);
+                    }
+                    __syncwarp();
+                    const int prounds = __reduce_max_sync(kFull, npf);
+                    for (int k = 0; k < prounds; ++k) {
+                        if (k < npf) {
+                            const int32_t u = stage[lane * kStageStride + k];
+                            float qa;
+                            if (smem_ppr_lookup(h, u, qa)) {
+                                const float qb = quantise(__ldg(p.ppr_val + pb0 + k));
+                                if (qa >= th_pre && qb >= th_pre) {
+                                    const bool in_a = hash_contains(h.tab, h.mask, h.shift, u);
+                                    const int x = lower_bound_from(p.adj_col + b0, 0, nb, u);
+                                    const bool in_b = x < nb && __ldg(p.adj_col + b0 + x) == u;
+                                    if ((in_a != in_b) && qa >= p.th_1hop && qb >= p.th_1hop) ++c_1h;
+                                    if (want_n1 && !in_a && !in_b && qa >= p.th_non1hop && qb >= p.th_non1hop) ++c_n1;
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (valid && !slow) {
+                    int64_t s_cn, s_1h, s_n1;
+                    if (alloc_segments(p, i, c_cn, c_1h, c_n1, s_cn, s_1h, s_n1) && (c_cn + c_1h + c_n1 > 0)) {
+                        const int q = atomicAdd(&sm.n_write, 1);
+                        sm.w_t[q] = t; sm.w_b0[q] = b0; sm.w_nb[q] = nb; sm.w_pb0[q] = pb0; sm.w_npb[q] = npb;
+                        sm.w_seg[0][q] = (int32_t)s_cn; sm.w_seg[1][q] = (int32_t)s_1h; sm.w_seg[2][q] = (int32_t)s_n1;
+                    }
+                }
+            }
+            __syncthreads();
+
+            // ---- phase B: links with long target rows, element-parallel over the whole CTA: thread e takes element e
+            // of the concatenated rows (all loads independent: one DRAM round trip per 256 elements in flight)
+            const int ns = sm.n_slow;
+            if (ns > 0) {
+                if (tid < ns) sm.q_cnt[0][tid] = sm.q_cnt[1][tid] = sm.q_cnt[2][tid] = 0;
+                cta_prefix(sm, sm.q_nb, ns);
+                const int totalA = sm.q_off[ns];
+                for (int e = tid; e < totalA; e += kRunThreads) {
+                    const int q = owner_of(sm.q_off, ns, e);
+                    const int32_t u = __ldg(p.adj_col + sm.q_b0[q] + (e - sm.q_off[q]));
+                    bool hit = hash_contains(h.tab, h.mask, h.shift, u);
+                    if (hit && p.th_cn > 0.0f) {
+                        float qa, qb = 0.f;
+                        smem_ppr_lookup(h, u, qa);
+                        const int32_t* pc = p.ppr_col + sm.q_pb0[q];
+                        const int x = lower_bound_from(pc, 0, sm.q_npb[q], u);
+                        if (x < sm.q_npb[q] && __ldg(pc + x) == u) qb = quantise(__ldg(p.ppr_val + sm.q_pb0[q] + x));
+                        hit = qa >= p.th_cn && qb >= p.th_cn;
+                    }
+                    if (hit) atomicAdd(&sm.q_cnt[0][q], 1);
+                }
+                __syncthreads();
+                if (want_pi) {
+                    cta_prefix(sm, sm.q_npb, ns);
+                    const int totalP = sm.q_off[ns];
+                    for (int e = tid; e < totalP; e += kRunThreads) {
+                        const int q = owner_of(sm.q_off, ns, e);
+                        const int k = e - sm.q_off[q];
+                        const int32_t u = __ldg(p.ppr_col + sm.q_pb0[q] + k);
+                        float qa;
+                        if (smem_ppr_lookup(h, u, qa)) {
+                            const float qb = quantise(__ldg(p.ppr_val + sm.q_pb0[q] + k));
+                            if (qa >= th_pre && qb >= th_pre) {
+                                const bool in_a = hash_contains(h.tab, h.mask, h.shift, u);
+                                const int32_t* ab = p.adj_col + sm.q_b0[q];
+                                const int x = lower_bound_from(ab, 0, sm.q_nb[q], u);
+                                const bool in_b = x < sm.q_nb[q] && __ldg(ab + x) == u;
+                                if ((in_a != in_b) && qa >= p.th_1hop && qb >= p.th_1hop) atomicAdd(&sm.q_cnt[1][q], 1);
+                                if (want_n1 && !in_a && !in_b && qa >= p.th_non1hop && qb >= p.th_non1hop)
+                                    atomicAdd(&sm.q_cnt[2][q], 1);
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+                if (tid < ns) {
+                    const int c0 = sm.q_cnt[0][tid], c1 = sm.q_cnt[1][tid], c2 = sm.q_cnt[2][tid];
+                    int64_t s_cn, s_1h, s_n1;
+                    if (alloc_segments(p, i0 + sm.q_t[tid], c0, c1, c2, s_cn, s_1h, s_n1) && (c0 + c1 + c2 > 0)) {
+                        const int q = atomicAdd(&sm.n_write, 1);
+                        sm.w_t[q] = sm.q_t[tid]; sm.w_b0[q] = sm.q_b0[tid]; sm.w_nb[q] = sm.q_nb[tid];
+                        sm.w_pb0[q] = sm.q_pb0[tid]; sm.w_npb[q] = sm.q_npb[tid];
+                        sm.w_seg[0][q] = (int32_t)s_cn; sm.w_seg[1][q] = (int32_t)s_1h; sm.w_seg[2][q] = (int32_t)s_n1;
+                    }
+                }
+                __syncthreads();
+            }
+
+            // ---- phase C: ordered write pass of the links that selected something, one warp per link
+            const int nw = sm.n_write;
+            while (true) {
+                int q = 0;
+                if (lane == 0) q = atomicAdd(&sm.next_write, 1);
+                q = __shfl_sync(kFull, q, 0);
+                if (q >= nw) break;
+                LinkRows r;
+                r.na = na; r.npa = npa;
+                r.Aa = p.adj_col + a0; r.Pac = p.ppr_col + pa0; r.Pav = p.ppr_val + pa0;
+                r.nb = sm.w_nb[q]; r.npb = sm.w_npb[q];
+                r.Ab = p.adj_col + sm.w_b0[q]; r.Pbc = p.ppr_col + sm.w_pb0[q]; r.Pbv = p.ppr_val + sm.w_pb0[q];
+                int d0, d1, d2;
+                walk_link_hashed<32, true>(p, h, r, i0 + sm.w_t[q], lane, (int64_t)sm.w_seg[0][q],
+                                           p.cap + sm.w_seg[1][q], 2 * p.cap + sm.w_seg[2][q], d0, d1, d2);
             }
             __syncthreads();     // the shared tables are rebuilt for the next run / chunk
         }
@@ -352,10 +473,20 @@ __global__ void __launch_bounds__(kRunThreads) select_onepass_runs_kernel(Select
 }
 
 int launch_select_runs(const SelectParams2& p, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(select_onepass_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(RunSmem));
+        if (e != cudaSuccess) {
+            set_error("lpf_select_onepass: cudaFuncSetAttribute(%zu B): %s", sizeof(RunSmem), cudaGetErrorString(e));
+            return LPF_ERR_CUDA;
+        }
+        configured = true;
+    }
     int64_t blocks = (p.bs + kRunChunk - 1) / kRunChunk;
-    const int64_t cap = (int64_t)kNumSMs * 6 * 4;
+    const int64_t cap = (int64_t)kNumSMs * 3 * 4;
     if (blocks > cap) blocks = cap;
-    select_onepass_runs_kernel<<<(unsigned)blocks, kRunThreads, 0, st>>>(p);
+    select_onepass_runs_kernel<<<(unsigned)blocks, kRunThreads, sizeof(RunSmem), st>>>(p);
     return check_launch("lpf_select_onepass");
 }
 

@@ -75,6 +75,7 @@ class ScorePlan:
         a.X, a.ldx, a.KV, a.ld_kv = ptr(X_node), X_node.stride(0), ptr(kv), kv.stride(0)
         a.node, a.src_ppr, a.tgt_ppr = ptr(self.node), ptr(self.pa), ptr(self.pb)
         a.seg_start, a.counts, a.cap, a.d, a.mode = ptr(self.seg_start), ptr(self.counts), cap, d, self.mode
+        a.header, a.R = self.hdr.data_ptr(), ptr(self.R)
         a.wlT, a.bl = ptr(self.keep[0]), ptr(self.w["bl"])
         for t, (w1, b1, g, b, _, cvec) in enumerate(self.rpe):
             a.rpe_w1[t], a.rpe_b1[t], a.rpe_ln_w[t], a.rpe_ln_b[t] = ptr(w1), ptr(b1), ptr(g), ptr(b)

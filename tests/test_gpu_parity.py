@@ -344,3 +344,49 @@ def test_select_onepass_vs_oracle(workload, scale, algo):
     small = ops.select_onepass(torch.from_numpy(links_np).to(dev), d["adj_mask"], d["ppr"], *th, mode, cap=max(1, total // 4), algo=algo)
     h2 = small["header"].tolist()
     assert h2[4] == 1 and h2[:4] == [0, 0, 0, 0]
+
+
+@pytest.mark.parametrize("dim,mode_th", [(64, (1e-3, 1e-2)), (32, (1e-3, 1e-2)), (64, (1e-3, 1)), (32, (1, 1))])
+def test_plan_fused_nonempty_path(dim, mode_th):
+    """Batches where few links select anything switch the plan to the fused one-warp-per-link kernel
+    (lpf_nz_links_fused); scores must equal the host-sized batched path and the float64 oracle in all three
+    selection modes (all / 1-hop / cn) and both supported widths."""
+    import lpformer_b200 as L
+    from lpformer_b200 import synthetic as S
+    g = S.make_graph("citation2", seed=6, scale=0.02, heldout=256)
+    targs = dict(S.train_args_of(g.cfg), dim=dim, thresh_1hop=mode_th[0], thresh_non1hop=mode_th[1])
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    model = L.LinkTransformer(targs, g.data_dict(dev), device=dev).to(dev).eval()
+    score = L.mlp_score(model.out_dim, model.out_dim, 1, 2).to(dev).eval()
+    with torch.no_grad():
+        for p in list(model.parameters()) + list(score.parameters()):
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    X = torch.randn(g.n, dim, generator=torch.Generator().manual_seed(1)).to(dev)
+    rng = np.random.default_rng(0)
+
+    def batch(seed):
+        q = S.citation2_queries(g, 5, 800, seed=seed)
+        pos = g.edges[:, rng.integers(0, g.edges.shape[1], 45)]
+        return np.concatenate([q, pos], 1).astype(np.int64)
+
+    batches = [batch(s) for s in range(3)]
+    model.use_plans = False
+    ref = [model.score_links(torch.from_numpy(b).to(dev), X, score).cpu().numpy() for b in batches]
+    model.use_plans = True
+    for rep in range(2):
+        for b, r in zip(batches, ref):
+            out = model.score_links(torch.from_numpy(b).to(dev), X, score).cpu().numpy()
+            np.testing.assert_allclose(out, r, rtol=2e-5, atol=1e-6)
+    plan = next(iter(model._plans.values()))
+    st = plan.stats()
+    assert plan.nz_mode == "fused" and "fused" in plan.graphs and 0 < st["nonempty_links"] < len(ref[0]) // 16
+    # oracle on the last batch
+    P = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in model.state_dict().items()}
+    Sd = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in score.state_dict().items()}
+    feats, _, _, _ = O.link_features(batches[2], X.cpu().numpy(), O.CSR(g.indptr, g.indices, None, g.n),
+                                     O.CSR(g.ppr[0], g.ppr[1], g.ppr[2], g.n), P, dict(targs, trans_layers=1, num_heads=1))
+    _, ref_prob = O.mlp_score(feats, Sd)
+    out = model.score_links(torch.from_numpy(batches[2]).to(dev), X, score).cpu().numpy()
+    np.testing.assert_allclose(out, ref_prob, rtol=FP32_RTOL, atol=1e-6)
