@@ -267,6 +267,11 @@ typedef struct lpf_nz_args {
 } lpf_nz_args;
 int lpf_nz_links_fused(const lpf_nz_args* args, void* stream);
 
+/* Profiling hook: later lpf_select_onepass launches add per-phase clock64() totals of the run-aware kernel into
+ * device_buffer (int64[16]: [0] source staging, [1] phase A, [2] phase B, [3] phase C, [4] generic fallback,
+ * [5] chunks, [6] queued long-row links, [7] written links); NULL disables. */
+int lpf_debug_select_clocks(void* device_buffer);
+
 /* Profiling hook: CTA 0 of later lpf_link_heads_tc launches writes clock64() stamps of its pipeline phases for
  * its first 8 tiles into device_buffer (int64 [8][16]); NULL disables. */
 int lpf_debug_heads_clocks(void* device_buffer);

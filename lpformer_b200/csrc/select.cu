@@ -406,6 +406,14 @@ extern "C" int lpf_select_onepass(const int64_t* links, int64_t bs, const int64_
                           src_ppr, tgt_ppr, (int32_t*)workspace, (cudaStream_t)stream);
 }
 
+namespace lpf { extern long long* g_select_dbg; }
+// Profiling hook: later lpf_select_onepass launches add per-phase clock64() totals (thread 0 of every CTA of the
+// run-aware kernel) into device_buffer (int64[16]: setup, phase A, phase B, phase C, generic, #chunks, ...).
+extern "C" int lpf_debug_select_clocks(void* device_buffer) {
+    lpf::g_select_dbg = (long long*)device_buffer;
+    return LPF_OK;
+}
+
 extern "C" int64_t lpf_select_workspace_bytes(int64_t bs) { return (bs + 4) * (int64_t)sizeof(int32_t); }
 
 extern "C" int64_t lpf_scan_scratch_bytes(int64_t n) {

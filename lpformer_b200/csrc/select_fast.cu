@@ -316,17 +316,19 @@ int select_fast(bool fill, int group, const int64_t* links, int64_t bs, const in
                 float th_cn, float th_1hop, float th_non1hop, int mode, int32_t* counts, const int64_t* ptr,
                 int32_t* node, float* pa, float* pb, int32_t* link, int32_t* heavy, cudaStream_t st) {
     SelectParams2 p{links, bs, adj_rowptr, adj_col, ppr_rowptr, ppr_col, ppr_val, th_cn, th_1hop, th_non1hop,
-                    mode, counts, ptr, node, pa, pb, link, heavy, 0, nullptr, nullptr, nullptr};
+                    mode, counts, ptr, node, pa, pb, link, heavy, 0, nullptr, nullptr, nullptr, nullptr};
     if (group == 32) return launch_fast<32>(fill, p, st);
     return launch_fast<8>(fill, p, st);
 }
+
+long long* g_select_dbg = nullptr;
 
 int select_onepass(int group, const int64_t* links, int64_t bs, const int64_t* adj_rowptr, const int32_t* adj_col,
                    const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val, float th_cn, float th_1hop,
                    float th_non1hop, int mode, int64_t cap, int32_t* counts, int32_t* seg_start, int32_t* nz_list,
                    int64_t* hdr, int32_t* node, float* pa, float* pb, int32_t* heavy, cudaStream_t st) {
     SelectParams2 p{links, bs, adj_rowptr, adj_col, ppr_rowptr, ppr_col, ppr_val, th_cn, th_1hop, th_non1hop,
-                    mode, counts, nullptr, node, pa, pb, nullptr, heavy, cap, hdr, seg_start, nz_list};
+                    mode, counts, nullptr, node, pa, pb, nullptr, heavy, cap, hdr, seg_start, nz_list, g_select_dbg};
     if (group == 32) return launch_fast<32>(false, p, st);
     return launch_fast<8>(false, p, st);
 }

@@ -223,9 +223,19 @@ __global__ void __launch_bounds__(kRunThreads) select_onepass_runs_kernel(Select
     const float th_pre = want_n1 ? fminf(p.th_1hop, p.th_non1hop) : p.th_1hop;
     const int64_t nchunks = (p.bs + kRunChunk - 1) / kRunChunk;
 
+    long long t_mark = clock64();
+#define LPF_PHASE(k)                                                              \
+    do {                                                                          \
+        if (p.dbg && tid == 0) {                                                  \
+            const long long now = clock64();                                      \
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + (k)), (unsigned long long)(now - t_mark)); \
+            t_mark = now;                                                         \
+        }                                                                         \
+    } while (0)
     for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         const int64_t i0 = chunk * kRunChunk;
         const int len = (int)min((int64_t)kRunChunk, p.bs - i0);
+        if (p.dbg && tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 5), 1ull);
         // ---- run structure of the chunk: boundaries where the source changes
         const int64_t a_me = (tid < len) ? __ldg(p.links + i0 + tid) : -1;
         const int64_t a_prev = (tid > 0 && tid < len) ? __ldg(p.links + i0 + tid - 1) : -2;
@@ -250,6 +260,7 @@ __global__ void __launch_bounds__(kRunThreads) select_onepass_runs_kernel(Select
                 onepass_link<8>(p, nullptr, r, i, lane);
             }
             __syncthreads();
+            LPF_PHASE(4);
             continue;
         }
         if (tid == 0) {      // sort the (at most kMaxRuns) boundaries, close the list
@@ -278,6 +289,7 @@ __global__ void __launch_bounds__(kRunThreads) select_onepass_runs_kernel(Select
                     onepass_link<8>(p, nullptr, r, i, lane);
                 }
                 __syncthreads();
+                LPF_PHASE(4);
                 continue;
             }
             // ---- stage the source: hash set of A(a), P(a) with its position hash
@@ -305,6 +317,7 @@ __global__ void __launch_bounds__(kRunThreads) select_onepass_runs_kernel(Select
                 while (atomicCAS(&sm.ppos[slot], -1, s) != -1) slot = (slot + 1) & (kPprHashSlots - 1);
             }
             __syncthreads();
+            LPF_PHASE(0);
 
             // ---- phase A: lane-per-link, 32 links per warp step; every target row of the 32 links is fetched by
             // one coalesced warp-wide load per link, all 32 issued back to back (one DRAM round trip), then each
@@ -392,6 +405,7 @@ __global__ void __launch_bounds__(kRunThreads) select_onepass_runs_kernel(Select
                 }
             }
             __syncthreads();
+            LPF_PHASE(1);
 
             // ---- phase B: links with long target rows, element-parallel over the whole CTA: thread e takes element e
             // of the concatenated rows (all loads independent: one DRAM round trip per 256 elements in flight)
@@ -451,8 +465,13 @@ __global__ void __launch_bounds__(kRunThreads) select_onepass_runs_kernel(Select
                 __syncthreads();
             }
 
+            LPF_PHASE(2);
             // ---- phase C: ordered write pass of the links that selected something, one warp per link
             const int nw = sm.n_write;
+            if (p.dbg && tid == 0) {
+                atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 6), (unsigned long long)ns);
+                atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 7), (unsigned long long)nw);
+            }
             while (true) {
                 int q = 0;
                 if (lane == 0) q = atomicAdd(&sm.next_write, 1);
@@ -468,9 +487,12 @@ __global__ void __launch_bounds__(kRunThreads) select_onepass_runs_kernel(Select
                                            p.cap + sm.w_seg[1][q], 2 * p.cap + sm.w_seg[2][q], d0, d1, d2);
             }
             __syncthreads();     // the shared tables are rebuilt for the next run / chunk
+            LPF_PHASE(3);
         }
     }
 }
+
+#undef LPF_PHASE
 
 int launch_select_runs(const SelectParams2& p, cudaStream_t st) {
     static bool configured = false;

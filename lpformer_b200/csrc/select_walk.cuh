@@ -27,6 +27,7 @@ struct SelectParams2 {
     int64_t* hdr;      // [0..2] pairs per type, [3] non-empty links, [4] overflow flag
     int32_t* seg_start;  // [3*bs] first row of link i's type-t segment, relative to t*cap
     int32_t* nz_list;    // [bs] batch positions of the non-empty links (any order)
+    long long* dbg;      // optional profiling buffer (lpf_debug_select_clocks): per-phase clock64() totals
 };
 
 // A link whose shorter adjacency (or PPR) row exceeds kHeavyPerLane elements per lane of its group is deferred

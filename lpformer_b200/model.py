@@ -332,6 +332,7 @@ class LinkTransformer(nn.Module):
         self._plan_cap = {}
         self.use_plans = True       # one-pass selection + device-side sizes (plan.py)
         self.use_graphs = True      # ... replayed as a CUDA graph
+        self.nz_fused_share = 1.0 / 16   # non-empty links below this share of the batch take the one-warp-per-link path
 
     # ------------------------------------------------------------------ graph tables
     def _dev(self):

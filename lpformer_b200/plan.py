@@ -167,7 +167,7 @@ class ScorePlan:
         h = self.hdr.tolist()                        # the batch's only host round trip
         # regime for the NEXT batch (either path is exact; this only picks the cheaper one)
         if self.fused_ok and self.fused_allowed:
-            self.nz_mode = "fused" if h[3] * 16 < self.bs else "batched"
+            self.nz_mode = "fused" if h[3] < self.model.nz_fused_share * self.bs else "batched"
         return self.prob, bool(h[4])
 
     def stats(self):

@@ -375,13 +375,14 @@ def test_plan_fused_nonempty_path(dim, mode_th):
     model.use_plans = False
     ref = [model.score_links(torch.from_numpy(b).to(dev), X, score).cpu().numpy() for b in batches]
     model.use_plans = True
+    model.nz_fused_share = 1.0          # force the fused kernel whatever the share of non-empty links
     for rep in range(2):
         for b, r in zip(batches, ref):
             out = model.score_links(torch.from_numpy(b).to(dev), X, score).cpu().numpy()
             np.testing.assert_allclose(out, r, rtol=2e-5, atol=1e-6)
     plan = next(iter(model._plans.values()))
     st = plan.stats()
-    assert plan.nz_mode == "fused" and "fused" in plan.graphs and 0 < st["nonempty_links"] < len(ref[0]) // 16
+    assert plan.nz_mode == "fused" and "fused" in plan.graphs and st["nonempty_links"] > 0
     # oracle on the last batch
     P = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in model.state_dict().items()}
     Sd = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in score.state_dict().items()}
