@@ -50,6 +50,9 @@ extern "C" {
 #define LPF_ALGO_GENERIC 0
 #define LPF_ALGO_INTERSECT8 1
 #define LPF_ALGO_INTERSECT32 2
+/* PACKED: one-pass selection over the packed link rows of lpf_pack_link_rows (lpf_select_onepass_packed only);
+ *         same preconditions as the INTERSECT algorithms. */
+#define LPF_ALGO_PACKED 3
 
 /* node-set types, concatenation order of models/link_transformer.py:161 */
 #define LPF_T_CN 0
@@ -118,6 +121,37 @@ int lpf_select_onepass(const int64_t* links, int64_t bs,
                        float th_cn, float th_1hop, float th_non1hop, int mode, int algo, int64_t cap,
                        int32_t* counts, int32_t* seg_start, int32_t* nz_list, int64_t* header,
                        int32_t* node, float* src_ppr, float* tgt_ppr, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Packed link rows: the HBM layout of the per-link walk.  The reference slices rows a and b out of two N x N
+ * sparse COO tensors with four index_select calls per batch (models/link_transformer.py:229-230, :290-291,
+ * :444-449); the CSR tables above already make that a direct row access, but a link's target still costs four
+ * dependent random reads in four arrays.  lpf_pack_link_rows rewrites (adjacency CSR, PPR CSR) once per graph as
+ *   node_desc int32 [n,4] : (first 16-byte chunk of the node's row, deg, nP, 0)
+ *   row_blob              : per node ceil(deg/4) chunks of ascending neighbour ids (pad -2), then ceil(nP/2)
+ *                           chunks of (PPR column, PPR value bits) pairs in ascending column order (pad col -2)
+ * so that a target is two dependent reads (16-byte descriptor, then one contiguous region).
+ * row_blob needs lpf_link_rows_bytes(n, adj_nnz, ppr_nnz) bytes (an upper bound; -1 if the chunk index would
+ * not fit 32 bits), scratch lpf_link_rows_scratch_bytes(n) bytes; both and node_desc 16-byte aligned.
+ *
+ * lpf_select_onepass_packed is lpf_select_onepass (same outputs, same header protocol, same preconditions as
+ * the INTERSECT algorithms) on those rows: a CTA stages the sources of 512 consecutive links in shared memory
+ * (hash set of A(a), table of P(a)), one thread screens one link's target row, and the links that select
+ * anything — or whose rows are long — are resolved by a warp each.  The CSR tables are still read by that
+ * resolution and by the fallbacks (hub sources, chunks that are not runs of equal source).
+ * ------------------------------------------------------------------------- */
+int64_t lpf_link_rows_bytes(int64_t n, int64_t adj_nnz, int64_t ppr_nnz);
+int64_t lpf_link_rows_scratch_bytes(int64_t n);
+int lpf_pack_link_rows(const int64_t* adj_rowptr, const int32_t* adj_col,
+                       const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val, int64_t n,
+                       int32_t* node_desc, void* row_blob, void* scratch, void* stream);
+int lpf_select_onepass_packed(const int64_t* links, int64_t bs,
+                              const int64_t* adj_rowptr, const int32_t* adj_col,
+                              const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val,
+                              const int32_t* node_desc, const void* row_blob,
+                              float th_cn, float th_1hop, float th_non1hop, int mode, int64_t cap,
+                              int32_t* counts, int32_t* seg_start, int32_t* nz_list, int64_t* header,
+                              int32_t* node, float* src_ppr, float* tgt_ppr, void* workspace, void* stream);
 
 /* After the scan: batch positions of the links with at least one selected node (nz_list int32 [<= BS], any
  * order) and header int64[4] = (S_cn, S_cn + S_1hop, S, number of non-empty links) — the one small read-back

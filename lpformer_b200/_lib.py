@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "_C", "liblpformer_b200.so")
 
 MODE = {"cn": 0, "1-hop": 1, "all": 2}
 EPI_NONE, EPI_RELU, EPI_SIGMOID = 0, 1, 2
-ALGO_GENERIC, ALGO_INTERSECT8, ALGO_INTERSECT32 = 0, 1, 2
+ALGO_GENERIC, ALGO_INTERSECT8, ALGO_INTERSECT32, ALGO_PACKED = 0, 1, 2, 3
 
 _p, _i64, _i32, _f32, _int = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_int
 
@@ -33,6 +33,11 @@ SIGNATURES = {
     "lpf_rpe_hidden": (_int, [_p, _p, _i64, _i64, _p, _p, _p, _p, _i32, _p, _i64, _p, _p]),
     "lpf_select_onepass": (_int, [_p, _i64, _p, _p, _p, _p, _p, _f32, _f32, _f32, _int, _int, _i64, _p, _p, _p, _p, _p,
                                   _p, _p, _p, _p]),
+    "lpf_link_rows_bytes": (_i64, [_i64, _i64, _i64]),
+    "lpf_link_rows_scratch_bytes": (_i64, [_i64]),
+    "lpf_pack_link_rows": (_int, [_p, _p, _p, _p, _p, _i64, _p, _p, _p, _p]),
+    "lpf_select_onepass_packed": (_int, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _f32, _f32, _f32, _int, _i64, _p, _p, _p,
+                                         _p, _p, _p, _p, _p, _p]),
     "lpf_gemm": (_int, [_p, _i64, _p, _i64, _p, _f32, _p, _i64, _i64, _i32, _i32, _int, _p]),
     "lpf_pack_weight_bytes": (_i64, [_i32, _i32]),
     "lpf_pack_weight": (_int, [_p, _i64, _i32, _i32, _p, _p]),
@@ -94,7 +99,7 @@ def load():
 # kernels launched per entry point (for bench.py's gpu_launches and per-kernel CUDA-event timing)
 KERNEL_LAUNCHES = {"lpf_select_count": 3, "lpf_scan_counts": 2, "lpf_select_fill": 2, "lpf_rpe_hidden": 1,
                    "lpf_gemm": 1, "lpf_gemm_tc": 1, "lpf_pack_weight": 1, "lpf_layernorm_act": 1, "lpf_gather_links": 1, "lpf_attend_fused": 1,
-                   "lpf_gcn_spmm": 1, "lpf_nz_links_fused": 2, "lpf_select_compact": 2, "lpf_select_onepass": 4, "lpf_scatter_rows": 2, "lpf_link_heads_tc": 1}
+                   "lpf_gcn_spmm": 1, "lpf_nz_links_fused": 2, "lpf_select_compact": 2, "lpf_select_onepass": 4, "lpf_select_onepass_packed": 6, "lpf_pack_link_rows": 4, "lpf_scatter_rows": 2, "lpf_link_heads_tc": 1}
 
 
 class Trace:

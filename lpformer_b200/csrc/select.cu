@@ -414,7 +414,10 @@ extern "C" int lpf_debug_select_clocks(void* device_buffer) {
     return LPF_OK;
 }
 
-extern "C" int64_t lpf_select_workspace_bytes(int64_t bs) { return (bs + 4) * (int64_t)sizeof(int32_t); }
+// [0, bs+4): deferred (heavy) links; [bs+4, ...): hub runs of the packed kernel (count + (first, length) pairs)
+extern "C" int64_t lpf_select_workspace_bytes(int64_t bs) {
+    return (bs + 4 + 1 + 2 * (bs / 128 + 3 * ((bs + 511) / 512 + 1)) + 3) * (int64_t)sizeof(int32_t);
+}
 
 extern "C" int64_t lpf_scan_scratch_bytes(int64_t n) {
     const int64_t tiles = (n + kScanTile - 1) / kScanTile;

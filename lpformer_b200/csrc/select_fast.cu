@@ -21,7 +21,6 @@
 
 namespace lpf {
 
-int launch_select_runs(const SelectParams2& p, cudaStream_t st);
 
 // ---- two-pass interface (count / fill with caller-side scan): output ordered by (type, link, node)
 template <int G, bool FILL>
@@ -279,6 +278,17 @@ __global__ void select_reset_onepass(int32_t* heavy, int64_t* hdr) {
     hdr[0] = hdr[1] = hdr[2] = hdr[3] = hdr[4] = 0;
 }
 
+// prologue / epilogue of a one-pass launch sequence, for the kernels of other translation units
+__global__ void select_reset_hub(int32_t* hub) { hub[0] = 0; }
+void launch_onepass_reset(const SelectParams2& p, cudaStream_t st) {
+    select_reset_onepass<<<1, 1, 0, st>>>(p.heavy, p.hdr);
+    if (p.hub) select_reset_hub<<<1, 1, 0, st>>>(p.hub);
+}
+void launch_onepass_tail(const SelectParams2& p, cudaStream_t st) {
+    select_heavy_onepass_kernel<<<kNumSMs * 2, kHeavyThreads, 0, st>>>(p);
+    select_finalize_onepass<<<1, 1, 0, st>>>(p.hdr);
+}
+
 template <int G>
 static int launch_fast(bool fill, const SelectParams2& p, cudaStream_t st) {
     const int64_t groups_per_block = 256 / G;
@@ -288,14 +298,7 @@ static int launch_fast(bool fill, const SelectParams2& p, cudaStream_t st) {
     const unsigned hgrid = kNumSMs * 2;
     if (p.hdr) {
         select_reset_onepass<<<1, 1, 0, st>>>(p.heavy, p.hdr);
-        if constexpr (G == 8) {
-            // run-aware kernel (select_runs.cu): shared-memory hash of the source row for runs of equal source,
-            // the generic group walk for everything else
-            const int rc = launch_select_runs(p, st);
-            if (rc) return rc;
-        } else {
-            select_onepass_kernel<G><<<(unsigned)blocks, 256, 0, st>>>(p);
-        }
+        select_onepass_kernel<G><<<(unsigned)blocks, 256, 0, st>>>(p);
         select_heavy_onepass_kernel<<<hgrid, kHeavyThreads, 0, st>>>(p);
         select_finalize_onepass<<<1, 1, 0, st>>>(p.hdr);
         return check_launch("lpf_select_onepass");

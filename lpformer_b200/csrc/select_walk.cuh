@@ -1,4 +1,4 @@
-// Shared device code of the K1 intersection kernels (select_fast.cu, select_runs.cu): parameters, row access,
+// Shared device code of the K1 intersection kernels (select_fast.cu, select_packed.cu): parameters, row access,
 // the group walk of one link and the one-pass segment allocation.
 #pragma once
 #include "common.cuh"
@@ -28,6 +28,7 @@ struct SelectParams2 {
     int32_t* seg_start;  // [3*bs] first row of link i's type-t segment, relative to t*cap
     int32_t* nz_list;    // [bs] batch positions of the non-empty links (any order)
     long long* dbg;      // optional profiling buffer (lpf_debug_select_clocks): per-phase clock64() totals
+    int32_t* hub = nullptr;   // packed kernel: [0] = number of hub runs, then (first link, length) pairs
 };
 
 // A link whose shorter adjacency (or PPR) row exceeds kHeavyPerLane elements per lane of its group is deferred

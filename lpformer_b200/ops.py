@@ -49,6 +49,7 @@ def gemm(A, W, bias=None, bias_scale=1.0, out=None, epilogue=EPI_NONE):
 
 
 _PACKED = {}          # (data_ptr, version, shape, stride) -> (packed image, weight kept alive)
+USE_PACKED_ROWS = os.environ.get("LPF_PACKED_ROWS", "1") != "0"   # one-pass selection over the packed link rows
 GEMM_BACKEND = os.environ.get("LPF_GEMM_BACKEND", "tc")   # "tc": tcgen05 3xTF32 kernel (lpf_gemm_tc);  "simt": fp32 FFMA kernel (lpf_gemm)
 
 
@@ -198,7 +199,7 @@ def select(links, adj: CSR, ppr: CSR, th_cn, th_1hop, th_non1hop, mode: str, wan
     args = (ptr(links), bs, ptr(adj.rowptr), ptr(adj.col), ptr(ppr.rowptr), ptr(ppr.col), ptr(ppr.val),
             float(th_cn), float(th_1hop), float(th_non1hop), m,
             pick_select_algo(adj, ppr, th_1hop, th_non1hop, mode) if algo is None else algo)
-    ws = torch.empty(bs + 4, dtype=torch.int32, device=dev)
+    ws = torch.empty(_lib.load().lpf_select_workspace_bytes(bs) // 4, dtype=torch.int32, device=dev)
     call("lpf_select_count", *args, ptr(counts), ptr(ws), st, meta=(bs,))
     p = torch.empty(3 * bs + 1, dtype=torch.int64, device=dev)
     scratch = torch.empty(max(1, _lib.load().lpf_scan_scratch_bytes(3 * bs) // 8), dtype=torch.int64, device=dev)
@@ -215,6 +216,36 @@ def select(links, adj: CSR, ppr: CSR, th_cn, th_1hop, th_non1hop, mode: str, wan
     if S > 0:
         call("lpf_select_fill", *args, ptr(p), ptr(node), ptr(pa), ptr(pb), ptr(link), ptr(ws), st, meta=(bs, S))
     return Selection(mode, bs, p, node, pa, pb, link, (0, b[0], b[1], b[2]), nz[:b[3]])
+
+
+class LinkRows:
+    """Packed link rows of one (adjacency, PPR) table pair (lpf_pack_link_rows): node_desc int32 [n,4], row_blob."""
+
+    def __init__(self, adj: CSR, ppr: CSR):
+        require_cuda(adj.rowptr, ppr.rowptr)
+        lib = _lib.load()
+        dev = adj.rowptr.device
+        n = adj.n
+        nbytes = lib.lpf_link_rows_bytes(n, adj.nnz, ppr.nnz)
+        if nbytes < 0:
+            raise _lib.LpfError("graph too large for 32-bit chunk indices in the packed link rows")
+        self.desc = torch.empty((max(n, 1), 4), dtype=torch.int32, device=dev)
+        self.blob = torch.empty(max(nbytes // 4, 4), dtype=torch.int32, device=dev)
+        scratch = torch.empty(max(lib.lpf_link_rows_scratch_bytes(n) // 8 + 2, 2), dtype=torch.int64, device=dev)
+        call("lpf_pack_link_rows", ptr(adj.rowptr), ptr(adj.col), ptr(ppr.rowptr), ptr(ppr.col), ptr(ppr.val), n,
+             ptr(self.desc), ptr(self.blob), ptr(scratch), stream())
+        torch.cuda.current_stream().synchronize()     # scratch is released here
+        self.adj, self.ppr = adj, ppr
+
+
+def link_rows(adj: CSR, ppr: CSR) -> LinkRows:
+    """The packed rows of (adj, ppr), built once per table pair and cached on the adjacency object."""
+    cache = adj.__dict__.setdefault("_link_rows", {})
+    key = id(ppr)
+    lr = cache.get(key)
+    if lr is None or lr.ppr is not ppr:
+        lr = cache[key] = LinkRows(adj, ppr)
+    return lr
 
 
 def select_onepass(links, adj: CSR, ppr: CSR, th_cn, th_1hop, th_non1hop, mode: str, cap: int, algo=None):
@@ -235,7 +266,14 @@ def select_onepass(links, adj: CSR, ppr: CSR, th_cn, th_1hop, th_non1hop, mode: 
         "tgt_ppr": torch.empty(3 * cap, dtype=torch.float32, device=dev),
         "cap": cap,
     }
-    ws = torch.empty(bs + 4, dtype=torch.int32, device=dev)
+    ws = torch.empty(_lib.load().lpf_select_workspace_bytes(bs) // 4, dtype=torch.int32, device=dev)
+    if algo == _lib.ALGO_PACKED:
+        lr = link_rows(adj, ppr)
+        call("lpf_select_onepass_packed", ptr(links), bs, ptr(adj.rowptr), ptr(adj.col), ptr(ppr.rowptr), ptr(ppr.col),
+             ptr(ppr.val), ptr(lr.desc), ptr(lr.blob), float(th_cn), float(th_1hop), float(th_non1hop), MODE[mode], cap,
+             ptr(out["counts"]), ptr(out["seg_start"]), ptr(out["nz"]), ptr(out["header"]), ptr(out["node"]),
+             ptr(out["src_ppr"]), ptr(out["tgt_ppr"]), ptr(ws), stream(), meta=(bs,))
+        return out
     call("lpf_select_onepass", ptr(links), bs, ptr(adj.rowptr), ptr(adj.col), ptr(ppr.rowptr), ptr(ppr.col), ptr(ppr.val),
          float(th_cn), float(th_1hop), float(th_non1hop), MODE[mode], algo, cap, ptr(out["counts"]),
          ptr(out["seg_start"]), ptr(out["nz"]), ptr(out["header"]), ptr(out["node"]), ptr(out["src_ppr"]),

@@ -29,6 +29,8 @@ class ScorePlan:
         self.algo = ops.pick_select_algo(self.adj, self.ppr, model.thresh_1hop, model.thresh_non1hop, model.mask)
         if self.algo == _lib.ALGO_GENERIC:
             raise _lib.LpfError("the one-pass plan needs an INTERSECT selection algorithm")
+        # sparse graphs: thread-per-link screening over the packed link rows (built once per table pair)
+        self.rows = ops.link_rows(self.adj, self.ppr) if (self.algo == _lib.ALGO_INTERSECT8 and ops.USE_PACKED_ROWS) else None
         d, H = model.dim, model.num_heads
         layer = model.att_layers[0]
         self.layer = layer
@@ -42,7 +44,7 @@ class ScorePlan:
         self.prob = e(bs)
         self.counts, self.seg_start, self.nz = e(3 * bs, dtype=i32), e(3 * bs, dtype=i32), e(bs, dtype=i32)
         self.hdr = torch.zeros(8, dtype=i64, device=dev)
-        self.ws = e(bs + 4, dtype=i32)
+        self.ws = e(_lib.load().lpf_select_workspace_bytes(bs) // 4, dtype=i32)
         self.node, self.pa, self.pb = e(3 * cap, dtype=i32), e(3 * cap), e(3 * cap)
         self.hsum, self.R = e(3 * cap, d), e(3 * cap, HC)
         pd = HC + model.count_dim
@@ -117,10 +119,16 @@ class ScorePlan:
         # every link with the empty-set pairwise constant (independent of the selection)
         heads(None, bs, None, None)
         # K1: one-pass selection into the per-type pools
-        call("lpf_select_onepass", ptr(links), bs, ptr(self.adj.rowptr), ptr(self.adj.col), ptr(self.ppr.rowptr),
-             ptr(self.ppr.col), ptr(self.ppr.val), *self.th, self.mode, self.algo, cap, ptr(self.counts),
-             ptr(self.seg_start), ptr(self.nz), hp, ptr(self.node), ptr(self.pa), ptr(self.pb), ptr(self.ws), st,
-             meta=(bs,))
+        if self.rows is not None:
+            call("lpf_select_onepass_packed", ptr(links), bs, ptr(self.adj.rowptr), ptr(self.adj.col),
+                 ptr(self.ppr.rowptr), ptr(self.ppr.col), ptr(self.ppr.val), ptr(self.rows.desc), ptr(self.rows.blob),
+                 *self.th, self.mode, cap, ptr(self.counts), ptr(self.seg_start), ptr(self.nz), hp, ptr(self.node),
+                 ptr(self.pa), ptr(self.pb), ptr(self.ws), st, meta=(bs,))
+        else:
+            call("lpf_select_onepass", ptr(links), bs, ptr(self.adj.rowptr), ptr(self.adj.col), ptr(self.ppr.rowptr),
+                 ptr(self.ppr.col), ptr(self.ppr.val), *self.th, self.mode, self.algo, cap, ptr(self.counts),
+                 ptr(self.seg_start), ptr(self.nz), hp, ptr(self.node), ptr(self.pa), ptr(self.pb), ptr(self.ws), st,
+                 meta=(bs,))
         if self.nz_mode == "fused":
             # few non-empty links: one warp per link, everything from node sets to score in one launch
             call("lpf_nz_links_fused", C.byref(self.nz_args), st, meta=(bs,))

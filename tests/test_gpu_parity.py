@@ -297,10 +297,12 @@ def _onepass_sets(out, bs):
 
 
 @pytest.mark.parametrize("workload,scale,algo", [("citation2", 0.05, 1), ("citation2", 0.05, 2), ("collab", 0.05, 1),
-                                                 ("ppa", 0.004, 2), ("ddi", 0.5, 2)])
+                                                 ("ppa", 0.004, 2), ("ddi", 0.5, 2),
+                                                 ("citation2", 0.05, 3), ("collab", 0.05, 3), ("ppa", 0.004, 3),
+                                                 ("ddi", 0.25, 3)])
 def test_select_onepass_vs_oracle(workload, scale, algo):
-    """One-pass selection (run-aware hashed kernel for algo 1, warp kernel for algo 2, deferred heavy links in both)
-    against the numpy oracle: long shared-source runs, short runs, unsorted links, hub-hub pairs, self pairs."""
+    """One-pass selection (run-aware hashed kernel for algo 1, warp kernel for algo 2, thread-per-link screening over
+    the packed link rows for algo 3, deferred heavy links in all) against the numpy oracle: long shared-source runs, short runs, unsorted links, hub-hub pairs, self pairs."""
     from lpformer_b200 import ops, synthetic as S
     g = S.make_graph(workload, seed=9, scale=scale, heldout=512)
     cfg = g.cfg
@@ -391,3 +393,30 @@ def test_plan_fused_nonempty_path(dim, mode_th):
     _, ref_prob = O.mlp_score(feats, Sd)
     out = model.score_links(torch.from_numpy(batches[2]).to(dev), X, score).cpu().numpy()
     np.testing.assert_allclose(out, ref_prob, rtol=FP32_RTOL, atol=1e-6)
+
+
+def test_packed_link_rows_layout():
+    """lpf_pack_link_rows: descriptor + row blob reproduce the two CSR tables (ids ascending, pads -2, PPR value bits)."""
+    from lpformer_b200 import ops, synthetic as S
+    g = S.make_graph("citation2", seed=3, scale=0.01, heldout=64)
+    dev = torch.device("cuda:0")
+    d = g.data_dict(dev)
+    lr = ops.link_rows(d["adj_mask"], d["ppr"])
+    assert ops.link_rows(d["adj_mask"], d["ppr"]) is lr          # cached per table pair
+    desc = lr.desc.cpu().numpy()
+    blob = lr.blob.cpu().numpy()
+    deg, npp = np.diff(g.indptr), np.diff(g.ppr[0])
+    assert np.array_equal(desc[:, 1], deg) and np.array_equal(desc[:, 2], npp)
+    chunks = (deg + 3) // 4 + (npp + 1) // 2
+    off = np.concatenate([[0], np.cumsum(chunks)[:-1]])
+    assert np.array_equal(desc[:, 0].view(np.uint32).astype(np.int64), off)
+    rng = np.random.default_rng(0)
+    for x in np.concatenate([rng.integers(0, g.n, 200), np.argsort(-deg)[:5], np.nonzero(deg == 0)[0][:5]]):
+        w = blob[4 * off[x]: 4 * (off[x] + chunks[x])]
+        ca4 = 4 * ((deg[x] + 3) // 4)
+        assert np.array_equal(w[:deg[x]], g.indices[g.indptr[x]:g.indptr[x + 1]])
+        assert np.all(w[deg[x]:ca4] == -2)
+        pw = w[ca4:].reshape(-1, 2)
+        assert np.array_equal(pw[:npp[x], 0], g.ppr[1][g.ppr[0][x]:g.ppr[0][x + 1]])
+        assert np.array_equal(pw[:npp[x], 1].view(np.float32), g.ppr[2][g.ppr[0][x]:g.ppr[0][x + 1]])
+        assert np.all(pw[npp[x]:, 0] == -2)

@@ -10,6 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from lpformer_b200 import _lib, ops, synthetic as S  # noqa: E402
 
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
+algo = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 dev = torch.device("cuda:0")
 g = S.make_graph("citation2", seed=0, scale=scale, heldout=8192)
 cfg = g.cfg
@@ -17,13 +18,13 @@ d = g.data_dict(dev)
 th = (cfg["thresh_cn"], cfg["thresh_1hop"], cfg["thresh_non1hop"])
 lib = _lib.load()
 buf = torch.zeros(16, dtype=torch.int64, device=dev)
-for it in range(4):
+for it in range(6):
     links = torch.from_numpy(S.citation2_queries(g, 256, 1000, seed=1000 + it)).to(dev)
-    if it == 3:
+    if it == 5:
         lib.lpf_debug_select_clocks(buf.data_ptr())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    out = ops.select_onepass(links, d["adj_mask"], d["ppr"], *th, "all", cap=1 << 19, algo=1)
+    out = ops.select_onepass(links, d["adj_mask"], d["ppr"], *th, "all", cap=1 << 19, algo=algo)
     e1.record()
     torch.cuda.synchronize()
     print("select_onepass %.1f us" % (1e3 * e0.elapsed_time(e1)), out["header"].tolist()[:5])
@@ -32,5 +33,6 @@ t = buf.cpu().numpy()
 n = max(1, int(t[5]))
 names = ["stage source", "phase A", "phase B", "phase C", "generic"]
 print("chunks %d, queued long-row links/chunk %.1f, written links/chunk %.1f" % (n, t[6] / n, t[7] / n))
+print("slowest chunk %.1f us, slowest CTA %.1f us" % (t[8] / 1965.0, t[9] / 1965.0))
 for nm, v in zip(names, t[:5]):
     print("  %-14s %9.0f cycles/chunk  (%.1f us)" % (nm, v / n, v / n / 1965.0))
