@@ -316,7 +316,7 @@ def run_b200(args):
             os.path.join(REPO, "MEASURED_PEAKS.json")) else {}
         avg_ms = top_ms / top_calls
         alg = alg_full = alg_flops = None
-        if top_name in ("lpf_select_count", "lpf_select_fill", "lpf_select_onepass"):
+        if top_name in ("lpf_select_count", "lpf_select_fill", "lpf_select_onepass", "lpf_select_onepass_packed"):
             alg = byt["select_dedup"] / args.steps          # per launch (one launch per step)
             alg_full = byt["select_full"] / args.steps
         elif top_name == "lpf_link_heads_tc":

@@ -127,28 +127,30 @@ int lpf_select_onepass(const int64_t* links, int64_t bs,
  * sparse COO tensors with four index_select calls per batch (models/link_transformer.py:229-230, :290-291,
  * :444-449); the CSR tables above already make that a direct row access, but a link's target still costs four
  * dependent random reads in four arrays.  lpf_pack_link_rows rewrites (adjacency CSR, PPR CSR) once per graph as
- *   node_desc int32 [n,4] : (first 16-byte chunk of the node's row, deg, nP, 0)
- *   row_blob              : per node ceil(deg/4) chunks of ascending neighbour ids (pad -2), then ceil(nP/2)
- *                           chunks of (PPR column, PPR value bits) pairs in ascending column order (pad col -2)
- * so that a target is two dependent reads (16-byte descriptor, then one contiguous region).
- * row_blob needs lpf_link_rows_bytes(n, adj_nnz, ppr_nnz) bytes (an upper bound; -1 if the chunk index would
- * not fit 32 bits), scratch lpf_link_rows_scratch_bytes(n) bytes; both and node_desc 16-byte aligned.
+ *   locator uint32 [n] : (first 64-byte unit of the node's row) << 6 | min(units, 63) — 4 B per node, L2-resident
+ *   row_blob           : per node a 64-byte-aligned row of `units` x 64 B: a header (deg, nP, 0, 0), then 8-byte
+ *                        slots — the nP PPR entries as (column | 0x80000000, value bits) in ascending column order,
+ *                        then the ascending neighbour ids two per slot — padded with 0x7fffffff
+ * so that a target is one DRAM round trip (the locator says where every 16-byte chunk of the row lies) and a
+ * chunk can be interpreted without the row's header.
+ * row_blob needs lpf_link_rows_bytes(n, adj_nnz, ppr_nnz) bytes (an upper bound; -1 if the unit index would not
+ * fit 26 bits, i.e. rows beyond 4 GiB) and 64-byte alignment, scratch lpf_link_rows_scratch_bytes(n) bytes.
  *
  * lpf_select_onepass_packed is lpf_select_onepass (same outputs, same header protocol, same preconditions as
  * the INTERSECT algorithms) on those rows: a CTA stages the sources of 512 consecutive links in shared memory
- * (hash set of A(a), table of P(a)), one thread screens one link's target row, and the links that select
- * anything — or whose rows are long — are resolved by a warp each.  The CSR tables are still read by that
- * resolution and by the fallbacks (hub sources, chunks that are not runs of equal source).
+ * (bucketed hash set of A(a), table of P(a)), flattens the target rows into 64-byte units screened by four lanes
+ * each, and the links that select anything — or whose rows are long — are resolved by a warp each.  The CSR
+ * tables are still read by that resolution and by the fallbacks (chunks that are not runs of equal source).
  * ------------------------------------------------------------------------- */
 int64_t lpf_link_rows_bytes(int64_t n, int64_t adj_nnz, int64_t ppr_nnz);
 int64_t lpf_link_rows_scratch_bytes(int64_t n);
 int lpf_pack_link_rows(const int64_t* adj_rowptr, const int32_t* adj_col,
                        const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val, int64_t n,
-                       int32_t* node_desc, void* row_blob, void* scratch, void* stream);
+                       uint32_t* locator, void* row_blob, void* scratch, void* stream);
 int lpf_select_onepass_packed(const int64_t* links, int64_t bs,
                               const int64_t* adj_rowptr, const int32_t* adj_col,
                               const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val,
-                              const int32_t* node_desc, const void* row_blob,
+                              const uint32_t* locator, const void* row_blob,
                               float th_cn, float th_1hop, float th_non1hop, int mode, int64_t cap,
                               int32_t* counts, int32_t* seg_start, int32_t* nz_list, int64_t* header,
                               int32_t* node, float* src_ppr, float* tgt_ppr, void* workspace, void* stream);

@@ -3,39 +3,44 @@
 // The CSR tables cost a link four dependent random reads per endpoint (two rowptr pairs, then the adjacency row,
 // the PPR columns and — on a match — the PPR values, all in different arrays).  lpf_pack_link_rows rewrites them
 // once per graph as
-//   node_desc[x] = (first 16-byte chunk of row x, deg x, nP x, 0)                      one 16-byte read
-//   row x        = ceil(deg/4) chunks of adjacency ids (pad -2), then ceil(nP/2) chunks of (PPR col, PPR value)
-//                  pairs (pad col -2), contiguous                                        one contiguous region
-// so a link's target is TWO dependent reads (descriptor, then its row region), and the PPR value arrives with
-// its column.
+//   locator[x] (uint32) = (first 64-byte unit of row x) << 6 | min(units, 63)       4 B/node: the whole array stays
+//                                                                                   in the 126 MB L2
+//   row x (64-byte aligned, `units` x 64 B) = header (deg, nP, 0, 0), then 8-byte SLOTS: the nP PPR entries as
+//           (col | 0x80000000, value bits), then the neighbour ids two per slot, padded with 0x7fffffff
+// so a target is ONE DRAM round trip: the locator read hits L2, and it tells where every 16-byte chunk of the row
+// lies, so all of them are fetched at once.  A slot says what it is (bit 31 of its first word), hence a chunk can be
+// screened without the row's header.
 //
 // Work shape (citation2-style evaluation: runs of links sharing their source, reference train/testing.py:20-23):
 // a CTA takes 512 consecutive links = at most kPkMaxRuns runs of equal source.  The sources' adjacency rows become
-// open-addressing hash sets in shared memory and their PPR rows small shared-memory tables (all runs of the chunk
-// side by side, so every thread works at the same time), then ONE THREAD OWNS ONE LINK: it streams its target's
-// row region with 16-byte loads and probes shared memory.  All 2,048 x 148 links in flight are independent, which
-// is what hides the DRAM latency.  Links that select something (about 1 % of a citation2-shaped batch) are queued
-// and written by a compacted second walk; target rows too long for one thread are queued and walked by a warp
-// each; sources that do not fit the hash, short runs and chunks that are not run-shaped take the generic group
-// walk of select_walk.cuh.  Selected sets, their order inside a link and the fp32 values are those of every other
-// K1 variant (tests compare all of them with the oracle).
+// bucketed hash sets in shared memory and their PPR rows small shared-memory tables (all runs of the chunk side by
+// side).  The chunk's target rows are then flattened into 64-byte UNITS; FOUR LANES take one unit (one coalesced
+// 64-byte read), every unit of every link is independent of every other, and each lane keeps four reads in flight:
+// that, not the arithmetic, is what the kernel is built around — it is bound by DRAM latency x bytes in flight.
+// A unit only answers "does this link select anything?" (a common neighbour, or a node in both PPR rows above the
+// smaller PPR threshold); 99 % of a citation2-shaped batch selects nothing and is finished there.  The links that
+// do, and target rows beyond kPkMaxUnits, are resolved by a warp each (count -> allocate -> ordered write, from the
+// CSR tables); hub sources that do not fit the hash go to a second launch with a 32K-slot table; chunks that are
+// not run-shaped take the generic group walk of select_walk.cuh.  Selected sets, their order inside a link and the
+// fp32 values are those of every other K1 variant (tests compare all of them with the oracle).
 #include <stdlib.h>
 
 #include "select_hashed.cuh"
 
 namespace lpf {
 
-constexpr int kPkThreads = 512;       // threads per CTA = links per chunk
+constexpr int kPkThreads = 512;       // threads per CTA
+constexpr int kPkChunk = 1024;        // most links of one chunk: the batch is cut evenly over the resident CTAs
 constexpr int kPkMaxRuns = 3;
 constexpr int kPkHashSlots = 8192;    // int32 slots shared by the runs of a chunk (load <= 0.5): sources up to 4,096
 constexpr int kPkHubSlots = 32768;    // second launch, one CTA per SM: hub sources up to 16,384 neighbours
 constexpr int kPkMaxPprRow = 128;
-constexpr int kPkLaneAdj = 32;        // target rows of up to 32 adjacency chunks (128 neighbours) ...
-constexpr int kPkLanePpr = 32;        // ... and 32 PPR chunks (64 entries) are screened by the link's own thread
+constexpr int kPkMaxUnits = 16;       // target rows of up to 16 units (1 KB: ~250 neighbours) are screened unit-wise
+constexpr int kPkMaxItems = 6144;     // units of one chunk that are screened unit-wise (the rest get a warp)
 constexpr int kPkWarpRow = 512;       // resolution: target rows up to this length take the hashed warp walk
 constexpr int kPkHubPiece = 128;      // links per entry of the hub list
-constexpr int kPkBins = 8;            // row-length bins of the in-chunk ordering
-constexpr int kPkPrefetchLines = 32;  // 128-byte lines of a target row prefetched into L2 by its thread
+constexpr uint32_t kPkPprTag = 0x80000000u;
+constexpr uint32_t kPkPad = 0x7fffffffu;
 
 struct PkRunTab {
     int32_t pac[kPkMaxPprRow];
@@ -47,18 +52,22 @@ template <int SLOTS>
 struct PkSmemT {
     int32_t tab[SLOTS];
     PkRunTab run[kPkMaxRuns];
-    int32_t q_slow[kPkThreads];          // chunk positions of the links that get a warp (long row / selects something)
-    int16_t order[kPkThreads];           // chunk positions ordered by row length
-    uint32_t l_off[kPkThreads];          // per link of the chunk: first chunk of the target's packed row,
-    uint16_t l_ca[kPkThreads], l_nc[kPkThreads];   // its adjacency chunks and the chunks the screening walks
-    int32_t bin_cnt[kPkBins];
+    uint32_t l_loc[kPkChunk];            // locator of every link's target row
+    uint16_t items[kPkMaxItems];         // (chunk position << 4 | unit) of every unit to screen
+    uint16_t q_slow[kPkChunk];           // chunk positions of the links that get a warp (long row / selects something)
+    uint8_t l_any[kPkChunk];             // "selects something" flags raised by the screening
+    int32_t warp_tot[kPkThreads / 32];
     int32_t run_start[kPkMaxRuns + 1];
     int32_t r_tab0[kPkMaxRuns], r_lg[kPkMaxRuns], r_na[kPkMaxRuns], r_npa[kPkMaxRuns], r_hashed[kPkMaxRuns];
-    uint32_t r_off[kPkMaxRuns];
-    int n_runs, n_slow, tab_used;
+    uint32_t r_loc[kPkMaxRuns];
+    int32_t r_slots[kPkMaxRuns];
+    int n_runs, n_slow, n_items, tab_used, items_full;
 };
 
 __device__ __forceinline__ uint4 ldg16(const uint4* p) { return __ldg(p); }
+__device__ __forceinline__ const uint4* row_of(const uint4* __restrict__ blob, uint32_t loc) {
+    return blob + (size_t)(loc >> 6) * 4;          // 64-byte units -> 16-byte chunks
+}
 
 template <class SM>
 __device__ __forceinline__ RunCtx make_ctx(const SM& sm, int r) {
@@ -74,54 +83,26 @@ __device__ __forceinline__ RunCtx make_ctx(const SM& sm, int r) {
     return h;
 }
 
-// Membership of u in the source's adjacency row: the shared-memory hash set when the row was staged, else a
-// binary search over the source's packed row in global memory (hub sources: the row stays L1/L2-resident because
-// every link of the run probes it).
+// One 8-byte slot of a target row against the staged source: a PPR entry (both values above the smaller PPR
+// threshold = a candidate 1-hop / >1-hop node) or two neighbour ids (either one in A(a) = a common neighbour).
+// HASHED = false: the source's adjacency row was not staged (a source beyond even the hub table); its ids in its
+// packed row in global memory (ascending) are searched instead.
 template <bool HASHED>
-__device__ __forceinline__ bool src_contains(const RunCtx& h, const int32_t* __restrict__ arow, int na, int32_t u) {
-    if (HASHED) return hash_contains(h.tab, h.mask, h.shift, u);
-    const int t = lower_bound_from(arow, 0, na, u);
-    return t < na && __ldg(arow + t) == u;
-}
-
-// One thread screens one link: does its packed target row select ANYTHING against the staged source?  (A common
-// neighbour, or a node in both PPR rows above the smaller PPR threshold — a superset test for the 1-hop / >1-hop
-// sets, exact for "nothing selected".)  Three 16-byte loads stay in flight; the rows were prefetched into L2.
-template <bool HASHED>
-__device__ __forceinline__ bool screen_packed(const RunCtx& h, const int32_t* __restrict__ arow, int na,
-                                              const uint4* __restrict__ row, int ca, int nc, float th_pre) {
-    if (nc == 0) return false;
-    const uint4 z = make_uint4(0xfffffffeu, 0, 0xfffffffeu, 0);
-    uint4 v0 = ldg16(row);
-    uint4 v1 = nc > 1 ? ldg16(row + 1) : z;
-    bool any = false;
-    int c = 0;
-    for (; c < ca; ++c) {
-        const uint4 v2 = (c + 2 < nc) ? ldg16(row + c + 2) : z;
-        if (HASHED) {
-            any |= hash_contains_any2(h.tab, h.mask, h.shift, (int32_t)v0.x, (int32_t)v0.y);
-            any |= hash_contains_any2(h.tab, h.mask, h.shift, (int32_t)v0.z, (int32_t)v0.w);
-        } else {
-            any |= src_contains<false>(h, arow, na, (int32_t)v0.x);
-            any |= src_contains<false>(h, arow, na, (int32_t)v0.y);
-            any |= src_contains<false>(h, arow, na, (int32_t)v0.z);
-            any |= src_contains<false>(h, arow, na, (int32_t)v0.w);
-        }
-        v0 = v1;
-        v1 = v2;
-    }
-    for (; c < nc; ++c) {
-        const uint4 v2 = (c + 2 < nc) ? ldg16(row + c + 2) : z;
+__device__ __forceinline__ bool screen_slot(const RunCtx& h, const int32_t* __restrict__ arow_ids, int na, uint32_t w0,
+                                            uint32_t w1, bool want_pi, float th_pre) {
+    if (w0 & kPkPprTag) {
         float qa;
-        if (smem_ppr_lookup(h, (int32_t)v0.x, qa)) any |= qa >= th_pre && quantise(__uint_as_float(v0.y)) >= th_pre;
-        if (smem_ppr_lookup(h, (int32_t)v0.z, qa)) any |= qa >= th_pre && quantise(__uint_as_float(v0.w)) >= th_pre;
-        v0 = v1;
-        v1 = v2;
+        return want_pi && smem_ppr_lookup(h, (int32_t)(w0 & ~kPkPprTag), qa) && qa >= th_pre &&
+               quantise(__uint_as_float(w1)) >= th_pre;
     }
-    return any;
+    if (HASHED) return hash_contains_any2(h.tab, h.mask, h.shift, (int32_t)w0, (int32_t)w1);
+    int t = lower_bound_from(arow_ids, 0, na, (int32_t)w0);
+    if (t < na && __ldg(arow_ids + t) == (int32_t)w0) return true;
+    t = lower_bound_from(arow_ids, 0, na, (int32_t)w1);
+    return t < na && __ldg(arow_ids + t) == (int32_t)w1;
 }
 
-// Rare, register-hungry paths kept out of line so that they do not set the register budget of the screening walk.
+// Rare, register-hungry paths kept out of line so that they do not set the register budget of the screening.
 __device__ __noinline__ void generic_link8(const SelectParams2& p, int64_t i, int lane) {
     const LinkRows r = load_rows(p, i);
     if (is_heavy(r, p.mode != LPF_MODE_CN, 8)) {
@@ -130,17 +111,116 @@ __device__ __noinline__ void generic_link8(const SelectParams2& p, int64_t i, in
     }
     onepass_link<8>(p, nullptr, r, i, lane);
 }
-// A link that needs resolving (it selects something, or its target row is long), by one warp: the hashed walk of
-// the target row when that row is short enough, else the generic walk (shorter row against the longer), else —
-// both rows long — the CTA-wide kernel that runs afterwards.
-template <class SM>
-__device__ __noinline__ void resolve_link32(const SelectParams2& p, const SM& sm, int r, int64_t i, int lane) {
-    const LinkRows rows = load_rows(p, i);
+// One warp walks one link's PACKED target row (L2-hot: the screening just read it) against the staged source:
+// lane l takes slot l, l + 32, ... — a PPR entry or two neighbour ids — so ascending node order within each set is
+// lane order, and the ordered write needs only ballots.  Same sets, order and values as walk_link_hashed.
+template <bool WRITE>
+__device__ __forceinline__ void walk_packed_warp(const SelectParams2& p, const RunCtx& h, const uint4* __restrict__ row,
+                                                 int lane, int64_t o_cn, int64_t o_1h, int64_t o_n1, int& c_cn, int& c_1h,
+                                                 int& c_n1) {
+    const uint4 hd = ldg16(row);
+    const int deg = (int)hd.x, npp = (int)hd.y;
+    const int32_t* words = reinterpret_cast<const int32_t*>(row) + 4;
+    const int32_t* ids = words + 2 * npp;
+    const int S = npp + ((deg + 1) >> 1);
+    const unsigned lt = (1u << lane) - 1u;
     const bool want_pi = p.mode != LPF_MODE_CN;
-    if (sm.r_hashed[r] == 1 && rows.nb <= kPkWarpRow && rows.npb <= kPkWarpRow) {
+    const bool want_n1 = p.mode == LPF_MODE_ALL;
+    const bool cn_needs_ppr = WRITE || p.th_cn > 0.0f;
+    const float th_pre = want_n1 ? fminf(p.th_1hop, p.th_non1hop) : p.th_1hop;
+    c_cn = c_1h = c_n1 = 0;
+    for (int s0 = want_pi ? 0 : (npp & ~31); s0 < S; s0 += 32) {
+        const int s = s0 + lane;
+        uint32_t w0 = kPkPad, w1 = kPkPad;
+        if (s < S && (want_pi || s >= npp)) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(words) + s);
+            w0 = v.x; w1 = v.y;
+        }
+        bool k1 = false, kn = false, h0 = false, h1 = false;
+        float qa = 0.f, qb = 0.f, qa1 = 0.f, qb1 = 0.f;
+        int32_t u = (int32_t)w0;
+        if (w0 & kPkPprTag) {
+            u = (int32_t)(w0 & ~kPkPprTag);
+            if (smem_ppr_lookup(h, u, qa)) {
+                qb = quantise(__uint_as_float(w1));
+                if (qa >= th_pre && qb >= th_pre) {
+                    const bool in_a = hash_contains(h.tab, h.mask, h.shift, u);
+                    const int t = lower_bound_from(ids, 0, deg, u);
+                    const bool in_b = t < deg && __ldg(ids + t) == u;
+                    k1 = (in_a != in_b) && qa >= p.th_1hop && qb >= p.th_1hop;
+                    kn = want_n1 && !in_a && !in_b && qa >= p.th_non1hop && qb >= p.th_non1hop;
+                }
+            }
+        } else {
+            h0 = hash_contains(h.tab, h.mask, h.shift, (int32_t)w0);
+            h1 = hash_contains(h.tab, h.mask, h.shift, (int32_t)w1);
+            if (cn_needs_ppr && (h0 || h1)) {
+                // PPR values of a common neighbour: P(a) from shared memory, P(b) by search over the row's PPR slots
+                auto pb_of = [&](int32_t x) -> float {
+                    int lo = 0, hi = npp;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if ((__ldg(words + 2 * mid) & 0x7fffffff) < x) lo = mid + 1; else hi = mid;
+                    }
+                    return (lo < npp && (__ldg(words + 2 * lo) & 0x7fffffff) == x) ? quantise(__int_as_float(__ldg(words + 2 * lo + 1))) : 0.f;
+                };
+                if (h0) {
+                    smem_ppr_lookup(h, (int32_t)w0, qa);
+                    qb = pb_of((int32_t)w0);
+                    h0 = qa >= p.th_cn && qb >= p.th_cn;
+                }
+                if (h1) {
+                    smem_ppr_lookup(h, (int32_t)w1, qa1);
+                    qb1 = pb_of((int32_t)w1);
+                    h1 = qa1 >= p.th_cn && qb1 >= p.th_cn;
+                }
+            }
+        }
+        const unsigned m1 = __ballot_sync(kFull, k1), mn = __ballot_sync(kFull, kn);
+        const unsigned mh0 = __ballot_sync(kFull, h0), mh1 = __ballot_sync(kFull, h1);
+        if (WRITE) {
+            if (k1 || kn) {
+                const int64_t r = k1 ? o_1h + c_1h + __popc(m1 & lt) : o_n1 + c_n1 + __popc(mn & lt);
+                p.node[r] = u; p.pa[r] = qa; p.pb[r] = qb;
+            }
+            const int64_t r0 = o_cn + c_cn + __popc(mh0 & lt) + __popc(mh1 & lt);
+            if (h0) { p.node[r0] = (int32_t)w0; p.pa[r0] = qa; p.pb[r0] = qb; }
+            if (h1) { const int64_t r1 = r0 + (h0 ? 1 : 0); p.node[r1] = (int32_t)w1; p.pa[r1] = qa1; p.pb[r1] = qb1; }
+        }
+        c_1h += __popc(m1);
+        c_n1 += __popc(mn);
+        c_cn += __popc(mh0) + __popc(mh1);
+    }
+}
+
+// A link that needs resolving (it selects something, or its target row is long), by one warp (count -> allocate ->
+// ordered write): the walk of its packed target row against the staged source when that row is short enough, else
+// the generic walk over the CSR tables (shorter row against the longer), else — both rows long — the CTA-wide kernel
+// that runs afterwards.
+template <class SM>
+__device__ __noinline__ void resolve_link32(const SelectParams2& p, const SM& sm, const uint4* __restrict__ blob, int r,
+                                            int t, int64_t i, int lane) {
+    const bool want_pi = p.mode != LPF_MODE_CN;
+    const uint4* row = row_of(blob, sm.l_loc[t]);
+    const uint4 hd = ldg16(row);
+    if (sm.r_hashed[r] == 1 && (int)hd.x <= kPkWarpRow && (int)hd.y <= kPkWarpRow) {
         const RunCtx h = make_ctx(sm, r);
-        onepass_link<32>(p, &h, rows, i, lane);
-    } else if (!is_heavy(rows, want_pi, 8)) {
+        int c_cn, c_1h, c_n1;
+        walk_packed_warp<false>(p, h, row, lane, 0, 0, 0, c_cn, c_1h, c_n1);
+        int64_t s_cn = 0, s_1h = 0, s_n1 = 0;
+        int ok = 1;
+        if (lane == 0) ok = alloc_segments(p, i, c_cn, c_1h, c_n1, s_cn, s_1h, s_n1) ? 1 : 0;
+        if (c_cn + c_1h + c_n1 == 0) return;
+        ok = __shfl_sync(kFull, ok, 0);
+        if (!ok) return;
+        s_cn = __shfl_sync(kFull, s_cn, 0);
+        s_1h = __shfl_sync(kFull, s_1h, 0);
+        s_n1 = __shfl_sync(kFull, s_n1, 0);
+        walk_packed_warp<true>(p, h, row, lane, s_cn, p.cap + s_1h, 2 * p.cap + s_n1, c_cn, c_1h, c_n1);
+        return;
+    }
+    const LinkRows rows = load_rows(p, i);
+    if (!is_heavy(rows, want_pi, 8)) {
         onepass_link<32>(p, nullptr, rows, i, lane);
     } else if (lane == 0) {
         p.heavy[4 + atomicAdd(p.heavy, 1)] = (int32_t)i;
@@ -148,10 +228,6 @@ __device__ __noinline__ void resolve_link32(const SelectParams2& p, const SM& sm
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
-// one instruction brings a whole contiguous row region (16-byte aligned, a multiple of 16 bytes) into L2
-__device__ __forceinline__ void prefetch_l2_bulk(const void* ptr, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
-}
 
 template <class SM>
 __device__ __forceinline__ int run_of(const SM& sm, int t) {
@@ -163,7 +239,7 @@ __device__ __forceinline__ int run_of(const SM& sm, int t) {
 // entries of that list.
 template <int SLOTS, bool HUB>
 __global__ void __launch_bounds__(kPkThreads, HUB ? 1 : 3)
-select_onepass_packed_kernel(SelectParams2 p, const int4* __restrict__ desc, const uint4* __restrict__ blob, int variant) {
+select_onepass_packed_kernel(SelectParams2 p, const uint32_t* __restrict__ locator, const uint4* __restrict__ blob) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     using SM = PkSmemT<SLOTS>;
     SM& sm = *reinterpret_cast<SM*>(smem_raw);
@@ -173,7 +249,9 @@ select_onepass_packed_kernel(SelectParams2 p, const int4* __restrict__ desc, con
     const bool want_pi = p.mode != LPF_MODE_CN;
     const bool want_n1 = p.mode == LPF_MODE_ALL;
     const float th_pre = want_n1 ? fminf(p.th_1hop, p.th_non1hop) : p.th_1hop;
-    const int64_t nchunks = HUB ? (int64_t)p.hub[0] : (p.bs + kPkThreads - 1) / kPkThreads;
+    // !HUB: the batch in `gridDim.x`-many (or more) even pieces of at most kPkChunk links
+    const int64_t per = HUB ? 0 : min((int64_t)kPkChunk, max((int64_t)kPkThreads, (p.bs + gridDim.x - 1) / gridDim.x));
+    const int64_t nchunks = HUB ? (int64_t)p.hub[0] : (p.bs + per - 1) / per;
 
     long long t_mark = clock64();
 #define LPF_PHASE(k)                                                              \
@@ -188,49 +266,34 @@ select_onepass_packed_kernel(SelectParams2 p, const int4* __restrict__ desc, con
     const long long t_cta = t_mark;
     for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         const long long t_chunk = clock64();
-        const int64_t i0 = HUB ? (int64_t)p.hub[1 + 2 * chunk] : chunk * kPkThreads;
-        const int len = HUB ? p.hub[2 + 2 * chunk] : (int)min((int64_t)kPkThreads, p.bs - i0);
-        const int64_t i = i0 + tid;
+        const int64_t i0 = HUB ? (int64_t)p.hub[1 + 2 * chunk] : chunk * per;
+        const int len = HUB ? p.hub[2 + 2 * chunk] : (int)min(per, p.bs - i0);
         if (p.dbg && tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 5), 1ull);
-        // ---- this thread's link: its target descriptor is fetched now and its row region prefetched into L2, so
-        // that both reads overlap the staging of the sources
-        const int64_t a_me = (tid < len) ? __ldg(p.links + i) : -1;
-        const int64_t a_prev = (tid > 0 && tid < len) ? __ldg(p.links + i - 1) : -2;
-        int4 db = make_int4(0, 0, 0, 0), da = make_int4(0, 0, 0, 0);
-        if (tid < len) {
-            db = __ldg(desc + __ldg(p.links + p.bs + i));
-            da = __ldg(desc + a_me);             // one address per run: a broadcast read
-            const int nc = ((db.y + 3) >> 2) + (want_pi ? ((db.z + 1) >> 1) : 0);
-            sm.l_off[tid] = (uint32_t)db.x;
-            sm.l_ca[tid] = (uint16_t)min((db.y + 3) >> 2, 65535);
-            sm.l_nc[tid] = (uint16_t)min(nc, 65535);
-            const uint8_t* r0 = reinterpret_cast<const uint8_t*>(blob + (uint32_t)db.x);
-            if (variant == 1) {
-                const uint8_t* r1 = r0 + 16 * nc;
-                const uint8_t* line = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(r0) & ~(uintptr_t)127);
-                for (int k = 0; k < kPkPrefetchLines && line < r1; ++k, line += 128) prefetch_l2(line);
-            } else if (variant == 2) {
-                if (nc > 0) prefetch_l2_bulk(r0, 16u * (uint32_t)min(nc, 8 * kPkPrefetchLines));
-            }
+        if (tid == 0) { sm.n_runs = 0; sm.n_slow = 0; sm.n_items = 0; sm.items_full = 0; }
+        __syncthreads();
+        // ---- the chunk's links (positions tid, tid + 512): locator of the target (an L2-resident array), run
+        // boundaries with the locator of their source
+        for (int t = tid; t < len; t += kPkThreads) {
+            const int64_t i = i0 + t;
+            const int64_t a_me = __ldg(p.links + i);
+            const int64_t a_prev = t > 0 ? __ldg(p.links + i - 1) : -1;
+            sm.l_loc[t] = __ldg(locator + __ldg(p.links + p.bs + i));
+            sm.l_any[t] = 0;
             if (!HUB) {
                 // every link starts as "nothing selected"; the links that are resolved later overwrite their entries
                 p.counts[i] = 0; p.counts[p.bs + i] = 0; p.counts[2 * p.bs + i] = 0;
                 p.seg_start[i] = 0; p.seg_start[p.bs + i] = 0; p.seg_start[2 * p.bs + i] = 0;
             }
-        }
-        const bool boundary = tid < len && (tid == 0 || a_me != a_prev);
-        if (tid == 0) sm.n_runs = 0;
-        if (tid < kPkBins) sm.bin_cnt[tid] = 0;
-        __syncthreads();
-        if (boundary) {
-            const int k = atomicAdd(&sm.n_runs, 1);
-            if (k < kPkMaxRuns) sm.run_start[k] = tid;
-            // the source's row: its first lines towards L2 while the run structure is sorted out
-            const uint8_t* r0 = reinterpret_cast<const uint8_t*>(blob + (uint32_t)da.x);
-            const uint8_t* r1 = r0 + 16 * (((da.y + 3) >> 2) + ((da.z + 1) >> 1));
-            for (int kk = 0; kk < kPkPrefetchLines && r0 < r1; ++kk, r0 += 128) prefetch_l2(r0);
+            if (t == 0 || a_me != a_prev) {
+                const int k = atomicAdd(&sm.n_runs, 1);
+                if (k < kPkMaxRuns) {
+                    sm.run_start[k] = t;
+                    sm.r_loc[k] = __ldg(locator + a_me);
+                }
+            }
         }
         __syncthreads();
+        LPF_PHASE(10);
         const int n_runs = sm.n_runs;
         if (n_runs > kPkMaxRuns) {
             // not run-shaped: generic one-pass walk, 8 lanes per link
@@ -239,26 +302,27 @@ select_onepass_packed_kernel(SelectParams2 p, const int4* __restrict__ desc, con
             LPF_PHASE(4);
             continue;
         }
-        if (tid == 0) {      // sort the (at most kPkMaxRuns) boundaries, close the list
+        if (tid == 0) {
+            // sort the (at most kPkMaxRuns) boundaries, close the list
             for (int x = 1; x < n_runs; ++x)
                 for (int y = x; y > 0 && sm.run_start[y] < sm.run_start[y - 1]; --y) {
                     const int tmp = sm.run_start[y]; sm.run_start[y] = sm.run_start[y - 1]; sm.run_start[y - 1] = tmp;
+                    const uint32_t tl = sm.r_loc[y]; sm.r_loc[y] = sm.r_loc[y - 1]; sm.r_loc[y - 1] = tl;
                 }
             for (int x = n_runs; x <= kPkMaxRuns; ++x) sm.run_start[x] = len;
-            sm.n_slow = 0;
-        }
-        __syncthreads();
-        if (boundary) {
-            const int r = run_of(sm, tid);
-            sm.r_off[r] = (uint32_t)da.x;
-            sm.r_na[r] = da.y;
-            sm.r_npa[r] = da.z;
-        }
-        __syncthreads();
-        if (tid == 0) {      // hash regions: power of two >= 2*na (>= 64) per run, side by side
+            // hash regions per run, side by side
             int used = 0;
             for (int r = 0; r < n_runs; ++r) {
-                const int na = sm.r_na[r];
+                // the source's size: from its locator when that says it all (an upper bound of the degree: every slot
+                // taken as two ids), from its header for rows of 63 units and more (one more read, big sources only)
+                const int units_a = (int)(sm.r_loc[r] & 63u);
+                int na = 2 * (8 * units_a - 2), slots_a = 8 * units_a - 2;
+                if (units_a == 63) {
+                    const uint4 hd = ldg16(row_of(blob, sm.r_loc[r]));
+                    na = (int)hd.x;
+                    slots_a = (int)hd.y + (((int)hd.x + 1) >> 1);
+                }
+                sm.r_slots[r] = slots_a;
                 // slots: a power of two >= 4*na (load <= 0.25: almost every probe ends in its home bucket) while
                 // the table has room, never less than 2*na
                 int lg = 6;
@@ -268,7 +332,7 @@ select_onepass_packed_kernel(SelectParams2 p, const int4* __restrict__ desc, con
                 // even the hub table); 3 = handed to the hub launch; 0 = no screening (source PPR row too long for the
                 // shared table): generic walk
                 const bool fits = used + (1 << lg) <= SLOTS;
-                int m = sm.r_npa[r] > kPkMaxPprRow ? 0 : (fits ? 1 : 2);
+                int m = fits ? 1 : 2;
                 if (!HUB && m == 2 && (1 << lg) <= kPkHubSlots) {
                     // in pieces of kPkHubPiece links: the hub launch has a CTA (and an SM) for each of them
                     m = 3;
@@ -288,72 +352,131 @@ select_onepass_packed_kernel(SelectParams2 p, const int4* __restrict__ desc, con
             sm.tab_used = used;
         }
         __syncthreads();
+        LPF_PHASE(12);
         {
             const int used = sm.tab_used;
             for (int s = tid; s < used; s += kPkThreads) sm.tab[s] = -1;
             for (int s = tid; s < n_runs * kPprHashSlots; s += kPkThreads)
                 sm.run[s / kPprHashSlots].ppos[s % kPprHashSlots] = -1;
         }
-        __syncthreads();
+        __syncthreads();     // tables cleared
+        // ---- flatten the chunk's target rows into 64-byte units: items[] = (chunk position << 4 | unit), in link
+        // order, 512 positions per pass.  The list holds a prefix of the chunk's units; what does not fit, and rows
+        // beyond kPkMaxUnits, get a warp.
+        for (int t0 = 0; t0 < len; t0 += kPkThreads) {
+            const int t = t0 + tid;
+            const int r = run_of(sm, min(t, len - 1));
+            const bool screened = t < len && (sm.r_hashed[r] == 1 || sm.r_hashed[r] == 2);
+            const uint32_t loc_b = t < len ? sm.l_loc[t] : 0u;
+            const int units = screened ? (int)(loc_b & 63u) : 0;
+            const int mine = units > kPkMaxUnits ? 0 : units;
+            int inc = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int x = __shfl_up_sync(kFull, inc, o);
+                if (lane >= o) inc += x;
+            }
+            if (lane == 31) sm.warp_tot[warp] = inc;
+            const int base0 = sm.n_items;        // units listed by the previous pass
+            const bool full_before = sm.items_full != 0;
+            __syncthreads();
+            int ex = base0 + inc - mine;
+#pragma unroll
+            for (int w = 0; w < kPkThreads / 32; ++w) ex += (w < warp) ? sm.warp_tot[w] : 0;
+            const bool fits = !full_before && ex + mine <= kPkMaxItems;
+            if (screened) {
+                if (units > kPkMaxUnits || !fits) {
+                    sm.q_slow[atomicAdd(&sm.n_slow, 1)] = (uint16_t)t;
+                    // a long row: its first lines towards L2 now, the warp that resolves it comes much later
+                    const uint8_t* r0 = reinterpret_cast<const uint8_t*>(row_of(blob, loc_b));
+                    for (int k = 0; k < min(units, 36); k += 2) prefetch_l2(r0 + 64 * k);
+                } else {
+                    for (int u = 0; u < units; ++u) sm.items[ex + u] = (uint16_t)((t << 4) | u);
+                }
+            }
+            __syncthreads();     // everyone has read n_items / items_full of the previous pass
+            // the listed units end at the first link that does not fit (later, shorter rows must not leave holes)
+            if (!full_before && mine > 0 && !fits && ex <= kPkMaxItems) { sm.n_items = ex; sm.items_full = 1; }
+            if (tid == kPkThreads - 1 && fits) sm.n_items = ex + mine;
+            __syncthreads();
+        }
+        LPF_PHASE(13);
+        // ---- stage the sources from their packed rows: the slots say what they are, so every thread just takes
+        // slot tid, tid + 512, ...: a PPR entry goes to the run's table, two ids go to its hash set
         for (int r = 0; r < n_runs; ++r) {
             const int mode_r = sm.r_hashed[r];
-            if (mode_r == 0 || mode_r == 3) continue;
-            const int na = sm.r_na[r], npa = sm.r_npa[r], lg = sm.r_lg[r];
+            if (mode_r == 3) continue;
+            const int lg = sm.r_lg[r], n_slots = sm.r_slots[r];
             int32_t* tab = sm.tab + sm.r_tab0[r];
-            const int32_t* arow = reinterpret_cast<const int32_t*>(blob + sm.r_off[r]);
-            if (mode_r == 1)
-                for (int s = tid; s < na; s += kPkThreads)
-                    hash_insert(tab, (1u << (lg - 2)) - 1u, 32 - (lg - 2), __ldg(arow + s));
-            const int32_t* prow = arow + 4 * ((na + 3) >> 2);
-            for (int s = tid; s < npa; s += kPkThreads) {
-                const int32_t u = __ldg(prow + 2 * s);
-                sm.run[r].pac[s] = u;
-                sm.run[r].pav[s] = __int_as_float(__ldg(prow + 2 * s + 1));
-                uint32_t slot = hash_slot(u, 32 - 8);
-                while (atomicCAS(&sm.run[r].ppos[slot], -1, s) != -1) slot = (slot + 1) & (kPprHashSlots - 1);
+            const uint4* row = row_of(blob, sm.r_loc[r]);
+            if (tid == 0) {
+                const uint4 hd = ldg16(row);
+                sm.r_na[r] = (int)hd.x;
+                sm.r_npa[r] = (int)hd.y;
+                if ((int)hd.y > kPkMaxPprRow) sm.r_hashed[r] = 0;     // PPR row beyond the shared table: generic walk
+            }
+            const uint2* slots = reinterpret_cast<const uint2*>(row) + 2;      // after the header
+            for (int s = tid; s < n_slots; s += kPkThreads) {
+                const uint2 v = __ldg(slots + s);
+                if (v.x & kPkPprTag) {
+                    if (s < kPkMaxPprRow) {
+                        const int32_t u = (int32_t)(v.x & ~kPkPprTag);
+                        sm.run[r].pac[s] = u;
+                        sm.run[r].pav[s] = __uint_as_float(v.y);
+                        uint32_t slot = hash_slot(u, 32 - 8);
+                        while (atomicCAS(&sm.run[r].ppos[slot], -1, s) != -1) slot = (slot + 1) & (kPprHashSlots - 1);
+                    }
+                } else if (mode_r == 1) {
+                    if (v.x != kPkPad) hash_insert(tab, (1u << (lg - 2)) - 1u, 32 - (lg - 2), (int32_t)v.x);
+                    if (v.y != kPkPad) hash_insert(tab, (1u << (lg - 2)) - 1u, 32 - (lg - 2), (int32_t)v.y);
+                }
             }
         }
-        // ---- order the chunk's links by row length (descending, 8 bins) so that the lanes of a warp finish together
-        const int my_run = run_of(sm, tid);
-        const int ca_me = (db.y + 3) >> 2, cp_me = (db.z + 1) >> 1;
-        const int nc_me = ca_me + (want_pi ? cp_me : 0);
-        const bool screened = tid < len && (sm.r_hashed[my_run] == 1 || sm.r_hashed[my_run] == 2);
-        const bool too_long = ca_me > kPkLaneAdj || cp_me > kPkLanePpr;
-        int bin = 0, rank_in_bin = 0;
-        if (screened) {
-            if (too_long) {
-                sm.q_slow[atomicAdd(&sm.n_slow, 1)] = tid;
-            } else {
-                bin = nc_me <= 1 ? 0 : min(kPkBins - 1, 32 - __clz(nc_me - 1));
-                rank_in_bin = atomicAdd(&sm.bin_cnt[bin], 1);
-            }
-        }
-        __syncthreads();
-        if (screened && !too_long) {
-            int base = 0;
-#pragma unroll
-            for (int k = kPkBins - 1; k > 0; --k) base += (k > bin) ? sm.bin_cnt[k] : 0;
-            sm.order[base + rank_in_bin] = (int16_t)tid;
-        }
-        int n_sorted = 0;
-#pragma unroll
-        for (int k = 0; k < kPkBins; ++k) n_sorted += sm.bin_cnt[k];
         __syncthreads();
         LPF_PHASE(0);
 
-        // ---- phase A: one thread, one link.  A link that selects nothing (99 % of a citation2-shaped batch) is
-        // finished here; the others are queued for a warp each.
-        if (tid < n_sorted) {
-            const int t = sm.order[tid];
-            const int r = run_of(sm, t);
-            const RunCtx h = make_ctx(sm, r);
-            const int32_t* arow = reinterpret_cast<const int32_t*>(blob + sm.r_off[r]);
-            const uint4* row = blob + sm.l_off[t];
-            const int ca = sm.l_ca[t], nc = sm.l_nc[t];
-            const bool any = sm.r_hashed[r] == 1 ? screen_packed<true>(h, arow, sm.r_na[r], row, ca, nc, th_pre)
-                                                 : screen_packed<false>(h, arow, sm.r_na[r], row, ca, nc, th_pre);
-            if (any) sm.q_slow[atomicAdd(&sm.n_slow, 1)] = t;
+        // ---- phase A: four lanes per 64-byte unit, four units in flight per lane
+        {
+            const int n_items = sm.n_items;
+            const int ql = tid & 3;
+            for (int q0 = tid >> 2; q0 < n_items; q0 += 4 * (kPkThreads / 4)) {
+                uint4 v[4];
+                int tt[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int q = q0 + k * (kPkThreads / 4);
+                    tt[k] = -1;
+                    v[k] = make_uint4(kPkPad, kPkPad, kPkPad, kPkPad);
+                    if (q < n_items) {
+                        const int it = sm.items[q];
+                        const int t = it >> 4, u = it & 15;
+                        tt[k] = (u == 0 && ql == 0) ? -1 : t;            // chunk 0 of unit 0 is the row's header
+                        v[k] = ldg16(row_of(blob, sm.l_loc[t]) + 4 * u + ql);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int t = tt[k];
+                    if (t < 0) continue;
+                    const int r = run_of(sm, t);
+                    const RunCtx h = make_ctx(sm, r);
+                    bool any;
+                    if (sm.r_hashed[r] == 0) continue;       // the run turned out not to be screenable
+                    if (sm.r_hashed[r] == 1) {
+                        any = screen_slot<true>(h, nullptr, 0, v[k].x, v[k].y, want_pi, th_pre) |
+                              screen_slot<true>(h, nullptr, 0, v[k].z, v[k].w, want_pi, th_pre);
+                    } else {
+                        const int32_t* ids = reinterpret_cast<const int32_t*>(row_of(blob, sm.r_loc[r])) + 4 + 2 * sm.r_npa[r];
+                        any = screen_slot<false>(h, ids, sm.r_na[r], v[k].x, v[k].y, want_pi, th_pre) |
+                              screen_slot<false>(h, ids, sm.r_na[r], v[k].z, v[k].w, want_pi, th_pre);
+                    }
+                    if (any) sm.l_any[t] = 1;
+                }
+            }
         }
+        __syncthreads();
+        for (int t = tid; t < len; t += kPkThreads)
+            if (sm.l_any[t]) sm.q_slow[atomicAdd(&sm.n_slow, 1)] = (uint16_t)t;
         __syncthreads();
         LPF_PHASE(1);
 
@@ -367,7 +490,9 @@ select_onepass_packed_kernel(SelectParams2 p, const int4* __restrict__ desc, con
         const int ns = sm.n_slow;
         for (int q = warp; q < ns; q += kPkThreads / 32) {
             const int t = sm.q_slow[q];
-            resolve_link32(p, sm, run_of(sm, t), i0 + t, lane);
+            const int r = run_of(sm, t);
+            if (sm.r_hashed[r] == 0) continue;       // its whole run took the generic walk above
+            resolve_link32(p, sm, blob, r, t, i0 + t, lane);
         }
         if (p.dbg && tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 6), (unsigned long long)ns);
         LPF_PHASE(2);
@@ -383,18 +508,21 @@ select_onepass_packed_kernel(SelectParams2 p, const int4* __restrict__ desc, con
 // ---------------------------------------------------------------------------------------------------------
 // Building the packed rows (once per graph).
 // ---------------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int64_t row_units(int64_t deg, int64_t npp) {
+    return (16 + 8 * (npp + ((deg + 1) >> 1)) + 63) >> 6;
+}
+
 __global__ void pack_count_kernel(const int64_t* __restrict__ arp, const int64_t* __restrict__ prp, int64_t n,
-                                  int32_t* __restrict__ chunks) {
+                                  int32_t* __restrict__ units) {
     const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= n) return;
-    const int64_t deg = arp[x + 1] - arp[x], npp = prp[x + 1] - prp[x];
-    chunks[x] = (int32_t)(((deg + 3) >> 2) + ((npp + 1) >> 1));
+    units[x] = (int32_t)row_units(arp[x + 1] - arp[x], prp[x + 1] - prp[x]);
 }
 
 __global__ void __launch_bounds__(256) pack_fill_kernel(const int64_t* __restrict__ arp, const int32_t* __restrict__ ac,
                                                         const int64_t* __restrict__ prp, const int32_t* __restrict__ pc,
                                                         const float* __restrict__ pv, int64_t n,
-                                                        const int64_t* __restrict__ off, int4* __restrict__ desc,
+                                                        const int64_t* __restrict__ off, uint32_t* __restrict__ locator,
                                                         uint4* __restrict__ blob) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -403,15 +531,16 @@ __global__ void __launch_bounds__(256) pack_fill_kernel(const int64_t* __restric
         const int64_t a0 = arp[x], p0 = prp[x];
         const int deg = (int)(arp[x + 1] - a0), npp = (int)(prp[x + 1] - p0);
         const int64_t o = off[x];
-        if (lane == 0) desc[x] = make_int4((int)(uint32_t)o, deg, npp, 0);
-        int32_t* w = reinterpret_cast<int32_t*>(blob + o);
-        const int ca4 = ((deg + 3) >> 2) * 4;
-        for (int k = lane; k < ca4; k += 32) w[k] = k < deg ? ac[a0 + k] : -2;
-        const int cp2 = ((npp + 1) >> 1) * 2;
-        for (int k = lane; k < cp2; k += 32) {
-            w[ca4 + 2 * k] = k < npp ? pc[p0 + k] : -2;
-            w[ca4 + 2 * k + 1] = k < npp ? __float_as_int(pv[p0 + k]) : 0;
+        const int units = (int)row_units(deg, npp);
+        if (lane == 0) locator[x] = ((uint32_t)o << 6) | (uint32_t)min(units, 63);
+        uint32_t* w = reinterpret_cast<uint32_t*>(blob + 4 * o);
+        if (lane < 4) w[lane] = lane == 0 ? (uint32_t)deg : (lane == 1 ? (uint32_t)npp : 0u);
+        for (int k = lane; k < npp; k += 32) {
+            w[4 + 2 * k] = (uint32_t)pc[p0 + k] | kPkPprTag;
+            w[4 + 2 * k + 1] = __float_as_uint(pv[p0 + k]);
         }
+        const int ids0 = 4 + 2 * npp, words = units * 16;
+        for (int k = lane; ids0 + k < words; k += 32) w[ids0 + k] = k < deg ? (uint32_t)ac[a0 + k] : kPkPad;
     }
 }
 
@@ -427,10 +556,10 @@ static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * 
 
 extern "C" int64_t lpf_link_rows_bytes(int64_t n, int64_t adj_nnz, int64_t ppr_nnz) {
     if (n < 0 || adj_nnz < 0 || ppr_nnz < 0) return -1;
-    // sum ceil(deg/4) <= (adj_nnz + 3n)/4, sum ceil(nP/2) <= (ppr_nnz + n)/2
-    const int64_t chunks = (adj_nnz + 3 * n) / 4 + (ppr_nnz + n) / 2 + 1;
-    if (chunks >= ((int64_t)1 << 32)) return -1;    // chunk indices are 32-bit
-    return chunks * 16;
+    // per node ceil((16 + 8 nP + 8 ceil(deg/2)) / 64) units <= (16 + 63 + 4 + 8 nP + 4 deg) / 64
+    const int64_t units = (83 * n + 8 * ppr_nnz + 4 * adj_nnz) / 64 + 1;
+    if (units >= ((int64_t)1 << 26)) return -1;    // 26-bit unit index in the locator
+    return units * 64;
 }
 
 extern "C" int64_t lpf_link_rows_scratch_bytes(int64_t n) {
@@ -439,33 +568,31 @@ extern "C" int64_t lpf_link_rows_scratch_bytes(int64_t n) {
 }
 
 extern "C" int lpf_pack_link_rows(const int64_t* adj_rowptr, const int32_t* adj_col, const int64_t* ppr_rowptr,
-                                  const int32_t* ppr_col, const float* ppr_val, int64_t n, int32_t* node_desc,
+                                  const int32_t* ppr_col, const float* ppr_val, int64_t n, uint32_t* locator,
                                   void* row_blob, void* scratch, void* stream) {
-    LPF_REQUIRE(n >= 0, "negative node count");
+    LPF_REQUIRE(n >= 0 && n < ((int64_t)1 << 31) - 1, "bad node count");
     LPF_REQUIRE(adj_rowptr && ppr_rowptr, "rowptr is NULL");
-    LPF_REQUIRE(n == 0 || (node_desc && row_blob && scratch), "NULL output");
-    LPF_REQUIRE((reinterpret_cast<uintptr_t>(row_blob) & 15) == 0 && (reinterpret_cast<uintptr_t>(node_desc) & 15) == 0,
-                "node_desc / row_blob must be 16-byte aligned");
+    LPF_REQUIRE(n == 0 || (locator && row_blob && scratch), "NULL output");
+    LPF_REQUIRE((reinterpret_cast<uintptr_t>(row_blob) & 63) == 0, "row_blob must be 64-byte aligned");
     if (n == 0) return LPF_OK;
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t* s = static_cast<uint8_t*>(scratch);
-    int32_t* chunks = reinterpret_cast<int32_t*>(s);
+    int32_t* units = reinterpret_cast<int32_t*>(s);
     int64_t* off = reinterpret_cast<int64_t*>(s + align_up(n * 4, 16));
     void* scan_scratch = s + align_up(n * 4, 16) + align_up((n + 1) * 8, 16);
-    pack_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(adj_rowptr, ppr_rowptr, n, chunks);
-    int rc = lpf_scan_counts(chunks, n, off, scan_scratch, stream);
+    pack_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(adj_rowptr, ppr_rowptr, n, units);
+    int rc = lpf_scan_counts(units, n, off, scan_scratch, stream);
     if (rc) return rc;
     int64_t blocks = (n + 7) / 8;
     if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
     pack_fill_kernel<<<(unsigned)blocks, 256, 0, st>>>(adj_rowptr, adj_col, ppr_rowptr, ppr_col, ppr_val, n, off,
-                                                       reinterpret_cast<int4*>(node_desc),
-                                                       static_cast<uint4*>(row_blob));
+                                                       locator, static_cast<uint4*>(row_blob));
     return check_launch("lpf_pack_link_rows");
 }
 
 extern "C" int lpf_select_onepass_packed(const int64_t* links, int64_t bs, const int64_t* adj_rowptr,
                                          const int32_t* adj_col, const int64_t* ppr_rowptr, const int32_t* ppr_col,
-                                         const float* ppr_val, const int32_t* node_desc, const void* row_blob,
+                                         const float* ppr_val, const uint32_t* locator, const void* row_blob,
                                          float th_cn, float th_1hop, float th_non1hop, int mode, int64_t cap,
                                          int32_t* counts, int32_t* seg_start, int32_t* nz_list, int64_t* header,
                                          int32_t* node, float* src_ppr, float* tgt_ppr, void* workspace, void* stream) {
@@ -478,7 +605,7 @@ extern "C" int lpf_select_onepass_packed(const int64_t* links, int64_t bs, const
         lpf::set_error("lpf_select_onepass_packed needs th_1hop > 0 (and th_non1hop > 0 in mode ALL)");
         return LPF_ERR_UNSUPPORTED;
     }
-    LPF_REQUIRE(node_desc && row_blob, "node_desc / row_blob is NULL (lpf_pack_link_rows)");
+    LPF_REQUIRE(locator && row_blob, "locator / row_blob is NULL (lpf_pack_link_rows)");
     LPF_REQUIRE(cap >= 0 && 3 * cap < ((int64_t)1 << 31), "bad pair capacity");
     LPF_REQUIRE(header && workspace, "header/workspace is NULL");
     LPF_REQUIRE(bs == 0 || (counts && seg_start && nz_list), "NULL output");
@@ -487,7 +614,6 @@ extern "C" int lpf_select_onepass_packed(const int64_t* links, int64_t bs, const
     SelectParams2 p{links, bs, adj_rowptr, adj_col, ppr_rowptr, ppr_col, ppr_val, th_cn, th_1hop, th_non1hop,
                     mode, counts, nullptr, node, src_ppr, tgt_ppr, nullptr, (int32_t*)workspace, cap, header,
                     seg_start, nz_list, g_select_dbg, (int32_t*)workspace + bs + 4};
-    static const int variant = getenv("LPF_PK_VARIANT") ? atoi(getenv("LPF_PK_VARIANT")) : 2;
     using SmMain = PkSmemT<kPkHashSlots>;
     using SmHub = PkSmemT<kPkHubSlots>;
     static bool configured = false;
@@ -506,13 +632,14 @@ extern "C" int lpf_select_onepass_packed(const int64_t* links, int64_t bs, const
     }
     launch_onepass_reset(p, st);
     if (bs > 0) {
+        // one resident wave (3 CTAs per SM), the batch cut evenly over it: pieces of 512 .. 1,024 links
         int64_t blocks = (bs + kPkThreads - 1) / kPkThreads;
         const int64_t cap_blocks = (int64_t)kNumSMs * 3;
         if (blocks > cap_blocks) blocks = cap_blocks;
         select_onepass_packed_kernel<kPkHashSlots, false><<<(unsigned)blocks, kPkThreads, sizeof(SmMain), st>>>(
-            p, reinterpret_cast<const int4*>(node_desc), static_cast<const uint4*>(row_blob), variant);
+            p, locator, static_cast<const uint4*>(row_blob));
         select_onepass_packed_kernel<kPkHubSlots, true><<<kNumSMs, kPkThreads, sizeof(SmHub), st>>>(
-            p, reinterpret_cast<const int4*>(node_desc), static_cast<const uint4*>(row_blob), variant);
+            p, locator, static_cast<const uint4*>(row_blob));
     }
     launch_onepass_tail(p, st);
     return check_launch("lpf_select_onepass_packed");

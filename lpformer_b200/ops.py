@@ -219,7 +219,8 @@ def select(links, adj: CSR, ppr: CSR, th_cn, th_1hop, th_non1hop, mode: str, wan
 
 
 class LinkRows:
-    """Packed link rows of one (adjacency, PPR) table pair (lpf_pack_link_rows): node_desc int32 [n,4], row_blob."""
+    """Packed link rows of one (adjacency, PPR) table pair (lpf_pack_link_rows): locator uint32 [n] (kept in an int32
+    tensor) and the 64-byte-aligned row blob."""
 
     def __init__(self, adj: CSR, ppr: CSR):
         require_cuda(adj.rowptr, ppr.rowptr)
@@ -228,12 +229,12 @@ class LinkRows:
         n = adj.n
         nbytes = lib.lpf_link_rows_bytes(n, adj.nnz, ppr.nnz)
         if nbytes < 0:
-            raise _lib.LpfError("graph too large for 32-bit chunk indices in the packed link rows")
-        self.desc = torch.empty((max(n, 1), 4), dtype=torch.int32, device=dev)
-        self.blob = torch.empty(max(nbytes // 4, 4), dtype=torch.int32, device=dev)
+            raise _lib.LpfError("graph too large for the 26-bit unit index of the packed link rows")
+        self.locator = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        self.blob = torch.empty(max(nbytes // 4, 16), dtype=torch.int32, device=dev)
         scratch = torch.empty(max(lib.lpf_link_rows_scratch_bytes(n) // 8 + 2, 2), dtype=torch.int64, device=dev)
         call("lpf_pack_link_rows", ptr(adj.rowptr), ptr(adj.col), ptr(ppr.rowptr), ptr(ppr.col), ptr(ppr.val), n,
-             ptr(self.desc), ptr(self.blob), ptr(scratch), stream())
+             ptr(self.locator), ptr(self.blob), ptr(scratch), stream())
         torch.cuda.current_stream().synchronize()     # scratch is released here
         self.adj, self.ppr = adj, ppr
 
@@ -270,7 +271,7 @@ def select_onepass(links, adj: CSR, ppr: CSR, th_cn, th_1hop, th_non1hop, mode: 
     if algo == _lib.ALGO_PACKED:
         lr = link_rows(adj, ppr)
         call("lpf_select_onepass_packed", ptr(links), bs, ptr(adj.rowptr), ptr(adj.col), ptr(ppr.rowptr), ptr(ppr.col),
-             ptr(ppr.val), ptr(lr.desc), ptr(lr.blob), float(th_cn), float(th_1hop), float(th_non1hop), MODE[mode], cap,
+             ptr(ppr.val), ptr(lr.locator), ptr(lr.blob), float(th_cn), float(th_1hop), float(th_non1hop), MODE[mode], cap,
              ptr(out["counts"]), ptr(out["seg_start"]), ptr(out["nz"]), ptr(out["header"]), ptr(out["node"]),
              ptr(out["src_ppr"]), ptr(out["tgt_ppr"]), ptr(ws), stream(), meta=(bs,))
         return out

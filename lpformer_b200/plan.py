@@ -91,6 +91,10 @@ class ScorePlan:
         self.fused_ok = H == 1 and HC == d and d in (32, 64)
         self.nz_mode = "batched"        # switched to "fused" when the observed share of non-empty links is small
         self.graphs = {}
+        # the tensor-core heads of ALL links (empty-set constant) do not depend on the selection: they run on a side
+        # stream next to it (a fork / join inside the captured graph) and fill the SMs the selection's tail leaves idle
+        self.side = torch.cuda.Stream(device=dev)
+        self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
         self.fused_allowed = True
         self.graph = None
         self.use_graph = use_graph
@@ -106,22 +110,27 @@ class ScorePlan:
         hp = hdr.data_ptr()
         n_dev = hp + 3 * 8                      # &header[3]: links with a non-empty set
 
-        def heads(idx, n, zb, ndev):
+        def heads(idx, n, zb, ndev, on=None):
             call("lpf_link_heads_tc", ptr(links), bs, idx, n, ptr(X), X.stride(0), d, ptr(c["w1p"]), ptr(c["b1"]),
                  ptr(c["ln_w"]), ptr(c["ln_b"]), ptr(c["w23p"]), ptr(c["c3"]) if zb is None else None,
                  ptr(zb), self.zb.stride(0) if zb is not None else 0, ptr(c["ws2"]), ptr(c["bs2"]), ptr(self.prob),
-                 int(self.logits), ndev, st, meta=(n,))
+                 int(self.logits), ndev, st if on is None else on, meta=(n,))
 
         def gemm(A, Wp, bias, scale, C, M, N, K, mdev):
             call("lpf_gemm_tc", ptr(A), A.stride(0), ptr(Wp), ptr(bias), float(scale), ptr(C), C.stride(0), M, N, K,
                  EPI_NONE, mdev, st, meta=(M, N, K))
 
-        # every link with the empty-set pairwise constant (independent of the selection)
-        heads(None, bs, None, None)
+        # every link with the empty-set pairwise constant (independent of the selection): side stream
+        main = torch.cuda.current_stream()
+        self.ev_fork.record(main)
+        self.side.wait_event(self.ev_fork)
+        with torch.cuda.stream(self.side):
+            heads(None, bs, None, None, on=self.side.cuda_stream)
+            self.ev_join.record(self.side)
         # K1: one-pass selection into the per-type pools
         if self.rows is not None:
             call("lpf_select_onepass_packed", ptr(links), bs, ptr(self.adj.rowptr), ptr(self.adj.col),
-                 ptr(self.ppr.rowptr), ptr(self.ppr.col), ptr(self.ppr.val), ptr(self.rows.desc), ptr(self.rows.blob),
+                 ptr(self.ppr.rowptr), ptr(self.ppr.col), ptr(self.ppr.val), ptr(self.rows.locator), ptr(self.rows.blob),
                  *self.th, self.mode, cap, ptr(self.counts), ptr(self.seg_start), ptr(self.nz), hp, ptr(self.node),
                  ptr(self.pa), ptr(self.pb), ptr(self.ws), st, meta=(bs,))
         else:
@@ -129,6 +138,7 @@ class ScorePlan:
                  ptr(self.ppr.col), ptr(self.ppr.val), *self.th, self.mode, self.algo, cap, ptr(self.counts),
                  ptr(self.seg_start), ptr(self.nz), hp, ptr(self.node), ptr(self.pa), ptr(self.pb), ptr(self.ws), st,
                  meta=(bs,))
+        main.wait_event(self.ev_join)
         if self.nz_mode == "fused":
             # few non-empty links: one warp per link, everything from node sets to score in one launch
             call("lpf_nz_links_fused", C.byref(self.nz_args), st, meta=(bs,))

@@ -396,27 +396,27 @@ def test_plan_fused_nonempty_path(dim, mode_th):
 
 
 def test_packed_link_rows_layout():
-    """lpf_pack_link_rows: descriptor + row blob reproduce the two CSR tables (ids ascending, pads -2, PPR value bits)."""
+    """lpf_pack_link_rows: locator + 64-byte-aligned rows reproduce the two CSR tables (header, tagged PPR slots in
+    ascending column order with their value bits, ascending neighbour ids, pads)."""
     from lpformer_b200 import ops, synthetic as S
     g = S.make_graph("citation2", seed=3, scale=0.01, heldout=64)
     dev = torch.device("cuda:0")
     d = g.data_dict(dev)
     lr = ops.link_rows(d["adj_mask"], d["ppr"])
     assert ops.link_rows(d["adj_mask"], d["ppr"]) is lr          # cached per table pair
-    desc = lr.desc.cpu().numpy()
-    blob = lr.blob.cpu().numpy()
+    loc = lr.locator.cpu().numpy().view(np.uint32).astype(np.int64)
+    blob = lr.blob.cpu().numpy().view(np.uint32)
     deg, npp = np.diff(g.indptr), np.diff(g.ppr[0])
-    assert np.array_equal(desc[:, 1], deg) and np.array_equal(desc[:, 2], npp)
-    chunks = (deg + 3) // 4 + (npp + 1) // 2
-    off = np.concatenate([[0], np.cumsum(chunks)[:-1]])
-    assert np.array_equal(desc[:, 0].view(np.uint32).astype(np.int64), off)
+    units = (16 + 8 * (npp + (deg + 1) // 2) + 63) // 64
+    off = np.concatenate([[0], np.cumsum(units)[:-1]])
+    assert np.array_equal(loc >> 6, off) and np.array_equal(loc & 63, np.minimum(units, 63))
     rng = np.random.default_rng(0)
     for x in np.concatenate([rng.integers(0, g.n, 200), np.argsort(-deg)[:5], np.nonzero(deg == 0)[0][:5]]):
-        w = blob[4 * off[x]: 4 * (off[x] + chunks[x])]
-        ca4 = 4 * ((deg[x] + 3) // 4)
-        assert np.array_equal(w[:deg[x]], g.indices[g.indptr[x]:g.indptr[x + 1]])
-        assert np.all(w[deg[x]:ca4] == -2)
-        pw = w[ca4:].reshape(-1, 2)
-        assert np.array_equal(pw[:npp[x], 0], g.ppr[1][g.ppr[0][x]:g.ppr[0][x + 1]])
-        assert np.array_equal(pw[:npp[x], 1].view(np.float32), g.ppr[2][g.ppr[0][x]:g.ppr[0][x + 1]])
-        assert np.all(pw[npp[x]:, 0] == -2)
+        w = blob[16 * off[x]: 16 * (off[x] + units[x])]
+        assert w[0] == deg[x] and w[1] == npp[x] and w[2] == 0 and w[3] == 0
+        pw = w[4:4 + 2 * npp[x]].reshape(-1, 2)
+        assert np.array_equal(pw[:, 0], g.ppr[1][g.ppr[0][x]:g.ppr[0][x + 1]].astype(np.uint32) | 0x80000000)
+        assert np.array_equal(pw[:, 1].view(np.float32), g.ppr[2][g.ppr[0][x]:g.ppr[0][x + 1]])
+        ids = w[4 + 2 * npp[x]:]
+        assert np.array_equal(ids[:deg[x]], g.indices[g.indptr[x]:g.indptr[x + 1]].astype(np.uint32))
+        assert np.all(ids[deg[x]:] == 0x7fffffff)

@@ -31,8 +31,10 @@ for it in range(6):
 lib.lpf_debug_select_clocks(None)
 t = buf.cpu().numpy()
 n = max(1, int(t[5]))
-names = ["stage source", "phase A", "phase B", "phase C", "generic"]
+names = ["flatten fill + stage source", "phase A", "phase B", "phase C", "generic"]
 print("chunks %d, queued long-row links/chunk %.1f, written links/chunk %.1f" % (n, t[6] / n, t[7] / n))
 print("slowest chunk %.1f us, slowest CTA %.1f us" % (t[8] / 1965.0, t[9] / 1965.0))
+for nm, v in zip(["  top loads+zero stores", "  run detection", "  table layout", "  clear+flatten scan"], t[10:14]):
+    print("  %-26s %9.0f cycles/chunk  (%.1f us)" % (nm, v / n, v / n / 1965.0))
 for nm, v in zip(names, t[:5]):
     print("  %-14s %9.0f cycles/chunk  (%.1f us)" % (nm, v / n, v / n / 1965.0))
