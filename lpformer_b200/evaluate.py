@@ -1,4 +1,5 @@
-"""Eval-side drivers around LinkTransformer: link-sharded multi-GPU scoring.
+"""Eval-side drivers around LinkTransformer: pipelined batch scoring, ranking metrics on the device, link-sharded
+multi-GPU scoring.
 
 Links are independent units, so candidate links are sharded across ranks with NO per-batch
 collective.  The only exchange is per eval: the last GCN layer (+ gnn_norm + the K/V
@@ -10,7 +11,8 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import _lib, ops
+from .plan import ScorePlan
 
 
 @torch.no_grad()
@@ -108,3 +110,163 @@ def score_links_sharded(model, score_func, links, X, test_set=False, group=None,
         a, b = shard_queries(ngroups, r, world)
         pieces.append(full[r * per:r * per + (b - a) * group_size])
     return torch.cat(pieces)
+
+
+class LinkScoreStream:
+    """The batch loop of the reference's eval drivers (train/testing.py:25-32, 36-43, 107-117: for every batch
+    `elementwise_lin` -> `calc_pairwise` -> `score_func` -> `.cpu()`), pipelined.
+
+    The reference synchronises with the host once per batch (`.cpu()`); `LinkTransformer.score_links` still reads
+    one 64-byte header per batch (the pair-pool overflow flag).  Here `depth` execution plans (plan.py) are kept in
+    flight: batch k+1 is launched before the header of batch k is looked at, host-resident links travel on a copy
+    stream next to the compute of the previous batch, and a batch whose pair pool overflowed (detected `depth`
+    batches later) is re-scored through the host-sized path at the end — so the scores are exactly those of
+    `score_links`, without a GPU idle gap per batch.
+    """
+
+    def __init__(self, model, score_func, X_node, batch_size, test_set=False, depth=2, return_logits=False):
+        self.model, self.score_func, self.bs = model, score_func, int(batch_size)
+        self.test_set, self.logits = bool(test_set), bool(return_logits)
+        self.X = model._check_x(X_node)
+        self.dev = self.X.device
+        consts = model._head_consts(score_func, self.X)
+        adj, ppr = model.get_adj(test_set, mask=True), model.get_ppr(test_set)
+        algo = ops.pick_select_algo(adj, ppr, model.thresh_1hop, model.thresh_non1hop, model.mask)
+        self.plans = None
+        if consts is not None and algo != _lib.ALGO_GENERIC and model.use_plans and self.bs > 0:
+            kv = model._get_kv(self.X)[0]
+            self.plans = [ScorePlan(model, score_func, consts, self.X, kv, self.bs, test_set, return_logits,
+                                    use_graph=model.use_graphs) for _ in range(max(1, int(depth)))]
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self._stage = None
+        self.batches = 0
+
+    def _sequential(self, links, out_dev):
+        for s in range(0, links.shape[1], max(1, self.bs)):
+            b = links[:, s:s + self.bs]
+            out_dev[s:s + b.shape[1]] = self.model.score_links(b, self.X, self.score_func, test_set=self.test_set,
+                                                               return_logits=self.logits)
+
+    @torch.no_grad()
+    def score(self, links, out_host=None, group=4):
+        """Scores links [2, L] (int64; a device tensor or pinned host memory).  Returns the [L] scores on the
+        device; with `out_host` (a pinned fp32 [L] tensor) the scores are also copied to the host as they are
+        produced (the reference's per-batch `.cpu()`), complete when the call returns.  Host-resident links and the
+        scores travel in groups of `group` batches on a copy stream: the links of group g+1 are on their way while
+        group g is scored."""
+        L = links.shape[1]
+        out_dev = torch.empty(L, dtype=torch.float32, device=self.dev)
+        main = torch.cuda.current_stream(self.dev)
+        if self.plans is None:
+            self._sequential(links, out_dev)
+            if out_host is not None:
+                out_host.copy_(out_dev)
+            return out_dev
+        bs, depth = self.bs, len(self.plans)
+        nb = L // bs
+        on_host = not links.is_cuda
+        G = max(int(group), depth)
+        cs = self.copy_stream
+        if on_host and (self._stage is None or self._stage[0].shape[1] != G * bs):
+            self._stage = [torch.empty((2, G * bs), dtype=torch.int64, device=self.dev) for _ in range(2)]
+        ev_in = [torch.cuda.Event(), torch.cuda.Event()]
+        ev_free = [torch.cuda.Event(), torch.cuda.Event()]
+        ev_out = torch.cuda.Event()
+
+        def h2d(g):          # links of the group that starts at batch g -> staging slot, on the copy stream
+            slot = (g // G) % 2
+            n = min(G, nb - g) * bs
+            with torch.cuda.stream(cs):
+                if g >= 2 * G:
+                    cs.wait_event(ev_free[slot])      # the plans have taken the slot's previous links
+                # row by row: a strided two-row host slice would go through a slow pitched copy (15 vs 48 GB/s measured)
+                self._stage[slot][0, :n].copy_(links[0, g * bs:g * bs + n], non_blocking=True)
+                self._stage[slot][1, :n].copy_(links[1, g * bs:g * bs + n], non_blocking=True)
+                ev_in[slot].record(cs)
+
+        pending = [None] * depth
+        redo = []
+        if on_host and nb > 0:
+            h2d(0)
+        for g in range(0, nb, G):
+            kb = min(G, nb - g)
+            slot = (g // G) % 2
+            if on_host:
+                if g + G < nb:
+                    h2d(g + G)
+                main.wait_event(ev_in[slot])
+                src = self._stage[slot]
+            else:
+                src = links[:, g * bs:(g + kb) * bs]
+            for j in range(kb):
+                k = g + j
+                P = self.plans[k % depth]
+                if pending[k % depth] is not None and P.collect():
+                    redo.append(pending[k % depth])
+                P.submit(src[:, j * bs:(j + 1) * bs])
+                out_dev[k * bs:(k + 1) * bs].copy_(P.prob, non_blocking=True)
+                pending[k % depth] = k
+                self.batches += 1
+            if on_host:
+                ev_free[slot].record(main)
+            if out_host is not None:
+                ev_out.record(main)
+                with torch.cuda.stream(cs):
+                    cs.wait_event(ev_out)
+                    out_host[g * bs:(g + kb) * bs].copy_(out_dev[g * bs:(g + kb) * bs], non_blocking=True)
+        for j, k in enumerate(pending):
+            if k is not None and self.plans[j].collect():
+                redo.append(k)
+        if nb * bs < L:
+            redo.append(nb)        # the ragged tail goes through score_links
+        main.synchronize()
+        cs.synchronize()
+        if redo:
+            use = self.model.use_plans
+            self.model.use_plans = False      # host-sized two-pass path: no pools to overflow
+            try:
+                for k in redo:
+                    lk = links[:, k * bs:(k + 1) * bs]
+                    pr = self.model.score_links(lk.to(self.dev), self.X, self.score_func, test_set=self.test_set,
+                                                return_logits=self.logits)
+                    out_dev[k * bs:k * bs + pr.numel()] = pr
+                    if out_host is not None:
+                        out_host[k * bs:k * bs + pr.numel()].copy_(pr)
+            finally:
+                self.model.use_plans = use
+            if any(k < nb for k in redo):     # larger pools for the batches to come
+                for P in self.plans:
+                    P.grow()
+            main.synchronize()
+        return out_dev
+
+
+@torch.no_grad()
+def evaluate_mrr(y_pred_pos, y_pred_neg):
+    """reference train/evaluation.py:23-50 on the device: rank = 1 + (optimistic + pessimistic) / 2 of every
+    positive among its negatives; Hits@{10,50,100} and MRR (one host read at the end, not one per metric)."""
+    y_pred_pos = y_pred_pos.reshape(-1, 1)
+    optimistic = (y_pred_neg >= y_pred_pos).sum(dim=1)
+    pessimistic = (y_pred_neg > y_pred_pos).sum(dim=1)
+    rank = 0.5 * (optimistic + pessimistic).to(torch.float32) + 1
+    res = torch.stack([(rank <= 10).float().mean(), (rank <= 50).float().mean(), (rank <= 100).float().mean(),
+                       (1.0 / rank).mean()]).tolist()
+    return {"Hits@10": res[0], "Hits@50": res[1], "Hits@100": res[2], "MRR": res[3]}
+
+
+@torch.no_grad()
+def test_edge_citation2(model, score_func, input_data, h, batch_size, mrr_mode=False, negative_data=None, test=False,
+                        stream=None):
+    """reference train/testing.py:14-47 with the batch loop pipelined (LinkScoreStream) and the predictions kept
+    on the device.  input_data [P, 2] positive edges; mrr_mode: negative_data [P, K] negative targets of each
+    positive's source, result [P, K]; else result [P]."""
+    dev = h.device
+    if mrr_mode:
+        k = negative_data.shape[1]
+        source = input_data.t()[0].reshape(-1, 1).repeat(1, k).reshape(-1)
+        links = torch.stack((source.to(dev), negative_data.reshape(-1).to(dev)))
+    else:
+        links = input_data.t().to(dev).contiguous()
+    st = stream if stream is not None else LinkScoreStream(model, score_func, h, batch_size, test_set=test)
+    pred = st.score(links)
+    return pred.view(-1, negative_data.shape[1]) if mrr_mode else pred

@@ -338,6 +338,20 @@ class LinkTransformer(nn.Module):
     def _dev(self):
         return self.gnn_norm.weight.device
 
+    def _weights_key(self, other=None):
+        """Versions of every parameter (cheap: the parameter list is walked once and kept), so that the derived /
+        packed weights are rebuilt after load_state_dict, .to() or an in-place update."""
+        pl = self.__dict__.get("_plist")
+        if pl is None:
+            pl = self.__dict__["_plist"] = list(self.parameters())
+        key = tuple([p._version for p in pl]) + (pl[0].device,)
+        if other is not None:
+            ol = other.__dict__.get("_plist")
+            if ol is None:
+                ol = other.__dict__["_plist"] = list(other.parameters())
+            key += tuple([p._version for p in ol]) + (id(other),)
+        return key
+
     def _graph_key(self, test_set, mask):
         suffix = "mask" if mask else "t"
         return f"full_adj_{suffix}" if test_set else f"adj_{suffix}"
@@ -382,7 +396,7 @@ class LinkTransformer(nn.Module):
     def _get_derived(self):
         """Per (layer, type): M = W_pe W2_t  [HC,d]  and  c = 2 W_pe b2_t + b_r  [HC]
         (lin_r([x | pe]) = W_x x + W_pe (W2 (h1+h2) + 2 b2) + b_r)."""
-        key = tuple(p._version for p in self.parameters()) + (self._dev(),)
+        key = self._weights_key()
         if self._derived is not None and self._derived[0] == key:
             return self._derived[1]
         d = self.dim
@@ -541,7 +555,7 @@ class LinkTransformer(nn.Module):
 
     def _pw_const(self, X_node):
         """[1, dim] pairwise vector of a link with empty node sets; depends on the weights only (cached)."""
-        key = tuple(p._version for p in self.parameters()) + (self._dev(),)
+        key = self._weights_key()
         if self._pw_const_cache is not None and self._pw_const_cache[0] == key:
             return self._pw_const_cache[1]
         dev = self._dev()
@@ -565,8 +579,7 @@ class LinkTransformer(nn.Module):
         if lins is None or len(lins) != 2 or tuple(lins[0].weight.shape) != (2 * d, 2 * d) or \
                 tuple(lins[1].weight.shape) != (1, 2 * d) or len(el.linears) != 2 or el.norm is None:
             return None
-        key = tuple(p._version for p in self.parameters()) + tuple(p._version for p in score_func.parameters()) + \
-            (self._dev(), id(score_func))
+        key = self._weights_key(score_func)
         if self._head_cache is not None and self._head_cache[0] == key:
             return self._head_cache[1]
         # no non-linearity between elementwise_lin's last Linear and mlp_score's first: fold them (fp64, once)

@@ -22,6 +22,7 @@ class ScorePlan:
     def __init__(self, model, score_func, consts, X_node, kv, bs, test_set, logits, cap=None, use_graph=True):
         dev = X_node.device
         self.model, self.bs, self.logits, self.dev = model, bs, bool(logits), dev
+        self.score_func, self.test_set = score_func, test_set
         self.X, self.kv, self.consts = X_node, kv, consts
         self.adj = model.get_adj(test_set, mask=True)
         self.ppr = model.get_ppr(test_set)
@@ -97,6 +98,9 @@ class ScorePlan:
         self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
         self.fused_allowed = True
         self.graph = None
+        self.hdr_host = torch.zeros(8, dtype=torch.int64).pin_memory()
+        self.done = torch.cuda.Event()
+        self.last = [0] * 8
         self.use_graph = use_graph
         self.runs = 0
 
@@ -163,10 +167,22 @@ class ScorePlan:
         gemm(self.pw, w["wz"], c["off"], 1.0, self.zb, bs, 2 * d, d, n_dev)
         heads(ptr(self.nz), bs, self.zb, n_dev)
 
-    def run(self, links):
-        """Scores `links` (int64 [2, bs], host-pinned or device).  Returns (prob [bs] — a buffer owned by the plan,
-        valid until the next run — and overflow: bool)."""
-        self.links.copy_(links, non_blocking=True)
+    def grow(self, factor=4):
+        """Larger pair pools after an overflow (buffers that depend on the capacity are re-allocated, graphs dropped)."""
+        self.__init__(self.model, self.score_func, self.consts, self.X, self.kv, self.bs, self.test_set, self.logits,
+                      cap=self.cap * factor, use_graph=self.use_graph)
+
+    def submit(self, links):
+        """Launches one batch on the current stream without any host synchronisation: copy of `links` (int64 [2, bs],
+        host-pinned or device) into the plan, the launch sequence (a CUDA-graph replay after the first batch), and an
+        asynchronous copy of the header to pinned host memory.  `collect()` later tells whether a pair pool overflowed;
+        `self.prob` holds the scores in stream order."""
+        if links is not None:          # None: the caller has already filled self.links (on a stream this one waits for)
+            if links.is_cuda or links.is_contiguous():
+                self.links.copy_(links, non_blocking=True)
+            else:                      # strided host slice: two contiguous row copies instead of a slow pitched one
+                self.links[0].copy_(links[0], non_blocking=True)
+                self.links[1].copy_(links[1], non_blocking=True)
         tracing = _lib.TRACE is not None
         if self.use_graph and not tracing and self.runs >= 1:
             g = self.graphs.get(self.nz_mode)
@@ -182,11 +198,24 @@ class ScorePlan:
         else:
             self._launch()
         self.runs += 1
-        h = self.hdr.tolist()                        # the batch's only host round trip
+        self.hdr_host.copy_(self.hdr, non_blocking=True)
+        self.done.record()
+
+    def collect(self):
+        """Waits for the batch submitted last and returns its overflow flag (the batch's only host round trip)."""
+        self.done.synchronize()
+        h = self.hdr_host.tolist()
+        self.last = h
         # regime for the NEXT batch (either path is exact; this only picks the cheaper one)
         if self.fused_ok and self.fused_allowed:
             self.nz_mode = "fused" if h[3] < self.model.nz_fused_share * self.bs else "batched"
-        return self.prob, bool(h[4])
+        return bool(h[4])
+
+    def run(self, links):
+        """Scores `links` (int64 [2, bs], host-pinned or device).  Returns (prob [bs] — a buffer owned by the plan,
+        valid until the next run — and overflow: bool)."""
+        self.submit(links)
+        return self.prob, self.collect()
 
     def stats(self):
         h = self.hdr.tolist()

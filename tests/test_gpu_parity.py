@@ -420,3 +420,56 @@ def test_packed_link_rows_layout():
         ids = w[4 + 2 * npp[x]:]
         assert np.array_equal(ids[:deg[x]], g.indices[g.indptr[x]:g.indptr[x + 1]].astype(np.uint32))
         assert np.all(ids[deg[x]:] == 0x7fffffff)
+
+
+def test_link_score_stream_matches_score_links():
+    """evaluate.LinkScoreStream (two plans in flight, lagged overflow check, copy stream for host links) returns exactly
+    the scores of per-batch score_links — device links, pinned host links with per-batch D2H, a ragged tail, and a
+    pool overflow that is only noticed one batch late."""
+    import lpformer_b200 as L
+    from lpformer_b200 import synthetic as S
+    from lpformer_b200.evaluate import LinkScoreStream, evaluate_mrr, test_edge_citation2
+    g = S.make_graph("citation2", seed=5, scale=0.02, heldout=256)
+    targs = S.train_args_of(g.cfg)
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    model = L.LinkTransformer(targs, g.data_dict(dev), device=dev).to(dev).eval()
+    score = L.mlp_score(model.out_dim, model.out_dim, 1, 2).to(dev).eval()
+    X = torch.randn(g.n, g.cfg["dim"], generator=torch.Generator().manual_seed(1)).to(dev)
+    nq, negs = 4, 200
+    bs = nq * (1 + negs)
+    batches = [S.citation2_queries(g, nq, negs, seed=50 + k) for k in range(7)]
+    links = torch.from_numpy(np.concatenate(batches + [batches[0][:, :301]], axis=1))        # 7 batches + a tail
+    ref = torch.cat([model.score_links(links[:, s:s + bs].to(dev), X, score) for s in range(0, links.shape[1], bs)])
+    def same(x, y):     # (the fused / batched regimes of the non-empty links differ in fp32 summation order)
+        np.testing.assert_allclose(x.cpu().numpy(), y.cpu().numpy(), rtol=1e-5, atol=1e-7)
+
+    st = LinkScoreStream(model, score, X, bs)
+    assert st.plans is not None and len(st.plans) == 2
+    out = st.score(links.to(dev))
+    same(out, ref)
+    out = st.score(links.to(dev))                    # graphs replayed
+    same(out, ref)
+    host_out = torch.empty(links.shape[1], dtype=torch.float32).pin_memory()
+    out = st.score(links.pin_memory(), out_host=host_out)
+    same(out, ref)
+    assert torch.equal(host_out, out.cpu())
+    # pools of 2 rows per type: every batch with a non-empty link overflows, is noticed late and re-scored
+    for P in st.plans:
+        P.__init__(P.model, P.score_func, P.consts, P.X, P.kv, P.bs, P.test_set, P.logits, cap=2, use_graph=P.use_graph)
+    out = st.score(links.to(dev))
+    same(out, ref)
+    assert st.plans[0].cap > 2
+    # the citation2 driver + ranking metrics on the device (reference train/testing.py:14-47, evaluation.py:23-50)
+    pos = torch.from_numpy(g.heldout[:, :16].T.copy())
+    neg = torch.from_numpy(np.random.default_rng(0).integers(0, g.n, (16, 50)))
+    neg_pred = test_edge_citation2(model, score, pos, X, 400, mrr_mode=True, negative_data=neg)
+    pos_pred = test_edge_citation2(model, score, pos, X, 400)
+    assert neg_pred.shape == (16, 50) and pos_pred.shape == (16,)
+    src = pos[:, 0].reshape(-1, 1).repeat(1, 50).reshape(-1)
+    chk = model.score_links(torch.stack((src, neg.reshape(-1))).to(dev), X, score).view(16, 50)
+    same(neg_pred, chk)
+    res = evaluate_mrr(pos_pred, neg_pred)
+    pp, nn_ = pos_pred.cpu().double().numpy(), neg_pred.cpu().double().numpy()
+    rank = 0.5 * ((nn_ >= pp[:, None]).sum(1) + (nn_ > pp[:, None]).sum(1)) + 1
+    assert abs(res["MRR"] - (1.0 / rank).mean()) < 1e-6 and abs(res["Hits@10"] - (rank <= 10).mean()) < 1e-6
