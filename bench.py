@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--cpu-sample-links", type=int, default=32768)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sampler", action="store_true", help="debug: do not poll nvidia-smi during the timed region")
+    ap.add_argument("--depth", type=int, default=4, help="execution plans (batches) in flight in the pipelined eval loop")
     ap.add_argument("--seed", type=int, default=0)
     return ap.parse_args()
 
@@ -251,8 +252,8 @@ def run_b200(args):
     # ---- device-resident throughput (`value`): the K batches through the pipelined eval loop (evaluate.LinkScoreStream:
     # the reference's batch loop, train/testing.py:25-32, with two execution plans in flight), between two events
     from lpformer_b200.evaluate import LinkScoreStream
-    scorer = LinkScoreStream(model, score, X, nlinks)
-    W = max(args.warmup, 6)        # both plans of the stream capture their CUDA graphs during the warm-up
+    scorer = LinkScoreStream(model, score, X, nlinks, depth=args.depth)
+    W = max(args.warmup, 3 * args.depth)        # both plans of the stream capture their CUDA graphs during the warm-up
     warm_links = torch.cat([dev_links[s % max(1, args.warmup)] for s in range(W)], dim=1)
     timed_dev = torch.cat(dev_links[args.warmup:], dim=1)
     timed_host = torch.cat([torch.from_numpy(l) for l in host_links[args.warmup:]], dim=1).pin_memory()
@@ -280,8 +281,22 @@ def run_b200(args):
     trace = _lib.Trace(events=True)
     _lib.TRACE = trace
     outs = []
+    import ctypes
+    lib = _lib.load()
+    lib.lpf_debug_select_timing(1)        # CUDA events around the kernels inside the selection entry point
+    sel_ms, ms3 = [0.0, 0.0, 0.0, 0], (ctypes.c_float * 3)()
+    nz_ms = [0.0, 0.0, 0]
     for s in range(args.warmup, total_steps):
         outs.append(model.score_links(dev_links[s], X, score))
+        if lib.lpf_debug_select_timing_read(ctypes.addressof(ms3)) == 0:
+            for k in range(3):
+                sel_ms[k] += ms3[k]
+            sel_ms[3] += 1
+        if lib.lpf_debug_nz_timing_read(ctypes.addressof(ms3)) == 0:
+            nz_ms[0] += ms3[0]
+            nz_ms[1] += ms3[1]
+            nz_ms[2] += 1
+    lib.lpf_debug_select_timing(0)
     barrier()
     _lib.TRACE = None
     stream_vs_single = float((torch.cat(outs) - out).abs().max())
@@ -320,14 +335,27 @@ def run_b200(args):
         sel_stats["pairs_per_link"] = tot_pairs / (nlinks * args.steps)
         sel_stats["empty_frac"] = tot_empty / (nlinks * args.steps)
 
+        if sel_ms[3] and "lpf_select_onepass_packed" in summ:
+            # the selection entry point is three kernels: time them separately (events recorded inside the launcher)
+            c, t = summ.pop("lpf_select_onepass_packed")
+            summ["lpf_select_onepass_packed/screen (select_onepass_packed_kernel<8192,0>)"] = (sel_ms[3], sel_ms[0])
+            summ["lpf_select_onepass_packed/hub sources (select_onepass_packed_kernel<32768,1>)"] = (sel_ms[3], sel_ms[1])
+            summ["lpf_select_onepass_packed/deferred links (select_heavy_onepass_kernel)"] = (sel_ms[3], sel_ms[2])
+            summ["lpf_select_onepass_packed/launch gaps + resets"] = (c, max(0.0, t - sum(sel_ms[:3])))
+        if nz_ms[2] and "lpf_nz_links_fused" in summ:
+            c, t = summ.pop("lpf_nz_links_fused")
+            summ["lpf_nz_links_fused/pair stage (nz_pairs_kernel)"] = (nz_ms[2], nz_ms[0])
+            summ["lpf_nz_links_fused/link stage (nz_fused_kernel)"] = (nz_ms[2], nz_ms[1])
+            summ["lpf_nz_links_fused/launch gaps"] = (c, max(0.0, t - nz_ms[0] - nz_ms[1]))
         kern = sorted(((n, c, t) for n, (c, t) in summ.items()), key=lambda r: -r[2])
-        top_name, top_calls, top_ms = kern[0]
+        top_name, top_calls, top_ms = [k for k in kern if "launch gaps" not in k[0]][0]
         peak, peak_src = load_peaks()
         peaks_all = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))) if os.path.exists(
             os.path.join(REPO, "MEASURED_PEAKS.json")) else {}
         avg_ms = top_ms / top_calls
         alg = alg_full = alg_flops = None
-        if top_name in ("lpf_select_count", "lpf_select_fill", "lpf_select_onepass", "lpf_select_onepass_packed"):
+        if top_name.startswith("lpf_select_onepass_packed/screen") or top_name in (
+                "lpf_select_count", "lpf_select_fill", "lpf_select_onepass", "lpf_select_onepass_packed"):
             alg = byt["select_dedup"] / args.steps          # per launch (one launch per step)
             alg_full = byt["select_full"] / args.steps
         elif top_name == "lpf_link_heads_tc":
@@ -336,8 +364,14 @@ def run_b200(args):
             alg = (nlinks * (d * 4 + 16 + 4) + nq * d * 4) / launches_per_step
             alg_full = nlinks * (2 * d * 4 + 16 + 4) / launches_per_step
             alg_flops = nlinks * 2.0 * (d * d + d * d + 2 * d * d + 2 * d) / launches_per_step
+        traffic = None
+        tpath = os.path.join(REPO, "profiles", "traffic.json")
+        if os.path.exists(tpath):       # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures
+            for key, val in json.load(open(tpath)).items():
+                if key in top_name:
+                    traffic = val
         roof = {"bound": "hbm", "kernel": top_name, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
-                "traffic": None, "peak_source": peak_src, "avg_launch_ms": avg_ms,
+                "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": avg_ms,
                 "share_of_kernel_time": top_ms / sum(t for _, _, t in kern)}
         if alg is not None:
             roof["achieved"] = alg / (avg_ms * 1e-3) / 1e9
@@ -371,7 +405,7 @@ def run_b200(args):
                 "e2e": {"value": e2e_val, "unit": "links/s", "h2d_bytes_per_step": int(host_links[0].nbytes),
                         "d2h_bytes_per_step": int(nlinks * 4), "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": int(trace.launches),
-                "api": {"value": "evaluate.LinkScoreStream.score(device links): 2 plans in flight, 1 CUDA-graph launch per "
+                "api": {"depth": args.depth, "value": "evaluate.LinkScoreStream.score(device links): `depth` plans in flight, 1 CUDA-graph launch per "
                                  "batch, overflow flags read one batch late",
                         "e2e": "evaluate.LinkScoreStream.score(pinned host links, out_host=pinned scores): H2D / D2H on a "
                                "copy stream inside the timed region",

@@ -308,6 +308,14 @@ int lpf_nz_links_fused(const lpf_nz_args* args, void* stream);
  * [5] chunks, [6] queued long-row links, [7] written links); NULL disables. */
 int lpf_debug_select_clocks(void* device_buffer);
 
+/* Profiling hook: with enable != 0 later lpf_select_onepass_packed calls record CUDA events on their stream around
+ * the screening kernel, the hub-source kernel and the deferred-link tail; lpf_debug_select_timing_read waits for
+ * the last such call and stores the three durations (milliseconds) in ms3_host[0..2]; -1 if nothing was recorded. */
+int lpf_debug_select_timing(int enable);
+int lpf_debug_select_timing_read(float* ms3_host);
+/* Same switch: the two kernels of the last lpf_nz_links_fused call (pair stage, link stage) in ms2_host[0..1]. */
+int lpf_debug_nz_timing_read(float* ms2_host);
+
 /* Profiling hook: CTA 0 of later lpf_link_heads_tc launches writes clock64() stamps of its pipeline phases for
  * its first 8 tiles into device_buffer (int64 [8][16]); NULL disables. */
 int lpf_debug_heads_clocks(void* device_buffer);

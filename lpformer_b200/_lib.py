@@ -47,6 +47,9 @@ SIGNATURES = {
     "lpf_scatter_rows": (_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _i32, _p, _p]),
     "lpf_debug_heads_clocks": (_int, [_p]),
     "lpf_debug_select_clocks": (_int, [_p]),
+    "lpf_debug_select_timing": (_int, [_int]),
+    "lpf_debug_select_timing_read": (_int, [_p]),
+    "lpf_debug_nz_timing_read": (_int, [_p]),
     "lpf_select_compact": (_int, [_p, _i64, _p, _p, _p]),
     "lpf_link_heads_tc": (_int, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p,
                                  _p, _int, _p, _p]),

@@ -295,6 +295,18 @@ __global__ void __launch_bounds__(256) nz_fused_kernel(NzParams p) {
 using namespace lpf;
 
 /* Pointer block of lpf_nz_links_fused, mirrored field by field by the ctypes Structure in _lib.py. */
+namespace lpf { extern bool g_kernel_timing; }
+static cudaEvent_t g_nz_ev[3];
+static bool g_nz_ev_ready = false, g_nz_ev_valid = false;
+// Profiling hook (see lpf_debug_select_timing): durations of nz_pairs_kernel and nz_fused_kernel of the last call.
+extern "C" int lpf_debug_nz_timing_read(float* ms2_host) {
+    if (!g_nz_ev_valid || !ms2_host) return -1;
+    if (cudaEventSynchronize(g_nz_ev[2]) != cudaSuccess) return -1;
+    for (int k = 0; k < 2; ++k)
+        if (cudaEventElapsedTime(ms2_host + k, g_nz_ev[k], g_nz_ev[k + 1]) != cudaSuccess) return -1;
+    return LPF_OK;
+}
+
 extern "C" int lpf_nz_links_fused(const lpf_nz_args* a, void* stream) {
     LPF_REQUIRE(a, "NULL argument block");
     LPF_REQUIRE(a->d == 32 || a->d == 64, "d must be 32 or 64");
@@ -331,12 +343,20 @@ extern "C" int lpf_nz_links_fused(const lpf_nz_args* a, void* stream) {
     int64_t pblocks = (3 * a->cap + 7) / 8;
     if (pblocks > cap) pblocks = cap;
     if (pblocks < 1) pblocks = 1;
-    if (a->d == 64) {
-        nz_pairs_kernel<64><<<(unsigned)pblocks, 256, 0, st>>>(p);
-        nz_fused_kernel<64><<<(unsigned)blocks, 256, 0, st>>>(p);
-    } else {
-        nz_pairs_kernel<32><<<(unsigned)pblocks, 256, 0, st>>>(p);
-        nz_fused_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(p);
+    const bool timing = lpf::g_kernel_timing;
+    if (timing && !g_nz_ev_ready) {
+        for (auto& e : g_nz_ev) cudaEventCreate(&e);
+        g_nz_ev_ready = true;
+    }
+    if (timing) cudaEventRecord(g_nz_ev[0], st);
+    if (a->d == 64) nz_pairs_kernel<64><<<(unsigned)pblocks, 256, 0, st>>>(p);
+    else nz_pairs_kernel<32><<<(unsigned)pblocks, 256, 0, st>>>(p);
+    if (timing) cudaEventRecord(g_nz_ev[1], st);
+    if (a->d == 64) nz_fused_kernel<64><<<(unsigned)blocks, 256, 0, st>>>(p);
+    else nz_fused_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(p);
+    if (timing) {
+        cudaEventRecord(g_nz_ev[2], st);
+        g_nz_ev_valid = true;
     }
     return check_launch("lpf_nz_links_fused");
 }

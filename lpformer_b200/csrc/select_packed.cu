@@ -39,6 +39,7 @@ constexpr int kPkMaxUnits = 16;       // target rows of up to 16 units (1 KB: ~2
 constexpr int kPkMaxItems = 6144;     // units of one chunk that are screened unit-wise (the rest get a warp)
 constexpr int kPkWarpRow = 512;       // resolution: target rows up to this length take the hashed warp walk
 constexpr int kPkHubPiece = 128;      // links per entry of the hub list
+static_assert(kPkChunk == 1024 && kPkMaxUnits == 16 && kPkMaxRuns <= 4, "items[] packs (run:2 | position:10 | unit:4)");
 constexpr uint32_t kPkPprTag = 0x80000000u;
 constexpr uint32_t kPkPad = 0x7fffffffu;
 
@@ -61,6 +62,7 @@ struct PkSmemT {
     int32_t r_tab0[kPkMaxRuns], r_lg[kPkMaxRuns], r_na[kPkMaxRuns], r_npa[kPkMaxRuns], r_hashed[kPkMaxRuns];
     uint32_t r_loc[kPkMaxRuns];
     int32_t r_slots[kPkMaxRuns];
+    int4 r_ctx[kPkMaxRuns];              // (first table slot, bucket mask, 32 - log2(buckets), 0): one read per unit
     int n_runs, n_slow, n_items, tab_used, items_full;
 };
 
@@ -95,6 +97,7 @@ __device__ __forceinline__ bool screen_slot(const RunCtx& h, const int32_t* __re
         return want_pi && smem_ppr_lookup(h, (int32_t)(w0 & ~kPkPprTag), qa) && qa >= th_pre &&
                quantise(__uint_as_float(w1)) >= th_pre;
     }
+    if (w0 == kPkPad) return false;          // ids ascend: a pad in front means the slot is all padding
     if (HASHED) return hash_contains_any2(h.tab, h.mask, h.shift, (int32_t)w0, (int32_t)w1);
     int t = lower_bound_from(arow_ids, 0, na, (int32_t)w0);
     if (t < na && __ldg(arow_ids + t) == (int32_t)w0) return true;
@@ -347,6 +350,7 @@ select_onepass_packed_kernel(SelectParams2 p, const uint32_t* __restrict__ locat
                 sm.r_hashed[r] = m;
                 sm.r_lg[r] = lg;
                 sm.r_tab0[r] = used;
+                sm.r_ctx[r] = make_int4(used, (1 << (lg - 2)) - 1, 32 - (lg - 2), 0);
                 if (m == 1) used += 1 << lg;
             }
             sm.tab_used = used;
@@ -391,7 +395,7 @@ select_onepass_packed_kernel(SelectParams2 p, const uint32_t* __restrict__ locat
                     const uint8_t* r0 = reinterpret_cast<const uint8_t*>(row_of(blob, loc_b));
                     for (int k = 0; k < min(units, 36); k += 2) prefetch_l2(r0 + 64 * k);
                 } else {
-                    for (int u = 0; u < units; ++u) sm.items[ex + u] = (uint16_t)((t << 4) | u);
+                    for (int u = 0; u < units; ++u) sm.items[ex + u] = (uint16_t)((r << 14) | (t << 4) | u);
                 }
             }
             __syncthreads();     // everyone has read n_items / items_full of the previous pass
@@ -449,20 +453,23 @@ select_onepass_packed_kernel(SelectParams2 p, const uint32_t* __restrict__ locat
                     v[k] = make_uint4(kPkPad, kPkPad, kPkPad, kPkPad);
                     if (q < n_items) {
                         const int it = sm.items[q];
-                        const int t = it >> 4, u = it & 15;
-                        tt[k] = (u == 0 && ql == 0) ? -1 : t;            // chunk 0 of unit 0 is the row's header
+                        const int t = (it >> 4) & (kPkChunk - 1), u = it & 15;
+                        tt[k] = (u == 0 && ql == 0) ? -1 : (it >> 4);      // chunk 0 of unit 0 is the row's header
                         v[k] = ldg16(row_of(blob, sm.l_loc[t]) + 4 * u + ql);
                     }
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const int t = tt[k];
-                    if (t < 0) continue;
-                    const int r = run_of(sm, t);
-                    const RunCtx h = make_ctx(sm, r);
+                    if (tt[k] < 0) continue;
+                    const int t = tt[k] & (kPkChunk - 1), r = tt[k] >> 10;
+                    const int mode_r = sm.r_hashed[r];
+                    if (mode_r == 0) continue;               // the run turned out not to be screenable
+                    const int4 cx = sm.r_ctx[r];
+                    RunCtx h;
+                    h.tab = sm.tab + cx.x; h.mask = (uint32_t)cx.y; h.shift = cx.z;
+                    h.pac = sm.run[r].pac; h.pav = sm.run[r].pav; h.ppos = sm.run[r].ppos; h.npa = 0;
                     bool any;
-                    if (sm.r_hashed[r] == 0) continue;       // the run turned out not to be screenable
-                    if (sm.r_hashed[r] == 1) {
+                    if (mode_r == 1) {
                         any = screen_slot<true>(h, nullptr, 0, v[k].x, v[k].y, want_pi, th_pre) |
                               screen_slot<true>(h, nullptr, 0, v[k].z, v[k].w, want_pi, th_pre);
                     } else {
@@ -545,6 +552,10 @@ __global__ void __launch_bounds__(256) pack_fill_kernel(const int64_t* __restric
 }
 
 extern long long* g_select_dbg;
+// profiling hook (lpf_debug_select_timing): CUDA events around the three kernels of the packed launch sequence
+bool g_kernel_timing = false;     // shared with nz_fused.cu
+static cudaEvent_t g_pk_ev[4];
+static bool g_pk_ev_ready = false, g_pk_ev_valid = false;
 void launch_onepass_reset(const SelectParams2& p, cudaStream_t st);
 void launch_onepass_tail(const SelectParams2& p, cudaStream_t st);
 
@@ -631,6 +642,12 @@ extern "C" int lpf_select_onepass_packed(const int64_t* links, int64_t bs, const
         configured = true;
     }
     launch_onepass_reset(p, st);
+    const bool timing = g_kernel_timing && bs > 0;
+    if (timing && !g_pk_ev_ready) {
+        for (auto& e : g_pk_ev) cudaEventCreate(&e);
+        g_pk_ev_ready = true;
+    }
+    if (timing) cudaEventRecord(g_pk_ev[0], st);
     if (bs > 0) {
         // one resident wave (3 CTAs per SM), the batch cut evenly over it: pieces of 512 .. 1,024 links
         int64_t blocks = (bs + kPkThreads - 1) / kPkThreads;
@@ -638,9 +655,31 @@ extern "C" int lpf_select_onepass_packed(const int64_t* links, int64_t bs, const
         if (blocks > cap_blocks) blocks = cap_blocks;
         select_onepass_packed_kernel<kPkHashSlots, false><<<(unsigned)blocks, kPkThreads, sizeof(SmMain), st>>>(
             p, locator, static_cast<const uint4*>(row_blob));
+        if (timing) cudaEventRecord(g_pk_ev[1], st);
         select_onepass_packed_kernel<kPkHubSlots, true><<<kNumSMs, kPkThreads, sizeof(SmHub), st>>>(
             p, locator, static_cast<const uint4*>(row_blob));
+        if (timing) cudaEventRecord(g_pk_ev[2], st);
     }
     launch_onepass_tail(p, st);
+    if (timing) {
+        cudaEventRecord(g_pk_ev[3], st);
+        g_pk_ev_valid = true;
+    }
     return check_launch("lpf_select_onepass_packed");
+}
+
+// Profiling hook: with enable != 0 later lpf_select_onepass_packed calls record CUDA events on their stream around
+// the screening kernel, the hub-source kernel and the deferred-link tail; lpf_debug_select_timing_read waits for the
+// last such call and returns the three durations in milliseconds (0 on success, -1 if nothing was recorded).
+extern "C" int lpf_debug_select_timing(int enable) {
+    lpf::g_kernel_timing = enable != 0;
+    if (!enable) lpf::g_pk_ev_valid = false;
+    return LPF_OK;
+}
+extern "C" int lpf_debug_select_timing_read(float* ms3_host) {
+    if (!lpf::g_pk_ev_valid || !ms3_host) return -1;
+    if (cudaEventSynchronize(lpf::g_pk_ev[3]) != cudaSuccess) return -1;
+    for (int k = 0; k < 3; ++k)
+        if (cudaEventElapsedTime(ms3_host + k, lpf::g_pk_ev[k], lpf::g_pk_ev[k + 1]) != cudaSuccess) return -1;
+    return LPF_OK;
 }

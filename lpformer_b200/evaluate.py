@@ -124,7 +124,7 @@ class LinkScoreStream:
     `score_links`, without a GPU idle gap per batch.
     """
 
-    def __init__(self, model, score_func, X_node, batch_size, test_set=False, depth=2, return_logits=False):
+    def __init__(self, model, score_func, X_node, batch_size, test_set=False, depth=4, return_logits=False):
         self.model, self.score_func, self.bs = model, score_func, int(batch_size)
         self.test_set, self.logits = bool(test_set), bool(return_logits)
         self.X = model._check_x(X_node)
@@ -138,6 +138,9 @@ class LinkScoreStream:
             self.plans = [ScorePlan(model, score_func, consts, self.X, kv, self.bs, test_set, return_logits,
                                     use_graph=model.use_graphs) for _ in range(max(1, int(depth)))]
         self.copy_stream = torch.cuda.Stream(device=self.dev)
+        # every plan launches on a stream of its own: the latency-bound tail of one batch (hub sources, heavy links,
+        # the non-empty links) overlaps the bandwidth-bound head of the next
+        self.streams = [torch.cuda.Stream(device=self.dev) for _ in (self.plans or [])]
         self._stage = None
         self.batches = 0
 
@@ -171,14 +174,12 @@ class LinkScoreStream:
             self._stage = [torch.empty((2, G * bs), dtype=torch.int64, device=self.dev) for _ in range(2)]
         ev_in = [torch.cuda.Event(), torch.cuda.Event()]
         ev_free = [torch.cuda.Event(), torch.cuda.Event()]
-        ev_out = torch.cuda.Event()
 
         def h2d(g):          # links of the group that starts at batch g -> staging slot, on the copy stream
             slot = (g // G) % 2
             n = min(G, nb - g) * bs
             with torch.cuda.stream(cs):
-                if g >= 2 * G:
-                    cs.wait_event(ev_free[slot])      # the plans have taken the slot's previous links
+                # (the copy stream has already waited for the plans to take the slot's previous links: ev_free)
                 # row by row: a strided two-row host slice would go through a slow pitched copy (15 vs 48 GB/s measured)
                 self._stage[slot][0, :n].copy_(links[0, g * bs:g * bs + n], non_blocking=True)
                 self._stage[slot][1, :n].copy_(links[1, g * bs:g * bs + n], non_blocking=True)
@@ -186,6 +187,10 @@ class LinkScoreStream:
 
         pending = [None] * depth
         redo = []
+        ev_start = torch.cuda.Event()
+        ev_start.record(main)                 # `links` / `out_dev` are ready in the caller's stream order
+        for st in self.streams:
+            st.wait_event(ev_start)
         if on_host and nb > 0:
             h2d(0)
         for g in range(0, nb, G):
@@ -194,32 +199,39 @@ class LinkScoreStream:
             if on_host:
                 if g + G < nb:
                     h2d(g + G)
-                main.wait_event(ev_in[slot])
                 src = self._stage[slot]
             else:
                 src = links[:, g * bs:(g + kb) * bs]
             for j in range(kb):
                 k = g + j
-                P = self.plans[k % depth]
+                P, st = self.plans[k % depth], self.streams[k % depth]
                 if pending[k % depth] is not None and P.collect():
                     redo.append(pending[k % depth])
-                P.submit(src[:, j * bs:(j + 1) * bs])
-                out_dev[k * bs:(k + 1) * bs].copy_(P.prob, non_blocking=True)
+                with torch.cuda.stream(st):
+                    if on_host and j < depth:
+                        st.wait_event(ev_in[slot])
+                    P.submit(src[:, j * bs:(j + 1) * bs])
+                    out_dev[k * bs:(k + 1) * bs].copy_(P.prob, non_blocking=True)
                 pending[k % depth] = k
                 self.batches += 1
-            if on_host:
-                ev_free[slot].record(main)
-            if out_host is not None:
-                ev_out.record(main)
-                with torch.cuda.stream(cs):
-                    cs.wait_event(ev_out)
-                    out_host[g * bs:(g + kb) * bs].copy_(out_dev[g * bs:(g + kb) * bs], non_blocking=True)
+            if on_host or out_host is not None:
+                # the group is through once every plan stream has passed this point
+                for st in self.streams:
+                    e = torch.cuda.Event()
+                    e.record(st)
+                    cs.wait_event(e)
+                if on_host:
+                    ev_free[slot].record(cs)
+                if out_host is not None:
+                    with torch.cuda.stream(cs):
+                        out_host[g * bs:(g + kb) * bs].copy_(out_dev[g * bs:(g + kb) * bs], non_blocking=True)
         for j, k in enumerate(pending):
             if k is not None and self.plans[j].collect():
                 redo.append(k)
         if nb * bs < L:
             redo.append(nb)        # the ragged tail goes through score_links
-        main.synchronize()
+        for st in self.streams:
+            st.synchronize()
         cs.synchronize()
         if redo:
             use = self.model.use_plans

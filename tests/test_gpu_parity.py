@@ -444,7 +444,7 @@ def test_link_score_stream_matches_score_links():
     def same(x, y):     # (the fused / batched regimes of the non-empty links differ in fp32 summation order)
         np.testing.assert_allclose(x.cpu().numpy(), y.cpu().numpy(), rtol=1e-5, atol=1e-7)
 
-    st = LinkScoreStream(model, score, X, bs)
+    st = LinkScoreStream(model, score, X, bs, depth=2)
     assert st.plans is not None and len(st.plans) == 2
     out = st.score(links.to(dev))
     same(out, ref)
