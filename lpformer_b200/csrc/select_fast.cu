@@ -214,7 +214,7 @@ __device__ __forceinline__ bool is_huge(const LinkRows& r, bool want_pi) {
     return max(min(r.na, r.nb), want_pi ? min(r.npa, r.npb) : 0) > kHugeRow;
 }
 
-__global__ void __launch_bounds__(kHeavyThreads) select_heavy_onepass_kernel(SelectParams2 p) {
+__global__ void __launch_bounds__(kHeavyThreads) select_heavy_onepass_kernel(const __grid_constant__ SelectParams2 p) {
     __shared__ int wt[kHeavyThreads / 32];
     __shared__ int64_t seg[3];
     __shared__ int ok_s;

@@ -240,9 +240,10 @@ __device__ __forceinline__ int run_of(const SM& sm, int t) {
 // HUB = false: the chunks are the batch cut into pieces of 512 links; runs whose source row does not fit the hash
 // are appended to the hub list.  HUB = true (second launch, one CTA per SM, a 32,768-slot table): the chunks are the
 // entries of that list.
-template <int SLOTS, bool HUB>
-__global__ void __launch_bounds__(kPkThreads, HUB ? 1 : 3)
-select_onepass_packed_kernel(SelectParams2 p, const uint32_t* __restrict__ locator, const uint4* __restrict__ blob) {
+template <int SLOTS, bool HUB, int MINB>
+__global__ void __launch_bounds__(kPkThreads, MINB)
+select_onepass_packed_kernel(const __grid_constant__ SelectParams2 p, const uint32_t* __restrict__ locator,
+                             const uint4* __restrict__ blob) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     using SM = PkSmemT<SLOTS>;
     SM& sm = *reinterpret_cast<SM*>(smem_raw);
@@ -556,6 +557,7 @@ extern long long* g_select_dbg;
 bool g_kernel_timing = false;     // shared with nz_fused.cu
 static cudaEvent_t g_pk_ev[4];
 static bool g_pk_ev_ready = false, g_pk_ev_valid = false;
+static int g_pk_ctas = 2;
 void launch_onepass_reset(const SelectParams2& p, cudaStream_t st);
 void launch_onepass_tail(const SelectParams2& p, cudaStream_t st);
 
@@ -629,10 +631,15 @@ extern "C" int lpf_select_onepass_packed(const int64_t* links, int64_t bs, const
     using SmHub = PkSmemT<kPkHubSlots>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(select_onepass_packed_kernel<kPkHashSlots, false>,
+        const char* env = getenv("LPF_PK_CTAS");      // tuning knob: resident screening CTAs per SM (2 or 3)
+        if (env && atoi(env) == 3) g_pk_ctas = 3;
+        cudaError_t e = cudaFuncSetAttribute(select_onepass_packed_kernel<kPkHashSlots, false, 2>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmMain));
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(select_onepass_packed_kernel<kPkHubSlots, true>,
+            e = cudaFuncSetAttribute(select_onepass_packed_kernel<kPkHashSlots, false, 3>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmMain));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(select_onepass_packed_kernel<kPkHubSlots, true, 1>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmHub));
         if (e != cudaSuccess) {
             set_error("lpf_select_onepass_packed: cudaFuncSetAttribute(%zu / %zu B): %s", sizeof(SmMain), sizeof(SmHub),
@@ -649,14 +656,18 @@ extern "C" int lpf_select_onepass_packed(const int64_t* links, int64_t bs, const
     }
     if (timing) cudaEventRecord(g_pk_ev[0], st);
     if (bs > 0) {
-        // one resident wave (3 CTAs per SM), the batch cut evenly over it: pieces of 512 .. 1,024 links
+        // one resident wave (g_pk_ctas CTAs per SM), the batch cut evenly over it: pieces of 512 .. 1,024 links
         int64_t blocks = (bs + kPkThreads - 1) / kPkThreads;
-        const int64_t cap_blocks = (int64_t)kNumSMs * 3;
+        const int64_t cap_blocks = (int64_t)kNumSMs * g_pk_ctas;
         if (blocks > cap_blocks) blocks = cap_blocks;
-        select_onepass_packed_kernel<kPkHashSlots, false><<<(unsigned)blocks, kPkThreads, sizeof(SmMain), st>>>(
-            p, locator, static_cast<const uint4*>(row_blob));
+        if (g_pk_ctas == 3)
+            select_onepass_packed_kernel<kPkHashSlots, false, 3><<<(unsigned)blocks, kPkThreads, sizeof(SmMain), st>>>(
+                p, locator, static_cast<const uint4*>(row_blob));
+        else
+            select_onepass_packed_kernel<kPkHashSlots, false, 2><<<(unsigned)blocks, kPkThreads, sizeof(SmMain), st>>>(
+                p, locator, static_cast<const uint4*>(row_blob));
         if (timing) cudaEventRecord(g_pk_ev[1], st);
-        select_onepass_packed_kernel<kPkHubSlots, true><<<kNumSMs, kPkThreads, sizeof(SmHub), st>>>(
+        select_onepass_packed_kernel<kPkHubSlots, true, 1><<<kNumSMs, kPkThreads, sizeof(SmHub), st>>>(
             p, locator, static_cast<const uint4*>(row_blob));
         if (timing) cudaEventRecord(g_pk_ev[2], st);
     }

@@ -371,9 +371,15 @@ def test_plan_fused_nonempty_path(dim, mode_th):
     def batch(seed):
         q = S.citation2_queries(g, 5, 800, seed=seed)
         pos = g.edges[:, rng.integers(0, g.edges.shape[1], 45)]
-        return np.concatenate([q, pos], 1).astype(np.int64)
+        # hub-hub links: hundreds of common neighbours each (the CTA-wide walk of lpf_nz_links_fused's link stage)
+        hubs = np.argsort(np.diff(g.indptr))[-6:]
+        hh = np.array([(x, y) for x in hubs for y in hubs if x < y][:11]).T
+        return np.concatenate([q, pos, hh], 1).astype(np.int64)
 
     batches = [batch(s) for s in range(3)]
+    sel = model._select(torch.from_numpy(batches[0]).to(dev), False)
+    if mode_th[0] < 1:
+        assert int(sel.counts().sum(0).max()) > 64      # kNzHeavy
     model.use_plans = False
     ref = [model.score_links(torch.from_numpy(b).to(dev), X, score).cpu().numpy() for b in batches]
     model.use_plans = True
