@@ -338,7 +338,7 @@ def run_b200(args):
         if sel_ms[3] and "lpf_select_onepass_packed" in summ:
             # the selection entry point is three kernels: time them separately (events recorded inside the launcher)
             c, t = summ.pop("lpf_select_onepass_packed")
-            summ["lpf_select_onepass_packed/screen (select_onepass_packed_kernel<8192,0>)"] = (sel_ms[3], sel_ms[0])
+            summ["lpf_select_onepass_packed/screen (select_onepass_packed_kernel<16384,0>)"] = (sel_ms[3], sel_ms[0])
             summ["lpf_select_onepass_packed/hub sources (select_onepass_packed_kernel<32768,1>)"] = (sel_ms[3], sel_ms[1])
             summ["lpf_select_onepass_packed/deferred links (select_heavy_onepass_kernel)"] = (sel_ms[3], sel_ms[2])
             summ["lpf_select_onepass_packed/launch gaps + resets"] = (c, max(0.0, t - sum(sel_ms[:3])))

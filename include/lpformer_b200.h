@@ -304,7 +304,7 @@ typedef struct lpf_nz_args {
 int lpf_nz_links_fused(const lpf_nz_args* args, void* stream);
 
 /* Profiling hook: later lpf_select_onepass launches add per-phase clock64() totals of the run-aware kernel into
- * device_buffer (int64[16]: [0] source staging, [1] phase A, [2] phase B, [3] phase C, [4] generic fallback,
+ * device_buffer (int64[48]: [0] source staging, [1] phase A, [2] phase B, [3] phase C, [4] generic fallback,
  * [5] chunks, [6] queued long-row links, [7] written links); NULL disables. */
 int lpf_debug_select_clocks(void* device_buffer);
 
@@ -313,6 +313,10 @@ int lpf_debug_select_clocks(void* device_buffer);
  * the last such call and stores the three durations (milliseconds) in ms3_host[0..2]; -1 if nothing was recorded. */
 int lpf_debug_select_timing(int enable);
 int lpf_debug_select_timing_read(float* ms3_host);
+/* Test hook: caps the hash slots lpf_select_onepass_packed's screening launch may use for the staged sources (its
+ * hub launch gets four times as many), so that small graphs reach the hub launch and the global-memory search of
+ * sources beyond it; 0 restores the full tables. */
+int lpf_debug_select_slots(int limit);
 /* Same switch: the two kernels of the last lpf_nz_links_fused call (pair stage, link stage) in ms2_host[0..1]. */
 int lpf_debug_nz_timing_read(float* ms2_host);
 

@@ -48,6 +48,7 @@ SIGNATURES = {
     "lpf_debug_heads_clocks": (_int, [_p]),
     "lpf_debug_select_clocks": (_int, [_p]),
     "lpf_debug_select_timing": (_int, [_int]),
+    "lpf_debug_select_slots": (_int, [_int]),
     "lpf_debug_select_timing_read": (_int, [_p]),
     "lpf_debug_nz_timing_read": (_int, [_p]),
     "lpf_select_compact": (_int, [_p, _i64, _p, _p, _p]),

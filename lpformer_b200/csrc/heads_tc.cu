@@ -8,12 +8,13 @@
 // folded once per weight set: z = ReLU(W23 h + offset), W23 = Ws1[:, :d] W2, offset = Ws1[:, :d] b2 + bs1 +
 // Ws1[:, d:] pw.  The two remaining contractions run as tcgen05.mma (kind::tf32, 3xTF32 split, accumulators in
 // TMEM); their weights (pre-split, pre-swizzled images from lpf_pack_weight) are brought into shared memory
-// ONCE per CTA by bulk TMA copies and stay resident while the CTA walks its tiles; each thread owns one link
-// (= one TMEM lane), so LayerNorm and the final dot product are thread-local.
+// ONCE per CTA by bulk TMA copies and stay resident while the CTA walks its tiles; two threads own one link
+// (= one TMEM lane, half of the accumulator columns each), so LayerNorm and the final dot product take one
+// shared-memory exchange between the two.
 //
-// Software pipeline across tiles: warps 4-7 (producers) gather tile t+1's X[a]*X[b] rows into registers while
+// Software pipeline across tiles: warps 8-11 (producers) gather tile t+1's X[a]*X[b] rows into registers while
 // tile t is computed; as soon as contraction 2 of tile t has finished reading the operand tile they store the
-// hi/lo split there and issue contraction 1 of tile t+1, which runs on the tensor pipe while warps 0-3
+// hi/lo split there and issue contraction 1 of tile t+1, which runs on the tensor pipe while warps 0-7
 // (consumers) are still in tile t's final epilogue.  HBM latency, the operand split and half of the MMA time
 // are off the consumers' critical path; hand-offs are mbarriers fed by tcgen05.commit.
 //
@@ -29,8 +30,11 @@ namespace lpf {
 
 using namespace tc;
 
-constexpr int kHeadConsumers = 128;   // warps 0-3: one link (= TMEM lane) per thread; thread 0 issues the MMAs
-constexpr int kHeadProducers = 128;   // warps 4-7: gather X[a]*X[b] of the NEXT tile while this one is computed
+constexpr int kHeadConsumers = 256;   // warps 0-7: TWO threads per link (= TMEM lane), half of the accumulator columns each: warp w
+                                      // reads lanes 32 (w % 4) .. + 31 (the hardware's lane quadrant of a warp), column half w / 4.
+                                      // The epilogues are CUDA-core work on 192 accumulator columns per link, and one warp per SM
+                                      // sub-partition cannot hide its own instruction latencies; thread 0 issues the MMAs
+constexpr int kHeadProducers = 128;   // warps 8-11: gather X[a]*X[b] of the NEXT tile while this one is computed
 constexpr int kHeadThreads = kHeadConsumers + kHeadProducers;
 
 struct HeadsParams {
@@ -63,7 +67,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int D>
+template <int D, bool ZB>
 __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsParams p) {
     constexpr int KB = D / 32;                       // k-blocks of both contractions (K = D)
     constexpr int N3 = 2 * D;                        // width of mlp_score's hidden layer
@@ -77,7 +81,8 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
     __shared__ uint64_t bar_w, bar_mma1, bar_mma3, bar_a_free;
     __shared__ uint32_t tmem_slot;
     __shared__ int32_t ids[2][2][kTileM];            // [tile parity][a, b][row]
-    __shared__ float s_b1[D], s_g[D], s_bt[D], s_c3[N3], s_ws2[N3];
+    __shared__ __align__(16) float s_b1[D], s_g[D], s_bt[D], s_c3[N3], s_ws2[N3];
+    __shared__ float s_sum[2][kTileM], s_sq[2][kTileM], s_dot[2][kTileM];   // exchanges between the two threads of a link
 
     const int tid = threadIdx.x, warp = tid >> 5;
     if (p.n_dev) p.n = min(p.n, *p.n_dev);
@@ -185,27 +190,42 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
 
     // =============================== consumers: one link (= TMEM lane) per thread
     const float bs2 = p.bs2[0];
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    const int row = (warp & 3) * 32 + (tid & 31), half = warp >> 2;      // this thread's link of the tile, its column half
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t it = 0;
     const bool stamp = p.dbg && blockIdx.x == 0 && tid == 0;
 #define LPF_STAMP(k) do { if (stamp && it < 8) p.dbg[it * 16 + (k)] = clock64(); } while (0)
 
     // epilogue 2 of a tile: prob = sigmoid(ws2 . ReLU(D3 + offset) + bs2)
     auto epilogue2 = [&](int64_t j) {
-        const float* zrow = (p.zb && j < p.n) ? p.zb + j * p.ld_zb : nullptr;
+        constexpr int NH = N3 / 2;                       // columns per thread
+        const float* zrow = (ZB && j < p.n) ? p.zb + j * p.ld_zb : nullptr;
         float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+        // the next 16 columns are on their way out of TMEM while these 16 are reduced
+        float buf[2][16];
+        const int cb = half * NH;
+        tmem_ld16_async(d3 + lane_sel + cb, buf[0]);
+        tmem_ld_wait();
 #pragma unroll
-        for (int c0 = 0; c0 < N3; c0 += 16) {
-            float v[16];
-            tmem_ld16(d3 + lane_sel + c0, v);
+        for (int c0 = 0; c0 < NH; c0 += 16) {
+            const int cur = (c0 >> 4) & 1;
+            if (c0 + 16 < NH) tmem_ld16_async(d3 + lane_sel + cb + c0 + 16, buf[cur ^ 1]);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                const float z = v[c] + (zrow ? __ldg(zrow + c0 + c) : s_c3[c0 + c]);
-                acc4[c & 3] = fmaf(fmaxf(z, 0.f), s_ws2[c0 + c], acc4[c & 3]);
+            for (int c = 0; c < 16; c += 4) {
+                const float4 o4 = ZB ? (zrow ? __ldg(reinterpret_cast<const float4*>(zrow + cb + c0 + c)) : make_float4(0.f, 0.f, 0.f, 0.f))
+                                     : *reinterpret_cast<const float4*>(&s_c3[cb + c0 + c]);
+                const float4 w4 = *reinterpret_cast<const float4*>(&s_ws2[cb + c0 + c]);
+                acc4[0] = fmaf(fmaxf(buf[cur][c] + o4.x, 0.f), w4.x, acc4[0]);
+                acc4[1] = fmaf(fmaxf(buf[cur][c + 1] + o4.y, 0.f), w4.y, acc4[1]);
+                acc4[2] = fmaf(fmaxf(buf[cur][c + 2] + o4.z, 0.f), w4.z, acc4[2]);
+                acc4[3] = fmaf(fmaxf(buf[cur][c + 3] + o4.w, 0.f), w4.w, acc4[3]);
             }
+            if (c0 + 16 < NH) tmem_ld_wait();
         }
-        if (j < p.n) {
-            const float logit = ((acc4[0] + acc4[1]) + (acc4[2] + acc4[3])) + bs2;
+        s_dot[half][row] = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
+        named_bar_sync(1, kHeadConsumers);
+        if (half == 0 && j < p.n) {
+            const float logit = (s_dot[0][row] + s_dot[1][row]) + bs2;
             const int64_t pos = p.idx ? (int64_t)__ldg(p.idx + j) : j;
             p.prob[pos] = p.logits ? logit : 1.0f / (1.0f + expf(-logit));
         }
@@ -213,7 +233,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
 
     int64_t j_prev = -1;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int64_t j = tile * kTileM + tid;
+        const int64_t j = tile * kTileM + row;
         LPF_STAMP(0);
         // ---- the previous tile's epilogue 2 runs while the producers refill the operand tile and the tensor
         // pipe works on this tile's contraction 1
@@ -228,33 +248,54 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
         tc_fence_after();
         LPF_STAMP(3);
 
-        // ---- epilogue 1: h = ReLU(LN(D1 + b1)), thread-local over the link's row; becomes the next A operand
+        // ---- epilogue 1: h = ReLU(LN(D1 + b1)) over the link's row, half of the columns per thread (the two partial
+        // sums of the mean and of the variance meet in shared memory); becomes the next A operand
         {
-            float v[D];
-#pragma unroll
-            for (int c0 = 0; c0 < D; c0 += 16) tmem_ld16(d1 + lane_sel + c0, v + c0);
+            constexpr int DH = D / 2;
+            const int cb = half * DH;
+            float v[DH];
             float s4[4] = {0.f, 0.f, 0.f, 0.f};
+            {
+                float (*vb)[16] = reinterpret_cast<float (*)[16]>(v);
+                tmem_ld16_async(d1 + lane_sel + cb, vb[0]);
+                tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < D; ++c) {
-                v[c] += s_b1[c];
-                s4[c & 3] += v[c];
+                for (int c0 = 0; c0 < DH; c0 += 16) {
+                    if (c0 + 16 < DH) tmem_ld16_async(d1 + lane_sel + cb + c0 + 16, vb[(c0 >> 4) + 1]);
+#pragma unroll
+                    for (int c = c0; c < c0 + 16; c += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(&s_b1[cb + c]);
+                        v[c] += b4.x; v[c + 1] += b4.y; v[c + 2] += b4.z; v[c + 3] += b4.w;
+                        s4[0] += v[c]; s4[1] += v[c + 1]; s4[2] += v[c + 2]; s4[3] += v[c + 3];
+                    }
+                    if (c0 + 16 < DH) tmem_ld_wait();
+                }
             }
-            const float mean = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.0f / D);
+            s_sum[half][row] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+            named_bar_sync(1, kHeadConsumers);
+            const float mean = (s_sum[0][row] + s_sum[1][row]) * (1.0f / D);
             float q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int c = 0; c < D; ++c) {
+            for (int c = 0; c < DH; ++c) {
                 const float dlt = v[c] - mean;
                 q4[c & 3] = fmaf(dlt, dlt, q4[c & 3]);
             }
-            const float rstd = rsqrtf(((q4[0] + q4[1]) + (q4[2] + q4[3])) * (1.0f / D) + 1e-5f);
+            s_sq[half][row] = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+            named_bar_sync(1, kHeadConsumers);
+            const float rstd = rsqrtf((s_sq[0][row] + s_sq[1][row]) * (1.0f / D) + 1e-5f);
 #pragma unroll
-            for (int c = 0; c < D; c += 4) {
+            for (int c = 0; c < DH; c += 4) {
+                const float4 g4 = *reinterpret_cast<const float4*>(&s_g[cb + c]);
+                const float4 t4 = *reinterpret_cast<const float4*>(&s_bt[cb + c]);
                 float h[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) h[e] = fmaxf(fmaf((v[c + e] - mean) * rstd, s_g[c + e], s_bt[c + e]), 0.f);
+                h[0] = fmaxf(fmaf((v[c] - mean) * rstd, g4.x, t4.x), 0.f);
+                h[1] = fmaxf(fmaf((v[c + 1] - mean) * rstd, g4.y, t4.y), 0.f);
+                h[2] = fmaxf(fmaf((v[c + 2] - mean) * rstd, g4.z, t4.z), 0.f);
+                h[3] = fmaxf(fmaf((v[c + 3] - mean) * rstd, g4.w, t4.w), 0.f);
                 const float4 hi = make_float4(tf32_hi(h[0]), tf32_hi(h[1]), tf32_hi(h[2]), tf32_hi(h[3]));
                 const float4 lo = make_float4(h[0] - hi.x, h[1] - hi.y, h[2] - hi.z, h[3] - hi.w);
-                const uint32_t off = (uint32_t)(c / 32) * 2 * kATileBytes + swz_chunk_off(tid, (c % 32) / 4);
+                const int cg = cb + c;                 // column of the row: k-block cg / 32, 16-byte chunk (cg % 32) / 4
+                const uint32_t off = (uint32_t)(cg / 32) * 2 * kATileBytes + swz_chunk_off(row, (cg % 32) / 4);
                 *reinterpret_cast<float4*>(sA + off) = hi;
                 *reinterpret_cast<float4*>(sA + off + kATileBytes) = lo;
             }
@@ -268,6 +309,8 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
         if (tid == 0) {
             if (it == 0) mbar_wait(&bar_w, 0);
             tc_fence_after();
+            // (one N = 2D instruction stream: the contraction is bound by the shared-memory reads of its operands — 4 KB
+            // of A and 32 N bytes of B per K-slice at 128 B per cycle — and halves of N would read A twice)
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb)
                 issue_kblock_3x(d3, aA + kb * 2 * kATileBytes, aA + kb * 2 * kATileBytes + kATileBytes,
@@ -290,13 +333,13 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
     if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
 }
 
-template <int D>
+template <int D, bool ZB>
 static int launch_heads(const HeadsParams& p, cudaStream_t st) {
     constexpr int KB = D / 32;
     constexpr size_t smem = (size_t)KB * 2 * D * 128 + (size_t)KB * 2 * 2 * D * 128 + (size_t)KB * 2 * tc::kATileBytes + 1024;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(link_heads_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(link_heads_tc_kernel<D, ZB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("lpf_link_heads_tc: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
             return LPF_ERR_CUDA;
@@ -306,7 +349,7 @@ static int launch_heads(const HeadsParams& p, cudaStream_t st) {
     const int64_t ntiles = (p.n + tc::kTileM - 1) / tc::kTileM;
     const int per_sm = D <= 32 ? 2 : 1;
     const unsigned grid = (unsigned)(ntiles < (int64_t)kNumSMs * per_sm ? ntiles : (int64_t)kNumSMs * per_sm);
-    link_heads_tc_kernel<D><<<grid, kHeadThreads, smem, st>>>(p);
+    link_heads_tc_kernel<D, ZB><<<grid, kHeadThreads, smem, st>>>(p);
     return check_launch("lpf_link_heads_tc");
 }
 
@@ -335,8 +378,9 @@ extern "C" int lpf_link_heads_tc(const int64_t* links, int64_t bs, const int32_t
     LPF_REQUIRE(ldx >= d && (!zb || ld_zb >= 2 * d), "leading dimension too small");
     HeadsParams p{links, bs, idx, n, X, ldx, w1_packed, b1, ln_w, ln_b, w23_packed, c3, zb, ld_zb, ws2, bs2, prob, logits, n_dev, g_heads_dbg};
     cudaStream_t st = (cudaStream_t)stream;
-    if (d == 64) return launch_heads<64>(p, st);
-    if (d == 32) return launch_heads<32>(p, st);
+    LPF_REQUIRE(!zb || ((reinterpret_cast<uintptr_t>(zb) & 15) == 0 && ld_zb % 4 == 0), "zb rows must be 16-byte aligned");
+    if (d == 64) return zb ? launch_heads<64, true>(p, st) : launch_heads<64, false>(p, st);
+    if (d == 32) return zb ? launch_heads<32, true>(p, st) : launch_heads<32, false>(p, st);
     set_error("lpf_link_heads_tc: d = %d not supported by the fused kernel (32 or 64)", d);
     return LPF_ERR_UNSUPPORTED;
 }

@@ -11,7 +11,7 @@
 // and values (q(p) = fl32(p+1)-1) are bit-identical to the reference's.
 #include <limits.h>
 
-#include "common.cuh"
+#include "select_walk.cuh"
 
 namespace lpf {
 
@@ -414,9 +414,9 @@ extern "C" int lpf_debug_select_clocks(void* device_buffer) {
     return LPF_OK;
 }
 
-// [0, bs+4): deferred (heavy) links; [bs+4, ...): hub runs of the packed kernel (count + (first, length) pairs)
+// layout: ws_total_words (select_walk.cuh)
 extern "C" int64_t lpf_select_workspace_bytes(int64_t bs) {
-    return (bs + 4 + 1 + 2 * (bs / 128 + 3 * ((bs + 511) / 512 + 1)) + 3) * (int64_t)sizeof(int32_t);
+    return lpf::ws_total_words(bs < 0 ? 0 : bs) * (int64_t)sizeof(int32_t);
 }
 
 extern "C" int64_t lpf_scan_scratch_bytes(int64_t n) {

@@ -279,10 +279,14 @@ __global__ void select_reset_onepass(int32_t* heavy, int64_t* hdr) {
 }
 
 // prologue / epilogue of a one-pass launch sequence, for the kernels of other translation units
-__global__ void select_reset_hub(int32_t* hub) { hub[0] = 0; }
+__global__ void select_reset_packed(int32_t* heavy, int64_t* hdr, int32_t* hub) {
+    heavy[0] = 0;
+    hdr[0] = hdr[1] = hdr[2] = hdr[3] = hdr[4] = 0;
+    hub[0] = 0;
+}
 void launch_onepass_reset(const SelectParams2& p, cudaStream_t st) {
-    select_reset_onepass<<<1, 1, 0, st>>>(p.heavy, p.hdr);
-    if (p.hub) select_reset_hub<<<1, 1, 0, st>>>(p.hub);
+    if (p.hub) select_reset_packed<<<1, 1, 0, st>>>(p.heavy, p.hdr, p.hub);
+    else select_reset_onepass<<<1, 1, 0, st>>>(p.heavy, p.hdr);
 }
 void launch_onepass_tail(const SelectParams2& p, cudaStream_t st) {
     select_heavy_onepass_kernel<<<kNumSMs * 2, kHeavyThreads, 0, st>>>(p);

@@ -32,14 +32,17 @@ namespace lpf {
 constexpr int kPkThreads = 512;       // threads per CTA
 constexpr int kPkChunk = 1024;        // most links of one chunk: the batch is cut evenly over the resident CTAs
 constexpr int kPkMaxRuns = 3;
-constexpr int kPkHashSlots = 8192;    // int32 slots shared by the runs of a chunk (load <= 0.5): sources up to 4,096
+constexpr int kPkHashSlots = 16384;   // int32 slots shared by the runs of a chunk (load <= 0.5): sources up to 8,192
 constexpr int kPkHubSlots = 32768;    // second launch, one CTA per SM: hub sources up to 16,384 neighbours
 constexpr int kPkMaxPprRow = 128;
-constexpr int kPkMaxUnits = 16;       // target rows of up to 16 units (1 KB: ~250 neighbours) are screened unit-wise
+constexpr int kPkMaxUnits = 16;       // target rows of up to 16 units (1 KB: ~250 neighbours) are screened unit-wise; longer rows are
+                                      // resolved unscreened (listing their units costs the screening more than it saves)
 constexpr int kPkMaxItems = 6144;     // units of one chunk that are screened unit-wise (the rest get a warp)
-constexpr int kPkWarpRow = 512;       // resolution: target rows up to this length take the hashed warp walk
-constexpr int kPkHubPiece = 128;      // links per entry of the hub list
-static_assert(kPkChunk == 1024 && kPkMaxUnits == 16 && kPkMaxRuns <= 4, "items[] packs (run:2 | position:10 | unit:4)");
+constexpr int kPkWarpUnits = 32;      // resolution by a warp of the screening CTA: target rows up to 32 units (~500 neighbours)
+constexpr int kPkHubDeg = 1 << 30;      // a source with more neighbours selects something with every tenth target: its run is
+                                      // cut into pieces for the hub launch, so that no CTA resolves hundreds of links
+constexpr int kPkHubPiece = 256;      // links per entry of the hub list
+static_assert(kPkChunk == 1024 && kPkMaxUnits < 65536, "items[] packs (position:16 | unit:16)");
 constexpr uint32_t kPkPprTag = 0x80000000u;
 constexpr uint32_t kPkPad = 0x7fffffffu;
 
@@ -54,8 +57,8 @@ struct PkSmemT {
     int32_t tab[SLOTS];
     PkRunTab run[kPkMaxRuns];
     uint32_t l_loc[kPkChunk];            // locator of every link's target row
-    uint16_t items[kPkMaxItems];         // (chunk position << 4 | unit) of every unit to screen
-    uint16_t q_slow[kPkChunk];           // chunk positions of the links that get a warp (long row / selects something)
+    uint32_t items[kPkMaxItems];         // (chunk position << 16 | unit) of every unit to screen
+    uint16_t q_slow[kPkChunk];           // chunk positions of the links a warp resolves here (they select something)
     uint8_t l_any[kPkChunk];             // "selects something" flags raised by the screening
     int32_t warp_tot[kPkThreads / 32];
     int32_t run_start[kPkMaxRuns + 1];
@@ -63,8 +66,17 @@ struct PkSmemT {
     uint32_t r_loc[kPkMaxRuns];
     int32_t r_slots[kPkMaxRuns];
     int4 r_ctx[kPkMaxRuns];              // (first table slot, bucket mask, 32 - log2(buckets), 0): one read per unit
-    int n_runs, n_slow, n_items, tab_used, items_full;
+    int n_runs, n_slow, n_items, tab_used, items_full, n_cta, cta_ok;
+    uint16_t q_cta[kPkChunk];             // chunk positions of the links the whole CTA walks (long target rows that select)
+    uint32_t scan_tot[2 * 4 * (kPkThreads / 32)];
+    int64_t cta_seg[3];
+    int dbg_ph[16];                      // profiling: this chunk's cycles per phase
 };
+
+// 64-byte units of a packed row: header (16 B) + 8-byte slots (PPR entries, then the neighbour ids two per slot)
+__host__ __device__ __forceinline__ int64_t row_units(int64_t deg, int64_t npp) {
+    return (16 + 8 * (npp + ((deg + 1) >> 1)) + 63) >> 6;
+}
 
 __device__ __forceinline__ uint4 ldg16(const uint4* p) { return __ldg(p); }
 __device__ __forceinline__ const uint4* row_of(const uint4* __restrict__ blob, uint32_t loc) {
@@ -114,116 +126,275 @@ __device__ __noinline__ void generic_link8(const SelectParams2& p, int64_t i, in
     }
     onepass_link<8>(p, nullptr, r, i, lane);
 }
-// One warp walks one link's PACKED target row (L2-hot: the screening just read it) against the staged source:
-// lane l takes slot l, l + 32, ... — a PPR entry or two neighbour ids — so ascending node order within each set is
-// lane order, and the ordered write needs only ballots.  Same sets, order and values as walk_link_hashed.
+// What slot s of a PACKED target row contributes against the staged source: a PPR entry is a candidate 1-hop /
+// >1-hop node (k1 / kn, node u, values qa, qb), a pair of neighbour ids up to two common neighbours (h0, h1 with
+// values (qa, qb) and (qa1, qb1)).  Slots ascend by node id within each kind, so slot order is the output order.
+struct SlotHit {
+    bool k1, kn, h0, h1;
+    int32_t u, w0, w1;
+    float qa, qb, qa1, qb1;
+};
 template <bool WRITE>
-__device__ __forceinline__ void walk_packed_warp(const SelectParams2& p, const RunCtx& h, const uint4* __restrict__ row,
-                                                 int lane, int64_t o_cn, int64_t o_1h, int64_t o_n1, int& c_cn, int& c_1h,
-                                                 int& c_n1) {
+__device__ __forceinline__ SlotHit eval_slot(const SelectParams2& p, const RunCtx& h, const int32_t* __restrict__ words,
+                                             const int32_t* __restrict__ ids, int deg, int npp, uint2 slot,
+                                             bool want_n1, float th_pre) {
+    const bool cn_needs_ppr = WRITE || p.th_cn > 0.0f;
+    SlotHit r;
+    r.k1 = r.kn = r.h0 = r.h1 = false;
+    r.qa = r.qb = r.qa1 = r.qb1 = 0.f;
+    const uint32_t w0 = slot.x, w1 = slot.y;
+    r.w0 = (int32_t)w0; r.w1 = (int32_t)w1;
+    r.u = (int32_t)w0;
+    if (w0 & kPkPprTag) {
+        r.u = (int32_t)(w0 & ~kPkPprTag);
+        if (smem_ppr_lookup(h, r.u, r.qa)) {
+            r.qb = quantise(__uint_as_float(w1));
+            if (r.qa >= th_pre && r.qb >= th_pre) {
+                const bool in_a = hash_contains(h.tab, h.mask, h.shift, r.u);
+                const int t = lower_bound_from(ids, 0, deg, r.u);
+                const bool in_b = t < deg && __ldg(ids + t) == r.u;
+                r.k1 = (in_a != in_b) && r.qa >= p.th_1hop && r.qb >= p.th_1hop;
+                r.kn = want_n1 && !in_a && !in_b && r.qa >= p.th_non1hop && r.qb >= p.th_non1hop;
+            }
+        }
+    } else {
+        r.h0 = hash_contains(h.tab, h.mask, h.shift, (int32_t)w0);
+        r.h1 = hash_contains(h.tab, h.mask, h.shift, (int32_t)w1);
+        if (cn_needs_ppr && (r.h0 || r.h1)) {
+            // PPR values of a common neighbour: P(a) from shared memory, P(b) by search over the row's PPR slots
+            auto pb_of = [&](int32_t x) -> float {
+                int lo = 0, hi = npp;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if ((__ldg(words + 2 * mid) & 0x7fffffff) < x) lo = mid + 1; else hi = mid;
+                }
+                return (lo < npp && (__ldg(words + 2 * lo) & 0x7fffffff) == x) ? quantise(__int_as_float(__ldg(words + 2 * lo + 1))) : 0.f;
+            };
+            if (r.h0) {
+                smem_ppr_lookup(h, (int32_t)w0, r.qa);
+                r.qb = pb_of((int32_t)w0);
+                r.h0 = r.qa >= p.th_cn && r.qb >= p.th_cn;
+            }
+            if (r.h1) {
+                smem_ppr_lookup(h, (int32_t)w1, r.qa1);
+                r.qb1 = pb_of((int32_t)w1);
+                r.h1 = r.qa1 >= p.th_cn && r.qb1 >= p.th_cn;
+            }
+        }
+    }
+    return r;
+}
+// slot s of a packed row (padding beyond the row, and for the PPR slots when they are not wanted)
+__device__ __forceinline__ uint2 load_slot(const int32_t* __restrict__ words, int npp, int s, int S, bool want_pi) {
+    if (s < S && (want_pi || s >= npp)) return __ldg(reinterpret_cast<const uint2*>(words) + s);
+    return make_uint2(kPkPad, kPkPad);
+}
+__device__ __forceinline__ void write_hits(const SelectParams2& p, const SlotHit& r, int64_t r_pi, int64_t r_cn) {
+    if (r.k1 || r.kn) { p.node[r_pi] = r.u; p.pa[r_pi] = r.qa; p.pb[r_pi] = r.qb; }
+    if (r.h0) { p.node[r_cn] = r.w0; p.pa[r_cn] = r.qa; p.pb[r_cn] = r.qb; }
+    if (r.h1) { const int64_t r1 = r_cn + (r.h0 ? 1 : 0); p.node[r1] = r.w1; p.pa[r1] = r.qa1; p.pb[r1] = r.qb1; }
+}
+
+// A group of G lanes (8 for the usual short row, a whole warp for rows of hundreds of ids) walks one link's PACKED
+// target row (L2-hot: the screening just read it) against the staged source: lane l of the group takes slot l,
+// l + G, ... so ascending node order within each set is lane order, and the ordered write needs only ballots.
+// Same sets, order and values as walk_link_hashed.
+template <int G, bool WRITE>
+__device__ __forceinline__ void walk_packed_group(const SelectParams2& p, const RunCtx& h, const uint4* __restrict__ row,
+                                                  int lane, int64_t o_cn, int64_t o_1h, int64_t o_n1, int& c_cn, int& c_1h,
+                                                  int& c_n1) {
+    constexpr unsigned GM = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
+    const unsigned gmask = group_mask<G>(lane);
+    const int gsh = lane & ~(G - 1), gl = lane & (G - 1);
     const uint4 hd = ldg16(row);
     const int deg = (int)hd.x, npp = (int)hd.y;
     const int32_t* words = reinterpret_cast<const int32_t*>(row) + 4;
     const int32_t* ids = words + 2 * npp;
     const int S = npp + ((deg + 1) >> 1);
-    const unsigned lt = (1u << lane) - 1u;
+    const unsigned lt = (1u << gl) - 1u;
     const bool want_pi = p.mode != LPF_MODE_CN;
     const bool want_n1 = p.mode == LPF_MODE_ALL;
-    const bool cn_needs_ppr = WRITE || p.th_cn > 0.0f;
     const float th_pre = want_n1 ? fminf(p.th_1hop, p.th_non1hop) : p.th_1hop;
     c_cn = c_1h = c_n1 = 0;
-    for (int s0 = want_pi ? 0 : (npp & ~31); s0 < S; s0 += 32) {
-        const int s = s0 + lane;
-        uint32_t w0 = kPkPad, w1 = kPkPad;
-        if (s < S && (want_pi || s >= npp)) {
-            const uint2 v = __ldg(reinterpret_cast<const uint2*>(words) + s);
-            w0 = v.x; w1 = v.y;
-        }
-        bool k1 = false, kn = false, h0 = false, h1 = false;
-        float qa = 0.f, qb = 0.f, qa1 = 0.f, qb1 = 0.f;
-        int32_t u = (int32_t)w0;
-        if (w0 & kPkPprTag) {
-            u = (int32_t)(w0 & ~kPkPprTag);
-            if (smem_ppr_lookup(h, u, qa)) {
-                qb = quantise(__uint_as_float(w1));
-                if (qa >= th_pre && qb >= th_pre) {
-                    const bool in_a = hash_contains(h.tab, h.mask, h.shift, u);
-                    const int t = lower_bound_from(ids, 0, deg, u);
-                    const bool in_b = t < deg && __ldg(ids + t) == u;
-                    k1 = (in_a != in_b) && qa >= p.th_1hop && qb >= p.th_1hop;
-                    kn = want_n1 && !in_a && !in_b && qa >= p.th_non1hop && qb >= p.th_non1hop;
-                }
-            }
-        } else {
-            h0 = hash_contains(h.tab, h.mask, h.shift, (int32_t)w0);
-            h1 = hash_contains(h.tab, h.mask, h.shift, (int32_t)w1);
-            if (cn_needs_ppr && (h0 || h1)) {
-                // PPR values of a common neighbour: P(a) from shared memory, P(b) by search over the row's PPR slots
-                auto pb_of = [&](int32_t x) -> float {
-                    int lo = 0, hi = npp;
-                    while (lo < hi) {
-                        const int mid = (lo + hi) >> 1;
-                        if ((__ldg(words + 2 * mid) & 0x7fffffff) < x) lo = mid + 1; else hi = mid;
-                    }
-                    return (lo < npp && (__ldg(words + 2 * lo) & 0x7fffffff) == x) ? quantise(__int_as_float(__ldg(words + 2 * lo + 1))) : 0.f;
-                };
-                if (h0) {
-                    smem_ppr_lookup(h, (int32_t)w0, qa);
-                    qb = pb_of((int32_t)w0);
-                    h0 = qa >= p.th_cn && qb >= p.th_cn;
-                }
-                if (h1) {
-                    smem_ppr_lookup(h, (int32_t)w1, qa1);
-                    qb1 = pb_of((int32_t)w1);
-                    h1 = qa1 >= p.th_cn && qb1 >= p.th_cn;
-                }
-            }
-        }
-        const unsigned m1 = __ballot_sync(kFull, k1), mn = __ballot_sync(kFull, kn);
-        const unsigned mh0 = __ballot_sync(kFull, h0), mh1 = __ballot_sync(kFull, h1);
-        if (WRITE) {
-            if (k1 || kn) {
-                const int64_t r = k1 ? o_1h + c_1h + __popc(m1 & lt) : o_n1 + c_n1 + __popc(mn & lt);
-                p.node[r] = u; p.pa[r] = qa; p.pb[r] = qb;
-            }
-            const int64_t r0 = o_cn + c_cn + __popc(mh0 & lt) + __popc(mh1 & lt);
-            if (h0) { p.node[r0] = (int32_t)w0; p.pa[r0] = qa; p.pb[r0] = qb; }
-            if (h1) { const int64_t r1 = r0 + (h0 ? 1 : 0); p.node[r1] = (int32_t)w1; p.pa[r1] = qa1; p.pb[r1] = qb1; }
-        }
+    for (int s0 = want_pi ? 0 : (npp & ~(G - 1)); s0 < S; s0 += G) {
+        const SlotHit r = eval_slot<WRITE>(p, h, words, ids, deg, npp, load_slot(words, npp, s0 + gl, S, want_pi), want_n1, th_pre);
+        const unsigned m1 = (__ballot_sync(gmask, r.k1) >> gsh) & GM, mn = (__ballot_sync(gmask, r.kn) >> gsh) & GM;
+        const unsigned mh0 = (__ballot_sync(gmask, r.h0) >> gsh) & GM, mh1 = (__ballot_sync(gmask, r.h1) >> gsh) & GM;
+        if (WRITE)
+            write_hits(p, r, r.k1 ? o_1h + c_1h + __popc(m1 & lt) : o_n1 + c_n1 + __popc(mn & lt),
+                       o_cn + c_cn + __popc(mh0 & lt) + __popc(mh1 & lt));
         c_1h += __popc(m1);
         c_n1 += __popc(mn);
         c_cn += __popc(mh0) + __popc(mh1);
     }
 }
 
-// A link that needs resolving (it selects something, or its target row is long), by one warp (count -> allocate ->
-// ordered write): the walk of its packed target row against the staged source when that row is short enough, else
-// the generic walk over the CSR tables (shorter row against the longer), else — both rows long — the CTA-wide kernel
-// that runs afterwards.
-template <class SM>
-__device__ __noinline__ void resolve_link32(const SelectParams2& p, const SM& sm, const uint4* __restrict__ blob, int r,
-                                            int t, int64_t i, int lane) {
-    const bool want_pi = p.mode != LPF_MODE_CN;
-    const uint4* row = row_of(blob, sm.l_loc[t]);
+// count -> allocate -> ordered write of one link of a staged source by a group of G lanes
+template <int G>
+__device__ __forceinline__ void resolve_packed_group(const SelectParams2& p, const RunCtx& h, const uint4* __restrict__ row,
+                                                     int64_t i, int lane) {
+    const unsigned gmask = group_mask<G>(lane);
+    const int leader = lane & ~(G - 1);
+    int c_cn, c_1h, c_n1;
+    walk_packed_group<G, false>(p, h, row, lane, 0, 0, 0, c_cn, c_1h, c_n1);
+    int64_t s_cn = 0, s_1h = 0, s_n1 = 0;
+    int ok = 1;
+    if (lane == leader) ok = alloc_segments(p, i, c_cn, c_1h, c_n1, s_cn, s_1h, s_n1) ? 1 : 0;
+    if (c_cn + c_1h + c_n1 == 0) return;       // uniform within the group
+    ok = __shfl_sync(gmask, ok, leader);
+    if (!ok) return;
+    s_cn = __shfl_sync(gmask, s_cn, leader);
+    s_1h = __shfl_sync(gmask, s_1h, leader);
+    s_n1 = __shfl_sync(gmask, s_n1, leader);
+    walk_packed_group<G, true>(p, h, row, lane, s_cn, p.cap + s_1h, 2 * p.cap + s_n1, c_cn, c_1h, c_n1);
+}
+
+// The whole CTA walks one link's packed target row (a hub target: thousands of slots): per step thread t takes the
+// slots t, t + 512, t + 1024, t + 1536 of the next 2,048 (four reads in flight), and the ordered positions come
+// from one block-wide scan per step of the three counts packed into one word per 512 slots (common neighbours: up
+// to two per slot | 1-hop | >1-hop).  `tot` = 2 x 4 x (kPkThreads / 32) words.
+constexpr int kPkCtaUnroll = 4;
+template <bool WRITE>
+__device__ __forceinline__ void walk_packed_cta(const SelectParams2& p, const RunCtx& h, const uint4* __restrict__ row,
+                                                uint32_t* tot, int64_t o_cn, int64_t o_1h, int64_t o_n1, int& c_cn,
+                                                int& c_1h, int& c_n1) {
+    constexpr int U = kPkCtaUnroll, NW = kPkThreads / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint4 hd = ldg16(row);
-    if (sm.r_hashed[r] == 1 && (int)hd.x <= kPkWarpRow && (int)hd.y <= kPkWarpRow) {
-        const RunCtx h = make_ctx(sm, r);
-        int c_cn, c_1h, c_n1;
-        walk_packed_warp<false>(p, h, row, lane, 0, 0, 0, c_cn, c_1h, c_n1);
-        int64_t s_cn = 0, s_1h = 0, s_n1 = 0;
-        int ok = 1;
-        if (lane == 0) ok = alloc_segments(p, i, c_cn, c_1h, c_n1, s_cn, s_1h, s_n1) ? 1 : 0;
-        if (c_cn + c_1h + c_n1 == 0) return;
-        ok = __shfl_sync(kFull, ok, 0);
-        if (!ok) return;
-        s_cn = __shfl_sync(kFull, s_cn, 0);
-        s_1h = __shfl_sync(kFull, s_1h, 0);
-        s_n1 = __shfl_sync(kFull, s_n1, 0);
-        walk_packed_warp<true>(p, h, row, lane, s_cn, p.cap + s_1h, 2 * p.cap + s_n1, c_cn, c_1h, c_n1);
+    const int deg = (int)hd.x, npp = (int)hd.y;
+    const int32_t* words = reinterpret_cast<const int32_t*>(row) + 4;
+    const int32_t* ids = words + 2 * npp;
+    const int S = npp + ((deg + 1) >> 1);
+    const bool want_pi = p.mode != LPF_MODE_CN;
+    const bool want_n1 = p.mode == LPF_MODE_ALL;
+    const float th_pre = want_n1 ? fminf(p.th_1hop, p.th_non1hop) : p.th_1hop;
+    c_cn = c_1h = c_n1 = 0;
+    int par = 0;
+    for (int s0 = 0; s0 < S; s0 += U * kPkThreads, par ^= 1) {
+        uint2 slot[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) slot[u] = load_slot(words, npp, s0 + u * kPkThreads + tid, S, want_pi);
+        SlotHit r[U];
+        uint32_t mine[U], inc[U];
+        uint32_t* tt = tot + par * (U * NW);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            r[u] = eval_slot<WRITE>(p, h, words, ids, deg, npp, slot[u], want_n1, th_pre);
+            mine[u] = (uint32_t)((r[u].h0 ? 1 : 0) + (r[u].h1 ? 1 : 0)) | (r[u].k1 ? 1u << 12 : 0u) | (r[u].kn ? 1u << 22 : 0u);
+            inc[u] = mine[u];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t x = __shfl_up_sync(kFull, inc[u], o);
+                if (lane >= o) inc[u] += x;
+            }
+            if (lane == 31) tt[u * NW + warp] = inc[u];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            uint32_t before = inc[u] - mine[u], total = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const uint32_t x = tt[u * NW + w];
+                before += (w < warp) ? x : 0u;
+                total += x;
+            }
+            if (WRITE)
+                write_hits(p, r[u], r[u].k1 ? o_1h + c_1h + (int)((before >> 12) & 1023u) : o_n1 + c_n1 + (int)(before >> 22),
+                           o_cn + c_cn + (int)(before & 4095u));
+            c_cn += (int)(total & 4095u);
+            c_1h += (int)((total >> 12) & 1023u);
+            c_n1 += (int)(total >> 22);
+        }
+    }
+}
+
+// count -> allocate -> ordered write of one link by the whole CTA.  A row of up to 2,048 slots (~4,000 neighbours)
+// is ONE step of the walk: the hits stay in registers while thread 0 allocates, and are written without a second
+// walk; longer rows are walked twice.  `seg` = 3 x int64 and `ok` in shared memory.
+__device__ __forceinline__ void resolve_packed_cta(const SelectParams2& p, const RunCtx& h, const uint4* __restrict__ row,
+                                                   uint32_t* tot, int64_t* seg, int* ok, int64_t i) {
+    constexpr int U = kPkCtaUnroll, NW = kPkThreads / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint4 hd = ldg16(row);
+    const int deg = (int)hd.x, npp = (int)hd.y;
+    const int S = npp + ((deg + 1) >> 1);
+    int c_cn, c_1h, c_n1;
+    if (S <= U * kPkThreads) {
+        const int32_t* words = reinterpret_cast<const int32_t*>(row) + 4;
+        const int32_t* ids = words + 2 * npp;
+        const bool want_pi = p.mode != LPF_MODE_CN;
+        const bool want_n1 = p.mode == LPF_MODE_ALL;
+        const float th_pre = want_n1 ? fminf(p.th_1hop, p.th_non1hop) : p.th_1hop;
+        uint2 slot[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) slot[u] = load_slot(words, npp, u * kPkThreads + tid, S, want_pi);
+        SlotHit r[U];
+        uint32_t mine[U], inc[U], before[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            r[u] = eval_slot<true>(p, h, words, ids, deg, npp, slot[u], want_n1, th_pre);
+            mine[u] = (uint32_t)((r[u].h0 ? 1 : 0) + (r[u].h1 ? 1 : 0)) | (r[u].k1 ? 1u << 12 : 0u) | (r[u].kn ? 1u << 22 : 0u);
+            inc[u] = mine[u];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t x = __shfl_up_sync(kFull, inc[u], o);
+                if (lane >= o) inc[u] += x;
+            }
+            if (lane == 31) tot[u * NW + warp] = inc[u];
+        }
+        __syncthreads();
+        c_cn = c_1h = c_n1 = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            uint32_t bf = inc[u] - mine[u], total = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const uint32_t x = tot[u * NW + w];
+                bf += (w < warp) ? x : 0u;
+                total += x;
+            }
+            // position of this thread's hits within the link's three sets
+            before[u] = (uint32_t)(c_cn + (int)(bf & 4095u)) | (uint32_t)(c_1h + (int)((bf >> 12) & 1023u)) << 12 |
+                        (uint32_t)(c_n1 + (int)(bf >> 22)) << 22;
+            c_cn += (int)(total & 4095u);
+            c_1h += (int)((total >> 12) & 1023u);
+            c_n1 += (int)(total >> 22);
+        }
+        if (tid == 0) {
+            int64_t s0, s1, s2;
+            *ok = alloc_segments(p, i, c_cn, c_1h, c_n1, s0, s1, s2) ? 1 : 0;
+            seg[0] = s0; seg[1] = s1; seg[2] = s2;
+        }
+        __syncthreads();
+        if (*ok && c_cn + c_1h + c_n1 > 0) {
+            const int64_t o_cn = seg[0], o_1h = p.cap + seg[1], o_n1 = 2 * p.cap + seg[2];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                write_hits(p, r[u], r[u].k1 ? o_1h + (int)((before[u] >> 12) & 1023u) : o_n1 + (int)(before[u] >> 22),
+                           o_cn + (int)(before[u] & 4095u));
+        }
+        __syncthreads();       // tot / seg / ok are reused by the next link
         return;
     }
+    walk_packed_cta<false>(p, h, row, tot, 0, 0, 0, c_cn, c_1h, c_n1);
+    if (tid == 0) {
+        int64_t s0, s1, s2;
+        *ok = alloc_segments(p, i, c_cn, c_1h, c_n1, s0, s1, s2) ? 1 : 0;
+        seg[0] = s0; seg[1] = s1; seg[2] = s2;
+    }
+    __syncthreads();
+    const bool go = *ok && (c_cn + c_1h + c_n1 > 0);
+    const int64_t s0 = seg[0], s1 = seg[1], s2 = seg[2];
+    __syncthreads();
+    if (go) walk_packed_cta<true>(p, h, row, tot, s0, p.cap + s1, 2 * p.cap + s2, c_cn, c_1h, c_n1);
+}
+
+// A link of a source that is not staged in shared memory (searched in global memory: beyond even the hub table),
+// by one warp over the CSR tables, or — both rows long — handed to the deferred-link kernel.
+__device__ __noinline__ void resolve_unstaged32(const SelectParams2& p, int64_t i, int lane) {
     const LinkRows rows = load_rows(p, i);
-    if (!is_heavy(rows, want_pi, 8)) {
+    if (!is_heavy(rows, p.mode != LPF_MODE_CN, 8)) {
         onepass_link<32>(p, nullptr, rows, i, lane);
     } else if (lane == 0) {
         p.heavy[4 + atomicAdd(p.heavy, 1)] = (int32_t)i;
@@ -256,6 +427,8 @@ select_onepass_packed_kernel(const __grid_constant__ SelectParams2 p, const uint
     // !HUB: the batch in `gridDim.x`-many (or more) even pieces of at most kPkChunk links
     const int64_t per = HUB ? 0 : min((int64_t)kPkChunk, max((int64_t)kPkThreads, (p.bs + gridDim.x - 1) / gridDim.x));
     const int64_t nchunks = HUB ? (int64_t)p.hub[0] : (p.bs + per - 1) / per;
+    const int slots_cap = p.slot_limit > 0 ? min(SLOTS, HUB ? 4 * p.slot_limit : p.slot_limit) : SLOTS;
+    const int hub_cap = p.slot_limit > 0 ? min(kPkHubSlots, 4 * p.slot_limit) : kPkHubSlots;
 
     long long t_mark = clock64();
 #define LPF_PHASE(k)                                                              \
@@ -263,6 +436,7 @@ select_onepass_packed_kernel(const __grid_constant__ SelectParams2 p, const uint
         if (p.dbg && tid == 0) {                                                  \
             const long long now = clock64();                                      \
             atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + (k)), (unsigned long long)(now - t_mark)); \
+            sm.dbg_ph[(k)] += (int)(now - t_mark);                                \
             t_mark = now;                                                         \
         }                                                                         \
     } while (0)
@@ -272,8 +446,11 @@ select_onepass_packed_kernel(const __grid_constant__ SelectParams2 p, const uint
         const long long t_chunk = clock64();
         const int64_t i0 = HUB ? (int64_t)p.hub[1 + 2 * chunk] : chunk * per;
         const int len = HUB ? p.hub[2 + 2 * chunk] : (int)min(per, p.bs - i0);
-        if (p.dbg && tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 5), 1ull);
-        if (tid == 0) { sm.n_runs = 0; sm.n_slow = 0; sm.n_items = 0; sm.items_full = 0; }
+        if (p.dbg && tid == 0) {
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 5), 1ull);
+            for (int k = 0; k < 16; ++k) sm.dbg_ph[k] = 0;
+        }
+        if (tid == 0) { sm.n_runs = 0; sm.n_slow = 0; sm.n_items = 0; sm.items_full = 0; sm.n_cta = 0; }
         __syncthreads();
         // ---- the chunk's links (positions tid, tid + 512): locator of the target (an L2-resident array), run
         // boundaries with the locator of their source
@@ -331,13 +508,13 @@ select_onepass_packed_kernel(const __grid_constant__ SelectParams2 p, const uint
                 // the table has room, never less than 2*na
                 int lg = 6;
                 while ((1 << lg) < 2 * na && lg < 30) ++lg;
-                if ((1 << lg) < 4 * na && used + (2 << lg) <= SLOTS / 2) ++lg;
+                if ((1 << lg) < 4 * na && used + (2 << lg) <= slots_cap / 2) ++lg;
                 // r_hashed: 1 = adjacency row hashed in shared memory; 2 = searched in global memory (a source beyond
                 // even the hub table); 3 = handed to the hub launch; 0 = no screening (source PPR row too long for the
                 // shared table): generic walk
-                const bool fits = used + (1 << lg) <= SLOTS;
+                const bool fits = used + (1 << lg) <= slots_cap;
                 int m = fits ? 1 : 2;
-                if (!HUB && m == 2 && (1 << lg) <= kPkHubSlots) {
+                if (!HUB && (m == 2 || (na > kPkHubDeg && p.slot_limit == 0)) && (1 << lg) <= hub_cap) {
                     // in pieces of kPkHubPiece links: the hub launch has a CTA (and an SM) for each of them
                     m = 3;
                     const int first = sm.run_start[r], n_links = sm.run_start[r + 1] - first;
@@ -365,15 +542,19 @@ select_onepass_packed_kernel(const __grid_constant__ SelectParams2 p, const uint
                 sm.run[s / kPprHashSlots].ppos[s % kPprHashSlots] = -1;
         }
         __syncthreads();     // tables cleared
-        // ---- flatten the chunk's target rows into 64-byte units: items[] = (chunk position << 4 | unit), in link
-        // order, 512 positions per pass.  The list holds a prefix of the chunk's units; what does not fit, and rows
-        // beyond kPkMaxUnits, get a warp.
+        // ---- flatten the chunk's target rows into 64-byte units: items[] = (chunk position << 16 | unit), in link
+        // order, 512 positions per pass.  Every row is listed, whatever its length (a row of 63 units and more says
+        // so in its header); the list holds a prefix of the chunk's units, what does not fit is resolved unscreened.
         for (int t0 = 0; t0 < len; t0 += kPkThreads) {
             const int t = t0 + tid;
             const int r = run_of(sm, min(t, len - 1));
             const bool screened = t < len && (sm.r_hashed[r] == 1 || sm.r_hashed[r] == 2);
             const uint32_t loc_b = t < len ? sm.l_loc[t] : 0u;
-            const int units = screened ? (int)(loc_b & 63u) : 0;
+            int units = screened ? (int)(loc_b & 63u) : 0;
+            if (units == 63) {
+                const uint4 hd = ldg16(row_of(blob, loc_b));
+                units = (int)row_units((int64_t)hd.x, (int64_t)hd.y);
+            }
             const int mine = units > kPkMaxUnits ? 0 : units;
             int inc = mine;
 #pragma unroll
@@ -391,12 +572,10 @@ select_onepass_packed_kernel(const __grid_constant__ SelectParams2 p, const uint
             const bool fits = !full_before && ex + mine <= kPkMaxItems;
             if (screened) {
                 if (units > kPkMaxUnits || !fits) {
-                    sm.q_slow[atomicAdd(&sm.n_slow, 1)] = (uint16_t)t;
-                    // a long row: its first lines towards L2 now, the warp that resolves it comes much later
-                    const uint8_t* r0 = reinterpret_cast<const uint8_t*>(row_of(blob, loc_b));
-                    for (int k = 0; k < min(units, 36); k += 2) prefetch_l2(r0 + 64 * k);
+                    if (units > kPkWarpUnits) sm.q_cta[atomicAdd(&sm.n_cta, 1)] = (uint16_t)t;
+                    else sm.q_slow[atomicAdd(&sm.n_slow, 1)] = (uint16_t)t;
                 } else {
-                    for (int u = 0; u < units; ++u) sm.items[ex + u] = (uint16_t)((r << 14) | (t << 4) | u);
+                    for (int u = 0; u < units; ++u) sm.items[ex + u] = ((uint32_t)t << 16) | (uint32_t)u;
                 }
             }
             __syncthreads();     // everyone has read n_items / items_full of the previous pass
@@ -453,16 +632,16 @@ select_onepass_packed_kernel(const __grid_constant__ SelectParams2 p, const uint
                     tt[k] = -1;
                     v[k] = make_uint4(kPkPad, kPkPad, kPkPad, kPkPad);
                     if (q < n_items) {
-                        const int it = sm.items[q];
-                        const int t = (it >> 4) & (kPkChunk - 1), u = it & 15;
-                        tt[k] = (u == 0 && ql == 0) ? -1 : (it >> 4);      // chunk 0 of unit 0 is the row's header
+                        const uint32_t it = sm.items[q];
+                        const int t = (int)(it >> 16), u = (int)(it & 0xffffu);
+                        tt[k] = (u == 0 && ql == 0) ? -1 : t;              // chunk 0 of unit 0 is the row's header
                         v[k] = ldg16(row_of(blob, sm.l_loc[t]) + 4 * u + ql);
                     }
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     if (tt[k] < 0) continue;
-                    const int t = tt[k] & (kPkChunk - 1), r = tt[k] >> 10;
+                    const int t = tt[k], r = run_of(sm, t);
                     const int mode_r = sm.r_hashed[r];
                     if (mode_r == 0) continue;               // the run turned out not to be screenable
                     const int4 cx = sm.r_ctx[r];
@@ -484,7 +663,11 @@ select_onepass_packed_kernel(const __grid_constant__ SelectParams2 p, const uint
         }
         __syncthreads();
         for (int t = tid; t < len; t += kPkThreads)
-            if (sm.l_any[t]) sm.q_slow[atomicAdd(&sm.n_slow, 1)] = (uint16_t)t;
+            if (sm.l_any[t]) {
+                // a long target row that selects something: the whole CTA walks it
+                if ((int)(sm.l_loc[t] & 63u) > kPkWarpUnits) sm.q_cta[atomicAdd(&sm.n_cta, 1)] = (uint16_t)t;
+                else sm.q_slow[atomicAdd(&sm.n_slow, 1)] = (uint16_t)t;
+            }
         __syncthreads();
         LPF_PHASE(1);
 
@@ -494,19 +677,41 @@ select_onepass_packed_kernel(const __grid_constant__ SelectParams2 p, const uint
             for (int t = sm.run_start[r] + group; t < sm.run_start[r + 1]; t += kPkThreads / 8)
                 generic_link8(p, i0 + t, lane);
         }
-        // ---- phase B: the queued links, one warp per link (count -> allocate -> write)
+        // ---- phase B: the links that select something (count -> allocate -> ordered write), one warp per link against
+        // the staged source (a handful per chunk: the runs of hub sources, which select something with every tenth
+        // target, were cut into pieces for the hub launch)
         const int ns = sm.n_slow;
         for (int q = warp; q < ns; q += kPkThreads / 32) {
             const int t = sm.q_slow[q];
             const int r = run_of(sm, t);
-            if (sm.r_hashed[r] == 0) continue;       // its whole run took the generic walk above
-            resolve_link32(p, sm, blob, r, t, i0 + t, lane);
+            if (sm.r_hashed[r] == 1) resolve_packed_group<32>(p, make_ctx(sm, r), row_of(blob, sm.l_loc[t]), i0 + t, lane);
+            else if (sm.r_hashed[r] == 2) resolve_unstaged32(p, i0 + t, lane);       // (searched in global memory: rare)
         }
         if (p.dbg && tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 6), (unsigned long long)ns);
         LPF_PHASE(2);
+        __syncthreads();
+        // ---- phase C: long target rows that select something, the whole CTA per link
+        const int nc = sm.n_cta;
+        for (int q = 0; q < nc; ++q) {
+            const int t = sm.q_cta[q];
+            const int r = run_of(sm, t);
+            if (sm.r_hashed[r] == 0) continue;
+            if (sm.r_hashed[r] != 1) {
+                if (warp == 0) resolve_unstaged32(p, i0 + t, lane);
+                continue;
+            }
+            resolve_packed_cta(p, make_ctx(sm, r), row_of(blob, sm.l_loc[t]), sm.scan_tot, sm.cta_seg, &sm.cta_ok, i0 + t);
+        }
+        if (p.dbg && tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 7), (unsigned long long)nc);
+        LPF_PHASE(3);
         __syncthreads();     // the shared tables are rebuilt for the next chunk
         if (p.dbg && tid == 0) {
-            atomicMax(p.dbg + 8, clock64() - t_chunk);
+            const long long dt = clock64() - t_chunk;
+            if (atomicMax(p.dbg + 8, dt) < dt) {          // the slowest chunk so far: its phases, size and queues
+                for (int k = 0; k < 16; ++k) p.dbg[16 + k] = sm.dbg_ph[k];
+                p.dbg[32] = len; p.dbg[33] = sm.n_runs; p.dbg[34] = sm.n_items; p.dbg[35] = sm.n_slow;
+                p.dbg[36] = sm.n_cta; p.dbg[37] = sm.tab_used; p.dbg[38] = HUB ? 1 : 0;
+            }
             atomicMax(p.dbg + 9, clock64() - t_cta);
         }
     }
@@ -516,9 +721,6 @@ select_onepass_packed_kernel(const __grid_constant__ SelectParams2 p, const uint
 // ---------------------------------------------------------------------------------------------------------
 // Building the packed rows (once per graph).
 // ---------------------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ int64_t row_units(int64_t deg, int64_t npp) {
-    return (16 + 8 * (npp + ((deg + 1) >> 1)) + 63) >> 6;
-}
 
 __global__ void pack_count_kernel(const int64_t* __restrict__ arp, const int64_t* __restrict__ prp, int64_t n,
                                   int32_t* __restrict__ units) {
@@ -557,7 +759,8 @@ extern long long* g_select_dbg;
 bool g_kernel_timing = false;     // shared with nz_fused.cu
 static cudaEvent_t g_pk_ev[4];
 static bool g_pk_ev_ready = false, g_pk_ev_valid = false;
-static int g_pk_ctas = 2;
+static constexpr int g_pk_ctas = 2;
+static int g_pk_slot_limit = 0;
 void launch_onepass_reset(const SelectParams2& p, cudaStream_t st);
 void launch_onepass_tail(const SelectParams2& p, cudaStream_t st);
 
@@ -626,18 +829,13 @@ extern "C" int lpf_select_onepass_packed(const int64_t* links, int64_t bs, const
     cudaStream_t st = (cudaStream_t)stream;
     SelectParams2 p{links, bs, adj_rowptr, adj_col, ppr_rowptr, ppr_col, ppr_val, th_cn, th_1hop, th_non1hop,
                     mode, counts, nullptr, node, src_ppr, tgt_ppr, nullptr, (int32_t*)workspace, cap, header,
-                    seg_start, nz_list, g_select_dbg, (int32_t*)workspace + bs + 4};
+                    seg_start, nz_list, g_select_dbg, (int32_t*)workspace + bs + 4, g_pk_slot_limit};
     using SmMain = PkSmemT<kPkHashSlots>;
     using SmHub = PkSmemT<kPkHubSlots>;
     static bool configured = false;
     if (!configured) {
-        const char* env = getenv("LPF_PK_CTAS");      // tuning knob: resident screening CTAs per SM (2 or 3)
-        if (env && atoi(env) == 3) g_pk_ctas = 3;
         cudaError_t e = cudaFuncSetAttribute(select_onepass_packed_kernel<kPkHashSlots, false, 2>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmMain));
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(select_onepass_packed_kernel<kPkHashSlots, false, 3>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmMain));
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(select_onepass_packed_kernel<kPkHubSlots, true, 1>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmHub));
@@ -660,12 +858,8 @@ extern "C" int lpf_select_onepass_packed(const int64_t* links, int64_t bs, const
         int64_t blocks = (bs + kPkThreads - 1) / kPkThreads;
         const int64_t cap_blocks = (int64_t)kNumSMs * g_pk_ctas;
         if (blocks > cap_blocks) blocks = cap_blocks;
-        if (g_pk_ctas == 3)
-            select_onepass_packed_kernel<kPkHashSlots, false, 3><<<(unsigned)blocks, kPkThreads, sizeof(SmMain), st>>>(
-                p, locator, static_cast<const uint4*>(row_blob));
-        else
-            select_onepass_packed_kernel<kPkHashSlots, false, 2><<<(unsigned)blocks, kPkThreads, sizeof(SmMain), st>>>(
-                p, locator, static_cast<const uint4*>(row_blob));
+        select_onepass_packed_kernel<kPkHashSlots, false, 2><<<(unsigned)blocks, kPkThreads, sizeof(SmMain), st>>>(
+            p, locator, static_cast<const uint4*>(row_blob));
         if (timing) cudaEventRecord(g_pk_ev[1], st);
         select_onepass_packed_kernel<kPkHubSlots, true, 1><<<kNumSMs, kPkThreads, sizeof(SmHub), st>>>(
             p, locator, static_cast<const uint4*>(row_blob));
@@ -677,6 +871,13 @@ extern "C" int lpf_select_onepass_packed(const int64_t* links, int64_t bs, const
         g_pk_ev_valid = true;
     }
     return check_launch("lpf_select_onepass_packed");
+}
+
+// Test hook: caps the hash slots the screening kernel may use (the hub launch gets four times as many), so that
+// small graphs reach the hub launch and the global-memory search of sources beyond it; 0 restores the full tables.
+extern "C" int lpf_debug_select_slots(int limit) {
+    lpf::g_pk_slot_limit = limit > 0 ? limit : 0;
+    return LPF_OK;
 }
 
 // Profiling hook: with enable != 0 later lpf_select_onepass_packed calls record CUDA events on their stream around

@@ -92,6 +92,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// The same load without the wait: the registers are valid after the next tmem_ld_wait() (which waits for every
+// tcgen05.ld this thread has issued).  TMEM reads run at 64 B per cycle per SM: a 128 x 128 fp32 accumulator takes
+// ~1,000 cycles to read back, worth overlapping with the arithmetic on the previous columns.
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, float (&v)[16]) {
+    // (the destination registers are the asm outputs themselves: no move may sit between the load and the wait)
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+          "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // ---- descriptors (bit layouts: cute/arch/mma_sm100_desc.hpp of CUTLASS 3.9+/4.x)
 // shared-memory matrix descriptor, K-major, SWIZZLE_128B: start>>4 [0,14), LBO>>4 [16,30) (=1, unused for
 // swizzled K-major), SBO>>4 [32,46) (= 1024 B between 8-row groups), version=1 [46,48), layout=2 [61,64)

@@ -324,24 +324,31 @@ def test_select_onepass_vs_oracle(workload, scale, algo):
     d = g.data_dict(dev)
     bs = links_np.shape[1]
     total = max(len(v[0]) for v in sets.values())
-    out = ops.select_onepass(torch.from_numpy(links_np).to(dev), d["adj_mask"], d["ppr"], *th, mode, cap=total + 8, algo=algo)
-    hdr = out["header"].tolist()
-    assert hdr[4] == 0
-    got = _onepass_sets(out, bs)
-    nz_ref = np.zeros(bs, bool)
-    for t, name in enumerate(("cn", "1hop", "non1hop")):
-        if name not in sets:
-            assert hdr[t] == 0
-            continue
-        li, nd, qa, qb = sets[name]
-        nz_ref[li] = True
-        assert hdr[t] == len(li), name
-        assert np.array_equal(got[t][0], li), name
-        assert np.array_equal(got[t][1], nd), name
-        assert np.array_equal(got[t][2], qa.view(np.uint32)), name
-        assert np.array_equal(got[t][3], qb.view(np.uint32)), name
-    nz = np.sort(out["nz"][:hdr[3]].cpu().numpy())
-    assert np.array_equal(nz, np.nonzero(nz_ref)[0])
+    from lpformer_b200 import _lib
+    # algo 3: also with the staged-source hash capped (hub launch; sources searched in global memory)
+    for slot_limit in ((0, 1024, 128) if algo == 3 else (0,)):
+        _lib.load().lpf_debug_select_slots(slot_limit)
+        try:
+            out = ops.select_onepass(torch.from_numpy(links_np).to(dev), d["adj_mask"], d["ppr"], *th, mode, cap=total + 8, algo=algo)
+            hdr = out["header"].tolist()
+        finally:
+            _lib.load().lpf_debug_select_slots(0)
+        assert hdr[4] == 0
+        got = _onepass_sets(out, bs)
+        nz_ref = np.zeros(bs, bool)
+        for t, name in enumerate(("cn", "1hop", "non1hop")):
+            if name not in sets:
+                assert hdr[t] == 0
+                continue
+            li, nd, qa, qb = sets[name]
+            nz_ref[li] = True
+            assert hdr[t] == len(li), (name, slot_limit)
+            assert np.array_equal(got[t][0], li), (name, slot_limit)
+            assert np.array_equal(got[t][1], nd), (name, slot_limit)
+            assert np.array_equal(got[t][2], qa.view(np.uint32)), (name, slot_limit)
+            assert np.array_equal(got[t][3], qb.view(np.uint32)), (name, slot_limit)
+        nz = np.sort(out["nz"][:hdr[3]].cpu().numpy())
+        assert np.array_equal(nz, np.nonzero(nz_ref)[0])
     # a pool that is too small is reported, never overrun
     small = ops.select_onepass(torch.from_numpy(links_np).to(dev), d["adj_mask"], d["ppr"], *th, mode, cap=max(1, total // 4), algo=algo)
     h2 = small["header"].tolist()
