@@ -35,7 +35,7 @@ constexpr int kHeadConsumers = 256;   // warps 0-7: TWO threads per link (= TMEM
                                       // The epilogues are CUDA-core work on 192 accumulator columns per link, and one warp per SM
                                       // sub-partition cannot hide its own instruction latencies; thread 0 issues the MMAs
 constexpr int kHeadProducers = 128;   // warps 8-11: gather X[a]*X[b] of the NEXT tile while this one is computed
-constexpr int kHeadThreads = kHeadConsumers + kHeadProducers;
+constexpr int kHeadThreads = kHeadConsumers + kHeadProducers + 32;   // + warp 12: one thread issues every MMA
 
 struct HeadsParams {
     const int64_t* links;
@@ -73,12 +73,15 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
     constexpr int N3 = 2 * D;                        // width of mlp_score's hidden layer
     constexpr uint32_t W1_BYTES = KB * 2 * D * 128;  // packed [D, D]
     constexpr uint32_t W3_BYTES = KB * 2 * N3 * 128; // packed [2D, D]
-    constexpr uint32_t TMEM_COLS = (D + N3) <= 128 ? 128 : 256;   // D1 | D3
+    constexpr uint32_t TMEM_COLS = 8 * D;            // D1 x 2 | D3 x 2 | H hi | H lo  (512 columns at D = 64: all of TMEM)
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // bar_w: weights landed;  bar_mma1 / bar_mma3: contraction 1 / 2 of the current tile complete;
-    // bar_a_free: contraction 2 has finished reading the operand tile (producers may overwrite it)
-    __shared__ uint64_t bar_w, bar_mma1, bar_mma3, bar_a_free;
+    // bar_w: weights landed;  bar_mma1[b]: contraction 1 into accumulator buffer b complete (the operand tile in shared
+    // memory may be overwritten);  bar_d1_free[b]: the consumers have read accumulator buffer b;  bar_mma3: contraction 2
+    // of the current tile complete (its accumulator is ready, the H operand in TMEM may be overwritten).
+    // One barrier per BUFFER where the waiting side can fall two completions behind (a parity wait cannot tell them apart).
+    // bar_a_ready: the producers have stored the next operand tile;  bar_h_ready: the consumers have stored H.
+    __shared__ uint64_t bar_w, bar_mma1[2], bar_d1_free[2], bar_mma3, bar_a_ready, bar_h_ready;
     __shared__ uint32_t tmem_slot;
     __shared__ int32_t ids[2][2][kTileM];            // [tile parity][a, b][row]
     __shared__ __align__(16) float s_b1[D], s_g[D], s_bt[D], s_c3[N3], s_ws2[N3];
@@ -95,9 +98,13 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
 
     if (tid == 0) {
         mbar_init(&bar_w, 1);
-        mbar_init(&bar_mma1, 1);
+        mbar_init(&bar_mma1[0], 1);
+        mbar_init(&bar_mma1[1], 1);
+        mbar_init(&bar_d1_free[0], 1);
+        mbar_init(&bar_d1_free[1], 1);
         mbar_init(&bar_mma3, 1);
-        mbar_init(&bar_a_free, 1);
+        mbar_init(&bar_a_ready, 1);
+        mbar_init(&bar_h_ready, 1);
         fence_mbar_init();
         mbar_arrive_expect_tx(&bar_w, W1_BYTES + W3_BYTES);
         bulk_g2s(sW1, p.w1p, W1_BYTES, &bar_w);
@@ -119,10 +126,61 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
     tc_fence_after();
 
     const uint32_t tmem_d = tmem_slot;
-    const uint32_t d1 = tmem_d, d3 = tmem_d + D;
+    const uint32_t d1 = tmem_d, d3 = tmem_d + 2 * D, h_hi = tmem_d + 6 * D, h_lo = tmem_d + 7 * D;
     const uint32_t idesc_d = make_idesc_tf32(kTileM, D), idesc_3 = make_idesc_tf32(kTileM, N3);
     const uint32_t aA = smem_u32(sA), aW1 = smem_u32(sW1), aW3 = smem_u32(sW3);
 
+    if (warp == (kHeadConsumers + kHeadProducers) / 32) {
+        // =========================== the MMA thread: contraction 1 of tile it + 1, then contraction 2 of tile it —
+        // the order in which their operands become ready when the tensor pipe is the bottleneck (neither the
+        // consumers nor the producers ever stall behind a full MMA queue)
+        // (the whole warp runs this loop; one elected lane issues: the descriptors are warp-uniform values)
+        {
+            const uint32_t n_my = (uint32_t)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+            const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_d, 0);
+            const uint32_t u_d1 = tbase, u_d3 = tbase + 2 * D, u_hhi = tbase + 6 * D, u_hlo = tbase + 7 * D;
+            mbar_wait(&bar_w, 0);
+            auto mma1 = [&](uint32_t it) {
+                mbar_wait(&bar_a_ready, it & 1);
+                if (it >= 2) mbar_wait(&bar_d1_free[it & 1], ((it >> 1) - 1) & 1);     // epilogue 1 of tile it - 2 has read this buffer
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb)
+                        issue_kblock_3x(u_d1 + (it & 1) * D, aA + kb * 2 * kATileBytes, aA + kb * 2 * kATileBytes + kATileBytes,
+                                        aW1 + kb * 2 * D * 128, aW1 + kb * 2 * D * 128 + D * 128, idesc_d, kb == 0);
+                    umma_commit(&bar_mma1[it & 1]);
+                }
+                __syncwarp();
+            };
+            const bool mstamp = p.dbg && blockIdx.x == 0 && (tid & 31) == 0;
+#define LPF_MSTAMP(k) do { if (mstamp && it < 8) p.dbg[it * 16 + 8 + (k)] = clock64(); } while (0)
+            mma1(0);
+            for (uint32_t it = 0; it < n_my; ++it) {
+                LPF_MSTAMP(0);
+                if (it + 1 < n_my) {
+                    mbar_wait(&bar_a_ready, (it + 1) & 1);
+                    LPF_MSTAMP(1);
+                    mma1(it + 1);
+                }
+                LPF_MSTAMP(2);
+                mbar_wait(&bar_h_ready, it & 1);
+                LPF_MSTAMP(3);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb)
+                        issue_kblock_3x_ts(u_d3 + (it & 1) * N3, u_hhi + kb * 32, u_hlo + kb * 32, aW3 + kb * 2 * N3 * 128,
+                                           aW3 + kb * 2 * N3 * 128 + N3 * 128, idesc_3, kb == 0);
+                    umma_commit(&bar_mma3);
+                }
+                __syncwarp();
+                LPF_MSTAMP(4);
+            }
+#undef LPF_MSTAMP
+        }
+        return;
+    }
     if (warp >= kHeadConsumers / 32) {
         // =========================== producers: gather tile t+1 while tile t is computed, then (once the operand
         // tile is free) split it into hi / lo, store it in the UMMA layout and issue contraction 1
@@ -130,16 +188,40 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
         const int chunk = ptid & 7, row_in_pass = ptid >> 3;
         const bool vec_x = ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0) && (p.ldx % 4 == 0);
         uint32_t it = 0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        auto load_ids = [&](int64_t tile, int32_t& a, int32_t& b) {
             const int64_t j = tile * kTileM + ptid;
-            int32_t a = 0, b = 0;
-            if (j < p.n) {
+            a = 0; b = 0;
+            if (tile < ntiles && j < p.n) {
                 const int64_t pos = p.idx ? (int64_t)__ldg(p.idx + j) : j;
                 a = (int32_t)__ldg(p.links + pos);
                 b = (int32_t)__ldg(p.links + p.bs + pos);
             }
-            ids[it & 1][0][ptid] = a;
-            ids[it & 1][1][ptid] = b;
+        };
+        auto prefetch_rows = [&](int32_t a, int32_t b) {
+            const char* ra = reinterpret_cast<const char*>(p.X + (int64_t)a * p.ldx);
+            const char* rb = reinterpret_cast<const char*>(p.X + (int64_t)b * p.ldx);
+#pragma unroll
+            for (int o = 0; o < D * 4; o += 128) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ra + o));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rb + o));
+            }
+        };
+        // The gather (random 256-byte rows) is a DRAM round trip of ~3,000 cycles under load, longer than everything else
+        // in the producers' loop: the ids run three tiles ahead of the gather and the rows are pulled into L2 two tiles ahead.
+        int32_t a_cur, b_cur, a_n1, b_n1, a_n2, b_n2;
+        load_ids(blockIdx.x, a_cur, b_cur);
+        load_ids((int64_t)blockIdx.x + gridDim.x, a_n1, b_n1);
+        load_ids((int64_t)blockIdx.x + 2 * (int64_t)gridDim.x, a_n2, b_n2);
+        if ((int64_t)blockIdx.x + gridDim.x < ntiles) prefetch_rows(a_n1, b_n1);
+        const bool pstamp = p.dbg && blockIdx.x == 0 && ptid == 0;
+#define LPF_PSTAMP(k) do { if (pstamp && it < 8) p.dbg[it * 16 + 13 + (k)] = clock64(); } while (0)
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            LPF_PSTAMP(0);
+            ids[it & 1][0][ptid] = a_cur;
+            ids[it & 1][1][ptid] = b_cur;
+            if (tile + 2 * (int64_t)gridDim.x < ntiles) prefetch_rows(a_n2, b_n2);
+            int32_t a_n3, b_n3;
+            load_ids(tile + 3 * (int64_t)gridDim.x, a_n3, b_n3);
             named_bar_sync(2, kHeadProducers);
             float4 v[KB][8];
 #pragma unroll
@@ -160,7 +242,9 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
                     v[kb][pass] = make_float4(xa.x * xb.x, xa.y * xb.y, xa.z * xb.z, xa.w * xb.w);
                 }
             }
-            if (it > 0) mbar_wait(&bar_a_free, (it - 1) & 1);     // contraction 2 of the previous tile is done
+            LPF_PSTAMP(1);
+            a_cur = a_n1; b_cur = b_n1; a_n1 = a_n2; b_n1 = b_n2; a_n2 = a_n3; b_n2 = b_n3;
+            if (it > 0) mbar_wait(&bar_mma1[(it - 1) & 1], ((it - 1) >> 1) & 1);     // contraction 1 of the previous tile has read the operand tile
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
@@ -174,15 +258,8 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
                 }
             fence_async_smem();
             named_bar_sync(2, kHeadProducers);
-            if (ptid == 0) {
-                if (it == 0) mbar_wait(&bar_w, 0);
-                tc_fence_after();
-#pragma unroll
-                for (int kb = 0; kb < KB; ++kb)
-                    issue_kblock_3x(d1, aA + kb * 2 * kATileBytes, aA + kb * 2 * kATileBytes + kATileBytes,
-                                    aW1 + kb * 2 * D * 128, aW1 + kb * 2 * D * 128 + D * 128, idesc_d, kb == 0);
-                umma_commit(&bar_mma1);
-            }
+            if (ptid == 0) mbar_arrive(&bar_a_ready);
+            LPF_PSTAMP(2);
             __syncwarp();
         }
         return;
@@ -197,19 +274,19 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
 #define LPF_STAMP(k) do { if (stamp && it < 8) p.dbg[it * 16 + (k)] = clock64(); } while (0)
 
     // epilogue 2 of a tile: prob = sigmoid(ws2 . ReLU(D3 + offset) + bs2)
-    auto epilogue2 = [&](int64_t j) {
+    auto epilogue2 = [&](int64_t j, uint32_t d3b) {
         constexpr int NH = N3 / 2;                       // columns per thread
         const float* zrow = (ZB && j < p.n) ? p.zb + j * p.ld_zb : nullptr;
         float acc4[4] = {0.f, 0.f, 0.f, 0.f};
         // the next 16 columns are on their way out of TMEM while these 16 are reduced
         float buf[2][16];
         const int cb = half * NH;
-        tmem_ld16_async(d3 + lane_sel + cb, buf[0]);
+        tmem_ld16_async(d3b + lane_sel + cb, buf[0]);
         tmem_ld_wait();
 #pragma unroll
         for (int c0 = 0; c0 < NH; c0 += 16) {
             const int cur = (c0 >> 4) & 1;
-            if (c0 + 16 < NH) tmem_ld16_async(d3 + lane_sel + cb + c0 + 16, buf[cur ^ 1]);
+            if (c0 + 16 < NH) tmem_ld16_async(d3b + lane_sel + cb + c0 + 16, buf[cur ^ 1]);
 #pragma unroll
             for (int c = 0; c < 16; c += 4) {
                 const float4 o4 = ZB ? (zrow ? __ldg(reinterpret_cast<const float4*>(zrow + cb + c0 + c)) : make_float4(0.f, 0.f, 0.f, 0.f))
@@ -234,45 +311,38 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
     int64_t j_prev = -1;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int64_t j = tile * kTileM + row;
+        const uint32_t d1b = d1 + (it & 1) * D;
         LPF_STAMP(0);
-        // ---- the previous tile's epilogue 2 runs while the producers refill the operand tile and the tensor
-        // pipe works on this tile's contraction 1
-        if (it > 0) {
-            mbar_wait(&bar_mma3, (it - 1) & 1);
-            tc_fence_after();
-            LPF_STAMP(1);
-            epilogue2(j_prev);
-        }
-        LPF_STAMP(2);
-        mbar_wait(&bar_mma1, it & 1);
+        mbar_wait(&bar_mma1[it & 1], (it >> 1) & 1);
         tc_fence_after();
-        LPF_STAMP(3);
+        LPF_STAMP(1);
 
         // ---- epilogue 1: h = ReLU(LN(D1 + b1)) over the link's row, half of the columns per thread (the two partial
-        // sums of the mean and of the variance meet in shared memory); becomes the next A operand
+        // sums of the mean and of the variance meet in shared memory).  h is the A operand of contraction 2 and goes
+        // back into TMEM (hi / lo halves of the split), not through shared memory.
+        constexpr int DH = D / 2;
+        const int cb = half * DH;
+        float v[DH];
         {
-            constexpr int DH = D / 2;
-            const int cb = half * DH;
-            float v[DH];
             float s4[4] = {0.f, 0.f, 0.f, 0.f};
-            {
-                float (*vb)[16] = reinterpret_cast<float (*)[16]>(v);
-                tmem_ld16_async(d1 + lane_sel + cb, vb[0]);
-                tmem_ld_wait();
+            float (*vb)[16] = reinterpret_cast<float (*)[16]>(v);
+            tmem_ld16_async(d1b + lane_sel + cb, vb[0]);
+            tmem_ld_wait();
 #pragma unroll
-                for (int c0 = 0; c0 < DH; c0 += 16) {
-                    if (c0 + 16 < DH) tmem_ld16_async(d1 + lane_sel + cb + c0 + 16, vb[(c0 >> 4) + 1]);
+            for (int c0 = 0; c0 < DH; c0 += 16) {
+                if (c0 + 16 < DH) tmem_ld16_async(d1b + lane_sel + cb + c0 + 16, vb[(c0 >> 4) + 1]);
 #pragma unroll
-                    for (int c = c0; c < c0 + 16; c += 4) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(&s_b1[cb + c]);
-                        v[c] += b4.x; v[c + 1] += b4.y; v[c + 2] += b4.z; v[c + 3] += b4.w;
-                        s4[0] += v[c]; s4[1] += v[c + 1]; s4[2] += v[c + 2]; s4[3] += v[c + 3];
-                    }
-                    if (c0 + 16 < DH) tmem_ld_wait();
+                for (int c = c0; c < c0 + 16; c += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(&s_b1[cb + c]);
+                    v[c] += b4.x; v[c + 1] += b4.y; v[c + 2] += b4.z; v[c + 3] += b4.w;
+                    s4[0] += v[c]; s4[1] += v[c + 1]; s4[2] += v[c + 2]; s4[3] += v[c + 3];
                 }
+                if (c0 + 16 < DH) tmem_ld_wait();
             }
             s_sum[half][row] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+            tc_fence_before();                              // (this thread's reads of the accumulator are complete)
             named_bar_sync(1, kHeadConsumers);
+            if (tid == 0) mbar_arrive(&bar_d1_free[it & 1]);     // contraction 1 of tile it + 2 may overwrite the buffer
             const float mean = (s_sum[0][row] + s_sum[1][row]) * (1.0f / D);
             float q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -287,45 +357,48 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
             for (int c = 0; c < DH; c += 4) {
                 const float4 g4 = *reinterpret_cast<const float4*>(&s_g[cb + c]);
                 const float4 t4 = *reinterpret_cast<const float4*>(&s_bt[cb + c]);
-                float h[4];
-                h[0] = fmaxf(fmaf((v[c] - mean) * rstd, g4.x, t4.x), 0.f);
-                h[1] = fmaxf(fmaf((v[c + 1] - mean) * rstd, g4.y, t4.y), 0.f);
-                h[2] = fmaxf(fmaf((v[c + 2] - mean) * rstd, g4.z, t4.z), 0.f);
-                h[3] = fmaxf(fmaf((v[c + 3] - mean) * rstd, g4.w, t4.w), 0.f);
-                const float4 hi = make_float4(tf32_hi(h[0]), tf32_hi(h[1]), tf32_hi(h[2]), tf32_hi(h[3]));
-                const float4 lo = make_float4(h[0] - hi.x, h[1] - hi.y, h[2] - hi.z, h[3] - hi.w);
-                const int cg = cb + c;                 // column of the row: k-block cg / 32, 16-byte chunk (cg % 32) / 4
-                const uint32_t off = (uint32_t)(cg / 32) * 2 * kATileBytes + swz_chunk_off(row, (cg % 32) / 4);
-                *reinterpret_cast<float4*>(sA + off) = hi;
-                *reinterpret_cast<float4*>(sA + off + kATileBytes) = lo;
+                v[c] = fmaxf(fmaf((v[c] - mean) * rstd, g4.x, t4.x), 0.f);
+                v[c + 1] = fmaxf(fmaf((v[c + 1] - mean) * rstd, g4.y, t4.y), 0.f);
+                v[c + 2] = fmaxf(fmaf((v[c + 2] - mean) * rstd, g4.z, t4.z), 0.f);
+                v[c + 3] = fmaxf(fmaf((v[c + 3] - mean) * rstd, g4.w, t4.w), 0.f);
             }
         }
+        LPF_STAMP(2);
+        // the H columns are free once contraction 2 of the previous tile has read them (its accumulator is then ready too)
+        if (it > 0) {
+            mbar_wait(&bar_mma3, (it - 1) & 1);
+            tc_fence_after();
+        }
+        LPF_STAMP(3);
+#pragma unroll
+        for (int c0 = 0; c0 < DH; c0 += 16) {
+            float hi[16], lo[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                hi[c] = tf32_hi(v[c0 + c]);
+                lo[c] = v[c0 + c] - hi[c];
+            }
+            tmem_st16(h_hi + lane_sel + cb + c0, hi);
+            tmem_st16(h_lo + lane_sel + cb + c0, lo);
+        }
+        tmem_st_wait();
         tc_fence_before();
-        fence_async_smem();
         named_bar_sync(1, kHeadConsumers);
         LPF_STAMP(4);
 
-        // ---- contraction 2: D3 = h . (Ws1[:, :d] W2)^T; its completion also frees the operand tile
-        if (tid == 0) {
-            if (it == 0) mbar_wait(&bar_w, 0);
-            tc_fence_after();
-            // (one N = 2D instruction stream: the contraction is bound by the shared-memory reads of its operands — 4 KB
-            // of A and 32 N bytes of B per K-slice at 128 B per cycle — and halves of N would read A twice)
-#pragma unroll
-            for (int kb = 0; kb < KB; ++kb)
-                issue_kblock_3x(d3, aA + kb * 2 * kATileBytes, aA + kb * 2 * kATileBytes + kATileBytes,
-                                aW3 + kb * 2 * N3 * 128, aW3 + kb * 2 * N3 * 128 + N3 * 128, idesc_3, kb == 0);
-            umma_commit(&bar_mma3);
-            umma_commit(&bar_a_free);
-        }
-        __syncwarp();
+        // ---- contraction 2: D3 = h . (Ws1[:, :d] W2)^T, A from TMEM (issued by the MMA thread); it runs while the
+        // consumers reduce the previous tile's accumulator (epilogue 2), and contraction 1 of the next tile does not
+        // wait for it
+        if (tid == 0) mbar_arrive(&bar_h_ready);
         LPF_STAMP(5);
+        if (it > 0) epilogue2(j_prev, d3 + ((it - 1) & 1) * N3);
+        LPF_STAMP(6);
         j_prev = j;
     }
     // drain: epilogue 2 of the last tile
     mbar_wait(&bar_mma3, (it - 1) & 1);
     tc_fence_after();
-    epilogue2(j_prev);
+    epilogue2(j_prev, d3 + ((it - 1) & 1) * N3);
 #undef LPF_STAMP
 
     tc_fence_before();

@@ -26,6 +26,20 @@ __device__ __forceinline__ uint32_t swz_chunk_off(int r, int chunk) {
     return (uint32_t)(((r >> 3) << 10) + ((r & 7) << 7) + (((chunk ^ (r & 7)) & 7) << 4));
 }
 
+// One lane of a converged warp (elect.sync): the warp-uniform way to issue tcgen05.mma / commit — the operands stay in
+// uniform registers; code under `if (lane == 0)` makes the compiler re-derive uniformity around every instruction.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -105,6 +119,16 @@ __device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, float (&v)[16]) 
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 16 consecutive fp32 columns of this thread's TMEM lane, written from registers (complete after tmem_st_wait())
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+        "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---- descriptors (bit layouts: cute/arch/mma_sm100_desc.hpp of CUTLASS 3.9+/4.x)
 // shared-memory matrix descriptor, K-major, SWIZZLE_128B: start>>4 [0,14), LBO>>4 [16,30) (=1, unused for
 // swizzled K-major), SBO>>4 [32,46) (= 1024 B between 8-row groups), version=1 [46,48), layout=2 [61,64)
@@ -135,6 +159,20 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem] (+)= A[tmem] . B[smem]^T: the A operand comes from TMEM (lane = row, one 32-bit column per tf32 element of
+// the K-slice: 8 consecutive columns), written there by tcgen05.st — an operand that is produced by the epilogue of the
+// previous contraction never goes through shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrive on `bar` when every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -152,6 +190,19 @@ __device__ __forceinline__ void issue_kblock_3x(uint32_t d_tmem, uint32_t a_hi, 
         umma_tf32(d_tmem, dal + o, dbh + o, idesc, (first && j == 0) ? 0u : 1u);
         umma_tf32(d_tmem, dah + o, dbl + o, idesc, 1u);
         umma_tf32(d_tmem, dah + o, dbh + o, idesc, 1u);
+    }
+}
+
+// the same with the A operand in TMEM: a_hi / a_lo = TMEM addresses of the k-block's 32 columns of the two halves
+__device__ __forceinline__ void issue_kblock_3x_ts(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                                   uint32_t b_lo, uint32_t idesc, bool first) {
+    const uint64_t dbh = make_smem_desc(b_hi), dbl = make_smem_desc(b_lo);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint64_t o = (uint64_t)(j * 2);  // 32 bytes >> 4
+        umma_tf32_ts(d_tmem, a_lo + 8 * j, dbh + o, idesc, (first && j == 0) ? 0u : 1u);
+        umma_tf32_ts(d_tmem, a_hi + 8 * j, dbl + o, idesc, 1u);
+        umma_tf32_ts(d_tmem, a_hi + 8 * j, dbh + o, idesc, 1u);
     }
 }
 

@@ -124,13 +124,18 @@ class ScorePlan:
             call("lpf_gemm_tc", ptr(A), A.stride(0), ptr(Wp), ptr(bias), float(scale), ptr(C), C.stride(0), M, N, K,
                  EPI_NONE, mdev, st, meta=(M, N, K))
 
-        # every link with the empty-set pairwise constant (independent of the selection): side stream
+        # every link with the empty-set pairwise constant (independent of the selection): side stream — except under
+        # the per-kernel tracer (bench.py), where a kernel running next to the one being timed would inflate its time
         main = torch.cuda.current_stream()
-        self.ev_fork.record(main)
-        self.side.wait_event(self.ev_fork)
-        with torch.cuda.stream(self.side):
-            heads(None, bs, None, None, on=self.side.cuda_stream)
-            self.ev_join.record(self.side)
+        traced = _lib.TRACE is not None
+        if traced:
+            heads(None, bs, None, None)
+        else:
+            self.ev_fork.record(main)
+            self.side.wait_event(self.ev_fork)
+            with torch.cuda.stream(self.side):
+                heads(None, bs, None, None, on=self.side.cuda_stream)
+                self.ev_join.record(self.side)
         # K1: one-pass selection into the per-type pools
         if self.rows is not None:
             call("lpf_select_onepass_packed", ptr(links), bs, ptr(self.adj.rowptr), ptr(self.adj.col),
@@ -142,7 +147,8 @@ class ScorePlan:
                  ptr(self.ppr.col), ptr(self.ppr.val), *self.th, self.mode, self.algo, cap, ptr(self.counts),
                  ptr(self.seg_start), ptr(self.nz), hp, ptr(self.node), ptr(self.pa), ptr(self.pb), ptr(self.ws), st,
                  meta=(bs,))
-        main.wait_event(self.ev_join)
+        if not traced:
+            main.wait_event(self.ev_join)
         if self.nz_mode == "fused":
             # few non-empty links: one warp per link, everything from node sets to score in one launch
             call("lpf_nz_links_fused", C.byref(self.nz_args), st, meta=(bs,))

@@ -36,10 +36,23 @@ ops.link_heads(links, X, consts, prob)
 e1.record()
 torch.cuda.synchronize()
 lib.lpf_debug_heads_clocks(None)
-t = buf.cpu().numpy().reshape(8, 16)[:, :6]
-names = ["wait_mma3(prev)", "epi2(prev)", "wait_mma1", "epi1+sync", "issue_mma3"]
+full = buf.cpu().numpy().reshape(8, 16)
+t = full[:, :7]
+names = ["wait_mma1", "epi1", "wait_mma3(prev)", "store_h+sync", "issue_mma3", "epi2(prev)"]
 print("kernel %.1f us for %d tiles/CTA" % (1e3 * e0.elapsed_time(e1), bs // 128 // 148))
 for i in range(1, 8):
     dt = np.diff(t[i])
     nxt = (" period=%d" % (t[i + 1, 0] - t[i, 0])) if i < 7 else ""
     print("tile %d: " % i + "  ".join("%s=%d" % (nm, v) for nm, v in zip(names, dt)) + nxt)
+
+# the MMA thread: [0] loop top, [1] next operand tile ready, [2] contraction 1 of tile it+1 issued, [3] H ready,
+# [4] contraction 2 of tile it issued (an issue blocks while the MMA queue is full, so these are roughly run times)
+m = full[:, 8:13]
+for i in range(1, 7):
+    d = np.diff(m[i])
+    print("mma thread tile %d: wait_a=%d issue_mma1=%d wait_h=%d issue_mma3=%d  period=%d" % (i, d[0], d[1], d[2], d[3], m[i + 1, 0] - m[i, 0]))
+
+# producer thread 0: [13] loop top, [14] gathered rows have arrived, [15] operand tile stored (after waiting for the
+# previous contraction 1)
+for i in range(1, 7):
+    print("producer tile %d: gather=%d wait+store=%d period=%d" % (i, full[i, 14] - full[i, 13], full[i, 15] - full[i, 14], full[i + 1, 13] - full[i, 13]))
