@@ -68,7 +68,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 template <int D, bool ZB>
-__global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsParams p) {
+__global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsParams p) {   // (13 warps are allocated as 16: 128 registers)
     constexpr int KB = D / 32;                       // k-blocks of both contractions (K = D)
     constexpr int N3 = 2 * D;                        // width of mlp_score's hidden layer
     constexpr uint32_t W1_BYTES = KB * 2 * D * 128;  // packed [D, D]
@@ -223,24 +223,41 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
             int32_t a_n3, b_n3;
             load_ids(tile + 3 * (int64_t)gridDim.x, a_n3, b_n3);
             named_bar_sync(2, kHeadProducers);
+            // X[b] first, every read in flight at once (the registers that will hold the products receive the rows); then
+            // X[a]: in an evaluation batch the links of a tile share their source (train/testing.py:20-23), so the thread's
+            // eight rows usually have the same a and one read per k-block serves them all
             float4 v[KB][8];
+            const int32_t a0 = ids[it & 1][0][row_in_pass];
+            bool same_a = true;
 #pragma unroll
-            for (int kb = 0; kb < KB; ++kb) {
+            for (int pass = 1; pass < 8; ++pass) same_a &= ids[it & 1][0][pass * 16 + row_in_pass] == a0;
+            auto ld4 = [&](const float* q) -> float4 {
+                if (vec_x) return __ldg(reinterpret_cast<const float4*>(q));
+                return make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
+            };
 #pragma unroll
-                for (int pass = 0; pass < 8; ++pass) {
-                    const int r = pass * 16 + row_in_pass;
-                    const float* pa = p.X + (int64_t)ids[it & 1][0][r] * p.ldx + kb * 32 + chunk * 4;
-                    const float* pb = p.X + (int64_t)ids[it & 1][1][r] * p.ldx + kb * 32 + chunk * 4;
-                    float4 xa, xb;
-                    if (vec_x) {
-                        xa = __ldg(reinterpret_cast<const float4*>(pa));
-                        xb = __ldg(reinterpret_cast<const float4*>(pb));
-                    } else {
-                        xa = make_float4(__ldg(pa), __ldg(pa + 1), __ldg(pa + 2), __ldg(pa + 3));
-                        xb = make_float4(__ldg(pb), __ldg(pb + 1), __ldg(pb + 2), __ldg(pb + 3));
+            for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                for (int pass = 0; pass < 8; ++pass)
+                    v[kb][pass] = ld4(p.X + (int64_t)ids[it & 1][1][pass * 16 + row_in_pass] * p.ldx + kb * 32 + chunk * 4);
+            if (same_a) {
+                float4 xa[KB];
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) xa[kb] = ld4(p.X + (int64_t)a0 * p.ldx + kb * 32 + chunk * 4);
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                    for (int pass = 0; pass < 8; ++pass) {
+                        v[kb][pass].x *= xa[kb].x; v[kb][pass].y *= xa[kb].y; v[kb][pass].z *= xa[kb].z; v[kb][pass].w *= xa[kb].w;
                     }
-                    v[kb][pass] = make_float4(xa.x * xb.x, xa.y * xb.y, xa.z * xb.z, xa.w * xb.w);
-                }
+            } else {
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                    for (int pass = 0; pass < 8; ++pass) {
+                        const float4 xa = ld4(p.X + (int64_t)ids[it & 1][0][pass * 16 + row_in_pass] * p.ldx + kb * 32 + chunk * 4);
+                        v[kb][pass].x *= xa.x; v[kb][pass].y *= xa.y; v[kb][pass].z *= xa.z; v[kb][pass].w *= xa.w;
+                    }
             }
             LPF_PSTAMP(1);
             a_cur = a_n1; b_cur = b_n1; a_n1 = a_n2; b_n1 = b_n2; a_n2 = a_n3; b_n2 = b_n3;
