@@ -260,13 +260,17 @@ int lpf_attend_fused(const int64_t* ptr, int64_t bs, const int32_t* idx /* NULL 
  * offset is either the constant c3 (links whose selected sets are all empty share one pw) or per-row zb [n, 2d].
  * w1_packed / w23_packed are lpf_pack_weight images.  idx (optional) lists the batch positions to score;
  * prob[pos] is written (the pre-sigmoid logit when logits != 0).
+ * tile_sched (optional): two zero-initialised int32 words owned by the caller, {next tile, finished CTAs}.  With
+ * it the CTAs of the launch take their 128-link tiles from a counter instead of a fixed stride (a CTA that starts
+ * late, because its SM was still busy with another stream's kernel, then simply takes fewer tiles); the last CTA
+ * to finish re-arms the words, so one pair serves every launch on a stream.
  * ------------------------------------------------------------------------- */
 int lpf_link_heads_tc(const int64_t* links, int64_t bs, const int32_t* idx, int64_t n,
                       const float* X, int64_t ldx, int32_t d,
                       const float* w1_packed, const float* b1, const float* ln_w, const float* ln_b,
                       const float* w23_packed, const float* c3, const float* zb, int64_t ld_zb,
                       const float* ws2, const float* bs2, float* prob, int logits, const int64_t* n_dev,
-                      void* stream);
+                      int32_t* tile_sched, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Fused path for links with a non-empty node set, small-batch regime: one warp takes one link of nz_list

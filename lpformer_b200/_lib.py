@@ -53,7 +53,7 @@ SIGNATURES = {
     "lpf_debug_nz_timing_read": (_int, [_p]),
     "lpf_select_compact": (_int, [_p, _i64, _p, _p, _p]),
     "lpf_link_heads_tc": (_int, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p,
-                                 _p, _int, _p, _p]),
+                                 _p, _int, _p, _p, _p]),
     "lpf_attend_fused": (_int, [_p, _i64, _p, _i64, _p, _p, _i64, _p, _i64, _p, _i64, _p, _p, _p, _p, _i32, _i32, _int, _int,
                                 _p, _i64, _p, _p, _p, _p, _i64, _p]),
     "lpf_ppr_push_host": (_p, [_p, _p, _i64, C.c_double, C.c_double, _int, _p]),

@@ -57,6 +57,7 @@ struct HeadsParams {
     float* prob;
     int logits;
     const int64_t* n_dev;   // optional device-side n
+    int32_t* sched;         // optional {next tile, finished CTAs}: tiles handed out dynamically (see lpf_link_heads_tc)
     long long* dbg;         // optional: per-phase clock64 stamps of CTA 0 / thread 0 (lpf_debug_heads_clocks)
 };
 
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
     // bar_a_ready: the producers have stored the next operand tile;  bar_h_ready: the consumers have stored H.
     __shared__ uint64_t bar_w, bar_mma1[2], bar_d1_free[2], bar_mma3, bar_a_ready, bar_h_ready;
     __shared__ uint32_t tmem_slot;
+    __shared__ int32_t s_tile[8];                    // ring of this CTA's tile numbers (-1: no more), written 3 ahead
     __shared__ int32_t ids[2][2][kTileM];            // [tile parity][a, b][row]
     __shared__ __align__(16) float s_b1[D], s_g[D], s_bt[D], s_c3[N3], s_ws2[N3];
     __shared__ float s_sum[2][kTileM], s_sq[2][kTileM], s_dot[2][kTileM];   // exchanges between the two threads of a link
@@ -90,7 +92,27 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
     const int tid = threadIdx.x, warp = tid >> 5;
     if (p.n_dev) p.n = min(p.n, *p.n_dev);
     const int64_t ntiles = (p.n + kTileM - 1) / kTileM;
-    if ((int64_t)blockIdx.x >= ntiles) return;       // nothing to do: before any barrier / TMEM / bulk-copy state
+    // Tile k of this CTA: blockIdx.x + k gridDim.x, or — with p.sched — the next tile nobody has taken yet.  The CTAs of
+    // this kernel start whenever an SM has all of its registers free, i.e. at very different times when another
+    // batch's selection is still resident; with a static assignment the last CTA to start sets the duration.
+    auto fetch_tile = [&](uint32_t k) -> int32_t {       // (one thread of the CTA calls this, in sequence)
+        const int64_t t = p.sched ? (int64_t)atomicAdd(p.sched, 1) : (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
+        return t < ntiles ? (int32_t)t : -1;
+    };
+    auto retire = [&]() {                                // the last CTA to finish re-arms the scheduler words
+        if (p.sched && atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
+            p.sched[0] = 0;
+            p.sched[1] = 0;
+        }
+    };
+    if (tid == 0) {
+        for (uint32_t k = 0; k < 3; ++k) s_tile[k] = fetch_tile(k);
+    }
+    __syncthreads();
+    if (s_tile[0] < 0) {                             // nothing to do: before any barrier / TMEM / bulk-copy state
+        if (tid == 0) retire();
+        return;
+    }
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sW1 = smem;
     uint8_t* sW3 = sW1 + W1_BYTES;
@@ -136,7 +158,6 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
         // consumers nor the producers ever stall behind a full MMA queue)
         // (the whole warp runs this loop; one elected lane issues: the descriptors are warp-uniform values)
         {
-            const uint32_t n_my = (uint32_t)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
             const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_d, 0);
             const uint32_t u_d1 = tbase, u_d3 = tbase + 2 * D, u_hhi = tbase + 6 * D, u_hlo = tbase + 7 * D;
             mbar_wait(&bar_w, 0);
@@ -156,9 +177,9 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
             const bool mstamp = p.dbg && blockIdx.x == 0 && (tid & 31) == 0;
 #define LPF_MSTAMP(k) do { if (mstamp && it < 8) p.dbg[it * 16 + 8 + (k)] = clock64(); } while (0)
             mma1(0);
-            for (uint32_t it = 0; it < n_my; ++it) {
+            for (uint32_t it = 0; s_tile[it & 7] >= 0; ++it) {
                 LPF_MSTAMP(0);
-                if (it + 1 < n_my) {
+                if (s_tile[(it + 1) & 7] >= 0) {
                     mbar_wait(&bar_a_ready, (it + 1) & 1);
                     LPF_MSTAMP(1);
                     mma1(it + 1);
@@ -188,10 +209,10 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
         const int chunk = ptid & 7, row_in_pass = ptid >> 3;
         const bool vec_x = ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0) && (p.ldx % 4 == 0);
         uint32_t it = 0;
-        auto load_ids = [&](int64_t tile, int32_t& a, int32_t& b) {
-            const int64_t j = tile * kTileM + ptid;
+        auto load_ids = [&](int32_t tile, int32_t& a, int32_t& b) {
+            const int64_t j = (int64_t)tile * kTileM + ptid;
             a = 0; b = 0;
-            if (tile < ntiles && j < p.n) {
+            if (tile >= 0 && j < p.n) {
                 const int64_t pos = p.idx ? (int64_t)__ldg(p.idx + j) : j;
                 a = (int32_t)__ldg(p.links + pos);
                 b = (int32_t)__ldg(p.links + p.bs + pos);
@@ -209,19 +230,21 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
         // The gather (random 256-byte rows) is a DRAM round trip of ~3,000 cycles under load, longer than everything else
         // in the producers' loop: the ids run three tiles ahead of the gather and the rows are pulled into L2 two tiles ahead.
         int32_t a_cur, b_cur, a_n1, b_n1, a_n2, b_n2;
-        load_ids(blockIdx.x, a_cur, b_cur);
-        load_ids((int64_t)blockIdx.x + gridDim.x, a_n1, b_n1);
-        load_ids((int64_t)blockIdx.x + 2 * (int64_t)gridDim.x, a_n2, b_n2);
-        if ((int64_t)blockIdx.x + gridDim.x < ntiles) prefetch_rows(a_n1, b_n1);
+        load_ids(s_tile[0], a_cur, b_cur);
+        load_ids(s_tile[1], a_n1, b_n1);
+        load_ids(s_tile[2], a_n2, b_n2);
+        if (s_tile[1] >= 0) prefetch_rows(a_n1, b_n1);
         const bool pstamp = p.dbg && blockIdx.x == 0 && ptid == 0;
 #define LPF_PSTAMP(k) do { if (pstamp && it < 8) p.dbg[it * 16 + 13 + (k)] = clock64(); } while (0)
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        for (; s_tile[it & 7] >= 0; ++it) {
             LPF_PSTAMP(0);
+            if (ptid == 0) s_tile[(it + 3) & 7] = fetch_tile(it + 3);
             ids[it & 1][0][ptid] = a_cur;
             ids[it & 1][1][ptid] = b_cur;
-            if (tile + 2 * (int64_t)gridDim.x < ntiles) prefetch_rows(a_n2, b_n2);
+            if (s_tile[(it + 2) & 7] >= 0) prefetch_rows(a_n2, b_n2);
+            named_bar_sync(2, kHeadProducers);
             int32_t a_n3, b_n3;
-            load_ids(tile + 3 * (int64_t)gridDim.x, a_n3, b_n3);
+            load_ids(s_tile[(it + 3) & 7], a_n3, b_n3);
             named_bar_sync(2, kHeadProducers);
             // X[b] first, every read in flight at once (the registers that will hold the products receive the rows); then
             // X[a]: in an evaluation batch the links of a tile share their source (train/testing.py:20-23), so the thread's
@@ -326,8 +349,8 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
     };
 
     int64_t j_prev = -1;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int64_t j = tile * kTileM + row;
+    for (; s_tile[it & 7] >= 0; ++it) {
+        const int64_t j = (int64_t)s_tile[it & 7] * kTileM + row;
         const uint32_t d1b = d1 + (it & 1) * D;
         LPF_STAMP(0);
         mbar_wait(&bar_mma1[it & 1], (it >> 1) & 1);
@@ -421,6 +444,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
     tc_fence_before();
     named_bar_sync(1, kHeadConsumers);
     if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
+    if (tid == 0) retire();
 }
 
 template <int D, bool ZB>
@@ -459,14 +483,14 @@ extern "C" int lpf_link_heads_tc(const int64_t* links, int64_t bs, const int32_t
                                  int64_t ldx, int32_t d, const float* w1_packed, const float* b1, const float* ln_w,
                                  const float* ln_b, const float* w23_packed, const float* c3, const float* zb,
                                  int64_t ld_zb, const float* ws2, const float* bs2, float* prob, int logits,
-                                 const int64_t* n_dev, void* stream) {
+                                 const int64_t* n_dev, int32_t* tile_sched, void* stream) {
     LPF_REQUIRE(bs >= 0 && n >= 0, "negative size");
     if (n == 0) return LPF_OK;
     LPF_REQUIRE(links && X && w1_packed && b1 && ln_w && ln_b && w23_packed && ws2 && bs2 && prob, "NULL argument");
     LPF_REQUIRE(c3 || zb, "either the constant c3 or per-row zb must be given");
     LPF_REQUIRE(idx || n == bs, "n must equal bs when idx is NULL");
     LPF_REQUIRE(ldx >= d && (!zb || ld_zb >= 2 * d), "leading dimension too small");
-    HeadsParams p{links, bs, idx, n, X, ldx, w1_packed, b1, ln_w, ln_b, w23_packed, c3, zb, ld_zb, ws2, bs2, prob, logits, n_dev, g_heads_dbg};
+    HeadsParams p{links, bs, idx, n, X, ldx, w1_packed, b1, ln_w, ln_b, w23_packed, c3, zb, ld_zb, ws2, bs2, prob, logits, n_dev, tile_sched, g_heads_dbg};
     cudaStream_t st = (cudaStream_t)stream;
     LPF_REQUIRE(!zb || ((reinterpret_cast<uintptr_t>(zb) & 15) == 0 && ld_zb % 4 == 0), "zb rows must be 16-byte aligned");
     if (d == 64) return zb ? launch_heads<64, true>(p, st) : launch_heads<64, false>(p, st);

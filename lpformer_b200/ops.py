@@ -301,17 +301,17 @@ def attend(sel: Selection, KV, R, Q, att, bias, ln_w, ln_b, heads, ch, write_cou
     return out
 
 
-def link_heads(links, X, consts, prob, idx=None, zb=None, logits=False):
+def link_heads(links, X, consts, prob, idx=None, zb=None, logits=False, sched=None):
     """Fused tensor-core heads (lpf_link_heads_tc): prob[pos] for every link (constant pairwise half `c3`) or for the
-    positions in idx with per-row zb."""
-    require_cuda(links, X, prob, idx, zb)
+    positions in idx with per-row zb.  `sched` (int32 [2], zeros): tiles handed out dynamically (see the header)."""
+    require_cuda(links, X, prob, idx, zb, sched)
     X = _rowmajor(X)
     bs = links.shape[1]
     n = bs if idx is None else idx.numel()
     call("lpf_link_heads_tc", ptr(links), bs, ptr(idx), n, ptr(X), X.stride(0), X.shape[1], ptr(consts["w1p"]),
          ptr(consts["b1"]), ptr(consts["ln_w"]), ptr(consts["ln_b"]), ptr(consts["w23p"]),
          ptr(consts["c3"]) if zb is None else None, ptr(zb), zb.stride(0) if zb is not None else 0,
-         ptr(consts["ws2"]), ptr(consts["bs2"]), ptr(prob), int(logits), None, stream(), meta=(n,))
+         ptr(consts["ws2"]), ptr(consts["bs2"]), ptr(prob), int(logits), None, ptr(sched), stream(), meta=(n,))
     return prob
 
 

@@ -45,6 +45,9 @@ class ScorePlan:
         self.prob = e(bs)
         self.counts, self.seg_start, self.nz = e(3 * bs, dtype=i32), e(3 * bs, dtype=i32), e(bs, dtype=i32)
         self.hdr = torch.zeros(8, dtype=i64, device=dev)
+        self.sched = torch.zeros(2, dtype=i32, device=dev)      # tile scheduler words of lpf_link_heads_tc (self re-arming)
+        # (measured on the citation2 shape: no gain over the fixed stride, 173 vs 167 us per step, so off by default)
+        self.dynamic_tiles = False
         self.ws = e(_lib.load().lpf_select_workspace_bytes(bs) // 4, dtype=i32)
         self.node, self.pa, self.pb = e(3 * cap, dtype=i32), e(3 * cap), e(3 * cap)
         self.hsum, self.R = e(3 * cap, d), e(3 * cap, HC)
@@ -118,7 +121,7 @@ class ScorePlan:
             call("lpf_link_heads_tc", ptr(links), bs, idx, n, ptr(X), X.stride(0), d, ptr(c["w1p"]), ptr(c["b1"]),
                  ptr(c["ln_w"]), ptr(c["ln_b"]), ptr(c["w23p"]), ptr(c["c3"]) if zb is None else None,
                  ptr(zb), self.zb.stride(0) if zb is not None else 0, ptr(c["ws2"]), ptr(c["bs2"]), ptr(self.prob),
-                 int(self.logits), ndev, st if on is None else on, meta=(n,))
+                 int(self.logits), ndev, ptr(self.sched) if self.dynamic_tiles else None, st if on is None else on, meta=(n,))
 
         def gemm(A, Wp, bias, scale, C, M, N, K, mdev):
             call("lpf_gemm_tc", ptr(A), A.stride(0), ptr(Wp), ptr(bias), float(scale), ptr(C), C.stride(0), M, N, K,

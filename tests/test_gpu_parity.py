@@ -486,3 +486,62 @@ def test_link_score_stream_matches_score_links():
     pp, nn_ = pos_pred.cpu().double().numpy(), neg_pred.cpu().double().numpy()
     rank = 0.5 * ((nn_ >= pp[:, None]).sum(1) + (nn_ > pp[:, None]).sum(1)) + 1
     assert abs(res["MRR"] - (1.0 / rank).mean()) < 1e-6 and abs(res["Hits@10"] - (rank <= 10).mean()) < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim", [64, 32])
+def test_link_heads_kernel_vs_float64_and_dynamic_tiles(dim):
+    """lpf_link_heads_tc alone (13-warp pipeline: H operand in TMEM, double-buffered accumulators, MMA warp) against
+    a float64 restatement of elementwise_lin -> mlp_score (models/other_models.py:125-138, 173-179) on ragged sizes
+    (1 tile, a partial last tile, more tiles than CTAs), with the per-row offset path (idx + zb), and with the tiles
+    handed out dynamically (tile_sched): same numbers, and the scheduler words re-arm themselves."""
+    import lpformer_b200 as L
+    from lpformer_b200 import ops
+    dev = torch.device("cuda:0")
+    n = 50000
+    targs = dict(dim=dim, num_heads=1, trans_layers=1, gnn_layers=1, residual=False, layer_norm=True, relu=True,
+                 thresh_cn=0, thresh_1hop=1e-3, thresh_non1hop=1e-2)
+    torch.manual_seed(5)
+    model = L.LinkTransformer(targs, {"x": torch.zeros(n, 4)}, device=dev).to(dev).eval()
+    score = L.mlp_score(2 * dim, 2 * dim, 1, 2).to(dev).eval()
+    with torch.no_grad():
+        for p in list(model.parameters()) + list(score.parameters()):
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    X = torch.randn(n, dim, device=dev)
+    consts = model._head_consts(score, X)
+    assert consts is not None
+    el, lins = model.elementwise_lin, score.lins
+    f64 = lambda t: t.detach().double().cpu()      # noqa: E731
+
+    def ref(links, off):
+        xp = f64(X)[links[0]] * f64(X)[links[1]]
+        h = xp @ f64(el.linears[0].weight).T + f64(el.linears[0].bias)
+        h = torch.nn.functional.layer_norm(h, (dim,), f64(el.norm.weight), f64(el.norm.bias), 1e-5).relu()
+        z = (h @ f64(consts["w23"]).T + off).relu()
+        return torch.sigmoid(z @ f64(consts["ws2"]) + f64(consts["bs2"]))
+
+    sched = torch.zeros(2, dtype=torch.int32, device=dev)
+    for bs in (77, 128, 148 * 128 * 3 + 5):
+        links = torch.randint(0, n, (2, bs), device=dev)
+        links[0, : bs // 2] = links[0, 0]                       # a run of equal source, then random sources
+        want = ref(links.cpu(), f64(consts["c3"]))
+        prob = torch.full((bs,), -1.0, device=dev)
+        ops.link_heads(links, X, consts, prob)
+        np.testing.assert_allclose(prob.cpu().numpy(), want.numpy(), rtol=FP32_RTOL, atol=1e-6)
+        for rep in range(2):
+            dyn = torch.full((bs,), -1.0, device=dev)
+            ops.link_heads(links, X, consts, dyn, sched=sched)
+            assert torch.equal(dyn, prob)
+            assert sched.tolist() == [0, 0]
+        # per-row offsets on a subset of the positions
+        idx = torch.randperm(bs, device=dev)[: max(1, bs // 3)].to(torch.int32)
+        zb = torch.randn(idx.numel(), 2 * dim, device=dev)
+        sub = torch.full((bs,), -1.0, device=dev)
+        ops.link_heads(links, X, consts, sub, idx=idx, zb=zb, sched=sched)
+        want_sub = ref(links[:, idx.long()].cpu(), f64(zb))
+        got = sub[idx.long()].cpu().numpy()
+        np.testing.assert_allclose(got, want_sub.numpy(), rtol=FP32_RTOL, atol=1e-6)
+        untouched = torch.ones(bs, dtype=torch.bool, device=dev)
+        untouched[idx.long()] = False
+        assert bool((sub[untouched] == -1.0).all())
