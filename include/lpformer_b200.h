@@ -345,6 +345,28 @@ int lpf_gcn_spmm(const int64_t* rowptr, const int32_t* col, const float* val,
  * lpf_ppr_push_host_fetch copies the CSR out (rowptr [n+1], col/val [nnz]) and
  * releases the handle.
  * ------------------------------------------------------------------------- */
+/* ------------------------------------------------------------------------- *
+ * PPR precompute on the GPU: the same push (util/calc_ppr_scores.py:137-192), one warp per
+ * source, bit-identical values (tests compare with lpf_ppr_push_host).  DEVICE pointers.
+ *   lpf_ppr_push_slots(alpha, eps): hash slots per warp = power of two >= 2 (1 + 1 / (alpha eps)), -1 if that is
+ *     beyond 2^24 (use the host tool for such eps);  lpf_ppr_push_scratch_bytes(slots, nwarps): scratch size.
+ *   lpf_ppr_push: sources [src0, src0 + nsrc) — or src_list[0 .. nsrc) when src_list is given — of the CSR graph
+ *     (sorted columns, no self loops) with `nwarps` resident warps (a multiple of 4) and `slots` hash slots each (any
+ *     power of two >= 64: a source whose table fills up is skipped, counted in status[1] and listed in ovf_list if
+ *     given, to be re-run with more slots); entries (row, col, fp32 value) are appended to the pool out_* [cap] through
+ *     cursor[0] (int64, not reset: several source ranges can share a pool; cursor[1] is the work counter and must be 0
+ *     on entry), in arbitrary order — sort by (row, col) for the CSR.  status[0] != 0: the pool was too small (the
+ *     entries that did not fit are lost: retry with a larger cap); status[1]: number of sources whose table filled up
+ *     (0 with slots = lpf_ppr_push_slots(alpha, eps) on a simple graph).
+ * ------------------------------------------------------------------------- */
+int32_t lpf_ppr_push_slots(double alpha, double eps);
+int64_t lpf_ppr_push_scratch_bytes(int32_t slots, int32_t nwarps);
+int lpf_ppr_push(const int64_t* indptr, const int32_t* indices, int64_t n, double alpha, double eps,
+                 int64_t src0, int64_t nsrc, const int32_t* src_list, int32_t* ovf_list,
+                 int32_t slots, int32_t nwarps, void* scratch,
+                 int32_t* out_row, int32_t* out_col, float* out_val, int64_t cap, int64_t* cursor,
+                 int32_t* status, void* stream);
+
 void* lpf_ppr_push_host(const int64_t* indptr_host, const int32_t* indices_host, int64_t n,
                         double alpha, double eps, int nthreads, int64_t* nnz);
 int lpf_ppr_push_host_fetch(void* handle, int64_t* rowptr_host, int32_t* col_host, float* val_host);

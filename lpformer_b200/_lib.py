@@ -57,6 +57,9 @@ SIGNATURES = {
     "lpf_attend_fused": (_int, [_p, _i64, _p, _i64, _p, _p, _i64, _p, _i64, _p, _i64, _p, _p, _p, _p, _i32, _i32, _int, _int,
                                 _p, _i64, _p, _p, _p, _p, _i64, _p]),
     "lpf_ppr_push_host": (_p, [_p, _p, _i64, C.c_double, C.c_double, _int, _p]),
+    "lpf_ppr_push_slots": (_i32, [C.c_double, C.c_double]),
+    "lpf_ppr_push_scratch_bytes": (_i64, [_i32, _i32]),
+    "lpf_ppr_push": (_int, [_p, _p, _i64, C.c_double, C.c_double, _i64, _i64, _p, _p, _i32, _i32, _p, _p, _p, _p, _i64, _p, _p, _p]),
     "lpf_ppr_push_host_fetch": (_int, [_p, _p, _p, _p]),
     "lpf_gcn_spmm": (_int, [_p, _p, _p, _i64, _i64, _p, _i64, _p, _i32, _p, _i64, _p]),
 }
