@@ -137,10 +137,12 @@ int lpf_select_onepass(const int64_t* links, int64_t bs,
  * fit 26 bits, i.e. rows beyond 4 GiB) and 64-byte alignment, scratch lpf_link_rows_scratch_bytes(n) bytes.
  *
  * lpf_select_onepass_packed is lpf_select_onepass (same outputs, same header protocol, same preconditions as
- * the INTERSECT algorithms) on those rows: a CTA stages the sources of 512 consecutive links in shared memory
- * (bucketed hash set of A(a), table of P(a)), flattens the target rows into 64-byte units screened by four lanes
- * each, and the links that select anything — or whose rows are long — are resolved by a warp each.  The CSR
- * tables are still read by that resolution and by the fallbacks (chunks that are not runs of equal source).
+ * the INTERSECT algorithms) on those rows: the batch is cut evenly over one resident wave of CTAs; a CTA stages the
+ * sources of its piece (<= 1,024 links, 1-3 runs of equal source) in shared memory (bucketed hash set of A(a),
+ * table of P(a)), flattens the target rows into 64-byte units screened by four lanes each, and resolves the links
+ * that select anything by a warp each (by the whole CTA for long target rows).  Runs whose source does not fit
+ * next to the others take a second launch with a larger table; the CSR tables are still read by the fallbacks
+ * (pieces that are not runs of equal source, sources beyond even the larger table).
  * ------------------------------------------------------------------------- */
 int64_t lpf_link_rows_bytes(int64_t n, int64_t adj_nnz, int64_t ppr_nnz);
 int64_t lpf_link_rows_scratch_bytes(int64_t n);
@@ -307,9 +309,10 @@ typedef struct lpf_nz_args {
 } lpf_nz_args;
 int lpf_nz_links_fused(const lpf_nz_args* args, void* stream);
 
-/* Profiling hook: later lpf_select_onepass launches add per-phase clock64() totals of the run-aware kernel into
+/* Profiling hook: later lpf_select_onepass_packed launches add per-phase clock64() totals of the screening kernel into
  * device_buffer (int64[48]: [0] source staging, [1] phase A, [2] phase B, [3] phase C, [4] generic fallback,
- * [5] chunks, [6] queued long-row links, [7] written links); NULL disables. */
+ * [5] pieces, [6] links resolved by a warp, [7] by the whole CTA, [8..9] slowest piece / CTA, [10..13] set-up phases,
+ * [16..38] the slowest piece's own phases and sizes; see tools/select_clocks.py); NULL disables. */
 int lpf_debug_select_clocks(void* device_buffer);
 
 /* Profiling hook: with enable != 0 later lpf_select_onepass_packed calls record CUDA events on their stream around

@@ -1,5 +1,5 @@
-"""Per-phase clock totals of the run-aware one-pass selection kernel on a citation2-shaped batch.
-Run on the GPU box:  python tools/select_clocks.py [scale]"""
+"""Per-phase clock totals of the packed-row screening kernel (lpf_select_onepass_packed) on a citation2-shaped batch, and
+the phase breakdown of its slowest piece.  Run on the GPU box:  python tools/select_clocks.py [scale]"""
 import os
 import sys
 
@@ -32,14 +32,14 @@ lib.lpf_debug_select_clocks(None)
 t = buf.cpu().numpy()
 n = max(1, int(t[5]))
 names = ["flatten fill + stage source", "phase A", "phase B", "phase C", "generic"]
-print("chunks %d, links resolved in-CTA or queued per chunk %.1f, handed to the resolve launch per chunk %.1f" % (n, t[6] / n, t[7] / n))
+print("chunks %d, links resolved by a warp per piece %.1f, by the whole CTA per piece %.1f" % (n, t[6] / n, t[7] / n))
 print("slowest chunk %.1f us, slowest CTA %.1f us" % (t[8] / 1965.0, t[9] / 1965.0))
 for nm, v in zip(["  top loads+zero stores", "  run detection", "  table layout", "  clear+flatten scan"], t[10:14]):
     print("  %-26s %9.0f cycles/chunk  (%.1f us)" % (nm, v / n, v / n / 1965.0))
 for nm, v in zip(names, t[:5]):
     print("  %-14s %9.0f cycles/chunk  (%.1f us)" % (nm, v / n, v / n / 1965.0))
 
-ph = {10: "top loads", 12: "table layout", 13: "clear+flatten", 0: "stage source", 1: "phase A", 2: "phase B", 3: "phase C (unused)", 4: "generic"}
-print("slowest chunk: len %d runs %d items %d slow %d to-resolve-launch %d table slots %d hub-launch %d" % tuple(int(x) for x in t[32:39]))
+ph = {10: "top loads", 12: "table layout", 13: "clear+flatten", 0: "stage source", 1: "phase A", 2: "phase B", 3: "phase C (CTA walks)", 4: "generic"}
+print("slowest chunk: len %d runs %d items %d slow %d cta-walked %d table slots %d hub-launch %d" % tuple(int(x) for x in t[32:39]))
 for k, nm in ph.items():
     print("    %-22s %8d cycles (%.1f us)" % (nm, t[16 + k], t[16 + k] / 1965.0))
