@@ -41,6 +41,7 @@ constexpr int kPkMaxItems = 6144;     // units of one chunk that are screened un
 constexpr int kPkWarpUnits = 32;      // resolution by a warp of the screening CTA: target rows up to 32 units (~500 neighbours)
 constexpr int kPkHubDeg = 1 << 30;      // a source with more neighbours selects something with every tenth target: its run is
                                       // cut into pieces for the hub launch, so that no CTA resolves hundreds of links
+constexpr int kPkInflight = 4;        // 16-byte reads a lane of the screening keeps in flight (8 spill at 64 registers: slower)
 constexpr int kPkHubPiece = 256;      // links per entry of the hub list
 static_assert(kPkChunk == 1024 && kPkMaxUnits < 65536, "items[] packs (position:16 | unit:16)");
 constexpr uint32_t kPkPprTag = 0x80000000u;
@@ -619,15 +620,16 @@ select_onepass_packed_kernel(const __grid_constant__ SelectParams2 p, const uint
         __syncthreads();
         LPF_PHASE(0);
 
-        // ---- phase A: four lanes per 64-byte unit, four units in flight per lane
+        // ---- phase A: four lanes per 64-byte unit, kPkInflight units in flight per lane
         {
+            constexpr int K = kPkInflight;
             const int n_items = sm.n_items;
             const int ql = tid & 3;
-            for (int q0 = tid >> 2; q0 < n_items; q0 += 4 * (kPkThreads / 4)) {
-                uint4 v[4];
-                int tt[4];
+            for (int q0 = tid >> 2; q0 < n_items; q0 += K * (kPkThreads / 4)) {
+                uint4 v[K];
+                int tt[K];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < K; ++k) {
                     const int q = q0 + k * (kPkThreads / 4);
                     tt[k] = -1;
                     v[k] = make_uint4(kPkPad, kPkPad, kPkPad, kPkPad);
@@ -639,7 +641,7 @@ select_onepass_packed_kernel(const __grid_constant__ SelectParams2 p, const uint
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < K; ++k) {
                     if (tt[k] < 0) continue;
                     const int t = tt[k], r = run_of(sm, t);
                     const int mode_r = sm.r_hashed[r];
