@@ -239,14 +239,19 @@ __device__ __forceinline__ void resolve_packed_group(const SelectParams2& p, con
     int c_cn, c_1h, c_n1;
     walk_packed_group<G, false>(p, h, row, lane, 0, 0, 0, c_cn, c_1h, c_n1);
     int64_t s_cn = 0, s_1h = 0, s_n1 = 0;
-    int ok = 1;
-    if (lane == leader) ok = alloc_segments(p, i, c_cn, c_1h, c_n1, s_cn, s_1h, s_n1) ? 1 : 0;
-    if (c_cn + c_1h + c_n1 == 0) return;       // uniform within the group
-    ok = __shfl_sync(gmask, ok, leader);
-    if (!ok) return;
-    s_cn = __shfl_sync(gmask, s_cn, leader);
-    s_1h = __shfl_sync(gmask, s_1h, leader);
-    s_n1 = __shfl_sync(gmask, s_n1, leader);
+    if constexpr (G == 32) {
+        const bool ok = alloc_segments_warp(p, i, c_cn, c_1h, c_n1, lane, s_cn, s_1h, s_n1);
+        if (c_cn + c_1h + c_n1 == 0 || !ok) return;
+    } else {
+        int ok = 1;
+        if (lane == leader) ok = alloc_segments(p, i, c_cn, c_1h, c_n1, s_cn, s_1h, s_n1) ? 1 : 0;
+        if (c_cn + c_1h + c_n1 == 0) return;       // uniform within the group
+        ok = __shfl_sync(gmask, ok, leader);
+        if (!ok) return;
+        s_cn = __shfl_sync(gmask, s_cn, leader);
+        s_1h = __shfl_sync(gmask, s_1h, leader);
+        s_n1 = __shfl_sync(gmask, s_n1, leader);
+    }
     walk_packed_group<G, true>(p, h, row, lane, s_cn, p.cap + s_1h, 2 * p.cap + s_n1, c_cn, c_1h, c_n1);
 }
 
@@ -362,10 +367,10 @@ __device__ __forceinline__ void resolve_packed_cta(const SelectParams2& p, const
             c_1h += (int)((total >> 12) & 1023u);
             c_n1 += (int)(total >> 22);
         }
-        if (tid == 0) {
+        if (warp == 0) {
             int64_t s0, s1, s2;
-            *ok = alloc_segments(p, i, c_cn, c_1h, c_n1, s0, s1, s2) ? 1 : 0;
-            seg[0] = s0; seg[1] = s1; seg[2] = s2;
+            const bool fits = alloc_segments_warp(p, i, c_cn, c_1h, c_n1, lane, s0, s1, s2);
+            if (lane == 0) { *ok = fits ? 1 : 0; seg[0] = s0; seg[1] = s1; seg[2] = s2; }
         }
         __syncthreads();
         if (*ok && c_cn + c_1h + c_n1 > 0) {

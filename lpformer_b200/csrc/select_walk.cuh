@@ -179,6 +179,34 @@ __device__ __forceinline__ void walk_link(const SelectParams2& p, const LinkRows
     }
 }
 
+// The same allocation by the first four lanes of a converged warp (lane t < 3: the pool of type t, lane 3: the slot
+// in the list of non-empty links): the four atomics are in flight together — one round trip to L2 instead of up
+// to four on the critical path of every resolved link.  (The list slot is taken before the capacity check: when a
+// pool overflows the batch is redone anyway and select_finalize_onepass zeroes the sizes.)  Every lane of the warp
+// calls this with the same counts and gets the three segment starts; returns false if a pool is full.
+__device__ __forceinline__ bool alloc_segments_warp(const SelectParams2& p, int64_t i, int c_cn, int c_1h, int c_n1,
+                                                    int lane, int64_t& s_cn, int64_t& s_1h, int64_t& s_n1) {
+    const int total = c_cn + c_1h + c_n1;
+    const int mine = lane == 0 ? c_cn : (lane == 1 ? c_1h : (lane == 2 ? c_n1 : (total > 0 ? 1 : 0)));
+    long long got = 0;
+    if (lane < 4 && mine > 0)
+        got = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(p.hdr + lane), (unsigned long long)mine);
+    s_cn = __shfl_sync(kFull, got, 0);
+    s_1h = __shfl_sync(kFull, got, 1);
+    s_n1 = __shfl_sync(kFull, got, 2);
+    const long long nzpos = __shfl_sync(kFull, got, 3);
+    const bool fits = s_cn + c_cn <= p.cap && s_1h + c_1h <= p.cap && s_n1 + c_n1 <= p.cap;
+    if (lane < 3) {
+        const int c = lane == 0 ? c_cn : (lane == 1 ? c_1h : c_n1);
+        p.counts[lane * p.bs + i] = c;
+        p.seg_start[lane * p.bs + i] = (int32_t)got;
+    } else if (lane == 3 && total > 0) {
+        if (fits) p.nz_list[nzpos] = (int32_t)i;
+        else p.hdr[4] = 1;
+    }
+    return fits;
+}
+
 // Segment allocation of the one-pass mode: rows for (c_cn, c_1h, c_n1) pairs in the three per-type pools.
 // Called by ONE thread; returns false (and raises the overflow flag) if a pool is full.
 __device__ __forceinline__ bool alloc_segments(const SelectParams2& p, int64_t i, int c_cn, int c_1h, int c_n1,
