@@ -281,6 +281,7 @@ __global__ void select_reset_onepass(int32_t* heavy, int64_t* hdr) {
 // prologue / epilogue of a one-pass launch sequence, for the kernels of other translation units
 __global__ void select_reset_packed(int32_t* heavy, int64_t* hdr, int32_t* hub) {
     heavy[0] = 0;
+    heavy[1] = 0;        // piece counter of the screening launch
     hdr[0] = hdr[1] = hdr[2] = hdr[3] = hdr[4] = 0;
     hub[0] = 0;
 }

@@ -35,12 +35,16 @@ constexpr int kPkMaxRuns = 3;
 constexpr int kPkHashSlots = 16384;   // int32 slots shared by the runs of a chunk (load <= 0.5): sources up to 8,192
 constexpr int kPkHubSlots = 32768;    // second launch, one CTA per SM: hub sources up to 16,384 neighbours
 constexpr int kPkMaxPprRow = 128;
-constexpr int kPkMaxUnits = 16;       // target rows of up to 16 units (1 KB: ~250 neighbours) are screened unit-wise; longer rows are
-                                      // resolved unscreened (listing their units costs the screening more than it saves)
+constexpr int kPkMaxUnits = 62;       // target rows of up to 62 units (4 KB: ~980 neighbours) are screened unit-wise (the locator's
+                                      // unit count saturates at 63: the few longer rows are resolved unscreened by the whole CTA)
 constexpr int kPkMaxItems = 6144;     // units of one chunk that are screened unit-wise (the rest get a warp)
-constexpr int kPkWarpUnits = 32;      // resolution by a warp of the screening CTA: target rows up to 32 units (~500 neighbours)
-constexpr int kPkHubDeg = 1 << 30;      // a source with more neighbours selects something with every tenth target: its run is
-                                      // cut into pieces for the hub launch, so that no CTA resolves hundreds of links
+constexpr int kPkWarpUnits = 32;      // resolution by a warp of the screening CTA: target rows up to 32 units (~500 neighbours);
+                                      // longer rows that select take the whole CTA
+constexpr int kPkHubDeg = 1 << 30;    // sources with more neighbours would be cut into pieces for the hub launch (a hub source selects
+                                      // something with every tenth target: ~100 links to resolve in its piece); off: with 1,500 the hub
+                                      // launch took 59 us and the step was no shorter
+constexpr int kPkSplit = 1;           // pieces per resident CTA (2 measured: the slowest CTA is no faster, more total work)
+constexpr int kPkMinPiece = 512;
 constexpr int kPkInflight = 4;        // 16-byte reads a lane of the screening keeps in flight (8 spill at 64 registers: slower)
 constexpr int kPkHubPiece = 256;      // links per entry of the hub list
 static_assert(kPkChunk == 1024 && kPkMaxUnits < 65536, "items[] packs (position:16 | unit:16)");
@@ -67,7 +71,7 @@ struct PkSmemT {
     uint32_t r_loc[kPkMaxRuns];
     int32_t r_slots[kPkMaxRuns];
     int4 r_ctx[kPkMaxRuns];              // (first table slot, bucket mask, 32 - log2(buckets), 0): one read per unit
-    int n_runs, n_slow, n_items, tab_used, items_full, n_cta, cta_ok;
+    int n_runs, n_slow, n_items, tab_used, items_full, n_cta, cta_ok, cur_chunk;
     uint16_t q_cta[kPkChunk];             // chunk positions of the links the whole CTA walks (long target rows that select)
     uint32_t scan_tot[2 * 4 * (kPkThreads / 32)];
     int64_t cta_seg[3];
@@ -430,8 +434,9 @@ select_onepass_packed_kernel(const __grid_constant__ SelectParams2 p, const uint
     const bool want_pi = p.mode != LPF_MODE_CN;
     const bool want_n1 = p.mode == LPF_MODE_ALL;
     const float th_pre = want_n1 ? fminf(p.th_1hop, p.th_non1hop) : p.th_1hop;
-    // !HUB: the batch in `gridDim.x`-many (or more) even pieces of at most kPkChunk links
-    const int64_t per = HUB ? 0 : min((int64_t)kPkChunk, max((int64_t)kPkThreads, (p.bs + gridDim.x - 1) / gridDim.x));
+    // !HUB: the batch in kPkSplit x `gridDim.x` (or more) even pieces of at most kPkChunk links, handed out through a
+    // counter: the launch lasts as long as its slowest CTA, and a piece with a hub source takes twice the average
+    const int64_t per = HUB ? 0 : min((int64_t)kPkChunk, max((int64_t)kPkMinPiece, (p.bs + kPkSplit * gridDim.x - 1) / (kPkSplit * gridDim.x)));
     const int64_t nchunks = HUB ? (int64_t)p.hub[0] : (p.bs + per - 1) / per;
     const int slots_cap = p.slot_limit > 0 ? min(SLOTS, HUB ? 4 * p.slot_limit : p.slot_limit) : SLOTS;
     const int hub_cap = p.slot_limit > 0 ? min(kPkHubSlots, 4 * p.slot_limit) : kPkHubSlots;
@@ -448,7 +453,16 @@ select_onepass_packed_kernel(const __grid_constant__ SelectParams2 p, const uint
     } while (0)
 
     const long long t_cta = t_mark;
-    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    for (int64_t round = 0;; ++round) {
+        int64_t chunk;
+        if (HUB) {
+            chunk = blockIdx.x + round * gridDim.x;
+        } else {
+            if (tid == 0) sm.cur_chunk = atomicAdd(p.heavy + 1, 1);       // (workspace word 1: reset with the counters)
+            __syncthreads();
+            chunk = sm.cur_chunk;
+        }
+        if (chunk >= nchunks) break;
         const long long t_chunk = clock64();
         const int64_t i0 = HUB ? (int64_t)p.hub[1 + 2 * chunk] : chunk * per;
         const int len = HUB ? p.hub[2 + 2 * chunk] : (int)min(per, p.bs - i0);
