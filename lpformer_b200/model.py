@@ -10,6 +10,8 @@ inference-only (no autograd through the kernels).
 """
 from __future__ import annotations
 
+import os
+
 import math
 from typing import Optional
 
@@ -332,7 +334,8 @@ class LinkTransformer(nn.Module):
         self._plan_cap = {}
         self.use_plans = True       # one-pass selection + device-side sizes (plan.py)
         self.use_graphs = True      # ... replayed as a CUDA graph
-        self.nz_fused_share = 1.0 / 16   # non-empty links below this share of the batch take the one-warp-per-link path
+        # non-empty links below this share of the batch take the one-warp-per-link path (LPF_NZ_FUSED_SHARE: tuning knob)
+        self.nz_fused_share = float(os.environ.get("LPF_NZ_FUSED_SHARE", 1.0 / 16))
 
     # ------------------------------------------------------------------ graph tables
     def _dev(self):
