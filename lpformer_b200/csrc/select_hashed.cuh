@@ -1,5 +1,5 @@
-// Device code of the run-aware selection kernel (select_packed.cu): the shared-memory hash set of a source
-// adjacency row, the staged source PPR row, and the warp/group walk of one link against them.
+// Device code of the packed-row selection kernel (select_packed.cu): the shared-memory hash set of a source
+// adjacency row, the staged source PPR row, and the CSR fallback for one link.
 #pragma once
 #include "select_walk.cuh"
 
@@ -76,78 +76,15 @@ __device__ __forceinline__ bool smem_ppr_lookup(const RunCtx& h, int32_t u, floa
     }
 }
 
-// One group of G lanes, one link of a hashed run: walks A(b) and P(b) only.
-template <int G, bool WRITE>
-__device__ __forceinline__ void walk_link_hashed(const SelectParams2& p, const RunCtx& h, const LinkRows& r, int64_t i,
-                                                 int lane, int64_t o_cn, int64_t o_1h, int64_t o_n1, int& c_cn,
-                                                 int& c_1h, int& c_n1) {
-    const int gl = lane & (G - 1);
-    const unsigned gmask = group_mask<G>(lane);
-    const unsigned lt = gmask & ((1u << lane) - 1u);
-    const bool want_pi = p.mode != LPF_MODE_CN;
-    const bool want_n1 = p.mode == LPF_MODE_ALL;
-    const bool cn_needs_ppr = WRITE || p.th_cn > 0.0f;
-    const float th_pre = want_n1 ? fminf(p.th_1hop, p.th_non1hop) : p.th_1hop;
-    c_cn = c_1h = c_n1 = 0;
-    for (int k = 0; k < r.nb; k += G) {          // CN = elements of A(b) found in the hash set of A(a)
-        const bool act = k + gl < r.nb;
-        const int32_t u = act ? __ldg(r.Ab + k + gl) : -1;
-        bool hit = act && hash_contains(h.tab, h.mask, h.shift, u);
-        float qa = 0.f, qb = 0.f;
-        if (hit && cn_needs_ppr) {
-            smem_ppr_lookup(h, u, qa);
-            const int t = lower_bound_from(r.Pbc, 0, r.npb, u);
-            if (t < r.npb && __ldg(r.Pbc + t) == u) qb = quantise(__ldg(r.Pbv + t));
-            hit = qa >= p.th_cn && qb >= p.th_cn;
-        }
-        const unsigned m = __ballot_sync(gmask, hit);
-        if (WRITE && hit) {
-            const int64_t s = o_cn + c_cn + __popc(m & lt);
-            p.node[s] = u;
-            p.pa[s] = qa;
-            p.pb[s] = qb;
-        }
-        c_cn += __popc(m);
-    }
-    if (want_pi) {                               // 1-hop / >1-hop = elements of P(b) present in P(a)
-        for (int k = 0; k < r.npb; k += G) {
-            const bool act = k + gl < r.npb;
-            const int32_t u = act ? __ldg(r.Pbc + k + gl) : -1;
-            bool k1 = false, kn = false;
-            float qa = 0.f, qb = 0.f;
-            if (act && smem_ppr_lookup(h, u, qa)) {
-                qb = quantise(__ldg(r.Pbv + k + gl));
-                if (qa >= th_pre && qb >= th_pre) {
-                    const bool in_a = hash_contains(h.tab, h.mask, h.shift, u);
-                    const int t = lower_bound_from(r.Ab, 0, r.nb, u);
-                    const bool in_b = t < r.nb && __ldg(r.Ab + t) == u;
-                    k1 = (in_a != in_b) && qa >= p.th_1hop && qb >= p.th_1hop;
-                    kn = want_n1 && !in_a && !in_b && qa >= p.th_non1hop && qb >= p.th_non1hop;
-                }
-            }
-            const unsigned m1 = __ballot_sync(gmask, k1);
-            const unsigned mn = __ballot_sync(gmask, kn);
-            if (WRITE && (k1 || kn)) {
-                const int64_t s = k1 ? o_1h + c_1h + __popc(m1 & lt) : o_n1 + c_n1 + __popc(mn & lt);
-                p.node[s] = u;
-                p.pa[s] = qa;
-                p.pb[s] = qb;
-            }
-            c_1h += __popc(m1);
-            c_n1 += __popc(mn);
-        }
-    }
-}
-
-// count -> allocate -> write for one link, by one group of G lanes; `h` != NULL selects the hashed walk
+// count -> allocate -> write of one link by a group of G lanes over the CSR tables (the generic walk of
+// select_walk.cuh: the shorter row is walked, the longer searched) — the fallback of the packed kernel for links
+// whose source is not staged in shared memory.
 template <int G>
-__device__ __forceinline__ void onepass_link(const SelectParams2& p, const RunCtx* h, const LinkRows& r, int64_t i,
-                                             int lane) {
+__device__ __forceinline__ void onepass_link(const SelectParams2& p, const LinkRows& r, int64_t i, int lane) {
     const int leader = lane & ~(G - 1);
     const unsigned gmask = group_mask<G>(lane);
     int c_cn, c_1h, c_n1;
-    if (h) walk_link_hashed<G, false>(p, *h, r, i, lane, 0, 0, 0, c_cn, c_1h, c_n1);
-    else walk_link<G, false>(p, r, i, lane, 0, 0, 0, c_cn, c_1h, c_n1);
+    walk_link<G, false>(p, r, i, lane, 0, 0, 0, c_cn, c_1h, c_n1);
     int64_t s_cn = 0, s_1h = 0, s_n1 = 0;
     int ok = 1;
     if (lane == leader) ok = alloc_segments(p, i, c_cn, c_1h, c_n1, s_cn, s_1h, s_n1) ? 1 : 0;
@@ -157,8 +94,7 @@ __device__ __forceinline__ void onepass_link(const SelectParams2& p, const RunCt
     s_cn = __shfl_sync(gmask, s_cn, leader);
     s_1h = __shfl_sync(gmask, s_1h, leader);
     s_n1 = __shfl_sync(gmask, s_n1, leader);
-    if (h) walk_link_hashed<G, true>(p, *h, r, i, lane, s_cn, p.cap + s_1h, 2 * p.cap + s_n1, c_cn, c_1h, c_n1);
-    else walk_link<G, true>(p, r, i, lane, s_cn, p.cap + s_1h, 2 * p.cap + s_n1, c_cn, c_1h, c_n1);
+    walk_link<G, true>(p, r, i, lane, s_cn, p.cap + s_1h, 2 * p.cap + s_n1, c_cn, c_1h, c_n1);
 }
 
 }  // namespace lpf

@@ -12,17 +12,23 @@
 // screened without the row's header.
 //
 // Work shape (citation2-style evaluation: runs of links sharing their source, reference train/testing.py:20-23):
-// a CTA takes 512 consecutive links = at most kPkMaxRuns runs of equal source.  The sources' adjacency rows become
-// bucketed hash sets in shared memory and their PPR rows small shared-memory tables (all runs of the chunk side by
-// side).  The chunk's target rows are then flattened into 64-byte UNITS; FOUR LANES take one unit (one coalesced
-// 64-byte read), every unit of every link is independent of every other, and each lane keeps four reads in flight:
-// that, not the arithmetic, is what the kernel is built around — it is bound by DRAM latency x bytes in flight.
+// the batch is cut evenly over one resident wave of CTAs (296 x 512 threads on a B200); a CTA's piece is at most
+// 1,024 consecutive links = at most kPkMaxRuns runs of equal source.  The sources' adjacency rows become bucketed
+// hash sets in shared memory and their PPR rows small shared-memory tables (all runs of the piece side by side).
+// The piece's target rows are then flattened into 64-byte UNITS; FOUR LANES take one unit (one coalesced 64-byte
+// read), every unit of every link is independent of every other, and each lane keeps four reads in flight.
 // A unit only answers "does this link select anything?" (a common neighbour, or a node in both PPR rows above the
 // smaller PPR threshold); 99 % of a citation2-shaped batch selects nothing and is finished there.  The links that
-// do, and target rows beyond kPkMaxUnits, are resolved by a warp each (count -> allocate -> ordered write, from the
-// CSR tables); hub sources that do not fit the hash go to a second launch with a 32K-slot table; chunks that are
-// not run-shaped take the generic group walk of select_walk.cuh.  Selected sets, their order inside a link and the
-// fp32 values are those of every other K1 variant (tests compare all of them with the oracle).
+// do are resolved — count -> allocate -> ordered write — from their packed row against the staged source: by a
+// warp each (phase B; the four header atomics of a link issued by four lanes at once), by the whole CTA for long
+// target rows (phase C: one block-wide scan per 2,048 slots, the hits kept in registers across the allocation).
+// Runs whose source does not fit next to the others of its piece go to a second launch of the same kernel with a
+// 32K-slot table (in pieces of 256 links); sources beyond even that are searched in global memory and resolved over
+// the CSR tables; pieces that are not run-shaped take the generic group walk of select_walk.cuh.  Selected sets,
+// their order inside a link and the fp32 values are those of every other K1 variant (tests compare all of them
+// with the oracle).  Measured (tools/select_clocks.py): a piece is a ~45 us chain of dependent phases of which only
+// the screening (~18 us, ~3 TB/s of random 64-byte reads) is bandwidth-like; the launch lasts as long as its slowest
+// piece (~100 us: a hub source selects something with every tenth target).
 #include <stdlib.h>
 
 #include "select_hashed.cuh"
@@ -129,7 +135,7 @@ __device__ __noinline__ void generic_link8(const SelectParams2& p, int64_t i, in
         if ((lane & 7) == 0) p.heavy[4 + atomicAdd(p.heavy, 1)] = (int32_t)i;
         return;
     }
-    onepass_link<8>(p, nullptr, r, i, lane);
+    onepass_link<8>(p, r, i, lane);
 }
 // What slot s of a PACKED target row contributes against the staged source: a PPR entry is a candidate 1-hop /
 // >1-hop node (k1 / kn, node u, values qa, qb), a pair of neighbour ids up to two common neighbours (h0, h1 with
@@ -203,7 +209,7 @@ __device__ __forceinline__ void write_hits(const SelectParams2& p, const SlotHit
 // A group of G lanes (8 for the usual short row, a whole warp for rows of hundreds of ids) walks one link's PACKED
 // target row (L2-hot: the screening just read it) against the staged source: lane l of the group takes slot l,
 // l + G, ... so ascending node order within each set is lane order, and the ordered write needs only ballots.
-// Same sets, order and values as walk_link_hashed.
+// Same sets, order and values as the generic walk (select_walk.cuh).
 template <int G, bool WRITE>
 __device__ __forceinline__ void walk_packed_group(const SelectParams2& p, const RunCtx& h, const uint4* __restrict__ row,
                                                   int lane, int64_t o_cn, int64_t o_1h, int64_t o_n1, int& c_cn, int& c_1h,
@@ -405,13 +411,11 @@ __device__ __forceinline__ void resolve_packed_cta(const SelectParams2& p, const
 __device__ __noinline__ void resolve_unstaged32(const SelectParams2& p, int64_t i, int lane) {
     const LinkRows rows = load_rows(p, i);
     if (!is_heavy(rows, p.mode != LPF_MODE_CN, 8)) {
-        onepass_link<32>(p, nullptr, rows, i, lane);
+        onepass_link<32>(p, rows, i, lane);
     } else if (lane == 0) {
         p.heavy[4 + atomicAdd(p.heavy, 1)] = (int32_t)i;
     }
 }
-
-__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 
 template <class SM>
 __device__ __forceinline__ int run_of(const SM& sm, int t) {
