@@ -81,6 +81,7 @@ struct PkSmemT {
     uint16_t q_cta[kPkChunk];             // chunk positions of the links the whole CTA walks (long target rows that select)
     uint32_t scan_tot[2 * 4 * (kPkThreads / 32)];
     int64_t cta_seg[3];
+    uint2 cta_ppr[kPkMaxPprRow];         // PPR slots of the row the whole CTA is walking
     int dbg_ph[16];                      // profiling: this chunk's cycles per phase
 };
 
@@ -148,7 +149,8 @@ struct SlotHit {
 template <bool WRITE>
 __device__ __forceinline__ SlotHit eval_slot(const SelectParams2& p, const RunCtx& h, const int32_t* __restrict__ words,
                                              const int32_t* __restrict__ ids, int deg, int npp, uint2 slot,
-                                             bool want_n1, float th_pre) {
+                                             bool want_pi, bool want_n1, float th_pre,
+                                             const uint2* ppr_sm = nullptr) {
     const bool cn_needs_ppr = WRITE || p.th_cn > 0.0f;
     SlotHit r;
     r.k1 = r.kn = r.h0 = r.h1 = false;
@@ -158,7 +160,7 @@ __device__ __forceinline__ SlotHit eval_slot(const SelectParams2& p, const RunCt
     r.u = (int32_t)w0;
     if (w0 & kPkPprTag) {
         r.u = (int32_t)(w0 & ~kPkPprTag);
-        if (smem_ppr_lookup(h, r.u, r.qa)) {
+        if (want_pi && smem_ppr_lookup(h, r.u, r.qa)) {
             r.qb = quantise(__uint_as_float(w1));
             if (r.qa >= th_pre && r.qb >= th_pre) {
                 const bool in_a = hash_contains(h.tab, h.mask, h.shift, r.u);
@@ -173,8 +175,16 @@ __device__ __forceinline__ SlotHit eval_slot(const SelectParams2& p, const RunCt
         r.h1 = hash_contains(h.tab, h.mask, h.shift, (int32_t)w1);
         if (cn_needs_ppr && (r.h0 || r.h1)) {
             // PPR values of a common neighbour: P(a) from shared memory, P(b) by search over the row's PPR slots
+            // (ppr_sm: the row's PPR slots staged in shared memory by the CTA-wide walk, else the row in global memory)
             auto pb_of = [&](int32_t x) -> float {
                 int lo = 0, hi = npp;
+                if (ppr_sm) {
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if ((int32_t)(ppr_sm[mid].x & 0x7fffffffu) < x) lo = mid + 1; else hi = mid;
+                    }
+                    return (lo < npp && (int32_t)(ppr_sm[lo].x & 0x7fffffffu) == x) ? quantise(__uint_as_float(ppr_sm[lo].y)) : 0.f;
+                }
                 while (lo < hi) {
                     const int mid = (lo + hi) >> 1;
                     if ((__ldg(words + 2 * mid) & 0x7fffffff) < x) lo = mid + 1; else hi = mid;
@@ -195,9 +205,10 @@ __device__ __forceinline__ SlotHit eval_slot(const SelectParams2& p, const RunCt
     }
     return r;
 }
-// slot s of a packed row (padding beyond the row, and for the PPR slots when they are not wanted)
-__device__ __forceinline__ uint2 load_slot(const int32_t* __restrict__ words, int npp, int s, int S, bool want_pi) {
-    if (s < S && (want_pi || s >= npp)) return __ldg(reinterpret_cast<const uint2*>(words) + s);
+// slot s of a packed row (padding beyond the row; S may be the upper bound the locator gives: the row's own padding
+// evaluates to nothing)
+__device__ __forceinline__ uint2 load_slot(const int32_t* __restrict__ words, int s, int S) {
+    if (s < S) return __ldg(reinterpret_cast<const uint2*>(words) + s);
     return make_uint2(kPkPad, kPkPad);
 }
 __device__ __forceinline__ void write_hits(const SelectParams2& p, const SlotHit& r, int64_t r_pi, int64_t r_cn) {
@@ -212,23 +223,25 @@ __device__ __forceinline__ void write_hits(const SelectParams2& p, const SlotHit
 // Same sets, order and values as the generic walk (select_walk.cuh).
 template <int G, bool WRITE>
 __device__ __forceinline__ void walk_packed_group(const SelectParams2& p, const RunCtx& h, const uint4* __restrict__ row,
-                                                  int lane, int64_t o_cn, int64_t o_1h, int64_t o_n1, int& c_cn, int& c_1h,
-                                                  int& c_n1) {
+                                                  int units, int lane, int64_t o_cn, int64_t o_1h, int64_t o_n1, int& c_cn,
+                                                  int& c_1h, int& c_n1) {
     constexpr unsigned GM = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
     const unsigned gmask = group_mask<G>(lane);
     const int gsh = lane & ~(G - 1), gl = lane & (G - 1);
+    // the header is read now but only NEEDED where something is found (and for the length of a row whose locator
+    // saturates): the slots are fetched without waiting for it — `units` (from the locator) bounds the row
     const uint4 hd = ldg16(row);
     const int deg = (int)hd.x, npp = (int)hd.y;
     const int32_t* words = reinterpret_cast<const int32_t*>(row) + 4;
     const int32_t* ids = words + 2 * npp;
-    const int S = npp + ((deg + 1) >> 1);
+    const int S = (units > 0 && units < 63) ? units * 8 - 2 : npp + ((deg + 1) >> 1);
     const unsigned lt = (1u << gl) - 1u;
     const bool want_pi = p.mode != LPF_MODE_CN;
     const bool want_n1 = p.mode == LPF_MODE_ALL;
     const float th_pre = want_n1 ? fminf(p.th_1hop, p.th_non1hop) : p.th_1hop;
     c_cn = c_1h = c_n1 = 0;
-    for (int s0 = want_pi ? 0 : (npp & ~(G - 1)); s0 < S; s0 += G) {
-        const SlotHit r = eval_slot<WRITE>(p, h, words, ids, deg, npp, load_slot(words, npp, s0 + gl, S, want_pi), want_n1, th_pre);
+    for (int s0 = 0; s0 < S; s0 += G) {
+        const SlotHit r = eval_slot<WRITE>(p, h, words, ids, deg, npp, load_slot(words, s0 + gl, S), want_pi, want_n1, th_pre);
         const unsigned m1 = (__ballot_sync(gmask, r.k1) >> gsh) & GM, mn = (__ballot_sync(gmask, r.kn) >> gsh) & GM;
         const unsigned mh0 = (__ballot_sync(gmask, r.h0) >> gsh) & GM, mh1 = (__ballot_sync(gmask, r.h1) >> gsh) & GM;
         if (WRITE)
@@ -243,11 +256,34 @@ __device__ __forceinline__ void walk_packed_group(const SelectParams2& p, const 
 // count -> allocate -> ordered write of one link of a staged source by a group of G lanes
 template <int G>
 __device__ __forceinline__ void resolve_packed_group(const SelectParams2& p, const RunCtx& h, const uint4* __restrict__ row,
-                                                     int64_t i, int lane) {
+                                                     int units, int64_t i, int lane) {
     const unsigned gmask = group_mask<G>(lane);
     const int leader = lane & ~(G - 1);
     int c_cn, c_1h, c_n1;
-    walk_packed_group<G, false>(p, h, row, lane, 0, 0, 0, c_cn, c_1h, c_n1);
+    if constexpr (G == 32) {
+        if (units > 0 && units <= 4) {
+            // a row of at most 30 slots is ONE step of the warp: the hits stay in registers across the allocation
+            const uint4 hd = ldg16(row);
+            const int deg = (int)hd.x, npp = (int)hd.y;
+            const int32_t* words = reinterpret_cast<const int32_t*>(row) + 4;
+            const bool want_pi = p.mode != LPF_MODE_CN;
+            const bool want_n1 = p.mode == LPF_MODE_ALL;
+            const float th_pre = want_n1 ? fminf(p.th_1hop, p.th_non1hop) : p.th_1hop;
+            const SlotHit r = eval_slot<true>(p, h, words, words + 2 * npp, deg, npp, load_slot(words, lane, units * 8 - 2),
+                                              want_pi, want_n1, th_pre);
+            const unsigned lt = (1u << lane) - 1u;
+            const unsigned m1 = __ballot_sync(kFull, r.k1), mn = __ballot_sync(kFull, r.kn);
+            const unsigned mh0 = __ballot_sync(kFull, r.h0), mh1 = __ballot_sync(kFull, r.h1);
+            c_cn = __popc(mh0) + __popc(mh1); c_1h = __popc(m1); c_n1 = __popc(mn);
+            int64_t s_cn, s_1h, s_n1;
+            const bool ok = alloc_segments_warp(p, i, c_cn, c_1h, c_n1, lane, s_cn, s_1h, s_n1);
+            if (c_cn + c_1h + c_n1 == 0 || !ok) return;
+            write_hits(p, r, r.k1 ? p.cap + s_1h + __popc(m1 & lt) : 2 * p.cap + s_n1 + __popc(mn & lt),
+                       s_cn + __popc(mh0 & lt) + __popc(mh1 & lt));
+            return;
+        }
+    }
+    walk_packed_group<G, false>(p, h, row, units, lane, 0, 0, 0, c_cn, c_1h, c_n1);
     int64_t s_cn = 0, s_1h = 0, s_n1 = 0;
     if constexpr (G == 32) {
         const bool ok = alloc_segments_warp(p, i, c_cn, c_1h, c_n1, lane, s_cn, s_1h, s_n1);
@@ -262,7 +298,7 @@ __device__ __forceinline__ void resolve_packed_group(const SelectParams2& p, con
         s_1h = __shfl_sync(gmask, s_1h, leader);
         s_n1 = __shfl_sync(gmask, s_n1, leader);
     }
-    walk_packed_group<G, true>(p, h, row, lane, s_cn, p.cap + s_1h, 2 * p.cap + s_n1, c_cn, c_1h, c_n1);
+    walk_packed_group<G, true>(p, h, row, units, lane, s_cn, p.cap + s_1h, 2 * p.cap + s_n1, c_cn, c_1h, c_n1);
 }
 
 // The whole CTA walks one link's packed target row (a hub target: thousands of slots): per step thread t takes the
@@ -289,13 +325,13 @@ __device__ __forceinline__ void walk_packed_cta(const SelectParams2& p, const Ru
     for (int s0 = 0; s0 < S; s0 += U * kPkThreads, par ^= 1) {
         uint2 slot[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) slot[u] = load_slot(words, npp, s0 + u * kPkThreads + tid, S, want_pi);
+        for (int u = 0; u < U; ++u) slot[u] = load_slot(words, s0 + u * kPkThreads + tid, S);
         SlotHit r[U];
         uint32_t mine[U], inc[U];
         uint32_t* tt = tot + par * (U * NW);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            r[u] = eval_slot<WRITE>(p, h, words, ids, deg, npp, slot[u], want_n1, th_pre);
+            r[u] = eval_slot<WRITE>(p, h, words, ids, deg, npp, slot[u], want_pi, want_n1, th_pre);
             mine[u] = (uint32_t)((r[u].h0 ? 1 : 0) + (r[u].h1 ? 1 : 0)) | (r[u].k1 ? 1u << 12 : 0u) | (r[u].kn ? 1u << 22 : 0u);
             inc[u] = mine[u];
 #pragma unroll
@@ -329,12 +365,14 @@ __device__ __forceinline__ void walk_packed_cta(const SelectParams2& p, const Ru
 // is ONE step of the walk: the hits stay in registers while thread 0 allocates, and are written without a second
 // walk; longer rows are walked twice.  `seg` = 3 x int64 and `ok` in shared memory.
 __device__ __forceinline__ void resolve_packed_cta(const SelectParams2& p, const RunCtx& h, const uint4* __restrict__ row,
-                                                   uint32_t* tot, int64_t* seg, int* ok, int64_t i) {
+                                                   int units, uint2* ppr_sm, uint32_t* tot, int64_t* seg, int* ok, int64_t i) {
     constexpr int U = kPkCtaUnroll, NW = kPkThreads / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // (the header is needed for the row's length only when the locator saturates: the slots of a shorter row are
+    // fetched without waiting for it)
     const uint4 hd = ldg16(row);
     const int deg = (int)hd.x, npp = (int)hd.y;
-    const int S = npp + ((deg + 1) >> 1);
+    const int S = (units > 0 && units < 63) ? units * 8 - 2 : npp + ((deg + 1) >> 1);
     int c_cn, c_1h, c_n1;
     if (S <= U * kPkThreads) {
         const int32_t* words = reinterpret_cast<const int32_t*>(row) + 4;
@@ -344,12 +382,17 @@ __device__ __forceinline__ void resolve_packed_cta(const SelectParams2& p, const
         const float th_pre = want_n1 ? fminf(p.th_1hop, p.th_non1hop) : p.th_1hop;
         uint2 slot[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) slot[u] = load_slot(words, npp, u * kPkThreads + tid, S, want_pi);
+        for (int u = 0; u < U; ++u) slot[u] = load_slot(words, u * kPkThreads + tid, S);
+        // the row's PPR slots (the first npp) into shared memory: a common neighbour's P(b) is then a search there
+        // instead of a chain of dependent global reads
+        const bool staged = npp <= kPkMaxPprRow;
+        if (staged && tid < npp) ppr_sm[tid] = slot[0];
+        __syncthreads();
         SlotHit r[U];
         uint32_t mine[U], inc[U], before[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            r[u] = eval_slot<true>(p, h, words, ids, deg, npp, slot[u], want_n1, th_pre);
+            r[u] = eval_slot<true>(p, h, words, ids, deg, npp, slot[u], want_pi, want_n1, th_pre, staged ? ppr_sm : nullptr);
             mine[u] = (uint32_t)((r[u].h0 ? 1 : 0) + (r[u].h1 ? 1 : 0)) | (r[u].k1 ? 1u << 12 : 0u) | (r[u].kn ? 1u << 22 : 0u);
             inc[u] = mine[u];
 #pragma unroll
@@ -709,7 +752,7 @@ select_onepass_packed_kernel(const __grid_constant__ SelectParams2 p, const uint
         for (int q = warp; q < ns; q += kPkThreads / 32) {
             const int t = sm.q_slow[q];
             const int r = run_of(sm, t);
-            if (sm.r_hashed[r] == 1) resolve_packed_group<32>(p, make_ctx(sm, r), row_of(blob, sm.l_loc[t]), i0 + t, lane);
+            if (sm.r_hashed[r] == 1) resolve_packed_group<32>(p, make_ctx(sm, r), row_of(blob, sm.l_loc[t]), (int)(sm.l_loc[t] & 63u), i0 + t, lane);
             else if (sm.r_hashed[r] == 2) resolve_unstaged32(p, i0 + t, lane);       // (searched in global memory: rare)
         }
         if (p.dbg && tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 6), (unsigned long long)ns);
@@ -725,7 +768,8 @@ select_onepass_packed_kernel(const __grid_constant__ SelectParams2 p, const uint
                 if (warp == 0) resolve_unstaged32(p, i0 + t, lane);
                 continue;
             }
-            resolve_packed_cta(p, make_ctx(sm, r), row_of(blob, sm.l_loc[t]), sm.scan_tot, sm.cta_seg, &sm.cta_ok, i0 + t);
+            resolve_packed_cta(p, make_ctx(sm, r), row_of(blob, sm.l_loc[t]), (int)(sm.l_loc[t] & 63u), sm.cta_ppr, sm.scan_tot,
+                               sm.cta_seg, &sm.cta_ok, i0 + t);
         }
         if (p.dbg && tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 7), (unsigned long long)nc);
         LPF_PHASE(3);
