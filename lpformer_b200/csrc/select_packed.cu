@@ -77,7 +77,8 @@ struct PkSmemT {
     uint32_t r_loc[kPkMaxRuns];
     int32_t r_slots[kPkMaxRuns];
     int4 r_ctx[kPkMaxRuns];              // (first table slot, bucket mask, 32 - log2(buckets), 0): one read per unit
-    int n_runs, n_slow, n_items, tab_used, items_full, n_cta, cta_ok, cur_chunk;
+    int n_runs, n_slow, n_items, tab_used, items_full, n_cta, cta_ok, cur_chunk, n_mid, b_next;
+    uint16_t q_mid[kPkChunk];             // ... of the links a warp resolves whose target row has more than four units
     uint16_t q_cta[kPkChunk];             // chunk positions of the links the whole CTA walks (long target rows that select)
     uint32_t scan_tot[2 * 4 * (kPkThreads / 32)];
     int64_t cta_seg[3];
@@ -517,7 +518,7 @@ select_onepass_packed_kernel(const __grid_constant__ SelectParams2 p, const uint
             atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 5), 1ull);
             for (int k = 0; k < 16; ++k) sm.dbg_ph[k] = 0;
         }
-        if (tid == 0) { sm.n_runs = 0; sm.n_slow = 0; sm.n_items = 0; sm.items_full = 0; sm.n_cta = 0; }
+        if (tid == 0) { sm.n_runs = 0; sm.n_slow = 0; sm.n_items = 0; sm.items_full = 0; sm.n_cta = 0; sm.n_mid = 0; sm.b_next = 0; }
         __syncthreads();
         // ---- the chunk's links (positions tid, tid + 512): locator of the target (an L2-resident array), run
         // boundaries with the locator of their source
@@ -734,6 +735,7 @@ select_onepass_packed_kernel(const __grid_constant__ SelectParams2 p, const uint
             if (sm.l_any[t]) {
                 // a long target row that selects something: the whole CTA walks it
                 if ((int)(sm.l_loc[t] & 63u) > kPkWarpUnits) sm.q_cta[atomicAdd(&sm.n_cta, 1)] = (uint16_t)t;
+                else if ((int)(sm.l_loc[t] & 63u) > 4) sm.q_mid[atomicAdd(&sm.n_mid, 1)] = (uint16_t)t;
                 else sm.q_slow[atomicAdd(&sm.n_slow, 1)] = (uint16_t)t;
             }
         __syncthreads();
@@ -748,9 +750,15 @@ select_onepass_packed_kernel(const __grid_constant__ SelectParams2 p, const uint
         // ---- phase B: the links that select something (count -> allocate -> ordered write), one warp per link against
         // the staged source (a handful per chunk: the runs of hub sources, which select something with every tenth
         // target, were cut into pieces for the hub launch)
-        const int ns = sm.n_slow;
-        for (int q = warp; q < ns; q += kPkThreads / 32) {
-            const int t = sm.q_slow[q];
+        // The warps take the next link from a counter, the longer rows (5 .. 32 units: up to eight steps of the warp,
+        // twice) first: a fixed round robin left the warp that drew two of them working long after the others.
+        const int nm = sm.n_mid, ns = nm + sm.n_slow;
+        for (;;) {
+            int q = 0;
+            if (lane == 0) q = atomicAdd(&sm.b_next, 1);
+            q = __shfl_sync(kFull, q, 0);
+            if (q >= ns) break;
+            const int t = q < nm ? sm.q_mid[q] : sm.q_slow[q - nm];
             const int r = run_of(sm, t);
             if (sm.r_hashed[r] == 1) resolve_packed_group<32>(p, make_ctx(sm, r), row_of(blob, sm.l_loc[t]), (int)(sm.l_loc[t] & 63u), i0 + t, lane);
             else if (sm.r_hashed[r] == 2) resolve_unstaged32(p, i0 + t, lane);       // (searched in global memory: rare)
