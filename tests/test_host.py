@@ -124,3 +124,22 @@ def test_synthetic_graph_and_queries(lib):
     small_ppr = O.ppr_push(small.indptr, small.indices, 0.15, 1e-4)
     rp, c, v = S.ppr_push(small.indptr, small.indices, 0.15, 1e-4)
     assert np.array_equal(c, small_ppr.indices) and np.array_equal(v.view(np.uint32), small_ppr.val.view(np.uint32))
+
+
+def test_ppr_gpu_entry_points_have_no_cpu_fallback():
+    """lpformer_b200.ppr (GPU PPR precompute): CPU tensors are refused, and the table-size helper follows
+    2 (1 + 1 / (alpha eps)) rounded up to a power of two."""
+    import torch
+    from lpformer_b200 import _lib, ppr
+    lib = _lib.load()
+    assert lib.lpf_ppr_push_slots(0.15, 2.5e-3) == 8192          # 2 * (1 + 2666.7) = 5335.3 -> 8192
+    assert lib.lpf_ppr_push_slots(0.15, 5e-5) == 1 << 19         # 2 * (1 + 133333.3) = 266668.7 -> 524288
+    assert lib.lpf_ppr_push_slots(0.15, 1e-9) == -1              # beyond 2^24 keys: host tool
+    assert lib.lpf_ppr_push_slots(1.5, 1e-3) == -1
+    assert lib.lpf_ppr_push_scratch_bytes(8192, 8) >= 8192 * 8 * 32
+    indptr = torch.tensor([0, 1, 2], dtype=torch.int64)
+    indices = torch.tensor([1, 0], dtype=torch.int32)
+    with pytest.raises(_lib.LpfError):
+        ppr.ppr_push(indptr, indices, 0.15, 1e-3)
+    ip, ix = ppr.csr_from_edge_index(torch.tensor([[1, 0, 1, 2], [0, 1, 0, 1]]), 3)       # a duplicate, unsorted
+    assert ip.tolist() == [0, 1, 2, 3] and ix.tolist() == [1, 0, 1]
