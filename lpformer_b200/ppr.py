@@ -41,9 +41,15 @@ def ppr_push(indptr: torch.Tensor, indices: torch.Tensor, alpha: float = 0.15, e
     n = indptr.numel() - 1
     indptr = indptr.to(torch.int64).contiguous()
     indices = indices.to(torch.int32).contiguous()
+    # worst-case keys per source: 1 + 1 / (alpha eps) (lpf_ppr_push_slots), and never more than the n nodes there are
+    slots_n = 64
+    while slots_n < 2 * (n + 1):
+        slots_n <<= 1
     slots_max = lib.lpf_ppr_push_slots(float(alpha), float(eps))
-    if slots_max < 0:
-        raise _lib.LpfError(f"eps = {eps} needs more than 2^24 hash slots per source: use the host tool for this table")
+    slots_max = slots_n if slots_max < 0 else min(slots_max, slots_n)
+    if slots_max > (1 << 25):
+        raise _lib.LpfError(f"eps = {eps} on {n} nodes needs more than 2^25 hash slots per source: use the host tool "
+                            "(lpformer_b200.synthetic.ppr_push) for this table")
 
     def warps_for(slots):
         w = 148 * 16 if nwarps is None else int(nwarps)

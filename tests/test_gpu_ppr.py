@@ -74,3 +74,18 @@ def test_ppr_push_feeds_the_selection():
     a, b = m_host._select(links, False), m_dev._select(links, False)
     assert torch.equal(a.ptr, b.ptr) and torch.equal(a.node, b.node)
     assert torch.equal(a.src_ppr, b.src_ppr) and torch.equal(a.tgt_ppr, b.tgt_ppr)
+
+
+def test_ppr_push_bit_exact_vs_reference_numba_golden(golden):
+    """Directly against the table the reference's own numba kernel produced for the golden graphs
+    (tests/golden/make_golden.py ran util/calc_ppr_scores.py:137-192): same pattern, same fp32 bits."""
+    from lpformer_b200 import ppr
+    if golden.cfg["eps"] < 1e-6:
+        pytest.skip("eps = 1e-7 (Cora script): ~1e6 pushes per source, a serial chain per warp — the host tool's case")
+    adj, _, want = golden.oracle_graph()
+    dev = torch.device("cuda:0")
+    got = ppr.ppr_push(torch.from_numpy(adj.indptr.astype(np.int64)).to(dev),
+                       torch.from_numpy(adj.indices.astype(np.int32)).to(dev), golden.cfg["alpha"], golden.cfg["eps"])
+    assert np.array_equal(got.rowptr.cpu().numpy(), want.indptr)
+    assert np.array_equal(got.col.cpu().numpy(), want.indices)
+    assert np.array_equal(got.val.cpu().numpy().view(np.uint32), want.val.view(np.uint32))
