@@ -93,3 +93,50 @@ def test_ref_port_scores(golden):
     prob, _ = R.score_links(torch.from_numpy(g["links"]), torch.from_numpy(g["X_node"]), A, Pm, P, S, g.cfg,
                             g.cfg["mask"])
     np.testing.assert_allclose(prob.numpy(), g["prob"], rtol=1e-4, atol=1e-6)
+
+
+# --------------------------------------------------------------------------- #
+# The two restatements against each other beyond the seven goldens: the set semantics of
+# oracle/lpformer_oracle.py and the reference's sparse-COO algebra as ported in
+# oracle/ref_port.py (models/link_transformer.py:214-319, 434-481) are independent derivations; on random
+# graphs, PPR tables and thresholds they must select the same (link, node, q(src), q(tgt)) triples.
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("seed,n,m,th", [(0, 40, 120, (0.0, 1e-2, 1e-2)), (1, 60, 90, (0.0, 1e-3, 1e-1)),
+                                         (2, 25, 200, (1e-2, 1e-2, 1.0)), (3, 80, 60, (0.0, 5e-2, 5e-2)),
+                                         (4, 30, 30, (0.0, 1e-4, 1e-3))])
+def test_restatements_agree_on_random_inputs(seed, n, m, th):
+    import torch
+    from oracle import ref_port as R
+    rng = np.random.default_rng(seed)
+    e = rng.integers(0, n, (2, m))
+    e = e[:, e[0] != e[1]]
+    e = np.unique(np.concatenate([e, e[::-1]], 1), axis=1)              # symmetric, simple; some nodes stay isolated
+    order = np.lexsort((e[1], e[0]))
+    e = e[:, order]
+    indptr = np.zeros(n + 1, np.int64)
+    np.add.at(indptr, e[0] + 1, 1)
+    indptr = np.cumsum(indptr)
+    adj = O.CSR(indptr, e[1].astype(np.int64), None, n)
+    ppr = O.ppr_push(adj.indptr, adj.indices, 0.15, 1e-3)
+    # links: in-graph positives, random pairs, self pairs, a duplicate, an isolated endpoint if there is one
+    deg = np.diff(indptr)
+    iso = np.nonzero(deg == 0)[0]
+    links = np.concatenate([e[:, rng.integers(0, e.shape[1], 25)], rng.integers(0, n, (2, 40)),
+                            np.tile(rng.integers(0, n, 3), (2, 1))], 1)
+    links = np.concatenate([links, links[:, :2]], 1)
+    if len(iso):
+        links = np.concatenate([links, np.array([[iso[0]], [int(np.argmax(deg))]])], 1)
+    links = links.astype(np.int64)
+    mode, sets = O.select_sets(adj, ppr, links, *th)
+    A = R.coo_from_csr(adj.indptr, adj.indices, None, n)
+    Pm = R.coo_from_csr(ppr.indptr, ppr.indices, ppr.val, n)
+    got = R.select_pairs(A, Pm, torch.from_numpy(links), *th, mode)
+    assert set(got) == set(sets)
+    total = 0
+    for t, (li, nd, qa, qb) in sets.items():
+        ix, src, tgt = got[t]
+        assert np.array_equal(ix[0].numpy(), li) and np.array_equal(ix[1].numpy(), nd), (t, seed)
+        assert np.array_equal(src.numpy().view(np.uint32), qa.view(np.uint32)), (t, seed)
+        assert np.array_equal(tgt.numpy().view(np.uint32), qb.view(np.uint32)), (t, seed)
+        total += len(li)
+    assert total > 0          # the case selects something
