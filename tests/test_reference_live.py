@@ -111,3 +111,41 @@ def test_oracle_matches_live_reference(reference, seed, n, m, feat, cfg):
     np.testing.assert_allclose(feats[:, dd:], pw.numpy(), rtol=1e-4, atol=2e-5)
     _, oprob = O.mlp_score(feats, Sd)
     np.testing.assert_allclose(oprob, prob.numpy(), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("seed,n,m,feat,cfg", CASES[:2])
+def test_ref_port_matches_live_reference(reference, seed, n, m, feat, cfg):
+    """oracle/ref_port.py — the port bench.py times as the CPU baseline — gives the live reference's scores."""
+    from oracle import lpformer_oracle as O, ref_port as R
+    LinkTransformer, mlp_score = reference
+    rng = np.random.default_rng(seed + 100)
+    torch.manual_seed(seed + 100)
+    e = rng.integers(0, n, (2, m))
+    e = e[:, e[0] != e[1]]
+    e = np.unique(np.concatenate([e, e[::-1]], 1), axis=1)
+    e = e[:, np.lexsort((e[1], e[0]))]
+    indptr = np.zeros(n + 1, np.int64)
+    np.add.at(indptr, e[0] + 1, 1)
+    indptr = np.cumsum(indptr)
+    ppr = O.ppr_push(indptr, e[1].astype(np.int64), 0.15, 2e-3)
+    prow = np.repeat(np.arange(n), np.diff(ppr.indptr))
+    ei = torch.from_numpy(e.astype(np.int64))
+    adj_t = torch.sparse_coo_tensor(ei, torch.ones(ei.shape[1]), (n, n)).coalesce()
+    adj_mask = adj_t.bool().int()
+    ppr_t = torch.sparse_coo_tensor(torch.from_numpy(np.stack([prow, ppr.indices])), torch.from_numpy(ppr.val), (n, n)).coalesce()
+    data = {"x": torch.randn(n, feat), "adj_t": adj_t, "adj_mask": adj_mask, "ppr": ppr_t, "full_adj_t": adj_t,
+            "full_adj_mask": adj_mask, "ppr_test": ppr_t}
+    model = LinkTransformer(dict(cfg), data, device="cpu").eval()
+    score = mlp_score(model.out_dim, model.out_dim, 1, 2).eval()
+    links = torch.from_numpy(np.concatenate([e[:, rng.integers(0, e.shape[1], 50)], rng.integers(0, n, (2, 80))], 1).astype(np.int64))
+    with torch.no_grad():
+        X = model.propagate()
+        el = model.elementwise_lin(X[links[0]] * X[links[1]])
+        pw, _ = model.calc_pairwise(links, X, test_set=False)
+        want = score(torch.cat((el, pw), dim=-1))
+    A = R.coo_from_csr(indptr, e[1].astype(np.int64), None, n)
+    Pm = R.coo_from_csr(ppr.indptr, ppr.indices, ppr.val, n)
+    P = {k: v.detach() for k, v in model.state_dict().items()}
+    Sd = {k: v.detach() for k, v in score.state_dict().items()}
+    got, _ = R.score_links(links, X, A, Pm, P, Sd, dict(cfg, mask=model.mask), model.mask)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-4, atol=1e-6)
