@@ -338,8 +338,8 @@ def run_b200(args):
         if sel_ms[3] and "lpf_select_onepass_packed" in summ:
             # the selection entry point is three kernels: time them separately (events recorded inside the launcher)
             c, t = summ.pop("lpf_select_onepass_packed")
-            summ["lpf_select_onepass_packed/screen (select_onepass_packed_kernel<16384,0>)"] = (sel_ms[3], sel_ms[0])
-            summ["lpf_select_onepass_packed/hub sources (select_onepass_packed_kernel<32768,1>)"] = (sel_ms[3], sel_ms[1])
+            summ["lpf_select_onepass_packed/screen (select_screen_packed_kernel)"] = (sel_ms[3], sel_ms[0])
+            summ["lpf_select_onepass_packed/resolve (select_resolve_packed_kernel)"] = (sel_ms[3], sel_ms[1])
             summ["lpf_select_onepass_packed/deferred links (select_heavy_onepass_kernel)"] = (sel_ms[3], sel_ms[2])
             summ["lpf_select_onepass_packed/launch gaps + resets"] = (c, max(0.0, t - sum(sel_ms[:3])))
         if nz_ms[2] and "lpf_nz_links_fused" in summ:

@@ -126,33 +126,38 @@ int lpf_select_onepass(const int64_t* links, int64_t bs,
  * Packed link rows: the HBM layout of the per-link walk.  The reference slices rows a and b out of two N x N
  * sparse COO tensors with four index_select calls per batch (models/link_transformer.py:229-230, :290-291,
  * :444-449); the CSR tables above already make that a direct row access, but a link's target still costs four
- * dependent random reads in four arrays.  lpf_pack_link_rows rewrites (adjacency CSR, PPR CSR) once per graph as
- *   locator uint32 [n] : (first 64-byte unit of the node's row) << 6 | min(units, 63) — 4 B per node, L2-resident
- *   row_blob           : per node a 64-byte-aligned row of `units` x 64 B: a header (deg, nP, 0, 0), then 8-byte
- *                        slots — the nP PPR entries as (column | 0x80000000, value bits) in ascending column order,
- *                        then the ascending neighbour ids two per slot — padded with 0x7fffffff
- * so that a target is one DRAM round trip (the locator says where every 16-byte chunk of the row lies) and a
- * chunk can be interpreted without the row's header.
- * row_blob needs lpf_link_rows_bytes(n, adj_nnz, ppr_nnz) bytes (an upper bound; -1 if the unit index would not
- * fit 26 bits, i.e. rows beyond 4 GiB) and 64-byte alignment, scratch lpf_link_rows_scratch_bytes(n) bytes.
+ * dependent random reads in four arrays, and DRAM serves random reads in 128-byte lines whatever part of a line is
+ * used (tools/gather_probe.cu).  lpf_pack_link_rows rewrites (adjacency CSR, PPR CSR) once per graph as
+ *   slab     : one 128-byte line per node, node x at byte x * 128 (no locator): chunk 0 = header
+ *              (uint32 deg, uint32 nP, uint32 first 128-byte unit of the row's overflow, 0), chunks 1..7 = the first
+ *              seven 16-byte chunks of the row
+ *   overflow : the remaining chunks of the rows longer than seven chunks, each row's part 128-byte aligned
+ *   a row    = ceil(nP/2) PPR chunks — two entries (column | 0x80000000, value bits) in ascending column order, the
+ *              odd one out padded with (0xffffffff, 0) — then ceil(deg/4) id chunks: four ascending neighbour ids,
+ *              padded with 0x7fffffff
+ * so that the median target is ONE line and one trip (link -> slab line) and the others one more.
+ * slab needs lpf_link_rows_slab_bytes(n) bytes, overflow lpf_link_rows_bytes(n, adj_nnz, ppr_nnz) bytes (an upper
+ * bound; -1 if the unit index would not fit 32 bits), both 128-byte aligned; scratch lpf_link_rows_scratch_bytes(n).
  *
  * lpf_select_onepass_packed is lpf_select_onepass (same outputs, same header protocol, same preconditions as
- * the INTERSECT algorithms) on those rows: the batch is cut evenly over one resident wave of CTAs; a CTA stages the
- * sources of its piece (<= 1,024 links, 1-3 runs of equal source) in shared memory (bucketed hash set of A(a),
- * table of P(a)), flattens the target rows into 64-byte units screened by four lanes each, and resolves the links
- * that select anything by a warp each (by the whole CTA for long target rows).  Runs whose source does not fit
- * next to the others take a second launch with a larger table; the CSR tables are still read by the fallbacks
- * (pieces that are not runs of equal source, sources beyond even the larger table).
+ * the INTERSECT algorithms) on those rows: one CTA per piece of 256 links (1-3 runs of equal source), four per SM.
+ * The CTA stages the sources of its piece in shared memory (bucketed hash set of A(a), tables of P(a)) while the
+ * slab lines of its targets are in flight; then every warp screens its own 32 links (slab line, then the overflow
+ * chunks flattened into a list, one lane per chunk) and resolves the ones that select anything.  Rows of more
+ * than 1,024 chunks go to the deferred-link kernel (walk of the short source row over the CSR tables); runs whose
+ * source does not fit the table take a second launch with a larger one; the CSR tables are also read by the
+ * fallbacks (pieces that are not runs of equal source, sources beyond even the larger table).
  * ------------------------------------------------------------------------- */
+int64_t lpf_link_rows_slab_bytes(int64_t n);
 int64_t lpf_link_rows_bytes(int64_t n, int64_t adj_nnz, int64_t ppr_nnz);
 int64_t lpf_link_rows_scratch_bytes(int64_t n);
 int lpf_pack_link_rows(const int64_t* adj_rowptr, const int32_t* adj_col,
                        const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val, int64_t n,
-                       uint32_t* locator, void* row_blob, void* scratch, void* stream);
+                       void* slab, void* overflow, void* scratch, void* stream);
 int lpf_select_onepass_packed(const int64_t* links, int64_t bs,
                               const int64_t* adj_rowptr, const int32_t* adj_col,
                               const int64_t* ppr_rowptr, const int32_t* ppr_col, const float* ppr_val,
-                              const uint32_t* locator, const void* row_blob,
+                              const void* slab, const void* overflow,
                               float th_cn, float th_1hop, float th_non1hop, int mode, int64_t cap,
                               int32_t* counts, int32_t* seg_start, int32_t* nz_list, int64_t* header,
                               int32_t* node, float* src_ppr, float* tgt_ppr, void* workspace, void* stream);

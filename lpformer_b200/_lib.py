@@ -34,6 +34,7 @@ SIGNATURES = {
     "lpf_select_onepass": (_int, [_p, _i64, _p, _p, _p, _p, _p, _f32, _f32, _f32, _int, _int, _i64, _p, _p, _p, _p, _p,
                                   _p, _p, _p, _p]),
     "lpf_link_rows_bytes": (_i64, [_i64, _i64, _i64]),
+    "lpf_link_rows_slab_bytes": (_i64, [_i64]),
     "lpf_link_rows_scratch_bytes": (_i64, [_i64]),
     "lpf_pack_link_rows": (_int, [_p, _p, _p, _p, _p, _i64, _p, _p, _p, _p]),
     "lpf_select_onepass_packed": (_int, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _f32, _f32, _f32, _int, _i64, _p, _p, _p,

@@ -28,15 +28,13 @@ struct SelectParams2 {
     int32_t* seg_start;  // [3*bs] first row of link i's type-t segment, relative to t*cap
     int32_t* nz_list;    // [bs] batch positions of the non-empty links (any order)
     long long* dbg;      // optional profiling buffer (lpf_debug_select_clocks): per-phase clock64() totals
-    int32_t* hub = nullptr;   // packed kernel: [0] = number of hub runs, then (first link, length) pairs
+    int32_t* hub = nullptr;   // packed kernel: candidate list ([0] = count, [4..] batch positions of the links the screening flagged)
     int slot_limit = 0;       // packed kernel, tests only (lpf_debug_select_slots): usable hash slots, 0 = all
 };
 
-// Workspace of the one-pass launch sequences, in int32 words: [0, bs + 4) deferred (heavy) links; then the hub runs
-// of the packed kernel (count + (first, length) pairs).
-__host__ __device__ inline int64_t ws_hub_words(int64_t bs) {
-    return (1 + 2 * (bs / 128 + 3 * ((bs + 511) / 512 + 1)) + 3 + 3) / 4 * 4;
-}
+// Workspace of the one-pass launch sequences, in int32 words: [0, bs + 4) deferred (heavy) links; then the candidate
+// list of the packed kernel (count in word 0, entries from word 4).
+__host__ __device__ inline int64_t ws_hub_words(int64_t bs) { return (bs + 4 + 3) / 4 * 4; }
 __host__ __device__ inline int64_t ws_total_words(int64_t bs) { return (bs + 4) + ws_hub_words(bs); }
 
 // A link whose shorter adjacency (or PPR) row exceeds kHeavyPerLane elements per lane of its group is deferred

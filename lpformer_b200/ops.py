@@ -219,8 +219,8 @@ def select(links, adj: CSR, ppr: CSR, th_cn, th_1hop, th_non1hop, mode: str, wan
 
 
 class LinkRows:
-    """Packed link rows of one (adjacency, PPR) table pair (lpf_pack_link_rows): locator uint32 [n] (kept in an int32
-    tensor) and the 64-byte-aligned row blob."""
+    """Packed link rows of one (adjacency, PPR) table pair (lpf_pack_link_rows): `slab` = one 128-byte line per node
+    (header + the first seven 16-byte chunks of its row) and `overflow` = the rest of the longer rows."""
 
     def __init__(self, adj: CSR, ppr: CSR):
         require_cuda(adj.rowptr, ppr.rowptr)
@@ -229,12 +229,13 @@ class LinkRows:
         n = adj.n
         nbytes = lib.lpf_link_rows_bytes(n, adj.nnz, ppr.nnz)
         if nbytes < 0:
-            raise _lib.LpfError("graph too large for the 26-bit unit index of the packed link rows")
-        self.locator = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-        self.blob = torch.empty(max(nbytes // 4, 16), dtype=torch.int32, device=dev)
+            raise _lib.LpfError("graph too large for the 32-bit unit index of the packed link rows")
+        # (torch's caching allocator aligns to 512 bytes; the rows need 128)
+        self.slab = torch.empty(max(lib.lpf_link_rows_slab_bytes(n) // 4, 32), dtype=torch.int32, device=dev)
+        self.overflow = torch.empty(max(nbytes // 4, 32), dtype=torch.int32, device=dev)
         scratch = torch.empty(max(lib.lpf_link_rows_scratch_bytes(n) // 8 + 2, 2), dtype=torch.int64, device=dev)
         call("lpf_pack_link_rows", ptr(adj.rowptr), ptr(adj.col), ptr(ppr.rowptr), ptr(ppr.col), ptr(ppr.val), n,
-             ptr(self.locator), ptr(self.blob), ptr(scratch), stream())
+             ptr(self.slab), ptr(self.overflow), ptr(scratch), stream())
         torch.cuda.current_stream().synchronize()     # scratch is released here
         self.adj, self.ppr = adj, ppr
 
@@ -271,7 +272,7 @@ def select_onepass(links, adj: CSR, ppr: CSR, th_cn, th_1hop, th_non1hop, mode: 
     if algo == _lib.ALGO_PACKED:
         lr = link_rows(adj, ppr)
         call("lpf_select_onepass_packed", ptr(links), bs, ptr(adj.rowptr), ptr(adj.col), ptr(ppr.rowptr), ptr(ppr.col),
-             ptr(ppr.val), ptr(lr.locator), ptr(lr.blob), float(th_cn), float(th_1hop), float(th_non1hop), MODE[mode], cap,
+             ptr(ppr.val), ptr(lr.slab), ptr(lr.overflow), float(th_cn), float(th_1hop), float(th_non1hop), MODE[mode], cap,
              ptr(out["counts"]), ptr(out["seg_start"]), ptr(out["nz"]), ptr(out["header"]), ptr(out["node"]),
              ptr(out["src_ppr"]), ptr(out["tgt_ppr"]), ptr(ws), stream(), meta=(bs,))
         return out

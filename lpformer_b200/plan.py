@@ -142,7 +142,7 @@ class ScorePlan:
         # K1: one-pass selection into the per-type pools
         if self.rows is not None:
             call("lpf_select_onepass_packed", ptr(links), bs, ptr(self.adj.rowptr), ptr(self.adj.col),
-                 ptr(self.ppr.rowptr), ptr(self.ppr.col), ptr(self.ppr.val), ptr(self.rows.locator), ptr(self.rows.blob),
+                 ptr(self.ppr.rowptr), ptr(self.ppr.col), ptr(self.ppr.val), ptr(self.rows.slab), ptr(self.rows.overflow),
                  *self.th, self.mode, cap, ptr(self.counts), ptr(self.seg_start), ptr(self.nz), hp, ptr(self.node),
                  ptr(self.pa), ptr(self.pb), ptr(self.ws), st, meta=(bs,))
         else:

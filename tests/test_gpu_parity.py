@@ -409,28 +409,32 @@ def test_plan_fused_nonempty_path(dim, mode_th):
 
 
 def test_packed_link_rows_layout():
-    """lpf_pack_link_rows: locator + 64-byte-aligned rows reproduce the two CSR tables (header, tagged PPR slots in
-    ascending column order with their value bits, ascending neighbour ids, pads)."""
+    """lpf_pack_link_rows: the slab line of a node (header + first seven chunks) and its overflow reproduce the two
+    CSR tables (tagged PPR entries in ascending column order with their value bits, padded to an even count;
+    ascending neighbour ids four per chunk; pads)."""
     from lpformer_b200 import ops, synthetic as S
     g = S.make_graph("citation2", seed=3, scale=0.01, heldout=64)
     dev = torch.device("cuda:0")
     d = g.data_dict(dev)
     lr = ops.link_rows(d["adj_mask"], d["ppr"])
     assert ops.link_rows(d["adj_mask"], d["ppr"]) is lr          # cached per table pair
-    loc = lr.locator.cpu().numpy().view(np.uint32).astype(np.int64)
-    blob = lr.blob.cpu().numpy().view(np.uint32)
+    slab = lr.slab.cpu().numpy().view(np.uint32)[:32 * g.n].reshape(g.n, 32)
+    ovf = lr.overflow.cpu().numpy().view(np.uint32)
     deg, npp = np.diff(g.indptr), np.diff(g.ppr[0])
-    units = (16 + 8 * (npp + (deg + 1) // 2) + 63) // 64
+    chunks = (npp + 1) // 2 + (deg + 3) // 4
+    units = np.where(chunks > 7, (chunks - 7 + 7) // 8, 0)
     off = np.concatenate([[0], np.cumsum(units)[:-1]])
-    assert np.array_equal(loc >> 6, off) and np.array_equal(loc & 63, np.minimum(units, 63))
+    assert np.array_equal(slab[:, 0], deg) and np.array_equal(slab[:, 1], npp) and np.all(slab[:, 3] == 0)
+    assert np.array_equal(slab[units > 0, 2], off[units > 0])
     rng = np.random.default_rng(0)
     for x in np.concatenate([rng.integers(0, g.n, 200), np.argsort(-deg)[:5], np.nonzero(deg == 0)[0][:5]]):
-        w = blob[16 * off[x]: 16 * (off[x] + units[x])]
-        assert w[0] == deg[x] and w[1] == npp[x] and w[2] == 0 and w[3] == 0
-        pw = w[4:4 + 2 * npp[x]].reshape(-1, 2)
-        assert np.array_equal(pw[:, 0], g.ppr[1][g.ppr[0][x]:g.ppr[0][x + 1]].astype(np.uint32) | 0x80000000)
-        assert np.array_equal(pw[:, 1].view(np.float32), g.ppr[2][g.ppr[0][x]:g.ppr[0][x + 1]])
-        ids = w[4 + 2 * npp[x]:]
+        w = np.concatenate([slab[x, 4:], ovf[32 * off[x]: 32 * (off[x] + units[x])]])      # the row, chunk by chunk
+        pslots = 2 * ((npp[x] + 1) // 2)
+        pw = w[:2 * pslots].reshape(-1, 2)
+        assert np.array_equal(pw[:npp[x], 0], g.ppr[1][g.ppr[0][x]:g.ppr[0][x + 1]].astype(np.uint32) | 0x80000000)
+        assert np.array_equal(pw[:npp[x], 1].view(np.float32), g.ppr[2][g.ppr[0][x]:g.ppr[0][x + 1]])
+        assert np.all(pw[npp[x]:, 0] == 0xffffffff) and np.all(pw[npp[x]:, 1] == 0)
+        ids = w[2 * pslots:]
         assert np.array_equal(ids[:deg[x]], g.indices[g.indptr[x]:g.indptr[x + 1]].astype(np.uint32))
         assert np.all(ids[deg[x]:] == 0x7fffffff)
 

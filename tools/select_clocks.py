@@ -31,15 +31,7 @@ for it in range(6):
 lib.lpf_debug_select_clocks(None)
 t = buf.cpu().numpy()
 n = max(1, int(t[5]))
-names = ["flatten fill + stage source", "phase A", "phase B", "phase C", "generic"]
-print("chunks %d, links resolved by a warp per piece %.1f, by the whole CTA per piece %.1f" % (n, t[6] / n, t[7] / n))
-print("slowest chunk %.1f us, slowest CTA %.1f us" % (t[8] / 1965.0, t[9] / 1965.0))
-for nm, v in zip(["  top loads+zero stores", "  run detection", "  table layout", "  clear+flatten scan"], t[10:14]):
-    print("  %-26s %9.0f cycles/chunk  (%.1f us)" % (nm, v / n, v / n / 1965.0))
-for nm, v in zip(names, t[:5]):
-    print("  %-14s %9.0f cycles/chunk  (%.1f us)" % (nm, v / n, v / n / 1965.0))
-
-ph = {10: "top loads", 12: "table layout", 13: "clear+flatten", 0: "stage source", 1: "phase A", 2: "phase B", 3: "phase C (CTA walks)", 4: "generic"}
-print("slowest chunk: len %d runs %d items %d slow %d cta-walked %d table slots %d hub-launch %d" % tuple(int(x) for x in t[32:39]))
+print("pieces %d" % n)
+ph = {10: "links + slab loads issued", 12: "source slab lines", 0: "source overflow + filters", 1: "screen (warp 0)", 2: "push"}
 for k, nm in ph.items():
-    print("    %-22s %8d cycles (%.1f us)" % (nm, t[16 + k], t[16 + k] / 1965.0))
+    print("  %-28s %9.0f cycles/piece  (%.2f us)" % (nm, t[k] / n, t[k] / n / 1965.0))
