@@ -6,7 +6,8 @@
 // is used, so the cost of a link is the number of lines it touches and the number of DEPENDENT trips it makes.
 // lpf_pack_link_rows therefore rewrites (adjacency CSR, PPR CSR) once per graph as
 //   slab[x]  one 128-byte line per node, at x * 128 (no locator, no indirection): chunk 0 = header (deg, nP, first
-//            128-byte unit of the row's overflow, 0), chunks 1..7 = the first seven 16-byte chunks of the row
+//            128-byte unit of the row's overflow, PPR chunks | row chunks << 16 (both saturating at 65,535)), chunks
+//            1..7 = the first seven 16-byte chunks of the row
 //   overflow the remaining chunks of rows longer than seven chunks, 128-byte aligned
 //   a row    = ceil(nP/2) PPR chunks: two entries (col | 0x80000000, value bits), the odd one out padded with
 //              (0xffffffff, 0); then ceil(deg/4) id chunks: four ascending neighbour ids, padded with 0x7fffffff
@@ -28,11 +29,11 @@
 //
 // RESOLVE — count -> allocate -> ordered write — one warp per candidate, grid-wide (the ~100 selecting links of a
 // hub source spread over the whole GPU instead of serialising in the CTA that screened them).  The warp walks the
-// target's packed row (L2-hot: just screened), lane per 8-byte slot, and searches the SOURCE's packed row in global
-// memory (sorted ids, sorted PPR columns; L1/L2-hot: every candidate of a run shares it): exact, so the filters'
-// false positives end here with three zero counts.  Candidates with a long target row (more than kPkResolveChunks
-// chunks) and rows beyond kPkMaxRowChunks (never screened) go to the deferred-link kernel of the launch sequence
-// instead, which walks the SHORT source row over the CSR tables and searches the long one (select_walk.cuh).
+// SHORTER of the link's two packed rows (L2-hot: just screened, or shared by every candidate of the run), lane per
+// 8-byte slot, and searches the other one in global memory (sorted ids, sorted PPR columns): exact, so the filters'
+// false positives end here with three zero counts.  The hits of the (at most four) steps stay in registers across
+// the allocation.  Only links whose shorter row exceeds 128 slots (hub-hub pairs) go on to the deferred-link kernel
+// of the launch sequence, where a whole CTA walks them over the CSR tables (select_fast.cu).
 // Pieces that are not run-shaped are appended to the candidate list whole.  Selected sets, their order inside a
 // link and the fp32 values are those of every other K1 variant (tests compare all of them with the oracle).
 #include <limits.h>
@@ -49,7 +50,6 @@ constexpr int kPkPprBloomWords = 256;  // ... of one run's PPR-column filter
 constexpr int kPkMaxRuns = 3;
 constexpr int kPkFirst = 7;            // row chunks in the slab line
 constexpr int kPkMaxRowChunks = 1024;  // target rows with more 16-byte chunks are not screened (deferred: CSR walk of the short source row)
-constexpr int kPkResolveChunks = 64;   // candidates with longer target rows are resolved by the deferred-link kernel too
 constexpr int kPkWarpItems = 512;      // overflow chunks of a warp's 32 links that are screened (the rest: candidates unscreened)
 constexpr int kPkInflight = 4;         // overflow reads a lane keeps in flight
 constexpr int kPkResolveThreads = 256;
@@ -88,11 +88,12 @@ struct RowView {
     const uint4* blk;        // slab line (chunk 0 = header)
     const uint4* ovf;        // overflow of this row (chunk kPkFirst onwards)
     int deg, npp, pc, S;     // pc = PPR chunks; S = 8-byte slots of the row (padding included)
+    int nb;                  // neighbour ids in the slab line; id k lives at idb[k] (k < nb) or ido[k] (k >= nb)
+    const int32_t* idb;
+    const int32_t* ido;
     __device__ __forceinline__ const uint4* chunk(int c) const { return c < kPkFirst ? blk + 1 + c : ovf + (c - kPkFirst); }
     __device__ __forceinline__ uint2 slot(int s) const { return __ldg(reinterpret_cast<const uint2*>(chunk(s >> 1)) + (s & 1)); }
-    __device__ __forceinline__ int32_t id_at(int k) const {
-        return __ldg(reinterpret_cast<const int32_t*>(chunk(pc + (k >> 2))) + (k & 3));
-    }
+    __device__ __forceinline__ int32_t id_at(int k) const { return __ldg((k < nb ? idb : ido) + k); }
     __device__ __forceinline__ uint2 ppr_at(int e) const { return slot(e); }      // PPR entry e = slot e
     // node u among the row's neighbour ids?
     __device__ __forceinline__ bool has_id(int32_t u) const {
@@ -126,6 +127,9 @@ __device__ __forceinline__ RowView view_row(const uint4* __restrict__ slab, cons
     v.blk = slab + (size_t)node * 8;
     v.ovf = ovf + (size_t)hdr.z * 8;
     v.S = 2 * (v.pc + ((v.deg + 3) >> 2));
+    v.nb = v.pc < kPkFirst ? 4 * (kPkFirst - v.pc) : 0;
+    v.idb = reinterpret_cast<const int32_t*>(v.blk + 1 + min(v.pc, kPkFirst));
+    v.ido = reinterpret_cast<const int32_t*>(v.ovf) + (v.pc > kPkFirst ? 4 * (v.pc - kPkFirst) : 0) - v.nb;
     return v;
 }
 
@@ -141,19 +145,25 @@ __device__ __forceinline__ bool bloom_has(const uint32_t* bl, int lgw, int32_t u
     const uint32_t h = bloom_hash(u), m = bloom_bits(h);
     return (bl[h >> (32 - lgw)] & m) == m;
 }
-// any of the four ids of a chunk (maybe) among the source's neighbours?
-__device__ __forceinline__ bool bloom_any4(const uint32_t* bl, int lgw, uint4 v) {
-    const uint32_t h0 = bloom_hash((int32_t)v.x), h1 = bloom_hash((int32_t)v.y), h2 = bloom_hash((int32_t)v.z), h3 = bloom_hash((int32_t)v.w);
-    const uint32_t w0 = bl[h0 >> (32 - lgw)], w1 = bl[h1 >> (32 - lgw)], w2 = bl[h2 >> (32 - lgw)], w3 = bl[h3 >> (32 - lgw)];
-    const uint32_t m0 = bloom_bits(h0), m1 = bloom_bits(h1), m2 = bloom_bits(h2), m3 = bloom_bits(h3);
-    // (ids ascend and the padding 0x7fffffff comes last: it is the only value that must not count)
-    return ((w0 & m0) == m0 && v.x != kPkPad) | ((w1 & m1) == m1 && v.y != kPkPad) | ((w2 & m2) == m2 && v.z != kPkPad) |
-           ((w3 & m3) == m3 && v.w != kPkPad);
-}
-// a PPR chunk of a target row: an entry above the smaller PPR threshold whose column the source (maybe) holds above it too
-__device__ __forceinline__ bool ppr_chunk_hit(const uint32_t* pbl, uint4 v, float th_pre) {
-    return (quantise(__uint_as_float(v.y)) >= th_pre && bloom_has(pbl, 8, (int32_t)(v.x & ~kPkPprTag))) ||
-           (quantise(__uint_as_float(v.w)) >= th_pre && bloom_has(pbl, 8, (int32_t)(v.z & ~kPkPprTag)));
+// One 16-byte chunk of a target row against the source's filters, without a branch on the chunk's kind (the lanes of
+// a warp hold both kinds).  An id chunk (x, y, z, w = four ids): any of them (maybe) a neighbour of the source.  A PPR
+// chunk ((x, y), (z, w) = two (col | tag, value) entries): an entry above the smaller PPR threshold whose column the
+// source (maybe) holds above it too.  Words x and z are probed in the filter of the chunk's kind, y and w in the id
+// filter (ignored for a PPR chunk, whose y and w are compared as values instead).
+__device__ __forceinline__ bool chunk_hit(const uint32_t* bl, int lgw, const uint32_t* pbl, bool is_ppr, uint4 v, float th_pre) {
+    const uint32_t* f = is_ppr ? pbl : bl;
+    const int lgf = is_ppr ? 8 : lgw;
+    const uint32_t hx = bloom_hash((int32_t)(v.x & 0x7fffffffu)), hz = bloom_hash((int32_t)(v.z & 0x7fffffffu));
+    const uint32_t hy = bloom_hash((int32_t)v.y), hw = bloom_hash((int32_t)v.w);
+    const uint32_t wx = f[hx >> (32 - lgf)], wz = f[hz >> (32 - lgf)];
+    const uint32_t wy = bl[hy >> (32 - lgw)], ww = bl[hw >> (32 - lgw)];
+    const uint32_t mx = bloom_bits(hx), mz = bloom_bits(hz), my = bloom_bits(hy), mw = bloom_bits(hw);
+    // (ids ascend and the padding 0x7fffffff comes last; the padding entry of a PPR chunk is (0xffffffff, 0): value 0
+    // fails the threshold)
+    const bool tx = (wx & mx) == mx, tz = (wz & mz) == mz;
+    const bool ty = (wy & my) == my && v.y != kPkPad, tw = (ww & mw) == mw && v.w != kPkPad;
+    const bool qy = quantise(__uint_as_float(v.y)) >= th_pre, qw = quantise(__uint_as_float(v.w)) >= th_pre;
+    return is_ppr ? ((tx && qy) || (tz && qw)) : ((tx && v.x != kPkPad) || ty || (tz && v.z != kPkPad) || tw);
 }
 static_assert(kPkPprBloomWords == 256, "ppr_chunk_hit / staging use lgw = 8");
 
@@ -165,10 +175,9 @@ struct SlotHit {
     int32_t u, w0, w1;
     float qa, qb, qa1, qb1;
 };
-template <bool WRITE>
+// in0 / in1: the slot's two ids are among the searched row's ids (found by resolve_packed_warp's lockstep search)
 __device__ __forceinline__ SlotHit eval_slot(const SelectParams2& p, const RowView& src, const RowView& row, uint2 slot,
-                                             bool want_pi, bool want_n1, float th_pre) {
-    const bool cn_needs_ppr = WRITE || p.th_cn > 0.0f;
+                                             bool in0, bool in1, bool want_pi, bool want_n1, float th_pre) {
     SlotHit r;
     r.k1 = r.kn = r.h0 = r.h1 = false;
     r.qa = r.qb = r.qa1 = r.qb1 = 0.f;
@@ -186,20 +195,17 @@ __device__ __forceinline__ SlotHit eval_slot(const SelectParams2& p, const RowVi
                 r.kn = want_n1 && !in_a && !in_b && r.qa >= p.th_non1hop && r.qb >= p.th_non1hop;
             }
         }
-    } else if (w0 != kPkPad) {       // ids ascend: a pad in front means the slot is all padding
-        r.h0 = src.has_id((int32_t)w0);
-        r.h1 = w1 != kPkPad && src.has_id((int32_t)w1);
-        if (cn_needs_ppr && (r.h0 || r.h1)) {
-            if (r.h0) {
-                src.ppr((int32_t)w0, r.qa);
-                row.ppr((int32_t)w0, r.qb);
-                r.h0 = r.qa >= p.th_cn && r.qb >= p.th_cn;
-            }
-            if (r.h1) {
-                src.ppr((int32_t)w1, r.qa1);
-                row.ppr((int32_t)w1, r.qb1);
-                r.h1 = r.qa1 >= p.th_cn && r.qb1 >= p.th_cn;
-            }
+    } else {
+        // PPR values of a common neighbour: by search over the PPR entries of both rows
+        if (in0) {
+            src.ppr((int32_t)w0, r.qa);
+            row.ppr((int32_t)w0, r.qb);
+            r.h0 = r.qa >= p.th_cn && r.qb >= p.th_cn;
+        }
+        if (in1) {
+            src.ppr((int32_t)w1, r.qa1);
+            row.ppr((int32_t)w1, r.qb1);
+            r.h1 = r.qa1 >= p.th_cn && r.qb1 >= p.th_cn;
         }
     }
     return r;
@@ -208,68 +214,178 @@ __device__ __forceinline__ uint2 load_slot(const RowView& row, int s) {
     if (s < row.S) return row.slot(s);
     return make_uint2(kPkPad, kPkPad);
 }
-__device__ __forceinline__ void write_hits(const SelectParams2& p, const SlotHit& r, int64_t r_pi, int64_t r_cn) {
-    if (r.k1 || r.kn) { p.node[r_pi] = r.u; p.pa[r_pi] = r.qa; p.pb[r_pi] = r.qb; }
-    if (r.h0) { p.node[r_cn] = r.w0; p.pa[r_cn] = r.qa; p.pb[r_cn] = r.qb; }
-    if (r.h1) { const int64_t r1 = r_cn + (r.h0 ? 1 : 0); p.node[r1] = r.w1; p.pa[r1] = r.qa1; p.pb[r1] = r.qb1; }
+// (swapped: the walked row is the SOURCE's and the searched one the target's, so qa / qb change places)
+__device__ __forceinline__ void write_hits(const SelectParams2& p, const SlotHit& r, bool swapped, int64_t r_pi, int64_t r_cn) {
+    if (r.k1 || r.kn) { p.node[r_pi] = r.u; p.pa[r_pi] = swapped ? r.qb : r.qa; p.pb[r_pi] = swapped ? r.qa : r.qb; }
+    if (r.h0) { p.node[r_cn] = r.w0; p.pa[r_cn] = swapped ? r.qb : r.qa; p.pb[r_cn] = swapped ? r.qa : r.qb; }
+    if (r.h1) {
+        const int64_t r1 = r_cn + (r.h0 ? 1 : 0);
+        p.node[r1] = r.w1; p.pa[r1] = swapped ? r.qb1 : r.qa1; p.pb[r1] = swapped ? r.qa1 : r.qb1;
+    }
 }
 
-// A warp walks one link's PACKED target row against the source's packed row: lane l takes slot l, l + 32, ... so
-// ascending node order within each set is lane order, and the ordered write needs only ballots.  Same sets, order
-// and values as the generic walk (select_walk.cuh).
-template <bool WRITE>
-__device__ __forceinline__ void walk_packed_warp(const SelectParams2& p, const RowView& src, const RowView& row, int lane,
-                                                 int64_t o_cn, int64_t o_1h, int64_t o_n1, int& c_cn, int& c_1h, int& c_n1) {
-    const unsigned lt = (1u << lane) - 1u;
+// count -> allocate -> ordered write of one link by a warp: the warp walks `row` (the shorter of the link's two packed
+// rows, at most kPkResolveSlots slots), lane l taking slot l, l + 32, ... so that ascending node order within each
+// set is lane order and the ordered write needs only ballots, and searches `src` (the other row).  The hits of all
+// (at most four) steps stay in registers across the allocation: one walk.  Same sets, order and values as the
+// generic walk (select_walk.cuh).
+constexpr int kPkResolveSlots = 128;
+__device__ __forceinline__ void resolve_packed_warp(const SelectParams2& p, const RowView& src, const RowView& row, bool swapped,
+                                                    int64_t i, int lane) {
+    constexpr int STEPS = kPkResolveSlots / 32;
     const bool want_pi = p.mode != LPF_MODE_CN;
     const bool want_n1 = p.mode == LPF_MODE_ALL;
     const float th_pre = want_n1 ? fminf(p.th_1hop, p.th_non1hop) : p.th_1hop;
-    c_cn = c_1h = c_n1 = 0;
-    for (int s0 = 0; s0 < row.S; s0 += 32) {
-        const SlotHit r = eval_slot<WRITE>(p, src, row, load_slot(row, s0 + lane), want_pi, want_n1, th_pre);
-        const unsigned m1 = __ballot_sync(kFull, r.k1), mn = __ballot_sync(kFull, r.kn);
-        const unsigned mh0 = __ballot_sync(kFull, r.h0), mh1 = __ballot_sync(kFull, r.h1);
-        if (WRITE)
-            write_hits(p, r, r.k1 ? o_1h + c_1h + __popc(m1 & lt) : o_n1 + c_n1 + __popc(mn & lt),
-                       o_cn + c_cn + __popc(mh0 & lt) + __popc(mh1 & lt));
-        c_1h += __popc(m1);
-        c_n1 += __popc(mn);
-        c_cn += __popc(mh0) + __popc(mh1);
+    const unsigned lt = (1u << lane) - 1u;
+    // the lane's slots of all steps, and its (up to 2 * STEPS) id keys searched in the other row's ids in LOCKSTEP: one
+    // dependent read per halving for all keys together instead of one binary search after the other
+    uint2 sl[STEPS];
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s) sl[s] = 32 * s < row.S ? load_slot(row, 32 * s + lane) : make_uint2(kPkPad, kPkPad);
+    int lo[2 * STEPS], hi[2 * STEPS];
+#pragma unroll
+    for (int x = 0; x < 2 * STEPS; ++x) {
+        const uint32_t key = (x & 1) ? sl[x >> 1].y : sl[x >> 1].x;
+        const bool active = !(sl[x >> 1].x & kPkPprTag) && key != kPkPad;
+        lo[x] = 0;
+        hi[x] = active ? src.deg : 0;
     }
-}
-
-// count -> allocate -> ordered write of one link by a warp
-__device__ __forceinline__ void resolve_packed_warp(const SelectParams2& p, const RowView& src, const RowView& row, int64_t i,
-                                                    int lane) {
-    int c_cn, c_1h, c_n1;
-    if (row.S <= 32) {
-        // a row of at most 32 slots is ONE step of the warp: the hits stay in registers across the allocation
-        const bool want_pi = p.mode != LPF_MODE_CN;
-        const bool want_n1 = p.mode == LPF_MODE_ALL;
-        const float th_pre = want_n1 ? fminf(p.th_1hop, p.th_non1hop) : p.th_1hop;
-        const SlotHit r = eval_slot<true>(p, src, row, load_slot(row, lane), want_pi, want_n1, th_pre);
-        const unsigned lt = (1u << lane) - 1u;
-        const unsigned m1 = __ballot_sync(kFull, r.k1), mn = __ballot_sync(kFull, r.kn);
-        const unsigned mh0 = __ballot_sync(kFull, r.h0), mh1 = __ballot_sync(kFull, r.h1);
-        c_cn = __popc(mh0) + __popc(mh1); c_1h = __popc(m1); c_n1 = __popc(mn);
-        int64_t s_cn, s_1h, s_n1;
-        const bool ok = alloc_segments_warp(p, i, c_cn, c_1h, c_n1, lane, s_cn, s_1h, s_n1);
-        if (c_cn + c_1h + c_n1 == 0 || !ok) return;
-        write_hits(p, r, r.k1 ? p.cap + s_1h + __popc(m1 & lt) : 2 * p.cap + s_n1 + __popc(mn & lt),
-                   s_cn + __popc(mh0 & lt) + __popc(mh1 & lt));
-        return;
+    const int iters = 32 - __clz(src.deg);          // halvings that empty [0, deg)
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int x = 0; x < 2 * STEPS; ++x) {
+            if (lo[x] < hi[x]) {
+                const int32_t key = (int32_t)((x & 1) ? sl[x >> 1].y : sl[x >> 1].x);
+                const int mid = (lo[x] + hi[x]) >> 1;
+                if (src.id_at(mid) < key) lo[x] = mid + 1; else hi[x] = mid;
+            }
+        }
     }
-    walk_packed_warp<false>(p, src, row, lane, 0, 0, 0, c_cn, c_1h, c_n1);
-    int64_t s_cn = 0, s_1h = 0, s_n1 = 0;
+    bool found[2 * STEPS];
+#pragma unroll
+    for (int x = 0; x < 2 * STEPS; ++x) {
+        const uint32_t key = (x & 1) ? sl[x >> 1].y : sl[x >> 1].x;
+        const bool active = !(sl[x >> 1].x & kPkPprTag) && key != kPkPad;
+        found[x] = active && lo[x] < src.deg && src.id_at(lo[x]) == (int32_t)key;
+    }
+    SlotHit r[STEPS];
+    unsigned m1[STEPS], mn[STEPS], mh0[STEPS], mh1[STEPS];
+    int c_cn = 0, c_1h = 0, c_n1 = 0;
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s) {
+        m1[s] = mn[s] = mh0[s] = mh1[s] = 0u;
+        r[s].k1 = r[s].kn = r[s].h0 = r[s].h1 = false;
+        if (32 * s < row.S) {       // uniform
+            r[s] = eval_slot(p, src, row, sl[s], found[2 * s], found[2 * s + 1], want_pi, want_n1, th_pre);
+            m1[s] = __ballot_sync(kFull, r[s].k1); mn[s] = __ballot_sync(kFull, r[s].kn);
+            mh0[s] = __ballot_sync(kFull, r[s].h0); mh1[s] = __ballot_sync(kFull, r[s].h1);
+            c_1h += __popc(m1[s]); c_n1 += __popc(mn[s]); c_cn += __popc(mh0[s]) + __popc(mh1[s]);
+        }
+    }
+    int64_t s_cn, s_1h, s_n1;
     const bool ok = alloc_segments_warp(p, i, c_cn, c_1h, c_n1, lane, s_cn, s_1h, s_n1);
     if (c_cn + c_1h + c_n1 == 0 || !ok) return;
-    walk_packed_warp<true>(p, src, row, lane, s_cn, p.cap + s_1h, 2 * p.cap + s_n1, c_cn, c_1h, c_n1);
+    int64_t o_cn = s_cn, o_1h = p.cap + s_1h, o_n1 = 2 * p.cap + s_n1;
+#pragma unroll
+    for (int s = 0; s < STEPS; ++s) {
+        write_hits(p, r[s], swapped, r[s].k1 ? o_1h + __popc(m1[s] & lt) : o_n1 + __popc(mn[s] & lt),
+                   o_cn + __popc(mh0[s] & lt) + __popc(mh1[s] & lt));
+        o_1h += __popc(m1[s]); o_n1 += __popc(mn[s]); o_cn += __popc(mh0[s]) + __popc(mh1[s]);
+    }
 }
 
-// RESOLVE launch: one warp per candidate of the screening
-__global__ void __launch_bounds__(kPkResolveThreads)
+// The common candidate — the walked row is one step of the warp (at most 32 slots) and both PPR rows have at most 32
+// entries — with two dependent reads instead of ~35: the walked row's slots and the searched row's PPR entries sit
+// in registers (one per lane) and are looked up by shuffle loops; the searched row's neighbour ids are staged in
+// shared memory (up to kPkStageIds of them; a longer row is searched in global memory, both keys in lockstep).
+constexpr int kPkStageIds = 256;
+__device__ __forceinline__ void resolve_packed_fast(const SelectParams2& p, const RowView& src, const RowView& row, bool swapped,
+                                                    int64_t i, int lane, int32_t* ids_sm) {
+    const bool want_pi = p.mode != LPF_MODE_CN;
+    const bool want_n1 = p.mode == LPF_MODE_ALL;
+    const float th_pre = want_n1 ? fminf(p.th_1hop, p.th_non1hop) : p.th_1hop;
+    const uint2 sl = load_slot(row, lane);
+    const uint2 sp = lane < src.npp ? src.ppr_at(lane) : make_uint2(0xffffffffu, 0u);
+    const bool staged = src.deg <= kPkStageIds;
+    if (staged)
+        for (int k = lane; k < src.deg; k += 32) ids_sm[k] = src.id_at(k);
+    __syncwarp();
+    const bool is_ppr = (sl.x & kPkPprTag) != 0u;
+    // keys: a PPR slot asks for its column u, an id slot for its two ids (-1: nothing to ask)
+    const int32_t u = (is_ppr && sl.x != 0xffffffffu) ? (int32_t)(sl.x & ~kPkPprTag) : -1;
+    const int32_t k0 = (!is_ppr && sl.x != kPkPad) ? (int32_t)sl.x : -1;
+    const int32_t k1 = (!is_ppr && sl.y != kPkPad) ? (int32_t)sl.y : -1;
+    // ---- the two ids among the searched row's ids?
+    bool in0 = false, in1 = false;
+    {
+        int lo0 = 0, hi0 = k0 >= 0 ? src.deg : 0, lo1 = 0, hi1 = k1 >= 0 ? src.deg : 0;
+        const int iters = 32 - __clz(src.deg);
+        if (staged) {
+            for (int it = 0; it < iters; ++it) {
+                if (lo0 < hi0) { const int mid = (lo0 + hi0) >> 1; if (ids_sm[mid] < k0) lo0 = mid + 1; else hi0 = mid; }
+                if (lo1 < hi1) { const int mid = (lo1 + hi1) >> 1; if (ids_sm[mid] < k1) lo1 = mid + 1; else hi1 = mid; }
+            }
+            in0 = k0 >= 0 && lo0 < src.deg && ids_sm[lo0] == k0;
+            in1 = k1 >= 0 && lo1 < src.deg && ids_sm[lo1] == k1;
+        } else {
+            for (int it = 0; it < iters; ++it) {
+                const int m0 = (lo0 + hi0) >> 1, m1 = (lo1 + hi1) >> 1;
+                const int32_t v0 = lo0 < hi0 ? src.id_at(m0) : 0, v1 = lo1 < hi1 ? src.id_at(m1) : 0;
+                if (lo0 < hi0) { if (v0 < k0) lo0 = m0 + 1; else hi0 = m0; }
+                if (lo1 < hi1) { if (v1 < k1) lo1 = m1 + 1; else hi1 = m1; }
+            }
+            const int32_t f0 = (k0 >= 0 && lo0 < src.deg) ? src.id_at(lo0) : -2, f1 = (k1 >= 0 && lo1 < src.deg) ? src.id_at(lo1) : -2;
+            in0 = f0 == k0;
+            in1 = f1 == k1;
+        }
+    }
+    // ---- PPR values by shuffle loops: q(P(src, .)) of u, k0, k1 from the searched row's entries; q(P(row, .)) of k0, k1
+    // from the walked row's own PPR slots (its first npp slots = the lanes below npp)
+    float qa_u = 0.f, qa0 = 0.f, qa1 = 0.f, qb0 = 0.f, qb1 = 0.f;
+    bool has_u = false;
+    for (int e = 0; e < src.npp; ++e) {
+        const int32_t c = (int32_t)(__shfl_sync(kFull, sp.x, e) & 0x7fffffffu);
+        const float q = quantise(__uint_as_float(__shfl_sync(kFull, sp.y, e)));
+        if (c == u) { has_u = true; qa_u = q; }
+        if (c == k0) qa0 = q;
+        if (c == k1) qa1 = q;
+    }
+    for (int e = 0; e < row.npp; ++e) {
+        const int32_t c = (int32_t)(__shfl_sync(kFull, sl.x, e) & 0x7fffffffu);
+        const float q = quantise(__uint_as_float(__shfl_sync(kFull, sl.y, e)));
+        if (c == k0) qb0 = q;
+        if (c == k1) qb1 = q;
+    }
+    SlotHit r;
+    r.k1 = r.kn = false;
+    r.u = u; r.w0 = k0; r.w1 = k1;
+    r.qa = is_ppr ? qa_u : qa0; r.qb = is_ppr ? quantise(__uint_as_float(sl.y)) : qb0;
+    r.qa1 = qa1; r.qb1 = qb1;
+    r.h0 = in0 && qa0 >= p.th_cn && qb0 >= p.th_cn;
+    r.h1 = in1 && qa1 >= p.th_cn && qb1 >= p.th_cn;
+    if (want_pi && has_u && r.qa >= th_pre && r.qb >= th_pre) {      // (rare: a node in both PPR rows above the threshold)
+        const bool in_a = src.has_id(u), in_b = row.has_id(u);
+        r.k1 = (in_a != in_b) && r.qa >= p.th_1hop && r.qb >= p.th_1hop;
+        r.kn = want_n1 && !in_a && !in_b && r.qa >= p.th_non1hop && r.qb >= p.th_non1hop;
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned m1 = __ballot_sync(kFull, r.k1), mn = __ballot_sync(kFull, r.kn);
+    const unsigned mh0 = __ballot_sync(kFull, r.h0), mh1 = __ballot_sync(kFull, r.h1);
+    const int c_cn = __popc(mh0) + __popc(mh1), c_1h = __popc(m1), c_n1 = __popc(mn);
+    int64_t s_cn, s_1h, s_n1;
+    const bool ok = alloc_segments_warp(p, i, c_cn, c_1h, c_n1, lane, s_cn, s_1h, s_n1);
+    if (c_cn + c_1h + c_n1 == 0 || !ok) return;
+    write_hits(p, r, swapped, r.k1 ? p.cap + s_1h + __popc(m1 & lt) : 2 * p.cap + s_n1 + __popc(mn & lt),
+               s_cn + __popc(mh0 & lt) + __popc(mh1 & lt));
+}
+
+// RESOLVE launch: one warp per candidate of the screening.  The warp walks the SHORTER of the link's two rows and
+// searches the other; a link whose shorter row has more than kPkResolveSlots slots (a hub-hub pair) goes to the
+// deferred-link kernel, where a whole CTA walks it.
+__global__ void __launch_bounds__(kPkResolveThreads, 2)
 select_resolve_packed_kernel(const __grid_constant__ SelectParams2 p, const uint4* __restrict__ slab,
                              const uint4* __restrict__ ovf) {
+    __shared__ int32_t ids_sm[kPkResolveThreads / 32][kPkStageIds];
     const int lane = threadIdx.x & 31;
     const int n = p.hub[0];
     const int warp0 = (blockIdx.x * kPkResolveThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kPkResolveThreads) >> 5;
@@ -277,12 +393,17 @@ select_resolve_packed_kernel(const __grid_constant__ SelectParams2 p, const uint
         const int64_t i = p.hub[4 + q];
         const int64_t a = __ldg(p.links + i), b = __ldg(p.links + p.bs + i);
         const uint4 ha = ldg16(slab + (size_t)a * 8), hb = ldg16(slab + (size_t)b * 8);
-        if (row_chunks((int64_t)hb.x, (int64_t)hb.y) > kPkResolveChunks) {
-            // (a piece that was not run-shaped is listed whole: its long target rows take the walk of the shorter row)
+        const RowView A = view_row(slab, ovf, a, ha), B = view_row(slab, ovf, b, hb);
+        const bool swapped = A.S < B.S;
+        if (min(A.S, B.S) > kPkResolveSlots) {
             if (lane == 0) p.heavy[4 + atomicAdd(p.heavy, 1)] = (int32_t)i;
             continue;
         }
-        resolve_packed_warp(p, view_row(slab, ovf, a, ha), view_row(slab, ovf, b, hb), i, lane);
+        const RowView& row = swapped ? A : B;
+        const RowView& src = swapped ? B : A;
+        __syncwarp();       // (ids_sm of the previous candidate is no longer read)
+        if (row.S <= 32 && row.npp <= 32 && src.npp <= 32) resolve_packed_fast(p, src, row, swapped, i, lane, ids_sm[threadIdx.x >> 5]);
+        else resolve_packed_warp(p, src, row, swapped, i, lane);
     }
 }
 
@@ -323,7 +444,16 @@ select_screen_packed_kernel(const __grid_constant__ SelectParams2 p, const uint4
     const int64_t i0 = (int64_t)blockIdx.x * NT;
     const int len = (int)min((int64_t)NT, p.bs - i0);
     const int t0 = 32 * warp;
-    if (p.dbg && tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 5), 1ull);
+    if (p.dbg && tid == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 5), 1ull);
+        if (blockIdx.x < 2048) {       // (profiling: start time and SM of every piece)
+            unsigned long long gt; unsigned smid;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            p.dbg[64 + 3 * blockIdx.x] = (long long)gt;
+            p.dbg[64 + 3 * blockIdx.x + 2] = (long long)smid;
+        }
+    }
     // ---- the piece's links, one per thread; run boundaries by ballot
     const bool valid = tid < len;
     int64_t b_me = 0;
@@ -397,7 +527,7 @@ select_screen_packed_kernel(const __grid_constant__ SelectParams2 p, const uint4
         lgw[r] = 5;
         if (r < n_runs) {
             const uint32_t na = min(sm.r_hdr[r].x, 1u << 20);
-            while ((1u << lgw[r]) < 8u * na && lgw[r] < share_lg) ++lgw[r];
+            lgw[r] = min(share_lg, max(5, 32 - __clz((int)(8u * na) - 1)));       // words: a power of two >= 8 * deg
         }
     }
     static_assert(kPkBloomWords == 4096, "share_lg");
@@ -436,39 +566,35 @@ select_screen_packed_kernel(const __grid_constant__ SelectParams2 p, const uint4
     __syncthreads();                                   // (3) sources staged: from here every warp is on its own
     LPF_PHASE(0);
 
-    // ---- this warp's 32 links: the slab lines
-    unsigned any_mask = 0;      // links that (maybe) select something
+    // ---- this warp's 32 links: the slab lines.  Lane 8g+j probes chunk j of link 4k+g; its hits of the eight reads
+    // are collected in a lane-local byte and OR-ed over the eight lanes of the group at the end.
+    unsigned lane_hits = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int l = 4 * k + grp;
-        uint4 h;
-        h.x = __shfl_sync(kFull, v[k].x, 8 * grp);
-        h.y = __shfl_sync(kFull, v[k].y, 8 * grp);
-        h.z = __shfl_sync(kFull, v[k].z, 8 * grp);
-        h.w = 0u;
-        if (j == 0) W.hdr[l] = h;
-        const int pc = (int)((min(h.y, 1u << 28) + 1) >> 1), rc = pc + (int)((min(h.x, 1u << 28) + 3) >> 2);
+        if (j == 0) W.hdr[l] = v[k];
+        const uint32_t geo = __shfl_sync(kFull, v[k].w, 8 * grp);       // header word 3: PPR chunks | row chunks << 16
+        const int pc = (int)(geo & 0xffffu), rc = (int)(geo >> 16);
         const int c = j - 1;
-        bool hit = false;
-        if (t0 + l < len && j >= 1 && c < rc) {
+        if (j >= 1 && c < rc && (want_pi || c >= pc)) {
             const int r = run_of(t0 + l);
-            if (c < pc) hit = want_pi && ppr_chunk_hit(sm.pbloom[r], v[k], th_pre);
-            else hit = bloom_any4(sm.bloom + (r << share_lg), r == 0 ? lgw[0] : (r == 1 ? lgw[1] : lgw[2]), v[k]);
+            if (chunk_hit(sm.bloom + (r << share_lg), r == 0 ? lgw[0] : (r == 1 ? lgw[1] : lgw[2]), sm.pbloom[r], c < pc, v[k], th_pre))
+                lane_hits |= 1u << k;
         }
-        const unsigned bm = __ballot_sync(kFull, hit);
-#pragma unroll
-        for (int gg = 0; gg < 4; ++gg)
-            if ((bm >> (8 * gg)) & 0xffu) any_mask |= 1u << (4 * k + gg);
     }
+    lane_hits |= __shfl_xor_sync(kFull, lane_hits, 1);
+    lane_hits |= __shfl_xor_sync(kFull, lane_hits, 2);
+    lane_hits |= __shfl_xor_sync(kFull, lane_hits, 4);
+    // bit l of any_mask: link l = 4k+g of this warp (maybe) selects something (lane l looks at group l&3, read l>>2)
+    unsigned any_mask = __ballot_sync(kFull, (__shfl_sync(kFull, lane_hits, 8 * (lane & 3)) >> (lane >> 2)) & 1u);
     __syncwarp();
     // ---- flatten the overflow chunks of the links not flagged yet: items[] = (link << 11 | row chunk)
-    int n_items, rc_me;
-    unsigned long_mask;         // rows too long to screen: deferred unscreened
+    int n_items;
+    unsigned long_mask;         // rows too long to screen: candidates unscreened
     {
         const int l = lane;
-        const uint4 h = W.hdr[l];
-        const int pc = (int)((min(h.y, 1u << 28) + 1) >> 1);
-        rc_me = pc + (int)((min(h.x, 1u << 28) + 3) >> 2);
+        const uint32_t geo = W.hdr[l].w;
+        const int rc_me = (int)(geo >> 16);
         const bool live = t0 + l < len;
         const bool too_long = live && rc_me > kPkMaxRowChunks;
         const bool listed = live && !too_long && !((any_mask >> l) & 1u) && rc_me > kPkFirst;
@@ -481,15 +607,21 @@ select_screen_packed_kernel(const __grid_constant__ SelectParams2 p, const uint4
         }
         const int ex = inc - mine;
         const bool fits = ex + mine <= kPkWarpItems;
-        if (listed && fits)
-            for (int e = 0; e < mine; ++e) W.items[ex + e] = (uint16_t)((l << 11) | (kPkFirst + e));
         // the list ends at the first link that does not fit (a suffix: the prefix sum is monotone); those links
         // become candidates unscreened
         const unsigned nofit = __ballot_sync(kFull, listed && !fits);
+        unsigned todo = __ballot_sync(kFull, listed && fits);
         long_mask = __ballot_sync(kFull, too_long);
         any_mask = (any_mask | nofit) & ~long_mask;
         const int first_nofit = nofit ? __ffs(nofit) - 1 : 31;
         n_items = __shfl_sync(kFull, nofit ? ex : inc, first_nofit);
+        // the whole warp writes the items of one link at a time
+        while (todo) {
+            const int ll = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int ex_l = __shfl_sync(kFull, ex, ll), n_l = __shfl_sync(kFull, mine, ll);
+            for (int e = lane; e < n_l; e += 32) W.items[ex_l + e] = (uint16_t)((ll << 11) | (kPkFirst + e));
+        }
     }
     __syncwarp();
     // ---- the overflow chunks: one lane per chunk, kPkInflight reads in flight per lane
@@ -512,23 +644,27 @@ select_screen_packed_kernel(const __grid_constant__ SelectParams2 p, const uint4
                 if (li[k] < 0) continue;
                 const int l = li[k] >> 11, c = li[k] & 2047;
                 const int r = run_of(t0 + l);
-                const int pc = (int)((min(W.hdr[l].y, 1u << 28) + 1) >> 1);
-                bool hit;
-                if (c < pc) hit = want_pi && ppr_chunk_hit(sm.pbloom[r], cv[k], th_pre);
-                else hit = bloom_any4(sm.bloom + (r << share_lg), r == 0 ? lgw[0] : (r == 1 ? lgw[1] : lgw[2]), cv[k]);
-                if (hit) atomicOr(&W.any, 1u << l);
+                const int pc = (int)(W.hdr[l].w & 0xffffu);
+                if (!want_pi && c < pc) continue;
+                if (chunk_hit(sm.bloom + (r << share_lg), r == 0 ? lgw[0] : (r == 1 ? lgw[1] : lgw[2]), sm.pbloom[r], c < pc, cv[k], th_pre))
+                    atomicOr(&W.any, 1u << l);
             }
         }
     }
     __syncwarp();
     any_mask |= W.any;
     LPF_PHASE(1);
-    // ---- the flagged links: to the candidate list (short target rows) or to the deferred links (long ones)
-    const unsigned heavy_mask = long_mask | (any_mask & __ballot_sync(kFull, rc_me > kPkResolveChunks));
-    push_links(p.hub, any_mask & ~heavy_mask, i0 + t0, lane);
-    push_links(p.heavy, heavy_mask, i0 + t0, lane);
+    // ---- the flagged links, and the rows too long to screen, to the candidate list
+    push_links(p.hub, any_mask | long_mask, i0 + t0, lane);
     LPF_PHASE(2);
-    if (p.dbg && tid == 0) atomicMax(p.dbg + 9, clock64() - (t_mark - 0));
+    if (p.dbg) {
+        __syncthreads();
+        if (tid == 0 && blockIdx.x < 2048) {
+            unsigned long long gt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+            p.dbg[64 + 3 * blockIdx.x + 1] = (long long)gt;
+        }
+    }
 }
 #undef LPF_PHASE
 
@@ -570,7 +706,8 @@ __global__ void __launch_bounds__(256) pack_fill_kernel(const int64_t* __restric
             return kPkPad;
         };
         uint32_t* line = slab + x * 32;
-        if (lane < 4) line[lane] = lane == 0 ? (uint32_t)deg : (lane == 1 ? (uint32_t)npp : (lane == 2 ? (uint32_t)o : 0u));
+        const uint32_t geo = (uint32_t)min(pcn, (int64_t)65535) | ((uint32_t)min(rc, (int64_t)65535) << 16);
+        if (lane < 4) line[lane] = lane == 0 ? (uint32_t)deg : (lane == 1 ? (uint32_t)npp : (lane == 2 ? (uint32_t)o : geo));
         else line[lane] = word((lane >> 2) - 1, lane & 3);
         uint32_t* w = ovf + o * 32;
         for (int64_t k = lane; k < units * 32; k += 32) w[k] = word(kPkFirst + (k >> 2), (int)(k & 3));
@@ -676,7 +813,7 @@ extern "C" int lpf_select_onepass_packed(const int64_t* links, int64_t bs, const
             p, static_cast<const uint4*>(slab), static_cast<const uint4*>(overflow));
         if (timing) cudaEventRecord(g_pk_ev[1], st);
         // RESOLVE: one warp per candidate (their number is on the device: a resident grid strides over the list)
-        select_resolve_packed_kernel<<<kNumSMs * 8, kPkResolveThreads, 0, st>>>(
+        select_resolve_packed_kernel<<<kNumSMs * 2, kPkResolveThreads, 0, st>>>(
             p, static_cast<const uint4*>(slab), static_cast<const uint4*>(overflow));
         if (timing) cudaEventRecord(g_pk_ev[2], st);
     }

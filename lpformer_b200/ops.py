@@ -269,6 +269,7 @@ def select_onepass(links, adj: CSR, ppr: CSR, th_cn, th_1hop, th_non1hop, mode: 
         "cap": cap,
     }
     ws = torch.empty(_lib.load().lpf_select_workspace_bytes(bs) // 4, dtype=torch.int32, device=dev)
+    out["workspace"] = ws        # (word 0: deferred links; word bs + 4: candidates of the packed screening)
     if algo == _lib.ALGO_PACKED:
         lr = link_rows(adj, ppr)
         call("lpf_select_onepass_packed", ptr(links), bs, ptr(adj.rowptr), ptr(adj.col), ptr(ppr.rowptr), ptr(ppr.col),

@@ -424,7 +424,8 @@ def test_packed_link_rows_layout():
     chunks = (npp + 1) // 2 + (deg + 3) // 4
     units = np.where(chunks > 7, (chunks - 7 + 7) // 8, 0)
     off = np.concatenate([[0], np.cumsum(units)[:-1]])
-    assert np.array_equal(slab[:, 0], deg) and np.array_equal(slab[:, 1], npp) and np.all(slab[:, 3] == 0)
+    assert np.array_equal(slab[:, 0], deg) and np.array_equal(slab[:, 1], npp)
+    assert np.array_equal(slab[:, 3], (npp + 1) // 2 | (chunks << 16))
     assert np.array_equal(slab[units > 0, 2], off[units > 0])
     rng = np.random.default_rng(0)
     for x in np.concatenate([rng.integers(0, g.n, 200), np.argsort(-deg)[:5], np.nonzero(deg == 0)[0][:5]]):

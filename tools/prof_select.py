@@ -26,4 +26,5 @@ for it in range(iters):
     out = ops.select_onepass(links, d["adj_mask"], d["ppr"], *th, "all", cap=1 << 19, algo=3)
     torch.cuda.synchronize()
     lib.lpf_debug_select_timing_read(ctypes.addressof(ms3))
-    print("screen %.1f us  resolve %.1f us  deferred %.1f us" % (1e3 * ms3[0], 1e3 * ms3[1], 1e3 * ms3[2]), out["header"].tolist()[:5])
+    print("screen %.1f us  resolve %.1f us  deferred %.1f us" % (1e3 * ms3[0], 1e3 * ms3[1], 1e3 * ms3[2]), out["header"].tolist()[:5],
+          "candidates %d deferred %d" % (int(out["workspace"][links.shape[1] + 4]), int(out["workspace"][0])))

@@ -17,7 +17,7 @@ cfg = g.cfg
 d = g.data_dict(dev)
 th = (cfg["thresh_cn"], cfg["thresh_1hop"], cfg["thresh_non1hop"])
 lib = _lib.load()
-buf = torch.zeros(48, dtype=torch.int64, device=dev)
+buf = torch.zeros(64 + 3 * 2048, dtype=torch.int64, device=dev)
 for it in range(6):
     links = torch.from_numpy(S.citation2_queries(g, 256, 1000, seed=1000 + it)).to(dev)
     if it == 5:
@@ -35,3 +35,22 @@ print("pieces %d" % n)
 ph = {10: "links + slab loads issued", 12: "source slab lines", 0: "source overflow + filters", 1: "screen (warp 0)", 2: "push"}
 for k, nm in ph.items():
     print("  %-28s %9.0f cycles/piece  (%.2f us)" % (nm, t[k] / n, t[k] / n / 1965.0))
+
+# per-piece timeline (globaltimer, ns): duration histogram and pieces in flight over time
+pc = t[64:64 + 3 * n].reshape(-1, 3)
+st, en, smid = pc[:, 0], pc[:, 1], pc[:, 2]
+t00 = st.min()
+dur = (en - st) / 1e3
+print("piece duration us: min %.1f p10 %.1f p50 %.1f p90 %.1f p99 %.1f max %.1f; kernel span %.1f us" % (
+    dur.min(), np.percentile(dur, 10), np.percentile(dur, 50), np.percentile(dur, 90), np.percentile(dur, 99), dur.max(), (en.max() - t00) / 1e3))
+print("start times us: p50 %.1f p90 %.1f max %.1f" % tuple((np.percentile(st - t00, q) / 1e3) for q in (50, 90, 100)))
+for tt in range(0, int((en.max() - t00) / 1e3) + 1, 4):
+    live = int(((st - t00) / 1e3 <= tt).sum() - ((en - t00) / 1e3 <= tt).sum())
+    print("  t=%3d us: %4d pieces in flight" % (tt, live))
+slow = np.argsort(-dur)[:8]
+deg = np.diff(g.indptr)
+lk = S.citation2_queries(g, 256, 1000, seed=1000 + 5)
+for q in slow:
+    a = lk[0, q * 256:(q + 1) * 256]
+    b = lk[1, q * 256:(q + 1) * 256]
+    print("  slow piece %4d: %.1f us, start %.1f us, SM %d, source deg %s, max target deg %d" % (q, dur[q], (st[q] - t00) / 1e3, smid[q], sorted(set(deg[a].tolist())), deg[b].max()))
