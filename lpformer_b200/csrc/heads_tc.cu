@@ -12,11 +12,16 @@
 // (= one TMEM lane, half of the accumulator columns each), so LayerNorm and the final dot product take one
 // shared-memory exchange between the two.
 //
-// Software pipeline across tiles: warps 8-11 (producers) gather tile t+1's X[a]*X[b] rows into registers while
-// tile t is computed; as soon as contraction 2 of tile t has finished reading the operand tile they store the
-// hi/lo split there and issue contraction 1 of tile t+1, which runs on the tensor pipe while warps 0-7
-// (consumers) are still in tile t's final epilogue.  HBM latency, the operand split and half of the MMA time
-// are off the consumers' critical path; hand-offs are mbarriers fed by tcgen05.commit.
+// Software pipeline across tiles: warps 8-15 (producers) gather the X[a]*X[b] rows of a tile in two halves whose
+// reads and stores alternate — while one half is split into hi / lo and stored in the UMMA layout, the reads of the
+// other half (and of the next tile) are in flight; link ids run three tiles ahead in a shared-memory ring and the rows
+// are pulled into L2 two tiles ahead.  As soon as contraction 2 of tile t has finished reading the operand tile the
+// MMA warp issues contraction 1 of tile t+1, which runs on the tensor pipe while warps 0-7 (consumers) are still in
+// tile t's final epilogue.  Hand-offs are mbarriers fed by tcgen05.commit.  Measured (tools/heads_clocks.py, sustained
+// load: the SM clock settles at ~1.3 GHz under the power cap): ~5.3 k cycles per tile, of which the two contractions
+// (fed from shared memory, 3xTF32) hold the tensor pipe ~3.5 k and the consumers' epilogues ~2.9 k; the gather is no
+// longer on the critical path (removing its reads altogether shortens the period by 10 %).  Per-row bulk TMA copies
+// were tried for the gather and are slower (128 small copies per tile: ~5 k cycles from issue to completion).
 //
 // `offset` carries the pairwise half of the concatenated feature vector [el | pw] (models/link_transformer.py:105,
 // train/testing.py:31): for a link whose selected node sets are all empty, pw is the same vector for every link
@@ -34,8 +39,8 @@ constexpr int kHeadConsumers = 256;   // warps 0-7: TWO threads per link (= TMEM
                                       // reads lanes 32 (w % 4) .. + 31 (the hardware's lane quadrant of a warp), column half w / 4.
                                       // The epilogues are CUDA-core work on 192 accumulator columns per link, and one warp per SM
                                       // sub-partition cannot hide its own instruction latencies; thread 0 issues the MMAs
-constexpr int kHeadProducers = 128;   // warps 8-11: gather X[a]*X[b] of the NEXT tile while this one is computed
-constexpr int kHeadThreads = kHeadConsumers + kHeadProducers + 32;   // + warp 12: one thread issues every MMA
+constexpr int kHeadProducers = 256;   // warps 8-15: gather X[a]*X[b] of the NEXT tile while this one is computed
+constexpr int kHeadThreads = kHeadConsumers + kHeadProducers + 32;   // + warp 16: one thread issues every MMA
 
 struct HeadsParams {
     const int64_t* links;
@@ -69,7 +74,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 template <int D, bool ZB>
-__global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsParams p) {   // (13 warps are allocated as 16: 128 registers)
+__global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsParams p) {
     constexpr int KB = D / 32;                       // k-blocks of both contractions (K = D)
     constexpr int N3 = 2 * D;                        // width of mlp_score's hidden layer
     constexpr uint32_t W1_BYTES = KB * 2 * D * 128;  // packed [D, D]
@@ -85,11 +90,12 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
     __shared__ uint64_t bar_w, bar_mma1[2], bar_d1_free[2], bar_mma3, bar_a_ready, bar_h_ready;
     __shared__ uint32_t tmem_slot;
     __shared__ int32_t s_tile[8];                    // ring of this CTA's tile numbers (-1: no more), written 3 ahead
-    __shared__ int32_t ids[2][2][kTileM];            // [tile parity][a, b][row]
+    __shared__ int32_t ids[4][2][kTileM];            // ring over tiles: [tile & 3][a, b][row], written three tiles ahead
     __shared__ __align__(16) float s_b1[D], s_g[D], s_bt[D], s_c3[N3], s_ws2[N3];
     __shared__ float s_sum[2][kTileM], s_sq[2][kTileM], s_dot[2][kTileM];   // exchanges between the two threads of a link
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[256] = clock64();       // (profiling: kernel start / end of CTA 0)
     if (p.n_dev) p.n = min(p.n, *p.n_dev);
     const int64_t ntiles = (p.n + kTileM - 1) / kTileM;
     // Tile k of this CTA: blockIdx.x + k gridDim.x, or — with p.sched — the next tile nobody has taken yet.  The CTAs of
@@ -175,7 +181,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
                 __syncwarp();
             };
             const bool mstamp = p.dbg && blockIdx.x == 0 && (tid & 31) == 0;
-#define LPF_MSTAMP(k) do { if (mstamp && it < 8) p.dbg[it * 16 + 8 + (k)] = clock64(); } while (0)
+#define LPF_MSTAMP(k) do { if (mstamp && it < 16) p.dbg[it * 16 + 8 + (k)] = clock64(); } while (0)
             mma1(0);
             for (uint32_t it = 0; s_tile[it & 7] >= 0; ++it) {
                 LPF_MSTAMP(0);
@@ -203,8 +209,13 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
         return;
     }
     if (warp >= kHeadConsumers / 32) {
-        // =========================== producers: gather tile t+1 while tile t is computed, then (once the operand
-        // tile is free) split it into hi / lo, store it in the UMMA layout and issue contraction 1
+        // =========================== producers: gather X[a]*X[b] of the tiles, split it into hi / lo and store it in the
+        // UMMA layout.  Measured: the gather of one tile (128 rows of 4D bytes through four warps' load-store path)
+        // streams at ~10 B/clk and takes longer than everything else in the loop, so it must never pause: the tile is
+        // handled in two HALVES (rows 0-63, 64-127) whose reads and stores alternate — while one half is split and
+        // stored, the reads of the other are in flight (the same 64 data registers as one whole tile).
+        constexpr int RPP = kHeadProducers / 8;          // rows per pass (eight threads per row)
+        constexpr int HP = kTileM / RPP / 2;             // passes per half tile
         const int ptid = tid - kHeadConsumers;
         const int chunk = ptid & 7, row_in_pass = ptid >> 3;
         const bool vec_x = ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0) && (p.ldx % 4 == 0);
@@ -212,7 +223,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
         auto load_ids = [&](int32_t tile, int32_t& a, int32_t& b) {
             const int64_t j = (int64_t)tile * kTileM + ptid;
             a = 0; b = 0;
-            if (tile >= 0 && j < p.n) {
+            if (tile >= 0 && j < p.n && ptid < kTileM) {
                 const int64_t pos = p.idx ? (int64_t)__ldg(p.idx + j) : j;
                 a = (int32_t)__ldg(p.links + pos);
                 b = (int32_t)__ldg(p.links + p.bs + pos);
@@ -227,76 +238,94 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(rb + o));
             }
         };
-        // The gather (random 256-byte rows) is a DRAM round trip of ~3,000 cycles under load, longer than everything else
-        // in the producers' loop: the ids run three tiles ahead of the gather and the rows are pulled into L2 two tiles ahead.
-        int32_t a_cur, b_cur, a_n1, b_n1, a_n2, b_n2;
-        load_ids(s_tile[0], a_cur, b_cur);
-        load_ids(s_tile[1], a_n1, b_n1);
-        load_ids(s_tile[2], a_n2, b_n2);
-        if (s_tile[1] >= 0) prefetch_rows(a_n1, b_n1);
-        const bool pstamp = p.dbg && blockIdx.x == 0 && ptid == 0;
-#define LPF_PSTAMP(k) do { if (pstamp && it < 8) p.dbg[it * 16 + 13 + (k)] = clock64(); } while (0)
-        for (; s_tile[it & 7] >= 0; ++it) {
-            LPF_PSTAMP(0);
-            if (ptid == 0) s_tile[(it + 3) & 7] = fetch_tile(it + 3);
-            ids[it & 1][0][ptid] = a_cur;
-            ids[it & 1][1][ptid] = b_cur;
-            if (s_tile[(it + 2) & 7] >= 0) prefetch_rows(a_n2, b_n2);
-            named_bar_sync(2, kHeadProducers);
-            int32_t a_n3, b_n3;
-            load_ids(s_tile[(it + 3) & 7], a_n3, b_n3);
-            named_bar_sync(2, kHeadProducers);
-            // X[b] first, every read in flight at once (the registers that will hold the products receive the rows); then
-            // X[a]: in an evaluation batch the links of a tile share their source (train/testing.py:20-23), so the thread's
-            // eight rows usually have the same a and one read per k-block serves them all
-            float4 v[KB][8];
-            const int32_t a0 = ids[it & 1][0][row_in_pass];
-            bool same_a = true;
+        // this thread's X[b] row of a tile into L1, without a register or a scoreboard entry (the four warps' loads alone
+        // keep too few requests in flight to cover the L2 latency)
+        auto prefetch_l1 = [&](int32_t b) {
+            const char* rb = reinterpret_cast<const char*>(p.X + (int64_t)b * p.ldx);
 #pragma unroll
-            for (int pass = 1; pass < 8; ++pass) same_a &= ids[it & 1][0][pass * 16 + row_in_pass] == a0;
-            auto ld4 = [&](const float* q) -> float4 {
-                if (vec_x) return __ldg(reinterpret_cast<const float4*>(q));
-                return make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
-            };
+            for (int o = 0; o < D * 4; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(rb + o));
+        };
+        auto ld4 = [&](const float* q) -> float4 {
+            if (vec_x) return __ldg(reinterpret_cast<const float4*>(q));
+            return make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
+        };
+        // the X[b] reads of half h (passes 4h .. 4h+3) of the tile in ring slot `slot`
+        auto load_half = [&](uint32_t slot, int h, float4 (&v)[KB][HP]) {
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
-                for (int pass = 0; pass < 8; ++pass)
-                    v[kb][pass] = ld4(p.X + (int64_t)ids[it & 1][1][pass * 16 + row_in_pass] * p.ldx + kb * 32 + chunk * 4);
-            if (same_a) {
-                float4 xa[KB];
-#pragma unroll
-                for (int kb = 0; kb < KB; ++kb) xa[kb] = ld4(p.X + (int64_t)a0 * p.ldx + kb * 32 + chunk * 4);
-#pragma unroll
-                for (int kb = 0; kb < KB; ++kb)
-#pragma unroll
-                    for (int pass = 0; pass < 8; ++pass) {
-                        v[kb][pass].x *= xa[kb].x; v[kb][pass].y *= xa[kb].y; v[kb][pass].z *= xa[kb].z; v[kb][pass].w *= xa[kb].w;
-                    }
-            } else {
-#pragma unroll
-                for (int kb = 0; kb < KB; ++kb)
-#pragma unroll
-                    for (int pass = 0; pass < 8; ++pass) {
-                        const float4 xa = ld4(p.X + (int64_t)ids[it & 1][0][pass * 16 + row_in_pass] * p.ldx + kb * 32 + chunk * 4);
-                        v[kb][pass].x *= xa.x; v[kb][pass].y *= xa.y; v[kb][pass].z *= xa.z; v[kb][pass].w *= xa.w;
-                    }
-            }
-            LPF_PSTAMP(1);
-            a_cur = a_n1; b_cur = b_n1; a_n1 = a_n2; b_n1 = b_n2; a_n2 = a_n3; b_n2 = b_n3;
-            if (it > 0) mbar_wait(&bar_mma1[(it - 1) & 1], ((it - 1) >> 1) & 1);     // contraction 1 of the previous tile has read the operand tile
+                for (int q = 0; q < HP; ++q)
+                    v[kb][q] = ld4(p.X + (int64_t)ids[slot][1][(HP * h + q) * RPP + row_in_pass] * p.ldx + kb * 32 + chunk * 4);
+        };
+        // X[a] * X[b], hi / lo split, store of half h.  In an evaluation batch the links of a tile share their source
+        // (train/testing.py:20-23): then one X[a] read per k-block (xa, read a tile ahead) serves the thread's rows.
+        auto store_half = [&](uint32_t slot, int h, float4 (&v)[KB][HP], bool same_a, const float4 (&xa)[KB]) {
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
-                for (int pass = 0; pass < 8; ++pass) {
-                    const float4 x = v[kb][pass];
+                for (int q = 0; q < HP; ++q) {
+                    const int row = (HP * h + q) * RPP + row_in_pass;
+                    float4 m = xa[kb];
+                    if (!same_a) m = ld4(p.X + (int64_t)ids[slot][0][row] * p.ldx + kb * 32 + chunk * 4);
+                    const float4 x = make_float4(v[kb][q].x * m.x, v[kb][q].y * m.y, v[kb][q].z * m.z, v[kb][q].w * m.w);
                     const float4 hi = make_float4(tf32_hi(x.x), tf32_hi(x.y), tf32_hi(x.z), tf32_hi(x.w));
                     const float4 lo = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
-                    const uint32_t off = (uint32_t)kb * 2 * kATileBytes + swz_chunk_off(pass * 16 + row_in_pass, chunk);
+                    const uint32_t off = (uint32_t)kb * 2 * kATileBytes + swz_chunk_off(row, chunk);
                     *reinterpret_cast<float4*>(sA + off) = hi;
                     *reinterpret_cast<float4*>(sA + off + kATileBytes) = lo;
                 }
+        };
+        // does every row of this thread in the tile of ring slot `slot` share its source?  (and that source's X row)
+        auto tile_source = [&](uint32_t slot, bool& same_a, float4 (&xa)[KB]) {
+            const int32_t a0 = ids[slot][0][row_in_pass];
+            same_a = true;
+#pragma unroll
+            for (int pass = 1; pass < 2 * HP; ++pass) same_a &= ids[slot][0][pass * RPP + row_in_pass] == a0;
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) xa[kb] = ld4(p.X + (int64_t)a0 * p.ldx + kb * 32 + chunk * 4);
+        };
+        // The link ids of a tile come from DRAM (the batch's links are streamed once) and its rows from L2 if they were
+        // prefetched: the ids run three tiles ahead in a shared-memory ring and the rows are pulled into L2 two tiles ahead.
+        {
+            int32_t a, b;
+            for (int k = 0; k < 3; ++k) {
+                load_ids(s_tile[k], a, b);
+                if (ptid < kTileM) { ids[k][0][ptid] = a; ids[k][1][ptid] = b; }
+            }
+        }
+        named_bar_sync(2, kHeadProducers);
+        if (s_tile[1] >= 0 && ptid < kTileM) prefetch_rows(ids[1][0][ptid], ids[1][1][ptid]);
+        float4 v0[KB][HP], v1[KB][HP], xa[KB];
+        bool same_a;
+        tile_source(0, same_a, xa);
+        load_half(0, 0, v0);
+        load_half(0, 1, v1);
+        const bool pstamp = p.dbg && blockIdx.x == 0 && ptid == 0;
+#define LPF_PSTAMP(k) do { if (pstamp && it < 16) p.dbg[it * 16 + 13 + (k)] = clock64(); } while (0)
+        for (; s_tile[it & 7] >= 0; ++it) {
+            LPF_PSTAMP(0);
+            if (ptid == 0) s_tile[(it + 3) & 7] = fetch_tile(it + 3);
+            if (s_tile[(it + 2) & 7] >= 0 && ptid < kTileM) prefetch_rows(ids[(it + 2) & 3][0][ptid], ids[(it + 2) & 3][1][ptid]);
+            named_bar_sync(2, kHeadProducers);
+            int32_t a_n3, b_n3;
+            load_ids(s_tile[(it + 3) & 7], a_n3, b_n3);      // (first used at the end of the iteration)
+            const bool more = s_tile[(it + 1) & 7] >= 0;
+            // the next tile's source row (a tile ahead: an L2 hit that is not waited for until the next iteration)
+            bool same_n = true;
+            float4 xa_n[KB];
+            if (more) tile_source((it + 1) & 3, same_n, xa_n);
+            if (it > 0) mbar_wait(&bar_mma1[(it - 1) & 1], ((it - 1) >> 1) & 1);     // contraction 1 of the previous tile has read the operand tile
+            LPF_PSTAMP(1);
+            store_half(it & 3, 0, v0, same_a, xa);
+            if (more) load_half((it + 1) & 3, 0, v0);
+            store_half(it & 3, 1, v1, same_a, xa);
+            if (more) load_half((it + 1) & 3, 1, v1);
+            same_a = same_n;
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) xa[kb] = xa_n[kb];
             fence_async_smem();
+            // (first use of this iteration's id reads; ring slot (it + 3) & 3 held tile it - 1, gathered an iteration ago)
+            if (ptid < kTileM) { ids[(it + 3) & 3][0][ptid] = a_n3; ids[(it + 3) & 3][1][ptid] = b_n3; }
             named_bar_sync(2, kHeadProducers);
             if (ptid == 0) mbar_arrive(&bar_a_ready);
             LPF_PSTAMP(2);
@@ -311,7 +340,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t it = 0;
     const bool stamp = p.dbg && blockIdx.x == 0 && tid == 0;
-#define LPF_STAMP(k) do { if (stamp && it < 8) p.dbg[it * 16 + (k)] = clock64(); } while (0)
+#define LPF_STAMP(k) do { if (stamp && it < 16) p.dbg[it * 16 + (k)] = clock64(); } while (0)
 
     // epilogue 2 of a tile: prob = sigmoid(ws2 . ReLU(D3 + offset) + bs2)
     auto epilogue2 = [&](int64_t j, uint32_t d3b) {
@@ -444,6 +473,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) link_heads_tc_kernel(HeadsPar
     tc_fence_before();
     named_bar_sync(1, kHeadConsumers);
     if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
+    if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[257] = clock64();
     if (tid == 0) retire();
 }
 
@@ -451,14 +481,11 @@ template <int D, bool ZB>
 static int launch_heads(const HeadsParams& p, cudaStream_t st) {
     constexpr int KB = D / 32;
     constexpr size_t smem = (size_t)KB * 2 * D * 128 + (size_t)KB * 2 * 2 * D * 128 + (size_t)KB * 2 * tc::kATileBytes + 1024;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(link_heads_tc_kernel<D, ZB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) {
-            set_error("lpf_link_heads_tc: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
-            return LPF_ERR_CUDA;
-        }
-        configured = true;
+    // (the attribute is per device: set on every call — a process may drive several GPUs)
+    cudaError_t e = cudaFuncSetAttribute(link_heads_tc_kernel<D, ZB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("lpf_link_heads_tc: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+        return LPF_ERR_CUDA;
     }
     const int64_t ntiles = (p.n + tc::kTileM - 1) / tc::kTileM;
     const int per_sm = D <= 32 ? 2 : 1;
@@ -472,8 +499,9 @@ static int launch_heads(const HeadsParams& p, cudaStream_t st) {
 using namespace lpf;
 
 static long long* g_heads_dbg = nullptr;
-// Debug hook (not part of the data path): device buffer of 8 x 16 int64 that CTA 0 of every later
-// lpf_link_heads_tc launch fills with per-phase clock64() stamps of its first 8 tiles; NULL switches it off.
+// Debug hook (not part of the data path): device buffer of 16 x 16 + 16 int64 that CTA 0 of every later
+// lpf_link_heads_tc launch fills with per-phase clock64() stamps of its first 16 tiles (+ kernel start / end at
+// [256], [257]); NULL switches it off.
 extern "C" int lpf_debug_heads_clocks(void* device_buffer) {
     g_heads_dbg = (long long*)device_buffer;
     return LPF_OK;

@@ -11,7 +11,7 @@ import lpformer_b200 as L  # noqa: E402
 from lpformer_b200 import _lib, ops  # noqa: E402
 
 dev = torch.device("cuda:0")
-n, d = 400000, 64
+n, d = 2927963, 64
 targs = dict(dim=d, num_heads=1, trans_layers=1, gnn_layers=1, residual=False, layer_norm=True, relu=True,
              thresh_cn=0, thresh_1hop=1e-3, thresh_non1hop=1e-2)
 data = {"x": torch.zeros(n, 4)}
@@ -20,13 +20,13 @@ model = L.LinkTransformer(targs, data, device=dev).to(dev).eval()
 score = L.mlp_score(2 * d, 2 * d, 1, 2).to(dev).eval()
 X = torch.randn(n, d, device=dev)
 consts = model._head_consts(score, X)
-bs = 148 * 128 * 10
+bs = 256 * 1001
 links = torch.randint(0, n, (2, bs), device=dev)
-links[0] = links[0, 0]
+links[0] = torch.randint(0, n, (256,), device=dev).repeat_interleave(1001)     # citation2-style runs of one source
 prob = torch.empty(bs, device=dev)
-buf = torch.zeros(8 * 16, dtype=torch.int64, device=dev)
+buf = torch.zeros(16 * 16 + 16, dtype=torch.int64, device=dev)
 lib = _lib.load()
-for rep in range(3):
+for rep in range(400):          # (long enough for the clocks to ramp up)
     ops.link_heads(links, X, consts, prob)
 torch.cuda.synchronize()
 lib.lpf_debug_heads_clocks(buf.data_ptr())
@@ -36,10 +36,12 @@ ops.link_heads(links, X, consts, prob)
 e1.record()
 torch.cuda.synchronize()
 lib.lpf_debug_heads_clocks(None)
-full = buf.cpu().numpy().reshape(8, 16)
+raw = buf.cpu().numpy()
+full = raw[:256].reshape(16, 16)
+print("kernel %.1f us for %.1f tiles/CTA -> SM clock %.2f GHz" % (1e3 * e0.elapsed_time(e1), bs / 128 / 148, (raw[257] - raw[256]) / (1e3 * e0.elapsed_time(e1)) / 1e3))
+print("CTA 0: kernel start -> first tile top %d cycles; tile tops (consumer) relative to start: %s; end %d" % (full[0, 0] - raw[256], [int(full[i, 0] - raw[256]) for i in range(10)], raw[257] - raw[256]))
 t = full[:, :7]
 names = ["wait_mma1", "epi1", "wait_mma3(prev)", "store_h+sync", "issue_mma3", "epi2(prev)"]
-print("kernel %.1f us for %d tiles/CTA" % (1e3 * e0.elapsed_time(e1), bs // 128 // 148))
 for i in range(1, 8):
     dt = np.diff(t[i])
     nxt = (" period=%d" % (t[i + 1, 0] - t[i, 0])) if i < 7 else ""
