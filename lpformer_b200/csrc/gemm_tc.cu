@@ -222,16 +222,18 @@ extern "C" int lpf_gemm_tc(const float* A, int64_t lda, const float* Wpacked, co
     p.M = M; p.N = N; p.K = K; p.NP = tc::round_up(N, 16); p.KB = (K + 31) / 32; p.epi = epilogue;
     p.tmem_cols = tc::tmem_cols_for(p.NP);
     p.m_dev = m_dev;
-    const int stages = p.KB < 2 ? 1 : 2;
+    // always two ring stages: the kernel indexes the ring with a k-block counter that keeps running across the tiles
+    // of a persistent CTA, so a single-k-block contraction (K <= 32) uses stage 1 for its second tile
+    const int stages = 2;
     const size_t smem = (size_t)stages * (2 * tc::kATileBytes + 2 * (size_t)p.NP * 128) + 1024;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // (the attribute is per device and a process may drive several GPUs: set it on every call, at its maximum)
+    {
+        const size_t smem_max = (size_t)stages * (2 * tc::kATileBytes + 2 * (size_t)256 * 128) + 1024;
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
         if (e != cudaSuccess) {
-            set_error("lpf_gemm_tc: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+            set_error("lpf_gemm_tc: cudaFuncSetAttribute(%zu B): %s", smem_max, cudaGetErrorString(e));
             return LPF_ERR_CUDA;
         }
-        configured = smem;
     }
     // one CTA per tile; with a device-side row count the host M is only a capacity, so cap the grid at a few
     // CTAs per SM and let them walk the tiles that really exist

@@ -46,9 +46,10 @@ class _GlorotLinear(nn.Module):
 
     def reset_parameters(self):
         stdv = math.sqrt(6.0 / (self.weight.size(-2) + self.weight.size(-1)))
-        self.weight.data.uniform_(-stdv, stdv)
-        if self.bias is not None:
-            self.bias.data.fill_(0)
+        with torch.no_grad():       # (in place on the Parameter itself: bumps _version, which keys the derived caches)
+            self.weight.uniform_(-stdv, stdv)
+            if self.bias is not None:
+                self.bias.fill_(0)
 
     def forward(self, x):
         return ops.linear(x, self.weight, self.bias)
@@ -141,7 +142,8 @@ class GCNConv(nn.Module):
 
     def reset_parameters(self):
         self.lin.reset_parameters()
-        self.bias.data.fill_(0)
+        with torch.no_grad():
+            self.bias.fill_(0)
 
     @torch.no_grad()
     def forward(self, x, adj_norm: CSR, out=None, row0=0, rows=None):
@@ -238,8 +240,9 @@ class LinkAttention(nn.Module):
         self.lin_l.reset_parameters()
         self.lin_r.reset_parameters()
         stdv = math.sqrt(6.0 / (self.att.size(-2) + self.att.size(-1)))
-        self.att.data.uniform_(-stdv, stdv)
-        self.bias.data.fill_(0)
+        with torch.no_grad():
+            self.att.uniform_(-stdv, stdv)
+            self.bias.fill_(0)
 
 
 class LinkTransformerLayer(nn.Module):
@@ -325,6 +328,7 @@ class LinkTransformer(nn.Module):
         pairwise_dim = self.dim * train_args["num_heads"] + count_dim
         self.pairwise_lin = MLP(2, pairwise_dim, pairwise_dim, self.dim)
 
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_weights())
         self._tables = {False: _Tables(), True: _Tables()}
         self._derived = None        # folded weights, keyed by parameter versions
         self._kv_cache = None       # per-layer KV tables, keyed by the X_node they were built from
@@ -386,6 +390,19 @@ class LinkTransformer(nn.Module):
     def invalidate_graph_tables(self):
         """Call after mutating the sparse tensors inside `data`."""
         self._tables = {False: _Tables(), True: _Tables()}
+
+    def invalidate_weights(self):
+        """Drops everything derived from the parameters (folded weights, packed tensor-core images, K/V tables, the
+        empty-set pairwise constant, head operands, execution plans and their CUDA graphs).  The caches are keyed on
+        Parameter._version, which writes through `.data` (reset_parameters, some optimisers) do not bump: call this
+        after such an update.  load_state_dict and reset_parameters call it themselves."""
+        self._derived = None
+        self._kv_cache = None
+        self._pw_const_cache = None
+        self._head_cache = None
+        self._plans = {}
+        self.__dict__.pop("_plist", None)
+        ops.drop_packed_weights()
 
     # ------------------------------------------------------------------ folded weights
     def _encoders(self):
@@ -481,9 +498,19 @@ class LinkTransformer(nn.Module):
 
     def _select(self, batch, test_set, adj_mask=None, want_link=False):
         _no_training(self, "node dropout (att_drop)" if self.att_drop > 0 else "")
-        adj = self.get_adj(test_set, mask=True) if adj_mask is None else csr_from_sparse(adj_mask, self._dev(), mask=True)
-        return ops.select(batch, adj, self.get_ppr(test_set), self.thresh_cn, self.thresh_1hop, self.thresh_non1hop,
-                          self.mask, want_link=want_link)
+        stored = self.get_adj(test_set, mask=True)
+        th = (self.thresh_cn, self.thresh_1hop, self.thresh_non1hop)
+        if adj_mask is None:
+            return ops.select(batch, stored, self.get_ppr(test_set), *th, self.mask, want_link=want_link)
+        # A caller-supplied adjacency (the reference's training loop passes the graph with the batch's positives
+        # removed) decides the CN and 1-hop sets only; the >1-hop set always comes from the STORED adjacency
+        # (reference get_non_1hop_ppr :434-447 calls get_adj itself).  Slow path: the CSR is rebuilt per call.
+        adj = csr_from_sparse(adj_mask, self._dev(), mask=True)
+        if self.mask != "all":
+            return ops.select(batch, adj, self.get_ppr(test_set), *th, self.mask, want_link=want_link)
+        near = ops.select(batch, adj, self.get_ppr(test_set), *th, "1-hop", want_link=want_link)
+        far = ops.select(batch, stored, self.get_ppr(test_set), *th, "all", want_link=want_link)
+        return ops.merge_selections(near, far)
 
     @torch.no_grad()
     def calc_pairwise(self, batch, X_node, test_set=False, adj_mask=None, return_weights=False, out=None):
@@ -577,6 +604,8 @@ class LinkTransformer(nn.Module):
         d = self.dim
         if ops.GEMM_BACKEND != "tc" or d not in (32, 64) or self.num_layers != 1:
             return None
+        if self.num_heads * self.att_layers[0].att.out_channels + self.count_dim > 256:
+            return None          # the plan's contractions are single UMMA tiles (N <= 256): host-sized path instead
         lins = getattr(score_func, "lins", None)
         el = self.elementwise_lin
         if lins is None or len(lins) != 2 or tuple(lins[0].weight.shape) != (2 * d, 2 * d) or \

@@ -166,6 +166,30 @@ class Selection:
         return (p[1:] - p[:-1]).view(3, self.bs)
 
 
+def merge_selections(near: Selection, far: Selection) -> Selection:
+    """CN and 1-hop sets of `near` with the >1-hop sets of `far` (two selections of the same batch over different
+    adjacency tables: a caller-supplied one decides CN / 1-hop, the stored one the >1-hop set — reference
+    models/link_transformer.py:226-254 vs :443-447).  Slow path (torch ops, one host sync)."""
+    bs, dev = near.bs, near.node.device
+    cn, hop = near.counts()[0], near.counts()[1]
+    far_cnt = far.counts()[2]
+    counts = torch.cat((cn, hop, far_cnt))
+    p = torch.zeros(3 * bs + 1, dtype=torch.int64, device=dev)
+    p[1:] = torch.cumsum(counts, 0)
+    n0, n1 = near.bounds[1], near.bounds[2]
+    f0, f1 = far.bounds[2], far.bounds[3]
+    cat = lambda a, b: torch.cat((a[:n1], b[f0:f1]))    # noqa: E731
+    link = None if near.link is None or far.link is None else cat(near.link, far.link)
+    nz = torch.nonzero((cn + hop + far_cnt) > 0).reshape(-1).to(torch.int32)
+    return Selection("all", bs, p, cat(near.node, far.node), cat(near.src_ppr, far.src_ppr), cat(near.tgt_ppr, far.tgt_ppr),
+                     link, (0, n0, n1, n1 + (f1 - f0)), nz)
+
+
+def drop_packed_weights():
+    """Forgets every cached tensor-core weight image (LinkTransformer.invalidate_weights)."""
+    _PACKED.clear()
+
+
 def links_tensor(batch, device) -> torch.Tensor:
     """int64 [2,BS] contiguous on `device` (reference forward() moves the batch, :98)."""
     b = torch.as_tensor(batch)

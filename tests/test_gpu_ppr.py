@@ -80,8 +80,6 @@ def test_ppr_push_bit_exact_vs_reference_numba_golden(golden):
     """Directly against the table the reference's own numba kernel produced for the golden graphs
     (tests/golden/make_golden.py ran util/calc_ppr_scores.py:137-192): same pattern, same fp32 bits."""
     from lpformer_b200 import ppr
-    if golden.cfg["eps"] < 1e-6:
-        pytest.skip("eps = 1e-7 (Cora script): ~1e6 pushes per source, a serial chain per warp — the host tool's case")
     adj, _, want = golden.oracle_graph()
     dev = torch.device("cuda:0")
     got = ppr.ppr_push(torch.from_numpy(adj.indptr.astype(np.int64)).to(dev),
@@ -89,3 +87,18 @@ def test_ppr_push_bit_exact_vs_reference_numba_golden(golden):
     assert np.array_equal(got.rowptr.cpu().numpy(), want.indptr)
     assert np.array_equal(got.col.cpu().numpy(), want.indices)
     assert np.array_equal(got.val.cpu().numpy().view(np.uint32), want.val.view(np.uint32))
+
+
+def test_ppr_push_cora_script_eps_bit_exact_vs_host_port():
+    """eps = 1e-7, the Cora line of the reference's scripts (scripts/replicate_heart.sh:4): the push touches nearly every
+    node of the component many times (~10^5 pops per source) — same table, bit for bit, as the host port of the
+    reference's numba kernel.  (Full Cora shape, 2,708 nodes / 5.66 M entries: 19 s on a B200 vs 16 s for the host port
+    on 16 cores and 447-552 s for the numba kernel on 8; `tools/ppr_cora.py`.)"""
+    from lpformer_b200 import ppr, synthetic as S
+    g = S.make_graph("cora", seed=3, scale=0.12, heldout=32)
+    assert g.cfg["eps"] == 1e-7
+    dev = torch.device("cuda:0")
+    got = ppr.ppr_push(torch.from_numpy(g.indptr).to(dev), torch.from_numpy(g.indices).to(dev), 0.15, g.cfg["eps"])
+    assert np.array_equal(got.rowptr.cpu().numpy(), g.ppr[0])
+    assert np.array_equal(got.col.cpu().numpy(), g.ppr[1])
+    assert np.array_equal(got.val.cpu().numpy().view(np.uint32), g.ppr[2].view(np.uint32))
