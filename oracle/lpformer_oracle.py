@@ -132,16 +132,22 @@ def select_link(adj: CSR, ppr: CSR, a, b, th_cn, th_1hop, th_non1hop, mode):
     return out
 
 
-def select_sets(adj: CSR, ppr: CSR, links, th_cn, th_1hop, th_non1hop):
+def select_sets(adj: CSR, ppr: CSR, links, th_cn, th_1hop, th_non1hop, adj_far: CSR = None):
     """All links of a batch.  Returns (mode, {type: (link_idx int64[S_t], node int64[S_t],
     src_ppr f32[S_t], tgt_ppr f32[S_t])}) sorted by (link, node) within a type, exactly
-    the tuples `compute_node_mask` returns (ix[0]=position in batch, ix[1]=node id)."""
+    the tuples `compute_node_mask` returns (ix[0]=position in batch, ix[1]=node id).
+
+    adj_far: the reference takes the >1-hop set from the STORED adjacency even when the caller hands
+    compute_node_mask another one for the CN / 1-hop sets (models/link_transformer.py:226-254 uses `adj`,
+    get_non_1hop_ppr :443-447 calls get_adj itself); pass the stored table here in that case."""
     links = np.asarray(links, dtype=np.int64)
     mode = model_mode(th_1hop, th_non1hop)
     types = {"cn": ["cn"], "1-hop": ["cn", "1hop"], "all": ["cn", "1hop", "non1hop"]}[mode]
     acc = {t: ([], [], [], []) for t in types}
     for i in range(links.shape[1]):
         res = select_link(adj, ppr, links[0, i], links[1, i], th_cn, th_1hop, th_non1hop, mode)
+        if adj_far is not None and mode == "all":
+            res = dict(res, non1hop=select_link(adj_far, ppr, links[0, i], links[1, i], th_cn, th_1hop, th_non1hop, mode)["non1hop"])
         for t in types:
             n, qa, qb = res[t]
             acc[t][0].append(np.full(len(n), i, np.int64))
@@ -311,7 +317,7 @@ def mlp_score(feats, S):
 
 # --------------------------------------------------------------------------- #
 # PPR push (util/calc_ppr_scores.py:137-192), pure Python: small graphs only.
-# oracle/oracle.c holds the same algorithm in C for larger ones.
+# larger ones take the host port of the same kernel (lpformer_b200/csrc/ppr_push.cpp, pinned by tests/test_host.py).
 # --------------------------------------------------------------------------- #
 def ppr_push(indptr, indices, alpha, eps):
     """Andersen push with a LIFO queue, float64 arithmetic, exactly the op order of

@@ -66,17 +66,90 @@ def test_features_scores_vs_reference_golden(golden):
     feats = torch.cat((torch.from_numpy(el).to(dev), pw), dim=-1)
     prob = score(feats).cpu().numpy()
     np.testing.assert_allclose(prob, g["prob"], rtol=FP32_RTOL, atol=1e-6)
-    logit = score(feats, return_logits=True).cpu().numpy().astype(np.float64)
-    ref_logit = np.log(g["prob"].astype(np.float64)) - np.log1p(-g["prob"].astype(np.float64))
-    np.testing.assert_allclose(logit, ref_logit, rtol=1e-3, atol=1e-4)   # logit recovered from fp32 prob: looser
+    logit = score(feats, return_logits=True).cpu().numpy()
+    np.testing.assert_allclose(logit, g["logit"], rtol=FP32_RTOL, atol=1e-6)     # the reference's pre-sigmoid values
     aw = attw.cpu().numpy()
     assert np.array_equal(aw[0], g["att_weights"][0])
     np.testing.assert_allclose(aw[1], g["att_weights"][1], rtol=1e-4, atol=1e-6)
     # the fused eval body and the full forward agree with the pieces
     fused = model.score_links(links, X, score).cpu().numpy()
     np.testing.assert_allclose(fused, g["prob"], rtol=FP32_RTOL, atol=1e-6)
-    full = model(links).cpu().numpy()                   # includes our own propagate()
-    np.testing.assert_allclose(full, g["feats"], rtol=1e-3, atol=1e-4)
+    fused_logit = model.score_links(links, X, score, return_logits=True).cpu().numpy()
+    np.testing.assert_allclose(fused_logit, g["logit"], rtol=FP32_RTOL, atol=2e-6)
+    # model(links) includes our own propagate(): X_node itself is within 1e-4 / 2e-5 of the reference's
+    # (test_propagate_vs_reference_golden); through the two LayerNorm + ReLU MLPs that input difference is amplified
+    # (measured: up to 3e-4 relative on features of magnitude ~1e-2), so the forward is checked at the tolerance the
+    # propagated difference allows and the per-link path at 1e-4 above, on the reference's own X_node
+    full = model(links).cpu().numpy()
+    np.testing.assert_allclose(full, g["feats"], rtol=5e-4, atol=5e-5)
+
+
+def _assert_sets(infos, ref):
+    for t, info in zip(("cn", "1hop", "non1hop"), infos):
+        if t not in ref:
+            assert info is None
+            continue
+        ix, src, tgt = ref[t]
+        assert np.array_equal(info[0].cpu().numpy(), ix), t
+        assert np.array_equal(info[1].cpu().numpy().view(np.uint32), src.view(np.uint32)), t
+        assert np.array_equal(info[2].cpu().numpy().view(np.uint32), tgt.view(np.uint32)), t
+
+
+def test_test_set_tables_vs_reference_golden():
+    """test_set=True must read full_adj_t / full_adj_mask / ppr_test (reference link_transformer.py:389-406); this
+    golden's full graph and PPR table DIFFER from the train ones, so a swapped table changes every output below.
+    Covers compute_node_mask, propagate, calc_pairwise, score_links (plan + CUDA-graph replay) and LinkScoreStream."""
+    from oracle.golden import Golden
+    from lpformer_b200.evaluate import LinkScoreStream
+    g = Golden("testset_d32")
+    model, score = build(g)
+    dev = torch.device("cuda:0")
+    links = torch.from_numpy(g["links"]).to(dev)
+    _assert_sets(model.compute_node_mask(links, True, None), g.sets("ts_"))
+    _assert_sets(model.compute_node_mask(links, False, None), g.sets())
+    np.testing.assert_allclose(model.propagate(test_set=True).cpu().numpy(), g["ts_X_node"], rtol=FP32_RTOL, atol=2e-5)
+    np.testing.assert_allclose(model.propagate().cpu().numpy(), g["X_node"], rtol=FP32_RTOL, atol=2e-5)
+    X = torch.from_numpy(g["X_node"]).to(dev)            # the eval loops score test links on the TRAIN-graph embeddings
+    pw, _ = model.calc_pairwise(links, X, test_set=True)
+    np.testing.assert_allclose(pw.cpu().numpy(), g["ts_pw"], rtol=FP32_RTOL, atol=2e-5)
+    for rep in range(3):                                  # eager, then CUDA-graph replays of the plan
+        prob = model.score_links(links, X, score, test_set=True).cpu().numpy()
+        np.testing.assert_allclose(prob, g["ts_prob"], rtol=FP32_RTOL, atol=1e-6)
+        np.testing.assert_allclose(model.score_links(links, X, score, test_set=False).cpu().numpy(), g["prob"], rtol=FP32_RTOL, atol=1e-6)
+    logit = model.score_links(links, X, score, test_set=True, return_logits=True).cpu().numpy()
+    np.testing.assert_allclose(logit, g["ts_logit"], rtol=FP32_RTOL, atol=2e-6)
+    stream = LinkScoreStream(model, score, X, 128, depth=2, test_set=True)
+    np.testing.assert_allclose(stream.score(links).cpu().numpy(), g["ts_prob"], rtol=FP32_RTOL, atol=1e-6)
+    assert not np.allclose(g["ts_prob"], g["prob"], rtol=1e-3)       # the two table sets really give different scores
+
+
+def test_caller_supplied_adjacency_vs_reference_golden():
+    """compute_node_mask / calc_pairwise with adj_mask= (the train graph without the batch's positives, as the
+    reference's training loop passes it): CN and 1-hop from the supplied table, >1-hop from the stored one
+    (reference link_transformer.py:226-254 vs :443-447)."""
+    from oracle.golden import Golden
+    g = Golden("testset_d32")
+    model, _ = build(g)
+    dev = torch.device("cuda:0")
+    links = torch.from_numpy(g["links"]).to(dev)
+    am = g.masked_adjacency_coo(dev)
+    _assert_sets(model.compute_node_mask(links, False, am), g.sets("am_"))
+    X = torch.from_numpy(g["X_node"]).to(dev)
+    pw, _ = model.calc_pairwise(links, X, test_set=False, adj_mask=am)
+    np.testing.assert_allclose(pw.cpu().numpy(), g["am_pw"], rtol=FP32_RTOL, atol=2e-5)
+    assert not np.array_equal(g.sets("am_")["cn"][0], g.sets()["cn"][0])
+
+
+def test_emb_features_vs_reference_golden():
+    """data['emb'](data['x']) feeds the GCN (reference link_transformer.py:122-123)."""
+    from oracle.golden import Golden
+    g = Golden("emb_d16")
+    model, score = build(g)
+    X = model.propagate()
+    np.testing.assert_allclose(X.cpu().numpy(), g["X_node"], rtol=FP32_RTOL, atol=2e-5)
+    links = torch.from_numpy(g["links"]).to(X.device)
+    Xr = torch.from_numpy(g["X_node"]).to(X.device)
+    np.testing.assert_allclose(model.score_links(links, Xr, score).cpu().numpy(), g["prob"], rtol=FP32_RTOL, atol=1e-6)
 
 
 def test_counts_vs_oracle(golden):
@@ -236,6 +309,49 @@ def test_score_links_synthetic_vs_oracle(workload, scale, nq, negs):
     np.testing.assert_allclose(pw_simt.cpu().numpy(), feats[:, cfg["dim"]:], rtol=FP32_RTOL, atol=2e-5)
     pw_tc, _ = model.calc_pairwise(links, X)
     np.testing.assert_allclose(pw_tc.cpu().numpy(), feats[:, cfg["dim"]:], rtol=FP32_RTOL, atol=2e-5)
+
+
+@pytest.mark.parametrize("workload,scale,nq,negs", [("collab", 0.03, 4, 100), ("ddi", 0.25, 3, 60), ("cora", 0.12, 4, 80)])
+def test_score_links_wide_dims_vs_oracle(workload, scale, nq, negs):
+    """d = 128 (collab script) and d = 256 (ddi: mode 1-hop with ~100 common neighbours per link; Cora: no LayerNorm /
+    ReLU in the GCN) — the unfused path: attend_kernel with 128 / 256 channels, the >= 260-wide pairwise_lin
+    contraction split over UMMA tiles — end to end against the float64 oracle at 1e-4 on logits."""
+    import lpformer_b200 as L
+    from lpformer_b200 import synthetic as S
+    g = S.make_graph(workload, seed=13, scale=scale, heldout=64)
+    cfg = g.cfg
+    targs = S.train_args_of(cfg)
+    dev = torch.device("cuda:0")
+    torch.manual_seed(7)
+    model = L.LinkTransformer(targs, g.data_dict(dev), device=dev).to(dev).eval()
+    score = L.mlp_score(model.out_dim, model.out_dim, 1, 2).to(dev).eval()
+    with torch.no_grad():
+        for p in list(model.parameters()) + list(score.parameters()):
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    rng = np.random.default_rng(4)
+    pos = g.edges[:, rng.integers(0, g.edges.shape[1], 60)]
+    links_np = np.concatenate([S.heart_queries(g, nq, negs, seed=2), pos], axis=1).astype(np.int64)
+    links = torch.from_numpy(links_np).to(dev)
+    X = model.propagate()                                   # our own GCN output (the oracle gets the same table)
+    assert X.shape[1] == cfg["dim"] and cfg["dim"] in (128, 256)
+    logit = model.score_links(links, X, score, return_logits=True).cpu().numpy()
+    prob = model.score_links(links, X, score).cpu().numpy()
+    P = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in model.state_dict().items()}
+    Sd = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in score.state_dict().items()}
+    adj_o = O.CSR(g.indptr, g.indices, None, g.n)
+    ppr_o = O.CSR(g.ppr[0], g.ppr[1], g.ppr[2], g.n)
+    feats, (mode, sets), counts, _ = O.link_features(links_np, X.cpu().numpy().astype(np.float64), adj_o, ppr_o, P, dict(targs))
+    ref_logit, ref_prob = O.mlp_score(feats, Sd)
+    assert mode == model.mask and (counts.sum(1) > 0).sum() > 20
+    if workload == "ddi":
+        assert mode == "1-hop" and counts[:, 0].mean() > 20            # dense graph: tens of common neighbours per link
+    np.testing.assert_allclose(logit, ref_logit, rtol=FP32_RTOL, atol=1e-5)
+    np.testing.assert_allclose(prob, ref_prob, rtol=FP32_RTOL, atol=1e-6)
+    # the GCN itself at these widths against the float64 oracle
+    adj_w = O.CSR(g.indptr, g.indices, np.ones(g.indices.size), g.n)
+    Xo = O.propagate(g.x.astype(np.float64), adj_w, P, dict(targs))
+    np.testing.assert_allclose(X.cpu().numpy(), Xo, rtol=FP32_RTOL, atol=2e-5)
 
 
 def test_plan_graph_replay_and_overflow():

@@ -30,8 +30,11 @@ def test_selection_bit_exact(golden):
 def test_propagate(golden):
     g = golden
     _, adj_w, _ = graph_of(g)
-    X = O.propagate(g["x"], adj_w, g.model_params, g.cfg)
+    X = O.propagate(g.features(), adj_w, g.model_params, g.cfg)
     np.testing.assert_allclose(X, g["X_node"], rtol=1e-4, atol=2e-5)
+    if g.has_full_graph:        # propagate(test_set=True): the full graph's weighted adjacency
+        _, full_w, _ = g.oracle_graph(full=True)
+        np.testing.assert_allclose(O.propagate(g.features(), full_w, g.model_params, g.cfg), g["ts_X_node"], rtol=1e-4, atol=2e-5)
 
 
 def test_features_and_scores(golden):
@@ -43,15 +46,53 @@ def test_features_and_scores(golden):
     np.testing.assert_allclose(feats[:, d:], g["pw"], rtol=1e-4, atol=2e-5)
     logit, prob = O.mlp_score(feats, g.score_params)
     np.testing.assert_allclose(prob, g["prob"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(logit, g["logit"], rtol=1e-4, atol=1e-6)      # the pre-sigmoid values: 1e-4 relative
     # attention weights (debug output of the last layer): [2, S] = (link idx, head-mean alpha)
     aw = g["att_weights"]
     np.testing.assert_allclose(alpha.mean(1), aw[1], rtol=1e-4, atol=1e-6)
 
 
+def _check_sets(ref, sets):
+    assert set(ref) == set(sets)
+    for t, (ix, src, tgt) in ref.items():
+        li, nd, qa, qb = sets[t]
+        assert np.array_equal(ix[0], li) and np.array_equal(ix[1], nd), t
+        assert np.array_equal(src.view(np.uint32), qa.view(np.uint32)), t
+        assert np.array_equal(tgt.view(np.uint32), qb.view(np.uint32)), t
+
+
+def test_test_set_tables_and_caller_adjacency(golden):
+    """test_set=True reads full_adj_mask / ppr_test (link_transformer.py:389-406) — tables that DIFFER from the train
+    ones in this golden — and a caller-supplied adjacency decides CN / 1-hop only (:226-254 vs :443-447)."""
+    g = golden
+    if not g.has_full_graph:
+        pytest.skip("case has one graph only")
+    th = (g.cfg["thresh_cn"], g.cfg["thresh_1hop"], g.cfg["thresh_non1hop"])
+    adj, _, ppr = g.oracle_graph()
+    fadj, _, fppr = g.oracle_graph(full=True)
+    assert fadj.indices.size > adj.indices.size and not np.array_equal(fppr.val, ppr.val)
+    mode, ts = O.select_sets(fadj, fppr, g["links"], *th)
+    _check_sets(g.sets("ts_"), ts)
+    assert np.array_equal(O.structure_counts(ts, mode, g["links"].shape[1]), g["ts_counts"])
+    # the train-graph sets differ from the full-graph sets: a swapped table cannot go unnoticed
+    assert g.sets()["cn"][0].shape != g.sets("ts_")["cn"][0].shape or not np.array_equal(g.sets()["cn"][0], g.sets("ts_")["cn"][0])
+    feats, _, _, _ = O.link_features(g["links"], g["X_node"], fadj, fppr, g.model_params, g.cfg)
+    d = g.cfg["dim"]
+    np.testing.assert_allclose(feats[:, d:], g["ts_pw"], rtol=1e-4, atol=2e-5)
+    logit, prob = O.mlp_score(feats, g.score_params)
+    np.testing.assert_allclose(prob, g["ts_prob"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(logit, g["ts_logit"], rtol=1e-4, atol=1e-6)
+    # caller-supplied adjacency
+    am = g.masked_adjacency()
+    assert am.indices.size < adj.indices.size
+    _, sets_am = O.select_sets(am, ppr, g["links"], *th, adj_far=adj)
+    _check_sets(g.sets("am_"), sets_am)
+
+
 def test_ppr_push_matches_reference_kernel(golden):
     g = golden
     if g.cfg["eps"] < 1e-4:
-        pytest.skip("pure-Python push is slow for tiny eps; covered by the C oracle test")
+        pytest.skip("pure-Python push is slow for tiny eps; covered by the host-port / GPU tests (tests/test_gpu_ppr.py)")
     adj, _, _ = graph_of(g)
     ppr = O.ppr_push(adj.indptr, adj.indices, g.cfg["alpha"], g.cfg["eps"])
     assert np.array_equal(ppr.indices, g["ppr_col"])
