@@ -2,10 +2,13 @@
 """bench.py — scored links/s of the per-link pairwise-encoding path (BASELINE.json metric).
 
 A "step" = one pass of the hot path (selection -> RPE -> attention -> heads -> mlp_score) over one
-batch of synthetic citation2-style queries (1 held-out positive + 1,000 random negatives sharing the
-source; reference train/testing.py:14-47) on a precomputed X_node, i.e. the body of the reference's
-eval loop.  Workload: the ogbl-citation2-shaped synthetic graph (2.93M nodes, 30.6M edges, dim 64,
-hyper-parameters of reference scripts/replicate_heart.sh:22).
+batch of synthetic queries on a precomputed X_node, i.e. the body of the reference's eval loop.
+Default workload (BASELINE.json's headline config): the ogbl-citation2-shaped synthetic graph (2.93M
+nodes, 30.6M edges, dim 64, hyper-parameters of reference scripts/replicate_heart.sh:22), 256 queries
+of 1 held-out positive + 1,000 random negatives sharing the source (reference train/testing.py:14-47)
+per step.  --workload {collab, ddi, ppa, cora} runs the other BASELINE shapes with HeaRT-style queries
+(1 positive + 500 negatives, half random / half 2-hop corruptions of the target; train/testing.py:95-121)
+in steps of the script's test batch size (scripts/replicate_heart.sh:4-19).
 
   python bench.py [--gpus N --steps K --warmup W]          this repo's CUDA path, one JSON line
   python bench.py --impl reference [...]                   the reference's CPU algorithm (oracle port)
@@ -40,7 +43,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="citation2", choices=["citation2", "ppa", "collab", "ddi", "cora"])
     ap.add_argument("--scale", type=float, default=1.0, help="graph size multiplier (1.0 = the named shape)")
-    ap.add_argument("--queries", type=int, default=256, help="queries per step per GPU (x (1+negs) links)")
+    ap.add_argument("--queries", type=int, default=None, help="queries per step per GPU (x (1+negs) links); default: "
+                    "256 for citation2, the script's test batch size // (1 + negs) for the other workloads")
     ap.add_argument("--negs", type=int, default=None)
     ap.add_argument("--cpu-sample-links", type=int, default=32768)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -133,6 +137,29 @@ def make_workload(args, rank):
     return g, negs, gen_s
 
 
+def queries_per_step(args, cfg, negs):
+    if args.queries is not None:
+        return args.queries
+    return 256 if args.workload == "citation2" else max(1, cfg["batch"] // (1 + negs))
+
+
+def make_queries(g, workload, nq, negs, seed):
+    """[2, nq * (1 + negs)] int64 links of one step: citation2-style (shared source, uniform negatives) or HeaRT-style."""
+    from lpformer_b200 import synthetic as S
+    if workload == "citation2":
+        return S.citation2_queries(g, nq, negs, seed=seed)
+    return S.heart_queries(g, nq, negs, seed=seed)
+
+
+def workload_name(workload, negs):
+    style = "1 positive + %d negatives per query" % negs
+    if workload != "citation2":
+        style = "HeaRT-style eval, " + style + " (half random, half 2-hop corruptions)"
+    else:
+        style = "eval, " + style
+    return f"ogbl-{workload}-shaped synthetic {style}" if workload != "cora" else f"Cora-shaped synthetic {style}"
+
+
 def batch_bytes(g, links, negs, S_total, d, hc):
     """Algorithmic bytes of one batch: per link 4(deg a+deg b) [adj col ids] +
     8(nP a + nP b) [PPR col+val] + 32 [4 rowptr pairs] + 16 [link ids]; `select` is what one selection
@@ -175,11 +202,15 @@ def run_reference(args):
     X = torch.randn(g.n, cfg["dim"], generator=torch.Generator().manual_seed(args.seed + 5))
     A = R.coo_from_csr(g.indptr, g.indices, None, g.n)
     Pm = R.coo_from_csr(*g.ppr, g.n)
-    nq = max(1, args.cpu_sample_links // (1 + negs))
+    nq_step = queries_per_step(args, cfg, negs)
+    nq = max(1, min(nq_step, args.cpu_sample_links // (1 + negs)))
     cfgd = dict(targs)
     times = []
     for step in range(args.warmup + args.steps):
-        links = torch.from_numpy(S.citation2_queries(g, nq, negs, seed=1000 + step))
+        # the SAME seeded batch the CUDA arm scores in this step (rank 0), of which the first `nq` queries are timed: the
+        # reference's sparse index_select is O(nnz) per call, so a whole 256-query step would take ~30 s of CPU time
+        full = make_queries(g, args.workload, nq_step, negs, seed=1000 + step)
+        links = torch.from_numpy(np.ascontiguousarray(full[:, : nq * (1 + negs)]))
         t0 = time.perf_counter()
         R.score_links(links, X, A, Pm, P, Sd, cfgd, model.mask)
         if step >= args.warmup:
@@ -190,11 +221,16 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "scored links/sec", "value": val, "unit": "links/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"ogbl-{args.workload}-shaped synthetic eval, 1 positive + {negs} negatives per query",
-                       "scale": args.scale, "graph": g.stats(), "links_per_step": nlinks},
+            "config": {"workload": workload_name(args.workload, negs), "scale": args.scale, "graph": g.stats(),
+                       "queries_per_step_per_gpu": nq_step, "links_per_step_per_gpu": nq_step * (1 + negs),
+                       "dim": cfg["dim"], "mode": model.mask,
+                       "thresholds": [cfg["thresh_cn"], cfg["thresh_1hop"], cfg["thresh_non1hop"]]},
             "cpu_baseline": {"value": val, "unit": "links/s", "cores": os.cpu_count(), "kind": "port",
-                             "sample": f"{nq} queries x {1 + negs} links per step (oracle/ref_port.py, torch sparse-COO "
-                                       f"algebra of the reference, X_node seeded N(0,1))"},
+                             "sample": f"the first {nq} of the {nq_step} queries of every step ({nlinks} links; the same "
+                                       f"seeded batches as the CUDA arm) through oracle/ref_port.py — the reference's torch "
+                                       f"sparse-COO algorithm, pinned to the unmodified reference by tests/test_reference_live.py; "
+                                       f"the unmodified reference itself needs /root/reference, which does not exist on the GPU "
+                                       f"box; X_node seeded N(0,1)"},
             "e2e": {"value": val, "unit": "links/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -238,9 +274,9 @@ def run_b200(args):
     torch.cuda.synchronize()
     propagate_ms = e0.elapsed_time(e1)
 
-    nq = args.queries
+    nq = queries_per_step(args, cfg, negs)
     total_steps = args.warmup + args.steps
-    host_links = [S.citation2_queries(g, nq, negs, seed=1000 + rank * 100003 + s) for s in range(total_steps)]
+    host_links = [make_queries(g, args.workload, nq, negs, seed=1000 + rank * 100003 + s) for s in range(total_steps)]
     dev_links = [torch.from_numpy(l).to(dev) for l in host_links]
     nlinks = nq * (1 + negs)
 
@@ -303,12 +339,15 @@ def run_b200(args):
 
     # ---- end to end through the public API with HOST buffers: every step's links come from pinned host memory
     # and its scores go back to pinned host memory inside the timed region
+    # (window: the K batches cycled until >= 200 batches have gone through, so that the wall-clock figure is stable)
     scorer.score(timed_host[:, :2 * nlinks], out_host=out_host[:2 * nlinks])
+    e2e_reps = max(1, -(-200 // args.steps)) if nlinks * args.steps < (1 << 26) else 1
     barrier()
     w0 = time.perf_counter()
-    scorer.score(timed_host, out_host=out_host)
+    for _ in range(e2e_reps):
+        scorer.score(timed_host, out_host=out_host)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - w0
+    e2e_s = (time.perf_counter() - w0) / e2e_reps
     barrier()
     e2e_vs_dev = float((out_host.to(dev) - out).abs().max())
 
@@ -323,17 +362,23 @@ def run_b200(args):
         # set statistics + algorithmic bytes of the timed batches
         sel_stats = {"pairs_per_link": 0.0, "empty_frac": 0.0}
         tot_pairs, tot_empty, byt = 0, 0, {"select_full": 0.0, "select_dedup": 0.0, "path_full": 0.0, "path_dedup": 0.0}
-        from lpformer_b200 import ops
+        per_type, max_type = np.zeros(3), np.zeros(3)
         for s in range(args.warmup, total_steps):
             sel = model._select(dev_links[s], False)
-            c = sel.counts().sum(0)
+            cn = sel.counts()
+            c = cn.sum(0)
             tot_pairs += int(c.sum())
             tot_empty += int((c == 0).sum())
+            per_type += cn.sum(1).cpu().numpy()
+            max_type = np.maximum(max_type, cn.max(1).values.cpu().numpy())
             bb = batch_bytes(g, host_links[s], negs, sel.total, d, hc)
             for k in byt:
                 byt[k] += bb[k]
         sel_stats["pairs_per_link"] = tot_pairs / (nlinks * args.steps)
         sel_stats["empty_frac"] = tot_empty / (nlinks * args.steps)
+        for t, nm in enumerate(("cn", "1hop", "non1hop")):
+            sel_stats["mean_" + nm] = float(per_type[t] / (nlinks * args.steps))
+            sel_stats["max_" + nm] = int(max_type[t])
 
         if sel_ms[3] and "lpf_select_onepass_packed" in summ:
             # the selection entry point is three kernels: time them separately (events recorded inside the launcher)
@@ -353,22 +398,40 @@ def run_b200(args):
         peaks_all = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))) if os.path.exists(
             os.path.join(REPO, "MEASURED_PEAKS.json")) else {}
         avg_ms = top_ms / top_calls
+        grouped = args.workload == "citation2"
         alg = alg_full = alg_flops = None
         if top_name.startswith("lpf_select_onepass_packed/screen") or top_name in (
                 "lpf_select_count", "lpf_select_fill", "lpf_select_onepass", "lpf_select_onepass_packed"):
-            alg = byt["select_dedup"] / args.steps          # per launch (one launch per step)
-            alg_full = byt["select_full"] / args.steps
+            # per link 4 deg + 8 nP of both rows + row pointers + ids; dedup'd = the shared source once per query
+            alg = (byt["select_dedup"] if grouped else byt["select_full"]) / top_calls
+            alg_full = byt["select_full"] / top_calls
         elif top_name == "lpf_link_heads_tc":
             # per link: X[b] row + link ids + score; the query's shared X[a] row once per query (dedup'd)
-            launches_per_step = top_calls / args.steps
-            alg = (nlinks * (d * 4 + 16 + 4) + nq * d * 4) / launches_per_step
-            alg_full = nlinks * (2 * d * 4 + 16 + 4) / launches_per_step
-            alg_flops = nlinks * 2.0 * (d * d + d * d + 2 * d * d + 2 * d) / launches_per_step
+            alg = (args.steps * (nlinks * (d * 4 + 16 + 4) + nq * d * 4)) / top_calls
+            alg_full = args.steps * nlinks * (2 * d * 4 + 16 + 4) / top_calls
+            alg_flops = args.steps * nlinks * 2.0 * (d * d + d * d + 2 * d * d + 2 * d) / top_calls
+        else:
+            # contractions / attention of the unfused path: bytes and flops from the shapes recorded with every call
+            tot_b = tot_f = 0.0
+            for name, meta, _, _ in trace.records:
+                if name != top_name or meta is None:
+                    continue
+                if name in ("lpf_gemm_tc", "lpf_gemm") and len(meta) == 3:
+                    M, N, K = meta
+                    tot_b += 4.0 * (M * K + M * N + N * K)
+                    tot_f += 2.0 * M * N * K
+                elif name == "lpf_attend_fused" and len(meta) == 3:
+                    n_l, S_p, HC = meta          # per pair a K/V row and an RPE row, per link a query row and an output row
+                    tot_b += 4.0 * HC * (2 * S_p + 2 * n_l) + 4.0 * S_p
+                    tot_f += 8.0 * HC * S_p
+            if tot_b > 0:
+                alg = alg_full = tot_b / top_calls
+                alg_flops = tot_f / top_calls if tot_f > 0 else None
         traffic = None
         tpath = os.path.join(REPO, "profiles", "traffic.json")
         if os.path.exists(tpath):       # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures
             for key, val in json.load(open(tpath)).items():
-                if key in top_name:
+                if key in top_name and grouped:
                     traffic = val
         roof = {"bound": "hbm", "kernel": top_name, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
                 "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": avg_ms,
@@ -382,8 +445,16 @@ def run_b200(args):
             tf = alg_flops / (avg_ms * 1e-3) / 1e12
             tpeak = float(peaks_all.get("bf16_tflops_sustained", 1400.0))
             roof["tensor"] = {"achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
-                              "note": "algorithmic fp32 flops (2MNK of the three contractions), executed as 3 tf32 "
+                              "note": "algorithmic fp32 flops (2MNK of the contractions), executed as 3 tf32 "
                                       "MMAs each; peak = measured sustained bf16 (tf32 runs at half that rate)"}
+        # the selection's screening kernel is always reported too (the north star's HBM-roofline kernel)
+        screen = [k for k in kern if k[0].startswith("lpf_select_onepass_packed/screen")]
+        if screen:
+            sc_ms = screen[0][2] / screen[0][1]
+            sc_alg = (byt["select_dedup"] if grouped else byt["select_full"]) / screen[0][1]
+            roof["screen"] = {"kernel": screen[0][0], "avg_launch_ms": sc_ms, "algorithmic_bytes_per_launch": sc_alg,
+                              "achieved": sc_alg / (sc_ms * 1e-3) / 1e9, "frac": sc_alg / (sc_ms * 1e-3) / 1e9 / peak,
+                              "traffic": (json.load(open(tpath)).get("select_screen_packed_kernel") if os.path.exists(tpath) and grouped else None)}
         path_gbs = byt["path_dedup"] / (dev_ms * 1e-3) / 1e9
         value = world * nlinks * args.steps / (dev_ms * 1e-3)
         e2e_val = world * nlinks * args.steps / (e2e_ms * 1e-3)
@@ -395,7 +466,7 @@ def run_b200(args):
         line = {"metric": "scored links/sec", "value": value, "unit": "links/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"ogbl-{args.workload}-shaped synthetic eval, 1 positive + {negs} negatives per query",
+                "config": {"workload": workload_name(args.workload, negs),
                            "scale": args.scale, "graph": g.stats(), "queries_per_step_per_gpu": nq,
                            "links_per_step_per_gpu": nlinks, "dim": d, "mode": model.mask,
                            "thresholds": [cfg["thresh_cn"], cfg["thresh_1hop"], cfg["thresh_non1hop"]],
@@ -408,7 +479,8 @@ def run_b200(args):
                 "api": {"depth": args.depth, "value": "evaluate.LinkScoreStream.score(device links): `depth` plans in flight, 1 CUDA-graph launch per "
                                  "batch, overflow flags read one batch late",
                         "e2e": "evaluate.LinkScoreStream.score(pinned host links, out_host=pinned scores): H2D / D2H on a "
-                               "copy stream inside the timed region",
+                               "copy stream inside the timed region; wall clock over %d passes of the K batches" % e2e_reps,
+                        "fast_path": scorer.plans is not None,
                         "max_abs_diff_stream_vs_score_links": stream_vs_single,
                         "max_abs_diff_e2e_vs_device": e2e_vs_dev},
                 "gpu_launches_per_step": launches_per_step,
@@ -437,10 +509,10 @@ def cpu_baseline(args, g, negs, model, score, X, targs):
     Xc = X.detach().cpu().contiguous()
     A = R.coo_from_csr(g.indptr, g.indices, None, g.n)
     Pm = R.coo_from_csr(*g.ppr, g.n)
-    nq = max(1, args.cpu_sample_links // (1 + negs))
+    nq = max(1, min(queries_per_step(args, g.cfg, negs), args.cpu_sample_links // (1 + negs)))
     spent, done, first, max_diff = 0.0, 0, None, None
     for it in range(4):
-        links_np = S.citation2_queries(g, nq, negs, seed=5000 + it)
+        links_np = make_queries(g, args.workload, nq, negs, seed=5000 + it)
         links = torch.from_numpy(links_np)
         t0 = time.perf_counter()
         prob, _ = R.score_links(links, Xc, A, Pm, P, Sd, dict(targs), model.mask)

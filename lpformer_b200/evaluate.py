@@ -253,19 +253,103 @@ class LinkScoreStream:
         return out_dev
 
 
+# ------------------------------------------------------------------------------------------------------------
+# Ranking metrics on the device (reference train/evaluation.py).  Predictions stay where the scoring left them;
+# every result dict costs ONE host read.
+# ------------------------------------------------------------------------------------------------------------
 @torch.no_grad()
-def evaluate_mrr(y_pred_pos, y_pred_neg):
-    """reference train/evaluation.py:23-50 on the device: rank = 1 + (optimistic + pessimistic) / 2 of every
-    positive among its negatives; Hits@{10,50,100} and MRR (one host read at the end, not one per metric)."""
+def get_ranking_list(y_pred_pos, y_pred_neg):
+    """reference train/evaluation.py:75-90: rank of every positive among ITS negatives (y_pred_neg [P, K]) or among a
+    shared list (y_pred_neg [M] / [1, M]), mean of the optimistic and the pessimistic rank."""
     y_pred_pos = y_pred_pos.reshape(-1, 1)
+    if y_pred_neg.dim() == 1:
+        y_pred_neg = y_pred_neg.reshape(1, -1)
     optimistic = (y_pred_neg >= y_pred_pos).sum(dim=1)
     pessimistic = (y_pred_neg > y_pred_pos).sum(dim=1)
-    rank = 0.5 * (optimistic + pessimistic).to(torch.float32) + 1
+    return 0.5 * (optimistic + pessimistic).to(torch.float32) + 1
+
+
+@torch.no_grad()
+def evaluate_mrr(y_pred_pos, y_pred_neg):
+    """reference train/evaluation.py:23-50: Hits@{10,50,100} and MRR of the ranking list."""
+    rank = get_ranking_list(y_pred_pos, y_pred_neg)
     res = torch.stack([(rank <= 10).float().mean(), (rank <= 50).float().mean(), (rank <= 100).float().mean(),
                        (1.0 / rank).mean()]).tolist()
     return {"Hits@10": res[0], "Hits@50": res[1], "Hits@100": res[2], "MRR": res[3]}
 
 
+@torch.no_grad()
+def sample_level_hits(y_pred_pos, y_pred_neg):
+    """reference train/evaluation.py:53-72: per-sample Hits@{20,50,100} (device tensors)."""
+    rank = get_ranking_list(y_pred_pos, y_pred_neg)
+    return {"Hits@20": (rank <= 20).float(), "Hits@50": (rank <= 50).float(), "Hits@100": (rank <= 100).float()}
+
+
+@torch.no_grad()
+def evaluate_hits(evaluator, pos_pred, neg_pred, k_list):
+    """reference train/evaluation.py:7-20 with OGB's Hits@K (ogb/linkproppred/evaluate.py `_eval_hits`: a positive is a
+    hit if it scores above the K-th highest negative; 1.0 when there are fewer than K negatives) computed on the
+    device for every K at once.  `evaluator` is accepted for signature compatibility and not called."""
+    pos, neg = pos_pred.reshape(-1), neg_pred.reshape(-1)
+    ks = [int(k) for k in k_list]
+    top = torch.topk(neg, min(max(ks), neg.numel()))[0] if neg.numel() > 0 else neg
+    vals = []
+    for k in ks:
+        if neg.numel() < k:
+            vals.append(torch.ones((), device=pos.device))
+        else:
+            vals.append((pos > top[k - 1]).float().sum() / max(1, pos.numel()))
+    vals = torch.stack(vals).tolist()
+    return {f"Hits@{k}": v for k, v in zip(ks, vals)}
+
+
+@torch.no_grad()
+def evaluate_auc(val_pred, val_true):
+    """reference train/evaluation.py:93-105 (sklearn roc_auc_score / average_precision_score, rounded to 4 places) on
+    the device: AUC from the rank-sum statistic with average ranks for ties, AP as the step-wise sum over the
+    distinct thresholds."""
+    pred = val_pred.reshape(-1).to(torch.float64)
+    true = val_true.reshape(-1).to(pred.device) > 0
+    n_pos, n_neg = int(true.sum()), int((~true).sum())
+    vals, inv, cnt = torch.unique(pred, return_inverse=True, return_counts=True)       # ascending distinct scores
+    end = torch.cumsum(cnt, 0).to(torch.float64)
+    avg_rank = end - (cnt.to(torch.float64) - 1) / 2                                   # average 1-based rank of a tie group
+    auc = (avg_rank[inv][true].sum() - n_pos * (n_pos + 1) / 2) / max(1, n_pos * n_neg)
+    # precision / recall at every distinct threshold, from the highest score down
+    pos_per = torch.zeros_like(end).index_add_(0, inv, true.to(torch.float64)).flip(0)
+    tp = torch.cumsum(pos_per, 0)
+    seen = torch.cumsum(cnt.flip(0), 0).to(torch.float64)
+    ap = (pos_per / max(1, n_pos) * (tp / seen)).sum()
+    auc, ap = torch.stack([auc, ap]).tolist()
+    return {"AUC": round(auc, 4), "AP": round(ap, 4)}
+
+
+def get_metric_score(evaluator_hit, evaluator_mrr, pos_train_pred, pos_val_pred, neg_val_pred, pos_test_pred, neg_test_pred,
+                     k_list=[100]):
+    """reference train/evaluation.py:108-130 (the MRR variant ranks every positive against the whole negative list)."""
+    result = {}
+    hit_train = evaluate_hits(evaluator_hit, pos_train_pred, neg_val_pred, k_list)
+    hit_val = evaluate_hits(evaluator_hit, pos_val_pred, neg_val_pred, k_list)
+    hit_test = evaluate_hits(evaluator_hit, pos_test_pred, neg_test_pred, k_list)
+    for K in k_list:
+        result[f"Hits@{K}"] = (hit_train[f"Hits@{K}"], hit_val[f"Hits@{K}"], hit_test[f"Hits@{K}"])
+    if evaluator_mrr is not None:
+        result["MRR"] = (evaluate_mrr(pos_train_pred, neg_val_pred.reshape(1, -1))["MRR"],
+                         evaluate_mrr(pos_val_pred, neg_val_pred.reshape(1, -1))["MRR"],
+                         evaluate_mrr(pos_test_pred, neg_test_pred.reshape(1, -1))["MRR"])
+    return result
+
+
+def get_metric_score_citation2(evaluator_mrr, pos_train_pred, pos_val_pred, neg_val_pred, pos_test_pred, neg_test_pred):
+    """reference train/evaluation.py:133-148."""
+    return {"MRR": (evaluate_mrr(pos_train_pred, neg_val_pred)["MRR"], evaluate_mrr(pos_val_pred, neg_val_pred)["MRR"],
+                    evaluate_mrr(pos_test_pred, neg_test_pred)["MRR"])}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Eval drivers (reference train/testing.py), same names and arguments; the batch loops are LinkScoreStreams and the
+# predictions are device tensors (the reference's per-batch .cpu() is what caps its throughput).
+# ------------------------------------------------------------------------------------------------------------
 @torch.no_grad()
 def test_edge_citation2(model, score_func, input_data, h, batch_size, mrr_mode=False, negative_data=None, test=False,
                         stream=None):
@@ -282,3 +366,66 @@ def test_edge_citation2(model, score_func, input_data, h, batch_size, mrr_mode=F
     st = stream if stream is not None else LinkScoreStream(model, score_func, h, batch_size, test_set=test)
     pred = st.score(links)
     return pred.view(-1, negative_data.shape[1]) if mrr_mode else pred
+
+
+@torch.no_grad()
+def test_citation2(model, score_func, data, evaluator_hit, evaluator_mrr, batch_size):
+    """reference train/testing.py:50-74 (citation2: propagate once; the train predictions are overwritten by the
+    validation ones there, :70 — kept, parity first)."""
+    model.eval()
+    score_func.eval()
+    h = model.propagate()
+    neg_valid_pred = test_edge_citation2(model, score_func, data["valid_pos"], h, batch_size, mrr_mode=True, negative_data=data["valid_neg"])
+    pos_valid_pred = test_edge_citation2(model, score_func, data["valid_pos"], h, batch_size)
+    pos_test_pred = test_edge_citation2(model, score_func, data["test_pos"], h, batch_size, test=True)
+    neg_test_pred = test_edge_citation2(model, score_func, data["test_pos"], h, batch_size, mrr_mode=True, negative_data=data["test_neg"], test=True)
+    test_edge_citation2(model, score_func, data["train_pos_val"], h, batch_size)
+    pos_valid_pred = pos_valid_pred.view(-1)
+    pos_test_pred = pos_test_pred.view(-1)
+    pos_train_pred = pos_valid_pred.view(-1)
+    return get_metric_score_citation2(evaluator_mrr, pos_train_pred, pos_valid_pred, neg_valid_pred, pos_test_pred, neg_test_pred)
+
+
+@torch.no_grad()
+def test_edge(model, score_func, input_data, batch_size, test_set=False, dump_att=False):
+    """reference train/testing.py:77-92.  The reference calls model(edge, test_set) per batch, i.e. re-runs the GCN on
+    the train (or, for test_set, the full) graph every time (:87 -> link_transformer.py:100); the embeddings do not
+    depend on the batch, so they are computed once here.  input_data [P, 2]; returns [P] scores on the device."""
+    h = model.propagate(test_set=test_set)
+    links = input_data.t().to(h.device).contiguous()
+    return LinkScoreStream(model, score_func, h, batch_size, test_set=test_set).score(links)
+
+
+@torch.no_grad()
+def test_heart_negatives(negative_data, model, score_func, batch_size=32768, test_set=False):
+    """reference train/testing.py:95-121 (HeaRT): negative_data [P, K, 2] -> scores [P, K].  As in the reference the
+    embeddings come from the TRAIN graph (h = model.propagate(), :105) also when test_set selects the full tables for
+    the pairwise part."""
+    num_negative = negative_data.size(1)
+    h = model.propagate()
+    links = torch.permute(negative_data, (2, 0, 1)).reshape(2, -1).to(h.device).contiguous()
+    return LinkScoreStream(model, score_func, h, batch_size, test_set=test_set).score(links).view(-1, num_negative)
+
+
+@torch.no_grad()
+def test(model, score_func, data, evaluator_hit, evaluator_mrr, batch_size, k_list=[100], heart=False, dump_att=False,
+         dump_test=False, metric="Hits@100"):
+    """reference train/testing.py:124-173."""
+    model.eval()
+    score_func.eval()
+    pos_train_pred = test_edge(model, score_func, data["train_pos_val"], batch_size)
+    pos_valid_pred = test_edge(model, score_func, data["valid_pos"], batch_size)
+    pos_test_pred = test_edge(model, score_func, data["test_pos"], batch_size, test_set=True, dump_att=dump_att)
+    if heart:
+        neg_valid_pred = test_heart_negatives(data["valid_neg"], model, score_func, batch_size=batch_size)
+        neg_test_pred = test_heart_negatives(data["test_neg"], model, score_func, batch_size=batch_size, test_set=True)
+        result = get_metric_score_citation2(evaluator_mrr, pos_train_pred.view(-1), pos_valid_pred.view(-1), neg_valid_pred,
+                                            pos_test_pred.view(-1), neg_test_pred)
+    else:
+        neg_valid_pred = test_edge(model, score_func, data["valid_neg"], batch_size)
+        neg_test_pred = test_edge(model, score_func, data["test_neg"], batch_size, test_set=True, dump_att=dump_att)
+        result = get_metric_score(evaluator_hit, evaluator_mrr, pos_train_pred, torch.flatten(pos_valid_pred),
+                                  torch.flatten(neg_valid_pred), pos_test_pred, neg_test_pred, k_list)
+    if dump_test:
+        return result, sample_level_hits(pos_test_pred, neg_test_pred)[metric]
+    return result
