@@ -344,6 +344,16 @@ int lpf_debug_heads_clocks(void* device_buffer);
 int lpf_gcn_spmm(const int64_t* rowptr, const int32_t* col, const float* val,
                  int64_t row0, int64_t rows, const float* XW, int64_t ld_xw, const float* bias,
                  int32_t d, float* Y, int64_t ldy, void* stream);
+/* The same SpMM with the rest of the GCN layer fused into its epilogue (GCN.forward, models/other_models.py:66-72,
+ * and for the last layer LinkTransformer.gnn_norm, models/link_transformer.py:126):
+ *     Y[r,:] = LN2( residual[r,:] + act( LN1( sum_k val[k] XW[col[k],:] + bias ) ) )
+ * ln_w/ln_b (LN1), relu, residual (rows indexed like Y), ln2_w/ln2_b (LN2) are each optional (NULL / 0).  Needs
+ * d % 4 == 0, d <= 512 and 16-byte aligned rows / vectors (LPF_ERR_UNSUPPORTED otherwise: use lpf_gcn_spmm +
+ * lpf_layernorm_act). */
+int lpf_gcn_layer(const int64_t* rowptr, const int32_t* col, const float* val,
+                  int64_t row0, int64_t rows, const float* XW, int64_t ld_xw, const float* bias, int32_t d,
+                  const float* ln_w, const float* ln_b, int relu, const float* residual, int64_t ld_res,
+                  const float* ln2_w, const float* ln2_b, float* Y, int64_t ldy, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Host-side PPR precompute (data preparation, not on the per-link path) — the

@@ -19,9 +19,11 @@ from .plan import ScorePlan
 def propagate_replicated(model, test_set=False, group=None):
     """X_node [N, dim] on every rank, with the K/V tables of all attention layers primed.
 
-    world_size 1: plain model.propagate().  Otherwise GCN layers 0..L-2 are computed redundantly,
-    the last layer's SpMM + LN/ReLU/residual + gnn_norm + K/V projection only for this rank's rows,
-    followed by a single all_gather_into_tensor of the packed [X | KV_0 | ...] rows."""
+    world_size 1: plain model.propagate().  Otherwise EVERY GCN layer is row-sharded: a rank applies the layer's Linear
+    to its own rows, the ranks all-gather the [N/W, d] products (the SpMM gathers rows of any node), and the fused
+    layer launch (SpMM + bias + LayerNorm + ReLU + residual; for the last layer also gnn_norm) runs for the rank's rows
+    only; the K/V projections follow on those rows and ONE all_gather_into_tensor of the packed [X | KV_0 | ...] rows
+    replicates the result.  Per eval: L all-gathers of [N, d] and one of [N, d + sum HC], no collective per batch."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         X = model.propagate(test_set=test_set)
         model._get_kv(X)
@@ -39,42 +41,42 @@ def propagate_replicated(model, test_set=False, group=None):
     per = (n + world - 1) // world
     r0 = min(n, rank * per)
     rows = min(n, r0 + per) - r0
+    x_own = x[r0:r0 + rows].contiguous()                 # this rank's rows of the layer input
     for i, conv in enumerate(convs):
         last = i == len(convs) - 1
         ln = gcn.lns[i] if gcn.lns is not None else None
-        res_ok = gcn.residual and x.shape[-1] == conv.bias.numel()
-        if not last:
-            xi = conv(x, adj)
-            if ln is not None or gcn.relu or res_ok:
-                xi = ops.layernorm_act(xi, None if ln is None else ln.weight, None if ln is None else ln.bias,
-                                       relu=gcn.relu, residual=x if res_ok else None, out=xi)
-            x = xi
-        else:
-            widths = [d] + [layer.att.heads * layer.att.out_channels for layer in model.att_layers]
-            packed = torch.zeros((per, sum(widths)), dtype=torch.float32, device=dev)
-            if rows > 0:
-                xi = torch.empty((n, d), dtype=torch.float32, device=dev)
-                conv(x, adj, out=xi, row0=r0, rows=rows)
-                sh = xi[r0:r0 + rows]
-                if ln is not None or gcn.relu or res_ok:
-                    ops.layernorm_act(sh, None if ln is None else ln.weight, None if ln is None else ln.bias,
-                                      relu=gcn.relu, residual=x[r0:r0 + rows] if res_ok else None, out=sh)
-                xs = packed[:rows, :d]
-                ops.layernorm_act(sh, model.gnn_norm.weight, model.gnn_norm.bias, relu=False, out=xs)
-                c0 = d
-                for layer, w in zip(model.att_layers, widths[1:]):
-                    ops.linear(xs, layer.att.lin_r.weight[:, :d], out=packed[:rows, c0:c0 + w])
-                    c0 += w
-            full = torch.empty((per * world, sum(widths)), dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(full, packed, group=group)          # the one collective of the eval
-            full = full[:n]
-            X = full[:, :d]
-            kvs, c0 = [], d
-            for w in widths[1:]:
-                kvs.append(full[:, c0:c0 + w])
-                c0 += w
-            model._prime_kv(X, kvs)
-            return X
+        width = conv.bias.numel()
+        xw_own = torch.zeros((per, width), dtype=torch.float32, device=dev)
+        if rows > 0:
+            ops.linear(x_own, conv.lin.weight, out=xw_own[:rows])
+        xw = torch.empty((per * world, width), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(xw, xw_own, group=group)
+        res = x_own if (gcn.residual and x_own.shape[-1] == width) else None
+        y_own = torch.empty((max(rows, 1), width), dtype=torch.float32, device=dev)
+        if rows > 0:
+            ops.gcn_layer(adj, xw[:n], conv.bias, ln=None if ln is None else (ln.weight, ln.bias), relu=gcn.relu, residual=res,
+                          ln2=(model.gnn_norm.weight, model.gnn_norm.bias) if last else None, out=y_own, row0=r0, rows=rows,
+                          local=True)
+        x_own = y_own[:rows]
+    widths = [d] + [layer.att.heads * layer.att.out_channels for layer in model.att_layers]
+    packed = torch.zeros((per, sum(widths)), dtype=torch.float32, device=dev)
+    if rows > 0:
+        packed[:rows, :d].copy_(x_own)
+        xs = packed[:rows, :d]
+        c0 = d
+        for layer, w in zip(model.att_layers, widths[1:]):
+            ops.linear(xs, layer.att.lin_r.weight[:, :d], out=packed[:rows, c0:c0 + w])
+            c0 += w
+    full = torch.empty((per * world, sum(widths)), dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(full, packed, group=group)          # the one collective that replicates the tables
+    full = full[:n]
+    X = full[:, :d]
+    kvs, c0 = [], d
+    for w in widths[1:]:
+        kvs.append(full[:, c0:c0 + w])
+        c0 += w
+    model._prime_kv(X, kvs)
+    return X
 
 
 def shard_queries(num_queries, rank, world):

@@ -183,16 +183,18 @@ class GCN(nn.Module):
             conv.reset_parameters()
 
     @torch.no_grad()
-    def forward(self, x, adj_norm: CSR):
+    def forward(self, x, adj_norm: CSR, final_norm=None):
+        """reference :61-76.  Per layer one contraction (x W^T) and ONE launch for the rest (SpMM + bias + LayerNorm +
+        ReLU + residual, ops.gcn_layer); final_norm = (weight, bias) of a LayerNorm applied to the last layer's output
+        in the same launch (LinkTransformer.gnn_norm)."""
         _no_training(self, "dropout" if self.dropout > 0 else "")
+        last = len(self.convs) - 1
         for i, conv in enumerate(self.convs):
-            xi = conv(x, adj_norm)
+            xw = ops.linear(x, conv.lin.weight)
             ln = self.lns[i] if self.lns is not None else None
-            res = x if (self.residual and x.shape[-1] == xi.shape[-1]) else None
-            if ln is not None or self.relu or res is not None:
-                xi = ops.layernorm_act(xi, None if ln is None else ln.weight, None if ln is None else ln.bias,
-                                       relu=self.relu, residual=res, out=xi)
-            x = xi
+            res = x if (self.residual and x.shape[-1] == xw.shape[-1]) else None
+            x = ops.gcn_layer(adj_norm, xw, conv.bias, ln=None if ln is None else (ln.weight, ln.bias), relu=self.relu,
+                              residual=res, ln2=final_norm if i == last else None)
         return x
 
 
@@ -211,9 +213,9 @@ class NodeEncoder(nn.Module):
                                layer_norm=train_args["layer_norm"], relu=train_args["relu"])
 
     @torch.no_grad()
-    def forward(self, features, adj_norm: CSR, test_set=False):
+    def forward(self, features, adj_norm: CSR, test_set=False, final_norm=None):
         _no_training(self, "feature dropout" if self.feat_drop > 0 else "")
-        return self.gnn_encoder(features, adj_norm)
+        return self.gnn_encoder(features, adj_norm, final_norm=final_norm)
 
 
 class LinkAttention(nn.Module):
@@ -478,8 +480,8 @@ class LinkTransformer(nn.Module):
         if "emb" in self.data:
             x = self.data["emb"](x)
         x = x.detach().to(self._dev(), torch.float32)
-        X_node = self.node_encoder(x, adj_norm, test_set)
-        return ops.layernorm_act(X_node, self.gnn_norm.weight, self.gnn_norm.bias, relu=False)
+        # (gnn_norm rides in the epilogue of the last GCN layer's launch)
+        return self.node_encoder(x, adj_norm, test_set, final_norm=(self.gnn_norm.weight, self.gnn_norm.bias))
 
     @torch.no_grad()
     def compute_node_mask(self, batch, test_set, adj):

@@ -341,6 +341,50 @@ def link_heads(links, X, consts, prob, idx=None, zb=None, logits=False, sched=No
     return prob
 
 
+def gcn_layer(adj: CSR, XW, bias, ln=None, relu=False, residual=None, ln2=None, out=None, row0=0, rows=None, local=False):
+    """One GCN layer after its Linear, in one launch (lpf_gcn_layer): out = LN2(residual + act(LN(A_hat XW + bias)))
+    for rows [row0, row0 + rows).  ln / ln2: (weight, bias) or None.  local=False: `out` and `residual` are [n, d]
+    tables indexed by node id; local=True: they hold only the rows of the range (row 0 = node row0: the row-sharded
+    multi-GPU layers).  Falls back to lpf_gcn_spmm + lpf_layernorm_act for widths / alignments the fused kernel does
+    not take."""
+    require_cuda(adj.rowptr, XW, bias, out, residual)
+    XW = _rowmajor(XW)
+    n, d = adj.n, XW.shape[1]
+    rows = n - row0 if rows is None else rows
+    if out is None:
+        out = torch.empty((rows if local else n, d), dtype=torch.float32, device=XW.device)
+    if residual is not None:
+        residual = _rowmajor(residual)
+    shift = row0 if local else 0          # the kernel indexes `out` / `residual` by node id
+    a16 = lambda t: t is None or t.data_ptr() % 16 == 0     # noqa: E731
+    fusable = d % 4 == 0 and d <= 512 and XW.stride(0) % 4 == 0 and out.stride(0) % 4 == 0 and a16(XW) and a16(out) and \
+        a16(bias) and (residual is None or (a16(residual) and residual.stride(0) % 4 == 0)) and \
+        all(a16(t) for pair in (ln, ln2) if pair is not None for t in pair)
+    if fusable:
+        call("lpf_gcn_layer", ptr(adj.rowptr), ptr(adj.col), ptr(adj.val), row0, rows, ptr(XW), XW.stride(0), ptr(bias), d,
+             ptr(ln[0]) if ln else None, ptr(ln[1]) if ln else None, int(relu),
+             (residual.data_ptr() - 4 * shift * residual.stride(0)) if residual is not None else None,
+             residual.stride(0) if residual is not None else 0,
+             ptr(ln2[0]) if ln2 else None, ptr(ln2[1]) if ln2 else None,
+             out.data_ptr() - 4 * shift * out.stride(0), out.stride(0), stream(), meta=(rows, d, adj.nnz))
+        return out
+    view = out if not local else None
+    if local:       # unfused kernels index by node id: go through a full-height scratch table
+        view = torch.empty((n, d), dtype=torch.float32, device=XW.device)
+    gcn_spmm(adj, XW, bias, out=view, row0=row0, rows=rows)
+    sh = view[row0:row0 + rows]
+    dst = out if local else out[row0:row0 + rows]
+    res = None if residual is None else (residual if local else residual[row0:row0 + rows])
+    if ln is not None or relu or res is not None:
+        layernorm_act(sh, None if ln is None else ln[0], None if ln is None else ln[1], relu=relu, residual=res, out=dst)
+        sh = dst
+    if ln2 is not None:
+        layernorm_act(sh, ln2[0], ln2[1], relu=False, out=dst)
+    elif sh is not dst:
+        dst.copy_(sh)
+    return out
+
+
 def gcn_spmm(adj: CSR, XW, bias, out=None, row0=0, rows=None):
     require_cuda(adj.rowptr, XW, bias, out)
     XW = _rowmajor(XW)
