@@ -273,6 +273,29 @@ def run_b200(args):
     e1.record()
     torch.cuda.synchronize()
     propagate_ms = e0.elapsed_time(e1)
+    # per-call breakdown of the per-eval work on rank 0 (eager, CUDA events around every C-ABI call): the GCN layer
+    # launches are gathers of 4d-byte rows — algorithmic bytes per layer nnz (8 + 4d) + rows (8d + 8)
+    per_eval_calls, gcn_roof = [], None
+    if rank == 0 and world == 1:
+        tr = _lib.Trace(events=True)
+        _lib.TRACE = tr
+        propagate_replicated(model)
+        torch.cuda.synchronize()
+        _lib.TRACE = None
+        agg = {}
+        for name, meta, a, b in tr.records:
+            c, t = agg.get(name, (0, 0.0))
+            agg[name] = (c + 1, t + a.elapsed_time(b))
+        per_eval_calls = [{"name": k, "calls": c, "total_ms": t} for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])]
+        lay = [(meta, a.elapsed_time(b)) for name, meta, a, b in tr.records if name == "lpf_gcn_layer" and meta]
+        if lay:
+            byt_l = sum(m[2] * (8 + 4 * m[1]) + m[0] * (8 * m[1] + 8) for m, _ in lay)
+            ms_l = sum(t for _, t in lay)
+            gcn_roof = {"kernel": "lpf_gcn_layer (gcn_spmm_kernel: SpMM + bias + LayerNorm + ReLU + residual)", "bound": "hbm",
+                        "launches": len(lay), "avg_launch_ms": ms_l / len(lay), "algorithmic_bytes_per_launch": byt_l / len(lay),
+                        "achieved": byt_l / (ms_l * 1e-3) / 1e9, "unit": "GB/s", "peak": load_peaks()[0],
+                        "frac": byt_l / (ms_l * 1e-3) / 1e9 / load_peaks()[0],
+                        "note": "gathered rows are counted once per edge (no credit for L2 reuse of a hub's row)"}
 
     nq = queries_per_step(args, cfg, negs)
     total_steps = args.warmup + args.steps
@@ -489,7 +512,7 @@ def run_b200(args):
                 "path_algorithmic_gbs": path_gbs,
                 "path_frac_of_peak": path_gbs / peak,
                 "kernels": [{"name": n, "calls": c, "total_ms": t} for n, c, t in kern],
-                "per_eval": {"propagate_ms": propagate_ms, "graph_gen_s": gen_s},
+                "per_eval": {"propagate_ms": propagate_ms, "graph_gen_s": gen_s, "calls": per_eval_calls, "roofline": gcn_roof},
                 "cpu_baseline": cpu_base,
                 "clocks": clocks}
         print(json.dumps(line))

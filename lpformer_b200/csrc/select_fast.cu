@@ -284,6 +284,7 @@ __global__ void select_reset_packed(int32_t* heavy, int64_t* hdr, int32_t* hub) 
     heavy[1] = 0;        // piece counter of the screening launch
     hdr[0] = hdr[1] = hdr[2] = hdr[3] = hdr[4] = 0;
     hub[0] = 0;
+    hub[1] = 0;          // links for the CTA-wide packed resolution
 }
 void launch_onepass_reset(const SelectParams2& p, cudaStream_t st) {
     if (p.hub) select_reset_packed<<<1, 1, 0, st>>>(p.heavy, p.hdr, p.hub);

@@ -53,6 +53,7 @@ constexpr int kPkMaxRowChunks = 1024;  // target rows with more 16-byte chunks a
 constexpr int kPkWarpItems = 512;      // overflow chunks of a warp's 32 links that are screened (the rest: candidates unscreened)
 constexpr int kPkInflight = 4;         // overflow reads a lane keeps in flight
 constexpr int kPkResolveThreads = 256;
+constexpr int kPkBigSlots = 2048;       // links whose shorter row has up to this many slots take a whole CTA (select_resolve_big_kernel)
 constexpr uint32_t kPkPprTag = 0x80000000u;
 constexpr uint32_t kPkPad = 0x7fffffffu;
 static_assert(kPkMaxRowChunks <= 2048, "items[] packs (link:5 | chunk:11)");
@@ -396,7 +397,12 @@ select_resolve_packed_kernel(const __grid_constant__ SelectParams2 p, const uint
         const RowView A = view_row(slab, ovf, a, ha), B = view_row(slab, ovf, b, hb);
         const bool swapped = A.S < B.S;
         if (min(A.S, B.S) > kPkResolveSlots) {
-            if (lane == 0) p.heavy[4 + atomicAdd(p.heavy, 1)] = (int32_t)i;
+            // a hub-hub pair: a whole CTA walks the shorter row (select_resolve_big_kernel), or — beyond kPkBigSlots —
+            // the deferred-link kernel over the CSR tables
+            if (lane == 0) {
+                if (min(A.S, B.S) <= kPkBigSlots) p.hub[ws_list_words(p.bs) + atomicAdd(p.hub + 1, 1)] = (int32_t)i;
+                else p.heavy[4 + atomicAdd(p.heavy, 1)] = (int32_t)i;
+            }
             continue;
         }
         const RowView& row = swapped ? A : B;
@@ -404,6 +410,109 @@ select_resolve_packed_kernel(const __grid_constant__ SelectParams2 p, const uint
         __syncwarp();       // (ids_sm of the previous candidate is no longer read)
         if (row.S <= 32 && row.npp <= 32 && src.npp <= 32) resolve_packed_fast(p, src, row, swapped, i, lane, ids_sm[threadIdx.x >> 5]);
         else resolve_packed_warp(p, src, row, swapped, i, lane);
+    }
+}
+
+// RESOLVE, hub-hub pairs: one CTA per link whose shorter row has 129 .. kPkBigSlots slots.  Thread t takes the slots
+// t, t + 256, ... (kPkBigPer of them), searches their (up to 2 kPkBigPer) ids in the other row in lockstep — one
+// dependent read per halving for all of them — and keeps its hits in registers; the ordered positions come from one
+// block-wide scan per group of 256 slots; one allocation, one write.  Same sets, order and values as every other
+// variant.
+constexpr int kPkBigThreads = 256;
+constexpr int kPkBigPer = 8;
+static_assert(kPkBigSlots == kPkBigThreads * kPkBigPer, "2,048 slots: a row of ~4,000 neighbours");
+__global__ void __launch_bounds__(kPkBigThreads)
+select_resolve_big_kernel(const __grid_constant__ SelectParams2 p, const uint4* __restrict__ slab, const uint4* __restrict__ ovf) {
+    constexpr int NW = kPkBigThreads / 32, M = kPkBigPer;
+    __shared__ uint32_t wtot[M][NW];
+    __shared__ int64_t seg[3];
+    __shared__ int ok_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = p.hub[1];
+    const int32_t* list = p.hub + ws_list_words(p.bs);
+    const bool want_pi = p.mode != LPF_MODE_CN;
+    const bool want_n1 = p.mode == LPF_MODE_ALL;
+    const float th_pre = want_n1 ? fminf(p.th_1hop, p.th_non1hop) : p.th_1hop;
+    for (int q = blockIdx.x; q < n; q += gridDim.x) {
+        const int64_t i = list[q];
+        const int64_t a = __ldg(p.links + i), b = __ldg(p.links + p.bs + i);
+        const uint4 ha = ldg16(slab + (size_t)a * 8), hb = ldg16(slab + (size_t)b * 8);
+        const RowView A = view_row(slab, ovf, a, ha), B = view_row(slab, ovf, b, hb);
+        const bool swapped = A.S < B.S;
+        const RowView& row = swapped ? A : B;
+        const RowView& src = swapped ? B : A;
+        uint2 sl[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) sl[m] = load_slot(row, m * kPkBigThreads + tid);
+        int lo[2 * M], hi[2 * M];
+#pragma unroll
+        for (int x = 0; x < 2 * M; ++x) {
+            const uint32_t key = (x & 1) ? sl[x >> 1].y : sl[x >> 1].x;
+            const bool active = !(sl[x >> 1].x & kPkPprTag) && key != kPkPad;
+            lo[x] = 0;
+            hi[x] = active ? src.deg : 0;
+        }
+        const int iters = 32 - __clz(src.deg);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int x = 0; x < 2 * M; ++x) {
+                if (lo[x] < hi[x]) {
+                    const int32_t key = (int32_t)((x & 1) ? sl[x >> 1].y : sl[x >> 1].x);
+                    const int mid = (lo[x] + hi[x]) >> 1;
+                    if (src.id_at(mid) < key) lo[x] = mid + 1; else hi[x] = mid;
+                }
+            }
+        }
+        SlotHit r[M];
+        uint32_t mine[M], inc[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            const uint32_t k0 = sl[m].x, k1 = sl[m].y;
+            const bool idslot = !(k0 & kPkPprTag);
+            const bool in0 = idslot && k0 != kPkPad && lo[2 * m] < src.deg && src.id_at(lo[2 * m]) == (int32_t)k0;
+            const bool in1 = idslot && k1 != kPkPad && lo[2 * m + 1] < src.deg && src.id_at(lo[2 * m + 1]) == (int32_t)k1;
+            r[m] = eval_slot(p, src, row, sl[m], in0, in1, want_pi, want_n1, th_pre);
+            // counts of this slot packed in one word: common neighbours (0..2) | 1-hop << 12 | >1-hop << 22
+            mine[m] = (uint32_t)((r[m].h0 ? 1 : 0) + (r[m].h1 ? 1 : 0)) | (r[m].k1 ? 1u << 12 : 0u) | (r[m].kn ? 1u << 22 : 0u);
+            inc[m] = mine[m];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t x = __shfl_up_sync(kFull, inc[m], o);
+                if (lane >= o) inc[m] += x;
+            }
+            if (lane == 31) wtot[m][warp] = inc[m];
+        }
+        __syncthreads();
+        // exclusive position of every slot's hits within the link: groups of 256 slots in order, warps in order
+        int c_cn = 0, c_1h = 0, c_n1 = 0;
+        int before[M];          // position of this slot's first hit within its set (a slot feeds one set only)
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            uint32_t bf = inc[m] - mine[m], total = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const uint32_t x = wtot[m][w];
+                bf += (w < warp) ? x : 0u;
+                total += x;
+            }
+            before[m] = r[m].k1 ? c_1h + (int)((bf >> 12) & 1023u) : (r[m].kn ? c_n1 + (int)(bf >> 22) : c_cn + (int)(bf & 4095u));
+            c_cn += (int)(total & 4095u);
+            c_1h += (int)((total >> 12) & 1023u);
+            c_n1 += (int)(total >> 22);
+        }
+        if (warp == 0) {
+            int64_t s0, s1, s2;
+            const bool fits = alloc_segments_warp(p, i, c_cn, c_1h, c_n1, lane, s0, s1, s2);
+            if (lane == 0) { ok_s = fits ? 1 : 0; seg[0] = s0; seg[1] = s1; seg[2] = s2; }
+        }
+        __syncthreads();
+        if (ok_s && c_cn + c_1h + c_n1 > 0) {
+            const int64_t o_cn = seg[0], o_1h = p.cap + seg[1], o_n1 = 2 * p.cap + seg[2];
+#pragma unroll
+            for (int m = 0; m < M; ++m)
+                write_hits(p, r[m], swapped, (r[m].k1 ? o_1h : o_n1) + before[m], o_cn + before[m]);
+        }
+        __syncthreads();       // wtot / seg / ok_s are reused by the next link
     }
 }
 
@@ -814,6 +923,8 @@ extern "C" int lpf_select_onepass_packed(const int64_t* links, int64_t bs, const
         if (timing) cudaEventRecord(g_pk_ev[1], st);
         // RESOLVE: one warp per candidate (their number is on the device: a resident grid strides over the list)
         select_resolve_packed_kernel<<<kNumSMs * 2, kPkResolveThreads, 0, st>>>(
+            p, static_cast<const uint4*>(slab), static_cast<const uint4*>(overflow));
+        select_resolve_big_kernel<<<kNumSMs * 2, kPkBigThreads, 0, st>>>(
             p, static_cast<const uint4*>(slab), static_cast<const uint4*>(overflow));
         if (timing) cudaEventRecord(g_pk_ev[2], st);
     }

@@ -33,8 +33,10 @@ struct SelectParams2 {
 };
 
 // Workspace of the one-pass launch sequences, in int32 words: [0, bs + 4) deferred (heavy) links; then the candidate
-// list of the packed kernel (count in word 0, entries from word 4).
-__host__ __device__ inline int64_t ws_hub_words(int64_t bs) { return (bs + 4 + 3) / 4 * 4; }
+// list of the packed kernel (count in word 0, entries from word 4) and, another ws_list_words further, the list of
+// the candidates whose shorter row takes a whole CTA (count in word 1 of the candidate list, entries from word 0).
+__host__ __device__ inline int64_t ws_list_words(int64_t bs) { return (bs + 4 + 3) / 4 * 4; }
+__host__ __device__ inline int64_t ws_hub_words(int64_t bs) { return 2 * ws_list_words(bs); }
 __host__ __device__ inline int64_t ws_total_words(int64_t bs) { return (bs + 4) + ws_hub_words(bs); }
 
 // A link whose shorter adjacency (or PPR) row exceeds kHeavyPerLane elements per lane of its group is deferred
