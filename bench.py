@@ -428,7 +428,7 @@ def run_b200(args):
             # per link 4 deg + 8 nP of both rows + row pointers + ids; dedup'd = the shared source once per query
             alg = (byt["select_dedup"] if grouped else byt["select_full"]) / top_calls
             alg_full = byt["select_full"] / top_calls
-        elif top_name == "lpf_link_heads_tc":
+        elif top_name in ("lpf_link_heads_tc", "lpf_link_heads_f16"):
             # per link: X[b] row + link ids + score; the query's shared X[a] row once per query (dedup'd)
             alg = (args.steps * (nlinks * (d * 4 + 16 + 4) + nq * d * 4)) / top_calls
             alg_full = args.steps * nlinks * (2 * d * 4 + 16 + 4) / top_calls

@@ -280,6 +280,31 @@ int lpf_link_heads_tc(const int64_t* links, int64_t bs, const int32_t* idx, int6
                       int32_t* tile_sched, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * The same head chain with fp16-split operands (d = 64): tcgen05.mma.kind::f16 on x = hi + lo, hi = fp16(x s),
+ * lo = fp16(x s - hi) — the 22 significand bits of the 3xTF32 split at half the tensor-pipe time and half the
+ * operand bytes.  s is an exact power of two per operand, undone in the epilogues:
+ *   * w1_packed / w23_packed: lpf_pack_weight_f16 images built with a scale that puts max|W| into [2^14, 2^15);
+ *     inv_scale_w1 = 1 / scale(W1), inv_scale_h_w23 = 1 / (s_h scale(W23));
+ *   * ln_w_scaled / ln_b_scaled: LayerNorm weight and bias times s_h, s_h a power of two with
+ *     s_h (sqrt(d) max|ln_w| + max|ln_b|) <= 2^15 (LayerNorm bounds h, so h s_h fits fp16);
+ *   * the gathered rows X[a]*X[b] are scaled per link inside the kernel.
+ * The X[b] rows are fetched by TMA row gathers (tile::gather4) through a tensor map of X [n_nodes, d] built per call:
+ * X must be 16-byte aligned with ldx % 4 == 0, and every link id must be < n_nodes.
+ * Everything else as lpf_link_heads_tc (no tile_sched).
+ * ------------------------------------------------------------------------- */
+int64_t lpf_pack_weight_f16_bytes(int32_t N, int32_t K);
+int lpf_pack_weight_f16(const float* W, int64_t ldw, int32_t N, int32_t K, float scale, void* packed, void* stream);
+int lpf_link_heads_f16(const int64_t* links, int64_t bs, const int32_t* idx, int64_t n,
+                       const float* X, int64_t ldx, int64_t n_nodes, int32_t d,
+                       const void* w1_packed, float inv_scale_w1, const float* b1,
+                       const float* ln_w_scaled, const float* ln_b_scaled,
+                       const void* w23_packed, float inv_scale_h_w23, const float* c3, const float* zb, int64_t ld_zb,
+                       const float* ws2, const float* bs2, float* prob, int logits, const int64_t* n_dev,
+                       void* stream);
+/* Profiling hook of lpf_link_heads_f16 (as lpf_debug_heads_clocks). */
+int lpf_debug_heads_f16_clocks(void* device_buffer);
+
+/* ------------------------------------------------------------------------- *
  * Fused path for links with a non-empty node set, small-batch regime: one warp takes one link of nz_list
  * (n = min(n_cap, *n_dev)) from its node sets (one-pass selection buffers) to its score — lin_l, the RPE MLP and
  * its contraction per pair, attention with online segment softmax, bias + LayerNorm + counts, pairwise_lin,

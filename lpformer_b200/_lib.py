@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_C", "liblpformer_b200.so")
+LIB_PATH = os.environ.get("LPF_LIB_PATH") or os.path.join(_HERE, "_C", "liblpformer_b200.so")   # (override: A/B builds in development)
 
 MODE = {"cn": 0, "1-hop": 1, "all": 2}
 EPI_NONE, EPI_RELU, EPI_SIGMOID = 0, 1, 2
@@ -55,6 +55,11 @@ SIGNATURES = {
     "lpf_select_compact": (_int, [_p, _i64, _p, _p, _p]),
     "lpf_link_heads_tc": (_int, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p,
                                  _p, _int, _p, _p, _p]),
+    "lpf_pack_weight_f16_bytes": (_i64, [_i32, _i32]),
+    "lpf_pack_weight_f16": (_int, [_p, _i64, _i32, _i32, _f32, _p, _p]),
+    "lpf_link_heads_f16": (_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _i32, _p, _f32, _p, _p, _p, _p, _f32, _p, _p, _i64, _p, _p,
+                                  _p, _int, _p, _p]),
+    "lpf_debug_heads_f16_clocks": (_int, [_p]),
     "lpf_attend_fused": (_int, [_p, _i64, _p, _i64, _p, _p, _i64, _p, _i64, _p, _i64, _p, _p, _p, _p, _i32, _i32, _int, _int,
                                 _p, _i64, _p, _p, _p, _p, _i64, _p]),
     "lpf_ppr_push_host": (_p, [_p, _p, _i64, C.c_double, C.c_double, _int, _p]),
@@ -108,7 +113,7 @@ def load():
 # kernels launched per entry point (for bench.py's gpu_launches and per-kernel CUDA-event timing)
 KERNEL_LAUNCHES = {"lpf_select_count": 3, "lpf_scan_counts": 2, "lpf_select_fill": 2, "lpf_rpe_hidden": 1,
                    "lpf_gemm": 1, "lpf_gemm_tc": 1, "lpf_pack_weight": 1, "lpf_layernorm_act": 1, "lpf_gather_links": 1, "lpf_attend_fused": 1,
-                   "lpf_gcn_spmm": 1, "lpf_gcn_layer": 1, "lpf_nz_links_fused": 2, "lpf_select_compact": 2, "lpf_select_onepass": 4, "lpf_select_onepass_packed": 6, "lpf_pack_link_rows": 4, "lpf_scatter_rows": 2, "lpf_link_heads_tc": 1}
+                   "lpf_gcn_spmm": 1, "lpf_gcn_layer": 1, "lpf_nz_links_fused": 2, "lpf_select_compact": 2, "lpf_select_onepass": 4, "lpf_select_onepass_packed": 6, "lpf_pack_link_rows": 4, "lpf_scatter_rows": 2, "lpf_link_heads_tc": 1, "lpf_link_heads_f16": 1, "lpf_pack_weight_f16": 1}
 
 
 class Trace:

@@ -48,16 +48,18 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// (the suspend-time hint lets the hardware park the thread until the phase flips — at most ~the hint in ns — instead of
+// returning at once: a waiting warp then costs no issue slots, which the busy warps of a warp-specialised CTA need)
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t"
         ".reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, P1;\n\t"
         "}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
         : "memory");
     return ok != 0;
 }
@@ -65,7 +67,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) __trap();
+        if (++spins > (1u << 22)) __trap();
     }
 }
 

@@ -627,6 +627,14 @@ class LinkTransformer(nn.Module):
             "off": (ws1[:, :d] @ b2 + lins[0].bias.detach().double()).float().contiguous(),
             "ws2": lins[1].weight.detach().reshape(-1).contiguous(), "bs2": lins[1].bias.detach().contiguous(),
         }
+        if d == 64 and ops.HEADS_F16:
+            # operands of lpf_link_heads_f16: fp16 hi / lo images with exact power-of-two scales (see the header)
+            import math
+            sh = ops.pow2_scale(math.sqrt(d) * float(consts["ln_w"].abs().max()) + float(consts["ln_b"].abs().max()))
+            consts["w1h"], sw1 = ops.pack_weight_f16(el.linears[0].weight)
+            consts["w23h"], sw3 = ops.pack_weight_f16(w23)
+            consts["inv_sw1"], consts["inv_s3"] = 1.0 / sw1, 1.0 / (sh * sw3)
+            consts["ln_w_s"], consts["ln_b_s"] = (consts["ln_w"] * sh).contiguous(), (consts["ln_b"] * sh).contiguous()
         consts["c3"] = ops.linear(self._pw_const(X_node), consts["ws1_pw"], consts["off"]).reshape(-1).contiguous()
         self._head_cache = (key, consts)
         return consts

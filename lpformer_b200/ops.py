@@ -72,6 +72,44 @@ def pack_weight(W):
     return packed
 
 
+HEADS_F16 = os.environ.get("LPF_HEADS", "f16") != "tf32"   # d = 64 heads: fp16-split operands (lpf_link_heads_f16) or 3xTF32
+
+
+def pow2_scale(bound, target_exp=15):
+    """Largest power of two s with bound * s < 2^target_exp (1.0 for a zero bound)."""
+    import math
+    if not (bound > 0.0) or not math.isfinite(bound):
+        return 1.0
+    return 2.0 ** (target_exp - 1 - math.floor(math.log2(bound)))
+
+
+def pack_weight_f16(W):
+    """(image, scale): fp16 hi / lo images of an nn.Linear weight [N, K] in the swizzled K-major layout of
+    tcgen05.mma.kind::f16 (lpf_pack_weight_f16), scaled by the power of two that puts max|W| into [2^14, 2^15)."""
+    require_cuda(W)
+    Wc = _rowmajor(W.detach())
+    N, K = Wc.shape
+    scale = pow2_scale(float(Wc.abs().max()))
+    nbytes = _lib.load().lpf_pack_weight_f16_bytes(N, K)
+    packed = torch.empty(nbytes // 4, dtype=torch.float32, device=W.device)
+    call("lpf_pack_weight_f16", ptr(Wc), Wc.stride(0), N, K, float(scale), ptr(packed), stream())
+    return packed, scale
+
+
+def heads_call(links, bs, idx, n, X, c, zb, ld_zb, prob, logits, n_dev, sched, st):
+    """One launch of the fused heads with the operand set `c` (model._head_consts): the fp16-split kernel when the
+    consts carry its images (d = 64), the 3xTF32 kernel otherwise.  idx / zb / n_dev / sched: raw pointers or None."""
+    d = X.shape[1]
+    if "w1h" in c and X.data_ptr() % 16 == 0 and X.stride(0) % 4 == 0:
+        call("lpf_link_heads_f16", ptr(links), bs, idx, n, ptr(X), X.stride(0), X.shape[0], d, ptr(c["w1h"]), c["inv_sw1"], ptr(c["b1"]),
+             ptr(c["ln_w_s"]), ptr(c["ln_b_s"]), ptr(c["w23h"]), c["inv_s3"], ptr(c["c3"]) if zb is None else None, zb, ld_zb,
+             ptr(c["ws2"]), ptr(c["bs2"]), ptr(prob), int(logits), n_dev, st, meta=(n,))
+    else:
+        call("lpf_link_heads_tc", ptr(links), bs, idx, n, ptr(X), X.stride(0), d, ptr(c["w1p"]), ptr(c["b1"]),
+             ptr(c["ln_w"]), ptr(c["ln_b"]), ptr(c["w23p"]), ptr(c["c3"]) if zb is None else None, zb, ld_zb,
+             ptr(c["ws2"]), ptr(c["bs2"]), ptr(prob), int(logits), n_dev, sched, st, meta=(n,))
+
+
 def linear(A, W, bias=None, bias_scale=1.0, out=None, epilogue=EPI_NONE):
     """out[M,N] = epi(A @ W^T + bias_scale*bias) on the tensor cores (rows of W in chunks of <= 256)."""
     if GEMM_BACKEND != "tc":
@@ -328,16 +366,14 @@ def attend(sel: Selection, KV, R, Q, att, bias, ln_w, ln_b, heads, ch, write_cou
 
 
 def link_heads(links, X, consts, prob, idx=None, zb=None, logits=False, sched=None):
-    """Fused tensor-core heads (lpf_link_heads_tc): prob[pos] for every link (constant pairwise half `c3`) or for the
+    """Fused tensor-core heads (lpf_link_heads_f16 / lpf_link_heads_tc): prob[pos] for every link (constant pairwise half `c3`) or for the
     positions in idx with per-row zb.  `sched` (int32 [2], zeros): tiles handed out dynamically (see the header)."""
     require_cuda(links, X, prob, idx, zb, sched)
     X = _rowmajor(X)
     bs = links.shape[1]
     n = bs if idx is None else idx.numel()
-    call("lpf_link_heads_tc", ptr(links), bs, ptr(idx), n, ptr(X), X.stride(0), X.shape[1], ptr(consts["w1p"]),
-         ptr(consts["b1"]), ptr(consts["ln_w"]), ptr(consts["ln_b"]), ptr(consts["w23p"]),
-         ptr(consts["c3"]) if zb is None else None, ptr(zb), zb.stride(0) if zb is not None else 0,
-         ptr(consts["ws2"]), ptr(consts["bs2"]), ptr(prob), int(logits), None, ptr(sched), stream(), meta=(n,))
+    heads_call(links, bs, ptr(idx), n, X, consts, ptr(zb), zb.stride(0) if zb is not None else 0, prob, logits, None,
+               ptr(sched), stream())
     return prob
 
 

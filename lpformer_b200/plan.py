@@ -110,6 +110,7 @@ class ScorePlan:
     # ------------------------------------------------------------------
     def _launch(self):
         """Every launch of one batch on the current stream; no host synchronisation, no allocation."""
+        from . import ops
         st = stream()
         bs, cap, d, HC, pd = self.bs, self.cap, self.d, self.HC, self.pd
         c, w, hdr = self.consts, self.w, self.hdr
@@ -118,10 +119,8 @@ class ScorePlan:
         n_dev = hp + 3 * 8                      # &header[3]: links with a non-empty set
 
         def heads(idx, n, zb, ndev, on=None):
-            call("lpf_link_heads_tc", ptr(links), bs, idx, n, ptr(X), X.stride(0), d, ptr(c["w1p"]), ptr(c["b1"]),
-                 ptr(c["ln_w"]), ptr(c["ln_b"]), ptr(c["w23p"]), ptr(c["c3"]) if zb is None else None,
-                 ptr(zb), self.zb.stride(0) if zb is not None else 0, ptr(c["ws2"]), ptr(c["bs2"]), ptr(self.prob),
-                 int(self.logits), ndev, ptr(self.sched) if self.dynamic_tiles else None, st if on is None else on, meta=(n,))
+            ops.heads_call(links, bs, idx, n, X, c, ptr(zb), self.zb.stride(0) if zb is not None else 0, self.prob,
+                           self.logits, ndev, ptr(self.sched) if self.dynamic_tiles else None, st if on is None else on)
 
         def gemm(A, Wp, bias, scale, C, M, N, K, mdev):
             call("lpf_gemm_tc", ptr(A), A.stride(0), ptr(Wp), ptr(bias), float(scale), ptr(C), C.stride(0), M, N, K,

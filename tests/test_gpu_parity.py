@@ -666,3 +666,56 @@ def test_link_heads_kernel_vs_float64_and_dynamic_tiles(dim):
         untouched = torch.ones(bs, dtype=torch.bool, device=dev)
         untouched[idx.long()] = False
         assert bool((sub[untouched] == -1.0).all())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("xscale", [1.0, 3e-4, 2e3])
+def test_link_heads_f16_split_range_and_agreement_with_tf32(xscale):
+    """lpf_link_heads_f16 (fp16 hi/lo split, per-link power-of-two scaling) on inputs far outside fp16's range — node
+    rows whose magnitudes differ by 1e6 between rows and by 1e3 inside a row, weights scaled away from 1 — against the
+    float64 restatement on LOGITS, and next to the 3xTF32 kernel on the same operands (models/other_models.py:125-138,
+    173-179)."""
+    import lpformer_b200 as L
+    from lpformer_b200 import ops
+    dev = torch.device("cuda:0")
+    n, dim = 20000, 64
+    targs = dict(dim=dim, num_heads=1, trans_layers=1, gnn_layers=1, residual=False, layer_norm=True, relu=True,
+                 thresh_cn=0, thresh_1hop=1e-3, thresh_non1hop=1e-2)
+    torch.manual_seed(11)
+    model = L.LinkTransformer(targs, {"x": torch.zeros(n, 4)}, device=dev).to(dev).eval()
+    score = L.mlp_score(2 * dim, 2 * dim, 1, 2).to(dev).eval()
+    with torch.no_grad():
+        for p in list(model.parameters()) + list(score.parameters()):
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+        model.elementwise_lin.linears[0].weight.mul_(37.0)
+        model.elementwise_lin.norm.weight.mul_(0.02)
+    X = torch.randn(n, dim, device=dev) * xscale
+    X *= torch.exp(torch.randn(n, 1, device=dev) * 3.0)           # row magnitudes over ~6 decades
+    X[:, ::7] *= 1e-3                                             # and 3 decades inside a row
+    X[17] = 0.0                                                   # a row of zeros
+    consts = model._head_consts(score, X)
+    assert consts is not None and "w1h" in consts
+    tf32 = {k: v for k, v in consts.items() if k not in ("w1h", "w23h")}
+    el = model.elementwise_lin
+    f64 = lambda t: t.detach().double().cpu()      # noqa: E731
+    bs = 148 * 128 * 2 + 61
+    links = torch.randint(0, n, (2, bs), device=dev)
+    links[0, : bs // 2] = links[0, 0]
+    links[1, 5] = 17
+    lc = links.cpu()
+    xp = f64(X)[lc[0]] * f64(X)[lc[1]]
+    h = xp @ f64(el.linears[0].weight).T + f64(el.linears[0].bias)
+    h = torch.nn.functional.layer_norm(h, (dim,), f64(el.norm.weight), f64(el.norm.bias), 1e-5).relu()
+    z = (h @ f64(consts["w23"]).T + f64(consts["c3"])).relu()
+    want = (z @ f64(consts["ws2"]) + f64(consts["bs2"])).numpy()
+    got = torch.empty(bs, device=dev)
+    ops.link_heads(links, X, consts, got, logits=True)
+    ref32 = torch.empty(bs, device=dev)
+    ops.link_heads(links, X, tf32, ref32, logits=True)
+    # (a logit is a sum of 128 terms of either sign: the tolerance is relative to the logits' scale, as for fp32 itself)
+    atol = 1e-5 * float(np.abs(want).max())
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=FP32_RTOL, atol=atol)
+    np.testing.assert_allclose(ref32.cpu().numpy(), want, rtol=FP32_RTOL, atol=atol)
+    e16, e32 = np.abs(got.cpu().numpy() - want).max(), np.abs(ref32.cpu().numpy() - want).max()
+    assert e16 <= 4 * e32 + atol / 10, (e16, e32)

@@ -24,21 +24,28 @@ bs = 256 * 1001
 links = torch.randint(0, n, (2, bs), device=dev)
 links[0] = torch.randint(0, n, (256,), device=dev).repeat_interleave(1001)     # citation2-style runs of one source
 prob = torch.empty(bs, device=dev)
-buf = torch.zeros(16 * 16 + 16, dtype=torch.int64, device=dev)
+buf = torch.zeros(400 + 2 * 148, dtype=torch.int64, device=dev)
 lib = _lib.load()
 for rep in range(400):          # (long enough for the clocks to ramp up)
     ops.link_heads(links, X, consts, prob)
 torch.cuda.synchronize()
-lib.lpf_debug_heads_clocks(buf.data_ptr())
+(lib.lpf_debug_heads_f16_clocks if "w1h" in consts else lib.lpf_debug_heads_clocks)(buf.data_ptr())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 ops.link_heads(links, X, consts, prob)
 e1.record()
 torch.cuda.synchronize()
-lib.lpf_debug_heads_clocks(None)
+(lib.lpf_debug_heads_f16_clocks if "w1h" in consts else lib.lpf_debug_heads_clocks)(None)
 raw = buf.cpu().numpy()
 full = raw[:256].reshape(16, 16)
 print("kernel %.1f us for %.1f tiles/CTA -> SM clock %.2f GHz" % (1e3 * e0.elapsed_time(e1), bs / 128 / 148, (raw[257] - raw[256]) / (1e3 * e0.elapsed_time(e1)) / 1e3))
+span = raw[400:400 + 296].reshape(148, 2)
+if span[0, 1] > span[0, 0]:
+    print("CTA 0 lived %.1f us (globaltimer) -> SM clock %.2f GHz" % ((span[0, 1] - span[0, 0]) / 1e3, (raw[257] - raw[256]) / (span[0, 1] - span[0, 0])))
+    t0 = span[:, 0].min()
+    st, en = (span[:, 0] - t0) / 1e3, (span[:, 1] - t0) / 1e3
+    print("all CTAs (us, globaltimer): start min/median/max %.1f/%.1f/%.1f  end min/median/max %.1f/%.1f/%.1f  life min/median/max %.1f/%.1f/%.1f"
+          % (st.min(), np.median(st), st.max(), en.min(), np.median(en), en.max(), (en - st).min(), np.median(en - st), (en - st).max()))
 print("CTA 0: kernel start -> first tile top %d cycles; tile tops (consumer) relative to start: %s; end %d" % (full[0, 0] - raw[256], [int(full[i, 0] - raw[256]) for i in range(10)], raw[257] - raw[256]))
 t = full[:, :7]
 names = ["wait_mma1", "epi1", "wait_mma3(prev)", "store_h+sync", "issue_mma3", "epi2(prev)"]
@@ -57,4 +64,15 @@ for i in range(1, 7):
 # producer thread 0: [13] loop top, [14] gathered rows have arrived, [15] operand tile stored (after waiting for the
 # previous contraction 1)
 for i in range(1, 7):
-    print("producer tile %d: gather=%d wait+store=%d period=%d" % (i, full[i, 14] - full[i, 13], full[i, 15] - full[i, 14], full[i + 1, 13] - full[i, 13]))
+    if full[i, 7]:
+        print("producer tile %d: issue+sync=%d wait_rows=%d store=%d period=%d" % (i, full[i, 7] - full[i, 13], full[i, 14] - full[i, 7], full[i, 15] - full[i, 14], full[i + 1, 13] - full[i, 13]))
+    else:
+        print("producer tile %d: gather=%d wait+store=%d period=%d" % (i, full[i, 14] - full[i, 13], full[i, 15] - full[i, 14], full[i + 1, 13] - full[i, 13]))
+
+p2 = raw[272:272 + 128].reshape(16, 8)
+if p2[1, 2]:
+    # relative to the loop top: next source row requested + operand buffer free, rows read + multiplied, maxima exchanged,
+    # tile stored, fence, end barrier passed
+    for i in range(1, 7):
+        t0 = full[i, 13]
+        print("producer detail tile %d: " % i + " ".join("%d" % (v - t0) for v in p2[i][2:]))
