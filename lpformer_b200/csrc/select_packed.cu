@@ -177,8 +177,11 @@ struct SlotHit {
     float qa, qb, qa1, qb1;
 };
 // in0 / in1: the slot's two ids are among the searched row's ids (found by resolve_packed_warp's lockstep search)
-__device__ __forceinline__ SlotHit eval_slot(const SelectParams2& p, const RowView& src, const RowView& row, uint2 slot,
-                                             bool in0, bool in1, bool want_pi, bool want_n1, float th_pre) {
+// has_src / has_row: "node u is a neighbour in the searched / the walked row" (global-memory search, or a staged copy)
+template <class HasSrc, class HasRow>
+__device__ __forceinline__ SlotHit eval_slot_t(const SelectParams2& p, const RowView& src, const RowView& row, uint2 slot,
+                                               bool in0, bool in1, bool want_pi, bool want_n1, float th_pre, HasSrc has_src,
+                                               HasRow has_row) {
     SlotHit r;
     r.k1 = r.kn = r.h0 = r.h1 = false;
     r.qa = r.qb = r.qa1 = r.qb1 = 0.f;
@@ -190,8 +193,8 @@ __device__ __forceinline__ SlotHit eval_slot(const SelectParams2& p, const RowVi
         if (want_pi && r.u != (int32_t)kPkPad && src.ppr(r.u, r.qa)) {
             r.qb = quantise(__uint_as_float(w1));
             if (r.qa >= th_pre && r.qb >= th_pre) {
-                const bool in_a = src.has_id(r.u);
-                const bool in_b = row.has_id(r.u);
+                const bool in_a = has_src(r.u);
+                const bool in_b = has_row(r.u);
                 r.k1 = (in_a != in_b) && r.qa >= p.th_1hop && r.qb >= p.th_1hop;
                 r.kn = want_n1 && !in_a && !in_b && r.qa >= p.th_non1hop && r.qb >= p.th_non1hop;
             }
@@ -210,6 +213,20 @@ __device__ __forceinline__ SlotHit eval_slot(const SelectParams2& p, const RowVi
         }
     }
     return r;
+}
+__device__ __forceinline__ SlotHit eval_slot(const SelectParams2& p, const RowView& src, const RowView& row, uint2 slot,
+                                             bool in0, bool in1, bool want_pi, bool want_n1, float th_pre) {
+    return eval_slot_t(p, src, row, slot, in0, in1, want_pi, want_n1, th_pre, [&](int32_t u) { return src.has_id(u); },
+                       [&](int32_t u) { return row.has_id(u); });
+}
+// node u among n ascending ids in shared memory?
+__device__ __forceinline__ bool has_id_s(const int32_t* ids, int n, int32_t u) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (ids[mid] < u) lo = mid + 1; else hi = mid;
+    }
+    return lo < n && ids[lo] == u;
 }
 __device__ __forceinline__ uint2 load_slot(const RowView& row, int s) {
     if (s < row.S) return row.slot(s);
@@ -420,6 +437,8 @@ select_resolve_packed_kernel(const __grid_constant__ SelectParams2 p, const uint
 // variant.
 constexpr int kPkBigThreads = 256;
 constexpr int kPkBigPer = 8;
+constexpr int kPkBigStage = 8192;      // neighbour ids of the searched row staged in shared memory (32 KB)
+constexpr int kPkBigSmem = (kPkBigStage + 2 * kPkBigSlots) * 4;    // + the walked row's ids (16 KB)
 static_assert(kPkBigSlots == kPkBigThreads * kPkBigPer, "2,048 slots: a row of ~4,000 neighbours");
 __global__ void __launch_bounds__(kPkBigThreads)
 select_resolve_big_kernel(const __grid_constant__ SelectParams2 p, const uint4* __restrict__ slab, const uint4* __restrict__ ovf) {
@@ -427,6 +446,13 @@ select_resolve_big_kernel(const __grid_constant__ SelectParams2 p, const uint4* 
     __shared__ uint32_t wtot[M][NW];
     __shared__ int64_t seg[3];
     __shared__ int ok_s;
+    // the searched row's neighbour ids: one coalesced pass over the row instead of ~13 dependent L2 / DRAM trips per
+    // search (the halvings then cost a shared-memory read each)
+    // ... and the walked row's (<= 2 kPkBigSlots of them, from the slots this CTA holds): the neighbour tests of the PPR
+    // slots are then two searches in shared memory instead of ~26 dependent trips
+    extern __shared__ __align__(16) int32_t big_smem[];
+    int32_t* ids_s = big_smem;
+    int32_t* ids_r = big_smem + kPkBigStage;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = p.hub[1];
     const int32_t* list = p.hub + ws_list_words(p.bs);
@@ -444,6 +470,16 @@ select_resolve_big_kernel(const __grid_constant__ SelectParams2 p, const uint4* 
         uint2 sl[M];
 #pragma unroll
         for (int m = 0; m < M; ++m) sl[m] = load_slot(row, m * kPkBigThreads + tid);
+        const bool staged = src.deg <= kPkBigStage;
+        if (staged)
+            for (int k = tid; k < src.deg; k += kPkBigThreads) ids_s[k] = src.id_at(k);
+#pragma unroll
+        for (int m = 0; m < M; ++m) {                    // id slot s holds ids 2 (s - PPR slots), + 1 (padded with the maximum)
+            const int k = 2 * (m * kPkBigThreads + tid - 2 * row.pc);
+            if (k >= 0 && m * kPkBigThreads + tid < row.S) { ids_r[k] = (int32_t)sl[m].x; ids_r[k + 1] = (int32_t)sl[m].y; }
+        }
+        __syncthreads();
+        auto sid = [&](int k) -> int32_t { return staged ? ids_s[k] : src.id_at(k); };
         int lo[2 * M], hi[2 * M];
 #pragma unroll
         for (int x = 0; x < 2 * M; ++x) {
@@ -459,7 +495,7 @@ select_resolve_big_kernel(const __grid_constant__ SelectParams2 p, const uint4* 
                 if (lo[x] < hi[x]) {
                     const int32_t key = (int32_t)((x & 1) ? sl[x >> 1].y : sl[x >> 1].x);
                     const int mid = (lo[x] + hi[x]) >> 1;
-                    if (src.id_at(mid) < key) lo[x] = mid + 1; else hi[x] = mid;
+                    if (sid(mid) < key) lo[x] = mid + 1; else hi[x] = mid;
                 }
             }
         }
@@ -469,9 +505,11 @@ select_resolve_big_kernel(const __grid_constant__ SelectParams2 p, const uint4* 
         for (int m = 0; m < M; ++m) {
             const uint32_t k0 = sl[m].x, k1 = sl[m].y;
             const bool idslot = !(k0 & kPkPprTag);
-            const bool in0 = idslot && k0 != kPkPad && lo[2 * m] < src.deg && src.id_at(lo[2 * m]) == (int32_t)k0;
-            const bool in1 = idslot && k1 != kPkPad && lo[2 * m + 1] < src.deg && src.id_at(lo[2 * m + 1]) == (int32_t)k1;
-            r[m] = eval_slot(p, src, row, sl[m], in0, in1, want_pi, want_n1, th_pre);
+            const bool in0 = idslot && k0 != kPkPad && lo[2 * m] < src.deg && sid(lo[2 * m]) == (int32_t)k0;
+            const bool in1 = idslot && k1 != kPkPad && lo[2 * m + 1] < src.deg && sid(lo[2 * m + 1]) == (int32_t)k1;
+            r[m] = eval_slot_t(p, src, row, sl[m], in0, in1, want_pi, want_n1, th_pre,
+                               [&](int32_t u) { return staged ? has_id_s(ids_s, src.deg, u) : src.has_id(u); },
+                               [&](int32_t u) { return has_id_s(ids_r, row.deg, u); });
             // counts of this slot packed in one word: common neighbours (0..2) | 1-hop << 12 | >1-hop << 22
             mine[m] = (uint32_t)((r[m].h0 ? 1 : 0) + (r[m].h1 ? 1 : 0)) | (r[m].k1 ? 1u << 12 : 0u) | (r[m].kn ? 1u << 22 : 0u);
             inc[m] = mine[m];
@@ -908,6 +946,11 @@ extern "C" int lpf_select_onepass_packed(const int64_t* links, int64_t bs, const
         set_error("lpf_select_onepass_packed: cudaFuncSetAttribute(%zu B): %s", sizeof(PkSmem), cudaGetErrorString(e));
         return LPF_ERR_CUDA;
     }
+    e = cudaFuncSetAttribute(select_resolve_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPkBigSmem);
+    if (e != cudaSuccess) {
+        set_error("lpf_select_onepass_packed: cudaFuncSetAttribute(%d B): %s", kPkBigSmem, cudaGetErrorString(e));
+        return LPF_ERR_CUDA;
+    }
     launch_onepass_reset(p, st);
     const bool timing = g_kernel_timing && bs > 0;
     if (timing && !g_pk_ev_ready) {
@@ -924,7 +967,7 @@ extern "C" int lpf_select_onepass_packed(const int64_t* links, int64_t bs, const
         // RESOLVE: one warp per candidate (their number is on the device: a resident grid strides over the list)
         select_resolve_packed_kernel<<<kNumSMs * 2, kPkResolveThreads, 0, st>>>(
             p, static_cast<const uint4*>(slab), static_cast<const uint4*>(overflow));
-        select_resolve_big_kernel<<<kNumSMs * 2, kPkBigThreads, 0, st>>>(
+        select_resolve_big_kernel<<<kNumSMs * 2, kPkBigThreads, kPkBigSmem, st>>>(
             p, static_cast<const uint4*>(slab), static_cast<const uint4*>(overflow));
         if (timing) cudaEventRecord(g_pk_ev[2], st);
     }
