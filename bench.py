@@ -4,9 +4,9 @@
 A "step" = one pass of the hot path (selection -> RPE -> attention -> heads -> mlp_score) over one
 batch of synthetic queries on a precomputed X_node, i.e. the body of the reference's eval loop.
 Default workload (BASELINE.json's headline config): the ogbl-citation2-shaped synthetic graph (2.93M
-nodes, 30.6M edges, dim 64, hyper-parameters of reference scripts/replicate_heart.sh:22), 256 queries
+nodes, 30.6M edges, dim 64, hyper-parameters of reference scripts/replicate_heart.sh:22), 1,024 queries
 of 1 held-out positive + 1,000 random negatives sharing the source (reference train/testing.py:14-47)
-per step.  --workload {collab, ddi, ppa, cora} runs the other BASELINE shapes with HeaRT-style queries
+per step (= one batch of the eval driver: 1,025,024 links).  --workload {collab, ddi, ppa, cora} runs the other BASELINE shapes with HeaRT-style queries
 (1 positive + 500 negatives, half random / half 2-hop corruptions of the target; train/testing.py:95-121)
 in steps of the script's test batch size (scripts/replicate_heart.sh:4-19).
 
@@ -22,6 +22,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
 import tempfile
@@ -44,7 +45,7 @@ def parse():
     ap.add_argument("--workload", default="citation2", choices=["citation2", "ppa", "collab", "ddi", "cora"])
     ap.add_argument("--scale", type=float, default=1.0, help="graph size multiplier (1.0 = the named shape)")
     ap.add_argument("--queries", type=int, default=None, help="queries per step per GPU (x (1+negs) links); default: "
-                    "256 for citation2, the script's test batch size // (1 + negs) for the other workloads")
+                    "1024 for citation2, the script's test batch size // (1 + negs) for the other workloads")
     ap.add_argument("--negs", type=int, default=None)
     ap.add_argument("--cpu-sample-links", type=int, default=32768)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -140,7 +141,11 @@ def make_workload(args, rank):
 def queries_per_step(args, cfg, negs):
     if args.queries is not None:
         return args.queries
-    return 256 if args.workload == "citation2" else max(1, cfg["batch"] // (1 + negs))
+    # citation2: 1,024 queries = 1,025,024 links per batch.  The batch size is a parameter of the eval driver
+    # (train/testing.py: `batch_size`), not of the workload; measured on a B200: 140 / 130 / 121 / 114 us per 256,256
+    # links at 256 / 512 / 1,024 / 2,048 queries per batch (launch, pipeline-fill and staging costs of the nine
+    # kernels of a batch are per launch)
+    return 1024 if args.workload == "citation2" else max(1, cfg["batch"] // (1 + negs))
 
 
 def make_queries(g, workload, nq, negs, seed):
@@ -160,7 +165,7 @@ def workload_name(workload, negs):
     return f"ogbl-{workload}-shaped synthetic {style}" if workload != "cora" else f"Cora-shaped synthetic {style}"
 
 
-def batch_bytes(g, links, negs, S_total, d, hc):
+def batch_bytes(g, links, negs, S_total, d, hc, nz_mask=None):
     """Algorithmic bytes of one batch: per link 4(deg a+deg b) [adj col ids] +
     8(nP a + nP b) [PPR col+val] + 32 [4 rowptr pairs] + 16 [link ids]; `select` is what one selection
     pass reads, dedup'd = the shared source's rows counted once per query instead of once per link."""
@@ -176,8 +181,16 @@ def batch_bytes(g, links, negs, S_total, d, hc):
     select_dedup = float(row_a_dedup + row_b.sum() + (32 / 2 + 8) * links.shape[1] + 24 * q)
     e = 4
     path_extra = float(links.shape[1] * (2 * d * e + 4) + S_total * hc * e)
-    return {"select_full": select_full, "select_dedup": select_dedup, "path_full": select_full + path_extra,
-            "path_dedup": select_dedup + path_extra - float((links.shape[1] - q) * d * e)}
+    out = {"select_full": select_full, "select_dedup": select_dedup, "path_full": select_full + path_extra,
+           "path_dedup": select_dedup + path_extra - float((links.shape[1] - q) * d * e)}
+    if nz_mask is not None:
+        # the links that select something: the resolution reads both of their rows again (count -> allocate -> write),
+        # the non-empty-link stage their two node rows, per selected pair a K/V row, the pair's RPE row (written once,
+        # read once) and (node, ppr a, ppr b), and writes a score
+        nnz = int(nz_mask.sum())
+        out["resolve"] = float((row_a[nz_mask] + row_b[nz_mask]).sum() + per_link_fixed * nnz + 12 * S_total)
+        out["nz_stage"] = float(nnz * (2 * d * e + 16 + 4) + S_total * (hc * e + 2 * d * e + 12))
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -208,7 +221,7 @@ def run_reference(args):
     times = []
     for step in range(args.warmup + args.steps):
         # the SAME seeded batch the CUDA arm scores in this step (rank 0), of which the first `nq` queries are timed: the
-        # reference's sparse index_select is O(nnz) per call, so a whole 256-query step would take ~30 s of CPU time
+        # reference's sparse index_select is O(nnz) per call, so a whole 1,024-query step would take minutes of CPU time
         full = make_queries(g, args.workload, nq_step, negs, seed=1000 + step)
         links = torch.from_numpy(np.ascontiguousarray(full[:, : nq * (1 + negs)]))
         t0 = time.perf_counter()
@@ -343,7 +356,7 @@ def run_b200(args):
     import ctypes
     lib = _lib.load()
     lib.lpf_debug_select_timing(1)        # CUDA events around the kernels inside the selection entry point
-    sel_ms, ms3 = [0.0, 0.0, 0.0, 0], (ctypes.c_float * 3)()
+    sel_ms, ms3 = [0.0, 0.0, 0.0, 0.0, 0], (ctypes.c_float * 4)()
     nz_ms = [0.0, 0.0, 0]
     for s in range(args.warmup, total_steps):
         # a 1 ms spin kernel first: the host enqueues the whole step behind it, so that every event pair brackets its
@@ -351,9 +364,9 @@ def run_b200(args):
         torch.cuda._sleep(2_000_000)
         outs.append(model.score_links(dev_links[s], X, score))
         if lib.lpf_debug_select_timing_read(ctypes.addressof(ms3)) == 0:
-            for k in range(3):
+            for k in range(4):
                 sel_ms[k] += ms3[k]
-            sel_ms[3] += 1
+            sel_ms[4] += 1
         if lib.lpf_debug_nz_timing_read(ctypes.addressof(ms3)) == 0:
             nz_ms[0] += ms3[0]
             nz_ms[1] += ms3[1]
@@ -387,7 +400,8 @@ def run_b200(args):
         launches_per_step = trace.launches / args.steps
         # set statistics + algorithmic bytes of the timed batches
         sel_stats = {"pairs_per_link": 0.0, "empty_frac": 0.0}
-        tot_pairs, tot_empty, byt = 0, 0, {"select_full": 0.0, "select_dedup": 0.0, "path_full": 0.0, "path_dedup": 0.0}
+        tot_pairs, tot_empty, byt = 0, 0, {"select_full": 0.0, "select_dedup": 0.0, "path_full": 0.0, "path_dedup": 0.0,
+                                           "resolve": 0.0, "nz_stage": 0.0}
         per_type, max_type = np.zeros(3), np.zeros(3)
         for s in range(args.warmup, total_steps):
             sel = model._select(dev_links[s], False)
@@ -397,7 +411,7 @@ def run_b200(args):
             tot_empty += int((c == 0).sum())
             per_type += cn.sum(1).cpu().numpy()
             max_type = np.maximum(max_type, cn.max(1).values.cpu().numpy())
-            bb = batch_bytes(g, host_links[s], negs, sel.total, d, hc)
+            bb = batch_bytes(g, host_links[s], negs, sel.total, d, hc, nz_mask=(c > 0).cpu().numpy())
             for k in byt:
                 byt[k] += bb[k]
         sel_stats["pairs_per_link"] = tot_pairs / (nlinks * args.steps)
@@ -406,13 +420,14 @@ def run_b200(args):
             sel_stats["mean_" + nm] = float(per_type[t] / (nlinks * args.steps))
             sel_stats["max_" + nm] = int(max_type[t])
 
-        if sel_ms[3] and "lpf_select_onepass_packed" in summ:
-            # the selection entry point is three kernels: time them separately (events recorded inside the launcher)
+        if sel_ms[4] and "lpf_select_onepass_packed" in summ:
+            # the selection entry point is several kernels: time them separately (events recorded inside the launcher)
             c, t = summ.pop("lpf_select_onepass_packed")
-            summ["lpf_select_onepass_packed/screen (select_screen_packed_kernel)"] = (sel_ms[3], sel_ms[0])
-            summ["lpf_select_onepass_packed/resolve (select_resolve_packed_kernel)"] = (sel_ms[3], sel_ms[1])
-            summ["lpf_select_onepass_packed/deferred links (select_heavy_onepass_kernel)"] = (sel_ms[3], sel_ms[2])
-            summ["lpf_select_onepass_packed/launch gaps + resets"] = (c, max(0.0, t - sum(sel_ms[:3])))
+            summ["lpf_select_onepass_packed/screen (select_screen_packed_kernel)"] = (sel_ms[4], sel_ms[0])
+            summ["lpf_select_onepass_packed/resolve (select_resolve_packed_kernel)"] = (sel_ms[4], sel_ms[1])
+            summ["lpf_select_onepass_packed/hub-hub resolve (select_resolve_big_kernel)"] = (sel_ms[4], sel_ms[2])
+            summ["lpf_select_onepass_packed/deferred links + finalize (select_heavy_onepass_kernel, select_finalize_onepass)"] = (sel_ms[4], sel_ms[3])
+            summ["lpf_select_onepass_packed/launch gaps + resets"] = (c, max(0.0, t - sum(sel_ms[:4])))
         if nz_ms[2] and "lpf_nz_links_fused" in summ:
             c, t = summ.pop("lpf_nz_links_fused")
             summ["lpf_nz_links_fused/pair stage (nz_pairs_kernel)"] = (nz_ms[2], nz_ms[0])
@@ -431,6 +446,12 @@ def run_b200(args):
             # per link 4 deg + 8 nP of both rows + row pointers + ids; dedup'd = the shared source once per query
             alg = (byt["select_dedup"] if grouped else byt["select_full"]) / top_calls
             alg_full = byt["select_full"] / top_calls
+        elif top_name.startswith("lpf_select_onepass_packed/") and "resolve" in top_name:
+            # (both rows of every selecting link; a latency-bound kernel: dependent reads per candidate, not a stream)
+            alg = alg_full = byt["resolve"] / top_calls
+        elif top_name.startswith("lpf_nz_links_fused"):
+            # (a latency-bound fp32 FFMA kernel on ~1 % of the links: bytes per non-empty link and selected pair)
+            alg = alg_full = byt["nz_stage"] / top_calls
         elif top_name in ("lpf_link_heads_tc", "lpf_link_heads_f16"):
             # per link: X[b] row + link ids + score; the query's shared X[a] row once per query (dedup'd)
             alg = (args.steps * (nlinks * (d * 4 + 16 + 4) + nq * d * 4)) / top_calls
@@ -456,9 +477,9 @@ def run_b200(args):
         traffic = None
         tpath = os.path.join(REPO, "profiles", "traffic.json")
         if os.path.exists(tpath):       # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures
-            for key, val in json.load(open(tpath)).items():
-                if key in top_name and grouped:
-                    traffic = val
+            m = re.search(r"\((\w+)", top_name)                 # "entry point/part (kernel, ...)" -> kernel
+            kname = m.group(1) if m else top_name.replace("lpf_", "") + "_kernel"
+            traffic = json.load(open(tpath)).get(kname) if grouped else None
         roof = {"bound": "hbm", "kernel": top_name, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
                 "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": avg_ms,
                 "share_of_kernel_time": top_ms / sum(t for _, _, t in kern)}
@@ -471,8 +492,9 @@ def run_b200(args):
             tf = alg_flops / (avg_ms * 1e-3) / 1e12
             tpeak = float(peaks_all.get("bf16_tflops_sustained", 1400.0))
             roof["tensor"] = {"achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
-                              "note": "algorithmic fp32 flops (2MNK of the contractions), executed as 3 tf32 "
-                                      "MMAs each; peak = measured sustained bf16 (tf32 runs at half that rate)"}
+                              "note": "algorithmic fp32 flops (2MNK of the contractions), executed as 3 split-precision "
+                                      "MMAs each (fp16 hi/lo halves on kind::f16 at d = 64, tf32 otherwise); peak = "
+                                      "measured sustained bf16"}
         # the selection's screening kernel is always reported too (the north star's HBM-roofline kernel)
         screen = [k for k in kern if k[0].startswith("lpf_select_onepass_packed/screen")]
         if screen:
@@ -481,6 +503,17 @@ def run_b200(args):
             roof["screen"] = {"kernel": screen[0][0], "avg_launch_ms": sc_ms, "algorithmic_bytes_per_launch": sc_alg,
                               "achieved": sc_alg / (sc_ms * 1e-3) / 1e9, "frac": sc_alg / (sc_ms * 1e-3) / 1e9 / peak,
                               "traffic": (json.load(open(tpath)).get("select_screen_packed_kernel") if os.path.exists(tpath) and grouped else None)}
+        # ... and so is the fused heads kernel (HBM gather + tensor pipe)
+        heads_k = [k for k in kern if k[0] in ("lpf_link_heads_tc", "lpf_link_heads_f16")]
+        if heads_k and grouped:
+            h_ms = heads_k[0][2] / heads_k[0][1]
+            h_alg = (args.steps * (nlinks * (d * 4 + 16 + 4) + nq * d * 4)) / heads_k[0][1]
+            h_fl = args.steps * nlinks * 2.0 * (d * d + d * d + 2 * d * d + 2 * d) / heads_k[0][1]
+            tpeak = float(peaks_all.get("bf16_tflops_sustained", 1400.0))
+            roof["heads"] = {"kernel": heads_k[0][0], "avg_launch_ms": h_ms, "algorithmic_bytes_per_launch": h_alg,
+                             "achieved": h_alg / (h_ms * 1e-3) / 1e9, "frac": h_alg / (h_ms * 1e-3) / 1e9 / peak,
+                             "tensor_tflops": h_fl / (h_ms * 1e-3) / 1e12, "tensor_frac": h_fl / (h_ms * 1e-3) / 1e12 / tpeak,
+                             "traffic": (json.load(open(tpath)).get("link_heads_f16_kernel") if os.path.exists(tpath) else None)}
         path_gbs = byt["path_dedup"] / (dev_ms * 1e-3) / 1e9
         value = world * nlinks * args.steps / (dev_ms * 1e-3)
         e2e_val = world * nlinks * args.steps / (e2e_ms * 1e-3)

@@ -346,10 +346,11 @@ int lpf_nz_links_fused(const lpf_nz_args* args, void* stream);
 int lpf_debug_select_clocks(void* device_buffer);
 
 /* Profiling hook: with enable != 0 later lpf_select_onepass_packed calls record CUDA events on their stream around
- * the screening kernel, the hub-source kernel and the deferred-link tail; lpf_debug_select_timing_read waits for
- * the last such call and stores the three durations (milliseconds) in ms3_host[0..2]; -1 if nothing was recorded. */
+ * the screening kernel, the resolve kernel, the hub-hub resolve kernel and the deferred-link tail;
+ * lpf_debug_select_timing_read waits for the last such call and stores the four durations (milliseconds) in
+ * ms4_host[0..3]; -1 if nothing was recorded. */
 int lpf_debug_select_timing(int enable);
-int lpf_debug_select_timing_read(float* ms3_host);
+int lpf_debug_select_timing_read(float* ms4_host);
 /* Test hook: caps the hash slots lpf_select_onepass_packed's screening launch may use for the staged sources (its
  * hub launch gets four times as many), so that small graphs reach the hub launch and the global-memory search of
  * sources beyond it; 0 restores the full tables. */

@@ -408,6 +408,23 @@ __global__ void __launch_bounds__(32 * kNzWarps, 1) nz_fused_kernel(const __grid
     NzW W;
     W.ldp = up4(pd);
     float* xs;
+    // this warp's first link: its position, endpoints and node rows are requested before the matrices are staged (four
+    // dependent DRAM trips that would otherwise start after the staging)
+    {
+        const int64_t j = (int64_t)blockIdx.x * kNzWarps + warp;
+        if (j < n) {
+            const int64_t pos = __ldg(p.nz + j);
+            const int64_t a = __ldg(p.links + pos), b = __ldg(p.links + p.bs + pos);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.X + a * p.ldx));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.X + a * p.ldx + 32));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.X + b * p.ldx));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.X + b * p.ldx + 32));
+            for (int t = 0; t < p.ntypes; ++t) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.counts + t * p.bs + pos));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.seg_start + t * p.bs + pos));
+            }
+        }
+    }
     {
         float* w = nz_smem;
         W.wlT = w;  stage_floats(w, p.wlT, D * D);              w += D * D;

@@ -290,9 +290,13 @@ void launch_onepass_reset(const SelectParams2& p, cudaStream_t st) {
     if (p.hub) select_reset_packed<<<1, 1, 0, st>>>(p.heavy, p.hdr, p.hub);
     else select_reset_onepass<<<1, 1, 0, st>>>(p.heavy, p.hdr);
 }
-void launch_onepass_tail(const SelectParams2& p, cudaStream_t st) {
+void launch_onepass_heavy(const SelectParams2& p, cudaStream_t st) {
     select_heavy_onepass_kernel<<<kNumSMs * 2, kHeavyThreads, 0, st>>>(p);
-    select_finalize_onepass<<<1, 1, 0, st>>>(p.hdr);
+}
+void launch_onepass_finalize(const SelectParams2& p, cudaStream_t st) { select_finalize_onepass<<<1, 1, 0, st>>>(p.hdr); }
+void launch_onepass_tail(const SelectParams2& p, cudaStream_t st) {
+    launch_onepass_heavy(p, st);
+    launch_onepass_finalize(p, st);
 }
 
 template <int G>

@@ -53,6 +53,10 @@ constexpr int kPkMaxRowChunks = 1024;  // target rows with more 16-byte chunks a
 constexpr int kPkWarpItems = 512;      // overflow chunks of a warp's 32 links that are screened (the rest: candidates unscreened)
 constexpr int kPkInflight = 4;         // overflow reads a lane keeps in flight
 constexpr int kPkResolveThreads = 256;
+#ifndef LPF_RESOLVE_CTAS
+#define LPF_RESOLVE_CTAS 3
+#endif
+constexpr int kPkResolveCtas = LPF_RESOLVE_CTAS;   // resolve CTAs per SM (one warp per candidate: ~3,500 candidates per citation2-shaped batch)
 constexpr int kPkBigSlots = 2048;       // links whose shorter row has up to this many slots take a whole CTA (select_resolve_big_kernel)
 constexpr uint32_t kPkPprTag = 0x80000000u;
 constexpr uint32_t kPkPad = 0x7fffffffu;
@@ -400,7 +404,7 @@ __device__ __forceinline__ void resolve_packed_fast(const SelectParams2& p, cons
 // RESOLVE launch: one warp per candidate of the screening.  The warp walks the SHORTER of the link's two rows and
 // searches the other; a link whose shorter row has more than kPkResolveSlots slots (a hub-hub pair) goes to the
 // deferred-link kernel, where a whole CTA walks it.
-__global__ void __launch_bounds__(kPkResolveThreads, 2)
+__global__ void __launch_bounds__(kPkResolveThreads, kPkResolveCtas)
 select_resolve_packed_kernel(const __grid_constant__ SelectParams2 p, const uint4* __restrict__ slab,
                              const uint4* __restrict__ ovf) {
     __shared__ int32_t ids_sm[kPkResolveThreads / 32][kPkStageIds];
@@ -440,7 +444,7 @@ constexpr int kPkBigPer = 8;
 constexpr int kPkBigStage = 8192;      // neighbour ids of the searched row staged in shared memory (32 KB)
 constexpr int kPkBigSmem = (kPkBigStage + 2 * kPkBigSlots) * 4;    // + the walked row's ids (16 KB)
 static_assert(kPkBigSlots == kPkBigThreads * kPkBigPer, "2,048 slots: a row of ~4,000 neighbours");
-__global__ void __launch_bounds__(kPkBigThreads)
+__global__ void __launch_bounds__(kPkBigThreads, 2)
 select_resolve_big_kernel(const __grid_constant__ SelectParams2 p, const uint4* __restrict__ slab, const uint4* __restrict__ ovf) {
     constexpr int NW = kPkBigThreads / 32, M = kPkBigPer;
     __shared__ uint32_t wtot[M][NW];
@@ -864,11 +868,13 @@ __global__ void __launch_bounds__(256) pack_fill_kernel(const int64_t* __restric
 extern long long* g_select_dbg;
 // profiling hook (lpf_debug_select_timing): CUDA events around the three kernels of the packed launch sequence
 bool g_kernel_timing = false;     // shared with nz_fused.cu
-static cudaEvent_t g_pk_ev[4];
+static cudaEvent_t g_pk_ev[5];
 static bool g_pk_ev_ready = false, g_pk_ev_valid = false;
 static int g_pk_slot_limit = 0;
 void launch_onepass_reset(const SelectParams2& p, cudaStream_t st);
 void launch_onepass_tail(const SelectParams2& p, cudaStream_t st);
+void launch_onepass_heavy(const SelectParams2& p, cudaStream_t st);
+void launch_onepass_finalize(const SelectParams2& p, cudaStream_t st);
 
 }  // namespace lpf
 
@@ -965,17 +971,43 @@ extern "C" int lpf_select_onepass_packed(const int64_t* links, int64_t bs, const
             p, static_cast<const uint4*>(slab), static_cast<const uint4*>(overflow));
         if (timing) cudaEventRecord(g_pk_ev[1], st);
         // RESOLVE: one warp per candidate (their number is on the device: a resident grid strides over the list)
-        select_resolve_packed_kernel<<<kNumSMs * 2, kPkResolveThreads, 0, st>>>(
+        select_resolve_packed_kernel<<<kNumSMs * kPkResolveCtas, kPkResolveThreads, 0, st>>>(
             p, static_cast<const uint4*>(slab), static_cast<const uint4*>(overflow));
-        select_resolve_big_kernel<<<kNumSMs * 2, kPkBigThreads, kPkBigSmem, st>>>(
+        if (timing) {
+            // (profiling: the kernels one after the other, each between two events)
+            cudaEventRecord(g_pk_ev[2], st);
+            select_resolve_big_kernel<<<kNumSMs * 2, kPkBigThreads, kPkBigSmem, st>>>(
+                p, static_cast<const uint4*>(slab), static_cast<const uint4*>(overflow));
+            cudaEventRecord(g_pk_ev[3], st);
+            launch_onepass_tail(p, st);
+            cudaEventRecord(g_pk_ev[4], st);
+            g_pk_ev_valid = true;
+            return check_launch("lpf_select_onepass_packed");
+        }
+        // The hub-hub resolve and the deferred-link kernel both take lists that are final once the resolve kernel has
+        // run, and both are a latency chain on a few CTAs: they run side by side (fork / join through a side stream
+        // per device; under stream capture the fork and the join become graph edges).
+        static cudaStream_t side[64] = {};
+        static cudaEvent_t ev_fork[64] = {}, ev_join[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64) dev = 0;
+        if (!side[dev]) {
+            cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking);
+            cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming);
+        }
+        cudaEventRecord(ev_fork[dev], st);
+        cudaStreamWaitEvent(side[dev], ev_fork[dev], 0);
+        select_resolve_big_kernel<<<kNumSMs * 2, kPkBigThreads, kPkBigSmem, side[dev]>>>(
             p, static_cast<const uint4*>(slab), static_cast<const uint4*>(overflow));
-        if (timing) cudaEventRecord(g_pk_ev[2], st);
+        cudaEventRecord(ev_join[dev], side[dev]);
+        launch_onepass_heavy(p, st);
+        cudaStreamWaitEvent(st, ev_join[dev], 0);
+        launch_onepass_finalize(p, st);
+        return check_launch("lpf_select_onepass_packed");
     }
     launch_onepass_tail(p, st);
-    if (timing) {
-        cudaEventRecord(g_pk_ev[3], st);
-        g_pk_ev_valid = true;
-    }
     return check_launch("lpf_select_onepass_packed");
 }
 
@@ -987,17 +1019,18 @@ extern "C" int lpf_debug_select_slots(int limit) {
 }
 
 // Profiling hook: with enable != 0 later lpf_select_onepass_packed calls record CUDA events on their stream around
-// the screening kernel, the resolve kernel and the deferred-link tail; lpf_debug_select_timing_read waits for the
-// last such call and returns the three durations in milliseconds (0 on success, -1 if nothing was recorded).
+// the screening kernel, the resolve kernel, the hub-hub resolve kernel and the deferred-link tail;
+// lpf_debug_select_timing_read waits for the last such call and returns the four durations in milliseconds (0 on
+// success, -1 if nothing was recorded).
 extern "C" int lpf_debug_select_timing(int enable) {
     lpf::g_kernel_timing = enable != 0;
     if (!enable) lpf::g_pk_ev_valid = false;
     return LPF_OK;
 }
-extern "C" int lpf_debug_select_timing_read(float* ms3_host) {
-    if (!lpf::g_pk_ev_valid || !ms3_host) return -1;
-    if (cudaEventSynchronize(lpf::g_pk_ev[3]) != cudaSuccess) return -1;
-    for (int k = 0; k < 3; ++k)
-        if (cudaEventElapsedTime(ms3_host + k, lpf::g_pk_ev[k], lpf::g_pk_ev[k + 1]) != cudaSuccess) return -1;
+extern "C" int lpf_debug_select_timing_read(float* ms4_host) {
+    if (!lpf::g_pk_ev_valid || !ms4_host) return -1;
+    if (cudaEventSynchronize(lpf::g_pk_ev[4]) != cudaSuccess) return -1;
+    for (int k = 0; k < 4; ++k)
+        if (cudaEventElapsedTime(ms4_host + k, lpf::g_pk_ev[k], lpf::g_pk_ev[k + 1]) != cudaSuccess) return -1;
     return LPF_OK;
 }

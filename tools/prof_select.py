@@ -17,7 +17,7 @@ d = g.data_dict(dev)
 th = (cfg["thresh_cn"], cfg["thresh_1hop"], cfg["thresh_non1hop"])
 lib = _lib.load()
 import ctypes
-ms3 = (ctypes.c_float * 3)()
+ms3 = (ctypes.c_float * 4)()
 lib.lpf_debug_select_timing(1)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for it in range(iters):
@@ -26,5 +26,5 @@ for it in range(iters):
     out = ops.select_onepass(links, d["adj_mask"], d["ppr"], *th, "all", cap=1 << 19, algo=3)
     torch.cuda.synchronize()
     lib.lpf_debug_select_timing_read(ctypes.addressof(ms3))
-    print("screen %.1f us  resolve %.1f us  deferred %.1f us" % (1e3 * ms3[0], 1e3 * ms3[1], 1e3 * ms3[2]), out["header"].tolist()[:5],
+    print("screen %.1f us  resolve %.1f us  hub-hub resolve %.1f us  deferred %.1f us" % (1e3 * ms3[0], 1e3 * ms3[1], 1e3 * ms3[2], 1e3 * ms3[3]), out["header"].tolist()[:5],
           "candidates %d deferred %d" % (int(out["workspace"][links.shape[1] + 4]), int(out["workspace"][0])))

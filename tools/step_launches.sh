@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu launch list (device time of every kernel, serialised) of the last eager citation2-shaped step: tools/step_launches.sh <tag>
 tag=$1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches.csv python tools/prof_step.py 6 2>&1 | tail -1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches.csv python tools/prof_step.py 6 ${2:-1024} 2>&1 | tail -1
 python - <<PY
 import csv,re
 rows=[r for r in csv.reader(open('gpurun_out/${tag}_launches.csv')) if len(r)>10]
