@@ -1,5 +1,6 @@
 // K4 — fused per-link attention: gather -> score -> segment softmax -> weighted sum ->
-// +bias -> LayerNorm (+ set counts), one warp per link, each link's set kept on chip.
+// +bias -> LayerNorm (+ set counts), one warp per link (all warps of the CTA for a link with hundreds of pairs), each
+// link's set kept on chip, the gathers of up to eight pairs in flight per warp.
 //
 // Replaces LinkTransformerLayer.forward + LinkAttention.forward/message (reference
 // modules/layers.py:39-82, :161-224), which materialise [S,2d] gathers, run lin_l / lin_r
@@ -42,9 +43,91 @@ struct AttendParams {
 };
 
 constexpr int kAttWarps = 8;
+constexpr int kAttHeavy = 256;     // a link with more pairs than this is walked by all warps of its CTA
 
-template <int H, int KC>
-__global__ void __launch_bounds__(kAttWarps * 32) attend_kernel(AttendParams p) {
+// One warp over (its share of) the pairs of one link: online softmax over groups of G pairs — the node ids of 32 pairs
+// come in with one coalesced read, then the G gathered K/V rows and RPE rows are all in flight before the first score
+// is reduced (one pair at a time, every pair paid its own DRAM / L2 round trip), one running-max update per group.
+// `wslot` / `nw`: this warp takes the blocks of 32 pairs wslot, wslot + nw, ... of every type.
+template <int H, int KC, int G>
+__device__ __forceinline__ void attend_link(const AttendParams& p, const int64_t (&seg_lo)[3], const int64_t (&seg_hi)[3],
+                                            const float (&q)[H][KC], const float (&att)[H][KC], int lane, int wslot, int nw,
+                                            float (&mx)[H], float (&den)[H], float (&acc)[H][KC]) {
+    const int C = p.ch;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        for (int64_t s0 = seg_lo[t] + 32 * wslot; s0 < seg_hi[t]; s0 += 32 * nw) {
+            const int cnt = (int)min((int64_t)32, seg_hi[t] - s0);
+            const int32_t my_node = (lane < cnt) ? __ldg(p.node + s0 + lane) : 0;
+            for (int g0 = 0; g0 < cnt; g0 += G) {
+                float v[G][H][KC], sc[G][H];
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    const int jj = g0 + j < cnt ? g0 + j : g0;          // (a short last group repeats its first pair: weight 0)
+                    const int64_t u = __shfl_sync(kFull, my_node, jj);
+                    const float* kv = p.KV + u * p.ld_kv;
+                    const float* rr = p.R + (s0 + jj) * p.ld_r;
+#pragma unroll
+                    for (int h = 0; h < H; ++h)
+#pragma unroll
+                        for (int k = 0; k < KC; ++k) {
+                            const int c = lane + 32 * k;
+                            v[j][h][k] = (c < C) ? __ldg(kv + h * C + c) + __ldg(rr + h * C + c) : 0.f;
+                        }
+                }
+#pragma unroll
+                for (int j = 0; j < G; ++j)
+#pragma unroll
+                    for (int h = 0; h < H; ++h) {
+                        float part = 0.f;
+#pragma unroll
+                        for (int k = 0; k < KC; ++k) {
+                            float x = v[j][h][k] * q[h][k];
+                            x = (x > 0.f) ? x : 0.2f * x;
+                            part = fmaf(att[h][k], x, part);
+                        }
+                        sc[j][h] = part;
+                    }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int j = 0; j < G; ++j)
+#pragma unroll
+                        for (int h = 0; h < H; ++h) sc[j][h] += __shfl_xor_sync(kFull, sc[j][h], o);
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    float m_new = mx[h];
+#pragma unroll
+                    for (int j = 0; j < G; ++j) {
+                        if (g0 + j >= cnt) sc[j][h] = -INFINITY;
+                        m_new = fmaxf(m_new, sc[j][h]);
+                    }
+                    const float scale = expf(mx[h] - m_new);          // exp(-inf) = 0 on the first group
+                    den[h] *= scale;
+#pragma unroll
+                    for (int k = 0; k < KC; ++k) acc[h][k] *= scale;
+#pragma unroll
+                    for (int j = 0; j < G; ++j) {
+                        const float w = expf(sc[j][h] - m_new);
+                        den[h] += w;
+#pragma unroll
+                        for (int k = 0; k < KC; ++k) acc[h][k] = fmaf(w, v[j][h][k], acc[h][k]);
+                    }
+                    mx[h] = m_new;
+                }
+            }
+        }
+    }
+}
+
+// One warp per link; a link with more than kAttHeavy pairs (dense graphs: thousands of common neighbours) is walked by
+// all warps of its CTA, which merge their softmax states in shared memory — otherwise the launch lasts as long as its
+// longest link (measured on the ogbl-ppa shape: one link with 29,513 common neighbours, 13.9 ms for a 32,565-link batch).
+template <int H, int KC, int G>
+__global__ void __launch_bounds__(kAttWarps * 32) attend_kernel(const __grid_constant__ AttendParams p) {
+    __shared__ float s_acc[kAttWarps][H * KC * 32];
+    __shared__ float s_mx[kAttWarps][H], s_den[kAttWarps][H];
+    __shared__ int s_heavy[kAttWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int C = p.ch, HC = H * C;
     float att[H][KC];
@@ -56,22 +139,16 @@ __global__ void __launch_bounds__(kAttWarps * 32) attend_kernel(AttendParams p) 
             att[h][k] = (c < C) ? __ldg(p.att + h * C + c) : 0.f;
         }
 
-    const int64_t n_links = p.n_dev ? min(p.n, *p.n_dev) : p.n;
-    for (int64_t j = (int64_t)blockIdx.x * kAttWarps + warp; j < n_links; j += (int64_t)gridDim.x * kAttWarps) {
-        const int64_t i = p.idx ? (int64_t)__ldg(p.idx + j) : j;   // position in the batch (indexes ptr)
-        float q[H][KC], acc[H][KC], mx[H], den[H];
+    // query vector and segment bounds of link j (list position) / i (batch position)
+    auto load_link = [&](int64_t j, float (&q)[H][KC], int64_t (&seg_lo)[3], int64_t (&seg_hi)[3]) {
+        const int64_t i = p.idx ? (int64_t)__ldg(p.idx + j) : j;
 #pragma unroll
-        for (int h = 0; h < H; ++h) {
-            mx[h] = -INFINITY;
-            den[h] = 0.f;
+        for (int h = 0; h < H; ++h)
 #pragma unroll
             for (int k = 0; k < KC; ++k) {
                 const int c = lane + 32 * k;
                 q[h][k] = (c < C) ? __ldg(p.Q + j * p.ld_q + h * C + c) : 0.f;
-                acc[h][k] = 0.f;
             }
-        }
-        int64_t seg_lo[3], seg_hi[3];
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
             if (p.seg_start) {
@@ -82,46 +159,10 @@ __global__ void __launch_bounds__(kAttWarps * 32) attend_kernel(AttendParams p) 
                 seg_hi[t] = __ldg(p.ptr + t * p.bs + i + 1);
             }
         }
-
-#pragma unroll
-        for (int t = 0; t < 3; ++t) {
-            for (int64_t s0 = seg_lo[t]; s0 < seg_hi[t]; s0 += 32) {
-                const int cnt = (int)min((int64_t)32, seg_hi[t] - s0);
-                const int32_t my_node = (lane < cnt) ? __ldg(p.node + s0 + lane) : 0;
-                for (int j = 0; j < cnt; ++j) {
-                    const int64_t u = __shfl_sync(kFull, my_node, j);
-                    const float* kv = p.KV + u * p.ld_kv;
-                    const float* rr = p.R + (s0 + j) * p.ld_r;
-                    float v[H][KC], sc[H];
-#pragma unroll
-                    for (int h = 0; h < H; ++h) {
-                        float part = 0.f;
-#pragma unroll
-                        for (int k = 0; k < KC; ++k) {
-                            const int c = lane + 32 * k;
-                            float val = 0.f;
-                            if (c < C) val = __ldg(kv + h * C + c) + __ldg(rr + h * C + c);
-                            v[h][k] = val;
-                            float x = val * q[h][k];
-                            x = (x > 0.f) ? x : 0.2f * x;
-                            part = fmaf(att[h][k], x, part);
-                        }
-                        sc[h] = warp_sum(part);
-                    }
-#pragma unroll
-                    for (int h = 0; h < H; ++h) {
-                        const float m_new = fmaxf(mx[h], sc[h]);
-                        const float scale = expf(mx[h] - m_new);  // exp(-inf) = 0 on the first pair
-                        const float w = expf(sc[h] - m_new);
-                        den[h] = fmaf(den[h], scale, w);
-#pragma unroll
-                        for (int k = 0; k < KC; ++k) acc[h][k] = fmaf(acc[h][k], scale, w * v[h][k]);
-                        mx[h] = m_new;
-                    }
-                }
-            }
-        }
-
+    };
+    // everything after the attention sums of link j, by one warp: attention weights (debug output), + bias, LayerNorm, counts
+    auto finish = [&](int64_t j, const float (&q)[H][KC], const int64_t (&seg_lo)[3], const int64_t (&seg_hi)[3],
+                      const float (&mx)[H], const float (&den)[H], const float (&acc)[H][KC]) {
         // head-mean attention weights (debug output of the reference, modules/layers.py:73-75)
         if (p.alpha_out) {
 #pragma unroll
@@ -150,7 +191,6 @@ __global__ void __launch_bounds__(kAttWarps * 32) attend_kernel(AttendParams p) 
                 }
             }
         }
-
         // out = LN(acc / (den + 1e-16) + bias)
         float o[H][KC];
         float sum = 0.f;
@@ -201,6 +241,73 @@ __global__ void __launch_bounds__(kAttWarps * 32) attend_kernel(AttendParams p) 
                 out[HC + 3] = n_cn + n_1h;
             }
         }
+    };
+
+    const int64_t n_links = p.n_dev ? min(p.n, *p.n_dev) : p.n;
+    for (int64_t j0 = (int64_t)blockIdx.x * kAttWarps; j0 < n_links; j0 += (int64_t)gridDim.x * kAttWarps) {
+        const int64_t j = j0 + warp;
+        float q[H][KC], acc[H][KC], mx[H], den[H];
+        int64_t seg_lo[3] = {0, 0, 0}, seg_hi[3] = {0, 0, 0};
+        bool heavy = false;
+        if (j < n_links) {
+            load_link(j, q, seg_lo, seg_hi);
+            heavy = (seg_hi[0] - seg_lo[0]) + (seg_hi[1] - seg_lo[1]) + (seg_hi[2] - seg_lo[2]) > kAttHeavy;
+        }
+        if (lane == 0) s_heavy[warp] = heavy ? 1 : 0;
+        __syncthreads();
+        if (j < n_links && !heavy) {
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                mx[h] = -INFINITY;
+                den[h] = 0.f;
+#pragma unroll
+                for (int k = 0; k < KC; ++k) acc[h][k] = 0.f;
+            }
+            attend_link<H, KC, G>(p, seg_lo, seg_hi, q, att, lane, 0, 1, mx, den, acc);
+            finish(j, q, seg_lo, seg_hi, mx, den, acc);
+        }
+        // the heavy links of the slice, one after the other, all warps together
+        for (int w = 0; w < kAttWarps; ++w) {
+            if (!s_heavy[w]) continue;                   // (uniform across the CTA)
+            load_link(j0 + w, q, seg_lo, seg_hi);
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                mx[h] = -INFINITY;
+                den[h] = 0.f;
+#pragma unroll
+                for (int k = 0; k < KC; ++k) acc[h][k] = 0.f;
+            }
+            attend_link<H, KC, G>(p, seg_lo, seg_hi, q, att, lane, warp, kAttWarps, mx, den, acc);
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+#pragma unroll
+                for (int k = 0; k < KC; ++k) s_acc[warp][(h * KC + k) * 32 + lane] = acc[h][k];
+                if (lane == 0) { s_mx[warp][h] = mx[h]; s_den[warp][h] = den[h]; }
+            }
+            __syncthreads();
+            if (warp == 0) {
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    float M = -INFINITY;
+#pragma unroll
+                    for (int x = 0; x < kAttWarps; ++x) M = fmaxf(M, s_mx[x][h]);
+                    den[h] = 0.f;
+#pragma unroll
+                    for (int k = 0; k < KC; ++k) acc[h][k] = 0.f;
+#pragma unroll
+                    for (int x = 0; x < kAttWarps; ++x) {
+                        const float sc = expf(s_mx[x][h] - M);      // a warp without pairs has mx = -inf, den = 0: weight 0
+                        den[h] = fmaf(s_den[x][h], sc, den[h]);
+#pragma unroll
+                        for (int k = 0; k < KC; ++k) acc[h][k] = fmaf(s_acc[x][(h * KC + k) * 32 + lane], sc, acc[h][k]);
+                    }
+                    mx[h] = M;
+                }
+                finish(j0 + w, q, seg_lo, seg_hi, mx, den, acc);
+            }
+            __syncthreads();
+        }
+        __syncthreads();       // s_heavy is rewritten by the next slice
     }
 }
 
@@ -215,11 +322,13 @@ static int launch_attend_h(const AttendParams& p, cudaStream_t st) {
         set_error("lpf_attend_fused: heads*ceil(ch/32) = %d exceeds 16", kc * H);
         return LPF_ERR_UNSUPPORTED;
     }
-    if (kc <= 1) attend_kernel<H, 1><<<g, kAttWarps * 32, 0, st>>>(p);
-    else if (kc <= 2) { if constexpr (H * 2 <= 16) attend_kernel<H, 2><<<g, kAttWarps * 32, 0, st>>>(p); }
-    else if (kc <= 4) { if constexpr (H * 4 <= 16) attend_kernel<H, 4><<<g, kAttWarps * 32, 0, st>>>(p); }
-    else if (kc <= 8) { if constexpr (H * 8 <= 16) attend_kernel<H, 8><<<g, kAttWarps * 32, 0, st>>>(p); }
-    else { if constexpr (H * 16 <= 16) attend_kernel<H, 16><<<g, kAttWarps * 32, 0, st>>>(p); }
+    // pairs in flight per warp: as many as 16 registers of gathered values per lane allow, at most 8
+    constexpr auto grp = [](int hk) { return hk <= 2 ? 8 : 16 / hk; };
+    if (kc <= 1) attend_kernel<H, 1, grp(H)><<<g, kAttWarps * 32, 0, st>>>(p);
+    else if (kc <= 2) { if constexpr (H * 2 <= 16) attend_kernel<H, 2, grp(H * 2)><<<g, kAttWarps * 32, 0, st>>>(p); }
+    else if (kc <= 4) { if constexpr (H * 4 <= 16) attend_kernel<H, 4, grp(H * 4)><<<g, kAttWarps * 32, 0, st>>>(p); }
+    else if (kc <= 8) { if constexpr (H * 8 <= 16) attend_kernel<H, 8, grp(H * 8)><<<g, kAttWarps * 32, 0, st>>>(p); }
+    else { if constexpr (H * 16 <= 16) attend_kernel<H, 16, 1><<<g, kAttWarps * 32, 0, st>>>(p); }
     return check_launch("lpf_attend_fused");
 }
 
