@@ -138,8 +138,9 @@ TRACE = None
 COUNTERS = None   # optional dict: bench.py counts CUDA-graph launches here
 
 
-def call(name, *args, meta=None):
-    """Invoke an int-returning entry point; raise LpfError with lpf_last_error() on failure."""
+def call(name, *args, meta=None, label=None):
+    """Invoke an int-returning entry point; raise LpfError with lpf_last_error() on failure.  `label`: the tracer
+    files the call under name/label (two uses of one entry point that should be timed apart)."""
     lib = load()
     tr = TRACE
     if tr is not None:
@@ -150,7 +151,7 @@ def call(name, *args, meta=None):
             a.record()
             rc = getattr(lib, name)(*args)
             b.record()
-            tr.records.append((name, meta, a, b))
+            tr.records.append((name if label is None else name + "/" + label, meta, a, b))
         else:
             rc = getattr(lib, name)(*args)
     else:

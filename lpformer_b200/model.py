@@ -342,6 +342,7 @@ class LinkTransformer(nn.Module):
         self.use_graphs = True      # ... replayed as a CUDA graph
         # non-empty links below this share of the batch take the one-warp-per-link path (LPF_NZ_FUSED_SHARE: tuning knob)
         self.nz_fused_share = float(os.environ.get("LPF_NZ_FUSED_SHARE", 1.0 / 16))
+        self.nz_fused_max_links = int(os.environ.get("LPF_NZ_FUSED_MAX_LINKS", 8192))
 
     # ------------------------------------------------------------------ graph tables
     def _dev(self):

@@ -103,11 +103,13 @@ def heads_call(links, bs, idx, n, X, c, zb, ld_zb, prob, logits, n_dev, sched, s
     if "w1h" in c and X.data_ptr() % 16 == 0 and X.stride(0) % 4 == 0:
         call("lpf_link_heads_f16", ptr(links), bs, idx, n, ptr(X), X.stride(0), X.shape[0], d, ptr(c["w1h"]), c["inv_sw1"], ptr(c["b1"]),
              ptr(c["ln_w_s"]), ptr(c["ln_b_s"]), ptr(c["w23h"]), c["inv_s3"], ptr(c["c3"]) if zb is None else None, zb, ld_zb,
-             ptr(c["ws2"]), ptr(c["bs2"]), ptr(prob), int(logits), n_dev, st, meta=(n,))
+             ptr(c["ws2"]), ptr(c["bs2"]), ptr(prob), int(logits), n_dev, st, meta=(n,),
+             label=None if zb is None else "non-empty links (per-row offsets)")
     else:
         call("lpf_link_heads_tc", ptr(links), bs, idx, n, ptr(X), X.stride(0), d, ptr(c["w1p"]), ptr(c["b1"]),
              ptr(c["ln_w"]), ptr(c["ln_b"]), ptr(c["w23p"]), ptr(c["c3"]) if zb is None else None, zb, ld_zb,
-             ptr(c["ws2"]), ptr(c["bs2"]), ptr(prob), int(logits), n_dev, sched, st, meta=(n,))
+             ptr(c["ws2"]), ptr(c["bs2"]), ptr(prob), int(logits), n_dev, sched, st, meta=(n,),
+             label=None if zb is None else "non-empty links (per-row offsets)")
 
 
 def linear(A, W, bias=None, bias_scale=1.0, out=None, epilogue=EPI_NONE):

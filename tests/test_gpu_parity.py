@@ -507,6 +507,7 @@ def test_plan_fused_nonempty_path(dim, mode_th):
     ref = [model.score_links(torch.from_numpy(b).to(dev), X, score).cpu().numpy() for b in batches]
     model.use_plans = True
     model.nz_fused_share = 1.0          # force the fused kernel whatever the share of non-empty links
+    model.nz_fused_max_links = 1 << 30
     for rep in range(2):
         for b, r in zip(batches, ref):
             out = model.score_links(torch.from_numpy(b).to(dev), X, score).cpu().numpy()
