@@ -86,31 +86,68 @@ def shard_queries(num_queries, rank, world):
     return lo, min(num_queries, lo + per)
 
 
+def shard_bounds(num_queries, world, cost=None):
+    """The world + 1 boundaries of the contiguous query-group shards.  cost (optional, one non-negative number per group):
+    the shards are cut so that every rank gets the same share of the total COST instead of the same number of groups —
+    a link costs what its two rows weigh ("balance by sum(deg + nP), not link count"), and a few hub
+    sources can double one rank's share.  Deterministic: every rank computes the same cuts from the same links."""
+    if cost is None or num_queries == 0 or world == 1:
+        return [shard_queries(num_queries, r, world)[0] for r in range(world)] + [num_queries]
+    csum = torch.cumsum(torch.as_tensor(cost, dtype=torch.float64).reshape(-1).cpu(), 0)
+    total = float(csum[-1])
+    if not total > 0.0:
+        return [shard_queries(num_queries, r, world)[0] for r in range(world)] + [num_queries]
+    targets = torch.tensor([total * r / world for r in range(1, world)], dtype=torch.float64)
+    cuts = torch.searchsorted(csum, targets, right=False).tolist()      # first group whose running cost reaches the target
+    bounds = [0] + [min(num_queries, int(c) + 1) for c in cuts] + [num_queries]
+    for i in range(1, len(bounds)):                                       # (monotone even with zero-cost groups)
+        bounds[i] = max(bounds[i], bounds[i - 1])
+    return bounds
+
+
+def link_group_cost(model, links, group_size, test_set=False):
+    """Cost of every group of `group_size` consecutive links: 4 deg + 8 nP (+ 48) bytes of both endpoints' rows, the
+    shared source of a citation2-style group counted once (the algorithmic bytes of the selection)."""
+    adj, ppr = model.get_adj(test_set, mask=True), model.get_ppr(test_set)
+    dev = adj.rowptr.device
+    row = (4 * (adj.rowptr[1:] - adj.rowptr[:-1]) + 8 * (ppr.rowptr[1:] - ppr.rowptr[:-1])).to(torch.float64)
+    lk = links.to(dev)
+    ng = lk.shape[1] // group_size
+    a = lk[0, :ng * group_size].reshape(ng, group_size)
+    b = lk[1, :ng * group_size].reshape(ng, group_size)
+    same_src = bool((a == a[:, :1]).all()) if ng > 0 else False
+    cost_a = row[a[:, 0]] if same_src else row[a].sum(1)
+    return cost_a + row[b].sum(1) + 48.0 * group_size
+
+
 @torch.no_grad()
-def score_links_sharded(model, score_func, links, X, test_set=False, group=None, group_size=1, batch_size=None):
+def score_links_sharded(model, score_func, links, X, test_set=False, group=None, group_size=1, batch_size=None,
+                        balance=True):
     """Scores `links` [2, L] (L a multiple of group_size) with link groups sharded over the ranks of
-    `group`; returns the full [L] probabilities on every rank (one all_gather of fp32 scores at the end)."""
+    `group`; returns the full [L] probabilities on every rank (one all_gather of fp32 scores at the end).
+    balance: cut the shards by the weight of the links' rows (shard_bounds / link_group_cost) instead of by count."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     dev = model._dev()
     L = links.shape[1]
     ngroups = L // group_size
-    lo, hi = shard_queries(ngroups, rank, world)
+    cost = link_group_cost(model, links, group_size, test_set) if (balance and world > 1 and hasattr(model, "get_adj")) else None
+    bounds = shard_bounds(ngroups, world, cost)
+    lo, hi = bounds[rank], bounds[rank + 1]
     mine = links[:, lo * group_size:hi * group_size].to(dev)
     bs = batch_size or max(1, mine.shape[1])
     outs = [model.score_links(mine[:, s:s + bs], X, score_func, test_set=test_set) for s in range(0, mine.shape[1], bs)]
     local = torch.cat(outs) if outs else torch.empty(0, device=dev)
     if world == 1:
         return local
-    per = (ngroups + world - 1) // world * group_size
+    per = max(1, max(bounds[r + 1] - bounds[r] for r in range(world)) * group_size)
     pad = torch.zeros(per, dtype=torch.float32, device=dev)
     pad[:local.numel()] = local
     full = torch.empty(per * world, dtype=torch.float32, device=dev)
     dist.all_gather_into_tensor(full, pad, group=group)
     pieces = []
     for r in range(world):
-        a, b = shard_queries(ngroups, r, world)
-        pieces.append(full[r * per:r * per + (b - a) * group_size])
+        pieces.append(full[r * per:r * per + (bounds[r + 1] - bounds[r]) * group_size])
     return torch.cat(pieces)
 
 

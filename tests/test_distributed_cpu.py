@@ -61,3 +61,23 @@ def test_shard_queries_partition():
             spans = [shard_queries(n, r, w) for r in range(w)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+
+
+def test_shard_bounds_balance_by_cost():
+    """shard_bounds with a cost per query group (balance by the weight of the links' rows, not by their
+    number): contiguous, complete, monotone, and every shard within one group's cost of the ideal share."""
+    from lpformer_b200.evaluate import shard_bounds, shard_queries
+    g = torch.Generator().manual_seed(3)
+    for n in (1, 7, 64, 1001):
+        for w in (1, 2, 3, 8):
+            assert shard_bounds(n, w) == [shard_queries(n, r, w)[0] for r in range(w)] + [n]
+            cost = torch.rand(n, generator=g, dtype=torch.float64) ** 4 * 1000 + 1      # a few heavy groups
+            cost[n // 2] = 5000.0
+            b = shard_bounds(n, w, cost)
+            assert b[0] == 0 and b[-1] == n and all(b[i] <= b[i + 1] for i in range(w))
+            share = float(cost.sum()) / w
+            for r in range(w):
+                got = float(cost[b[r]:b[r + 1]].sum())
+                assert got <= share + float(cost.max()) + 1e-6, (n, w, r, got, share)
+    assert shard_bounds(0, 4, torch.zeros(0)) == [0, 0, 0, 0, 0]
+    assert shard_bounds(5, 2, torch.zeros(5)) == [0, 3, 5]                              # zero cost: by count
