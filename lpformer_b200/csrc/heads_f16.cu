@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kThreads, 1) link_heads_f16_kernel(const __gri
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // bar_w: weights landed;  bar_a_ready[b]: the producers have stored operand buffer b;  bar_mma1[b]: contraction 1
     // from operand buffer b into accumulator buffer b complete;  bar_d1_free[b]: the consumers have read accumulator
-    // buffer b;  bar_h_ready: the consumers have stored H;  bar_mma3: contraction 2 complete (accumulator ready, H free).
+    // buffer b (four arrivals: one per lane quadrant);  bar_h_ready: the consumers have stored H (four arrivals);  bar_mma3: contraction 2 complete (accumulator ready, H free).
     // bar_ids[s]: the gather warp has written id-ring slot s (32 arrivals);  bar_stage[s]: the 32 four-row gathers of staging
     // slot s have landed (32 arrivals: every issuing lane announces its own bytes);  bar_stage_free[s]: the producers have
     // converted the rows of staging slot s.
@@ -216,11 +216,11 @@ __global__ void __launch_bounds__(kThreads, 1) link_heads_f16_kernel(const __gri
         mbar_init(&bar_w, 1);
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bar_mma1[b], 1);
-            mbar_init(&bar_d1_free[b], 1);
+            mbar_init(&bar_d1_free[b], 4);
             mbar_init(&bar_a_ready[b], 1);
         }
         mbar_init(&bar_mma3, 1);
-        mbar_init(&bar_h_ready, 1);
+        mbar_init(&bar_h_ready, 4);
         for (int b = 0; b < kStages; ++b) {
             mbar_init(&bar_stage[b], kTileM / 4);
             mbar_init(&bar_stage_free[b], 1);
@@ -492,6 +492,11 @@ __global__ void __launch_bounds__(kThreads, 1) link_heads_f16_kernel(const __gri
     // =============================== consumers: kSplit threads per link (= TMEM lane), 1/kSplit of the columns each
     const float bs2 = p.bs2[0];
     const int row = (warp & 3) * 32 + (tid & 31), part = warp >> 2;
+    // The kSplit warps that share a TMEM lane quadrant (32 links) exchange their partial sums among themselves only —
+    // a named barrier per quadrant — and announce their share of H / of the accumulator reads on their own (the
+    // mbarriers count four arrivals): the four groups drift apart and one group's TMEM reads run under another's
+    // arithmetic instead of all eight warps meeting four times per tile.
+    const int qbar = 3 + (warp & 3);
     auto xsum = [&](const float (&a)[kSplit][kTileM]) -> float {
         float t = a[0][row];
 #pragma unroll
@@ -528,7 +533,7 @@ __global__ void __launch_bounds__(kThreads, 1) link_heads_f16_kernel(const __gri
             if (c0 + 16 < NH) tmem_ld_wait();
         }
         s_dot[part][row] = (acc[0].x + acc[0].y) + (acc[1].x + acc[1].y);
-        named_bar_sync(1, kConsumers);
+        named_bar_sync(qbar, 32 * kSplit);
         if (part == 0 && j < n_links) {
             const float logit = xsum(s_dot) + bs2;
             const int64_t pos = p.idx ? (int64_t)__ldg(p.idx + j) : j;
@@ -571,8 +576,8 @@ __global__ void __launch_bounds__(kThreads, 1) link_heads_f16_kernel(const __gri
             }
             s_sum[part][row] = (s2[0].x + s2[0].y) + (s2[1].x + s2[1].y);
             tc_fence_before();
-            named_bar_sync(1, kConsumers);
-            if (tid == 0) mbar_arrive(&bar_d1_free[it & 1]);     // contraction 1 of tile it + 2 may overwrite the buffer
+            named_bar_sync(qbar, 32 * kSplit);
+            if (part == 0 && (tid & 31) == 0) mbar_arrive(&bar_d1_free[it & 1]);     // contraction 1 of tile it + 2 may overwrite the buffer
             const float mean = xsum(s_sum) * (1.0f / D);
             const float2 nmean = dup2(-mean);
             float2 q2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
@@ -582,7 +587,7 @@ __global__ void __launch_bounds__(kThreads, 1) link_heads_f16_kernel(const __gri
                 q2[c & 1] = fma2(dlt, dlt, q2[c & 1]);
             }
             s_sq[part][row] = (q2[0].x + q2[0].y) + (q2[1].x + q2[1].y);
-            named_bar_sync(1, kConsumers);
+            named_bar_sync(qbar, 32 * kSplit);
             const float rstd = rsqrtf(xsum(s_sq) * (1.0f / D) + 1e-5f);
             const float2 rstd2 = dup2(rstd), nmr = dup2(-mean * rstd);     // (v - mean) rstd as one fma
 #pragma unroll
@@ -610,9 +615,9 @@ __global__ void __launch_bounds__(kThreads, 1) link_heads_f16_kernel(const __gri
         }
         tmem_st_wait();
         tc_fence_before();
-        named_bar_sync(1, kConsumers);
+        named_bar_sync(qbar, 32 * kSplit);
         LPF_STAMP(4);
-        if (tid == 0) mbar_arrive(&bar_h_ready);
+        if (part == 0 && (tid & 31) == 0) mbar_arrive(&bar_h_ready);
         LPF_STAMP(5);
         if (it > 0) epilogue2(j_prev, d3 + ((it - 1) & 1) * N3);
         LPF_STAMP(6);

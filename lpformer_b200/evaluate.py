@@ -177,6 +177,7 @@ class LinkScoreStream:
             self.plans = [ScorePlan(model, score_func, consts, self.X, kv, self.bs, test_set, return_logits,
                                     use_graph=model.use_graphs) for _ in range(max(1, int(depth)))]
         self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.out_stream = torch.cuda.Stream(device=self.dev)     # scores to the host: the other direction of the link
         # every plan launches on a stream of its own: the latency-bound tail of one batch (hub sources, heavy links,
         # the non-empty links) overlaps the bandwidth-bound head of the next
         self.streams = [torch.cuda.Stream(device=self.dev) for _ in (self.plans or [])]
@@ -211,18 +212,21 @@ class LinkScoreStream:
         cs = self.copy_stream
         if on_host and (self._stage is None or self._stage[0].shape[1] != G * bs):
             self._stage = [torch.empty((2, G * bs), dtype=torch.int64, device=self.dev) for _ in range(2)]
-        ev_in = [torch.cuda.Event(), torch.cuda.Event()]
+        ev_in = [[torch.cuda.Event() for _ in range(G)] for _ in range(2)]     # [slot][batch of the group]: its links are in
         ev_free = [torch.cuda.Event(), torch.cuda.Event()]
 
         def h2d(g):          # links of the group that starts at batch g -> staging slot, on the copy stream
             slot = (g // G) % 2
-            n = min(G, nb - g) * bs
             with torch.cuda.stream(cs):
                 # (the copy stream has already waited for the plans to take the slot's previous links: ev_free)
-                # row by row: a strided two-row host slice would go through a slow pitched copy (15 vs 48 GB/s measured)
-                self._stage[slot][0, :n].copy_(links[0, g * bs:g * bs + n], non_blocking=True)
-                self._stage[slot][1, :n].copy_(links[1, g * bs:g * bs + n], non_blocking=True)
-                ev_in[slot].record(cs)
+                # batch by batch, each announced on its own: the first batch of a call starts after 16 bytes per link of
+                # ITS links have arrived, not after the whole group's; row by row: a strided two-row host slice would go
+                # through a slow pitched copy (15 vs 48 GB/s measured)
+                for j in range(min(G, nb - g)):
+                    lo = (g + j) * bs
+                    self._stage[slot][0, j * bs:(j + 1) * bs].copy_(links[0, lo:lo + bs], non_blocking=True)
+                    self._stage[slot][1, j * bs:(j + 1) * bs].copy_(links[1, lo:lo + bs], non_blocking=True)
+                    ev_in[slot][j].record(cs)
 
         pending = [None] * depth
         redo = []
@@ -247,22 +251,27 @@ class LinkScoreStream:
                 if pending[k % depth] is not None and P.collect():
                     redo.append(pending[k % depth])
                 with torch.cuda.stream(st):
-                    if on_host and j < depth:
-                        st.wait_event(ev_in[slot])
+                    if on_host:
+                        st.wait_event(ev_in[slot][j])
                     P.submit(src[:, j * bs:(j + 1) * bs])
                     out_dev[k * bs:(k + 1) * bs].copy_(P.prob, non_blocking=True)
                 pending[k % depth] = k
                 self.batches += 1
             if on_host or out_host is not None:
                 # the group is through once every plan stream has passed this point
+                # (the links come in on one stream and the scores leave on another: PCIe is full duplex, and on one
+                # stream the 4 bytes per link going out would queue behind the 16 coming in)
                 for st in self.streams:
                     e = torch.cuda.Event()
                     e.record(st)
-                    cs.wait_event(e)
+                    if on_host:
+                        cs.wait_event(e)
+                    if out_host is not None:
+                        self.out_stream.wait_event(e)
                 if on_host:
                     ev_free[slot].record(cs)
                 if out_host is not None:
-                    with torch.cuda.stream(cs):
+                    with torch.cuda.stream(self.out_stream):
                         out_host[g * bs:(g + kb) * bs].copy_(out_dev[g * bs:(g + kb) * bs], non_blocking=True)
         for j, k in enumerate(pending):
             if k is not None and self.plans[j].collect():
@@ -272,6 +281,7 @@ class LinkScoreStream:
         for st in self.streams:
             st.synchronize()
         cs.synchronize()
+        self.out_stream.synchronize()
         if redo:
             use = self.model.use_plans
             self.model.use_plans = False      # host-sized two-pass path: no pools to overflow
