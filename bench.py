@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sampler", action="store_true", help="debug: do not poll nvidia-smi during the timed region")
     ap.add_argument("--depth", type=int, default=4, help="execution plans (batches) in flight in the pipelined eval loop")
+    ap.add_argument("--node-dtype", default="f32", choices=["f32", "bf16"], help="storage of the node tables X / KV read by "
+                    "the scoring plans (arithmetic is fp32 / fp16-split with fp32 accumulation either way)")
     ap.add_argument("--seed", type=int, default=0)
     return ap.parse_args()
 
@@ -273,6 +275,7 @@ def run_b200(args):
     targs = S.train_args_of(cfg)
     torch.manual_seed(args.seed)
     model = L.LinkTransformer(targs, g.data_dict(dev), device=dev).to(dev).eval()
+    model.node_dtype = args.node_dtype
     score = L.mlp_score(model.out_dim, model.out_dim, 1, 2).to(dev).eval()
     d, hc = cfg["dim"], cfg["dim"]
 
@@ -527,7 +530,7 @@ def run_b200(args):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload_name(args.workload, negs),
                            "scale": args.scale, "graph": g.stats(), "queries_per_step_per_gpu": nq,
-                           "links_per_step_per_gpu": nlinks, "dim": d, "mode": model.mask,
+                           "links_per_step_per_gpu": nlinks, "dim": d, "mode": model.mask, "node_table_dtype": args.node_dtype,
                            "thresholds": [cfg["thresh_cn"], cfg["thresh_1hop"], cfg["thresh_non1hop"]],
                            "l2_policy": "distinct link batch every step; node/graph tables (%.2f GB) exceed the 126 MB L2"
                                         % ((g.indices.nbytes + g.ppr[1].nbytes * 2 + 2 * g.n * d * 4) / 1e9),

@@ -221,7 +221,7 @@ int lpf_layernorm_act(const float* X, int64_t ldx, const float* gamma, const flo
 int lpf_gather_links(const int64_t* links, int64_t bs, const int32_t* idx /* NULL or [n] batch positions */,
                      int64_t n, const float* X, int64_t ldx, int32_t d,
                      float* xsum, int64_t ld_sum, float* xprod, int64_t ld_prod, const int64_t* n_dev,
-                     void* stream);
+                     int x_bf16 /* X holds bf16 (ldx in elements) */, void* stream);
 
 /* dst[r,:] = fill_row[:] for all `rows` rows (skipped when fill_row is NULL), then dst[idx[j],:] = src[j,:]
  * for j < n: puts the pairwise rows of the compacted non-empty links back in batch order, every other link
@@ -253,7 +253,7 @@ int lpf_attend_fused(const int64_t* ptr, int64_t bs, const int32_t* idx /* NULL 
                      const float* att, const float* bias, const float* ln_w, const float* ln_b,
                      int32_t heads, int32_t ch, int mode, int write_counts,
                      float* out, int64_t ld_out, float* alpha_out,
-                     const int64_t* n_dev, const int32_t* seg_start, const int32_t* seg_cnt, int64_t type_stride,
+                     const int64_t* n_dev, const int32_t* seg_start, const int32_t* seg_cnt, int64_t type_stride, int kv_bf16 /* KV holds bf16 (ld_kv in elements) */,
                      void* stream);
 
 /* ------------------------------------------------------------------------- *
@@ -289,13 +289,14 @@ int lpf_link_heads_tc(const int64_t* links, int64_t bs, const int32_t* idx, int6
  *     s_h (sqrt(d) max|ln_w| + max|ln_b|) <= 2^15 (LayerNorm bounds h, so h s_h fits fp16);
  *   * the gathered rows X[a]*X[b] are scaled per link inside the kernel.
  * The X[b] rows are fetched by TMA row gathers (tile::gather4) through a tensor map of X [n_nodes, d] built per call:
- * X must be 16-byte aligned with ldx % 4 == 0, and every link id must be < n_nodes.
+ * X rows must be 16-byte aligned, and every link id must be < n_nodes.  x_bf16 != 0: X holds bf16 (the node table at
+ * half the bytes; ldx in elements; arithmetic unchanged: fp32 products, fp16-split contractions, fp32 accumulation).
  * Everything else as lpf_link_heads_tc (no tile_sched).
  * ------------------------------------------------------------------------- */
 int64_t lpf_pack_weight_f16_bytes(int32_t N, int32_t K);
 int lpf_pack_weight_f16(const float* W, int64_t ldw, int32_t N, int32_t K, float scale, void* packed, void* stream);
 int lpf_link_heads_f16(const int64_t* links, int64_t bs, const int32_t* idx, int64_t n,
-                       const float* X, int64_t ldx, int64_t n_nodes, int32_t d,
+                       const void* X, int x_bf16, int64_t ldx, int64_t n_nodes, int32_t d,
                        const void* w1_packed, float inv_scale_w1, const float* b1,
                        const float* ln_w_scaled, const float* ln_b_scaled,
                        const void* w23_packed, float inv_scale_h_w23, const float* c3, const float* zb, int64_t ld_zb,
@@ -336,6 +337,7 @@ typedef struct lpf_nz_args {
     const float* w1T; const float* b1; const float* ln_w; const float* ln_b;
     const float* w23T; const float* ws2; const float* bs2;
     float* prob; int32_t logits;
+    int32_t tab_bf16;   /* X and KV hold bf16 (leading dimensions in elements) */
 } lpf_nz_args;
 int lpf_nz_links_fused(const lpf_nz_args* args, void* stream);
 

@@ -44,7 +44,7 @@ SIGNATURES = {
     "lpf_pack_weight": (_int, [_p, _i64, _i32, _i32, _p, _p]),
     "lpf_gemm_tc": (_int, [_p, _i64, _p, _p, _f32, _p, _i64, _i64, _i32, _i32, _int, _p, _p]),
     "lpf_layernorm_act": (_int, [_p, _i64, _p, _p, _p, _i64, _p, _i64, _i64, _i32, _int, _p, _p]),
-    "lpf_gather_links": (_int, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _i64, _p, _i64, _p, _p]),
+    "lpf_gather_links": (_int, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _i64, _p, _i64, _p, _int, _p]),
     "lpf_scatter_rows": (_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _i32, _p, _p]),
     "lpf_debug_heads_clocks": (_int, [_p]),
     "lpf_debug_select_clocks": (_int, [_p]),
@@ -57,11 +57,11 @@ SIGNATURES = {
                                  _p, _int, _p, _p, _p]),
     "lpf_pack_weight_f16_bytes": (_i64, [_i32, _i32]),
     "lpf_pack_weight_f16": (_int, [_p, _i64, _i32, _i32, _f32, _p, _p]),
-    "lpf_link_heads_f16": (_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _i32, _p, _f32, _p, _p, _p, _p, _f32, _p, _p, _i64, _p, _p,
+    "lpf_link_heads_f16": (_int, [_p, _i64, _p, _i64, _p, _int, _i64, _i64, _i32, _p, _f32, _p, _p, _p, _p, _f32, _p, _p, _i64, _p, _p,
                                   _p, _int, _p, _p]),
     "lpf_debug_heads_f16_clocks": (_int, [_p]),
     "lpf_attend_fused": (_int, [_p, _i64, _p, _i64, _p, _p, _i64, _p, _i64, _p, _i64, _p, _p, _p, _p, _i32, _i32, _int, _int,
-                                _p, _i64, _p, _p, _p, _p, _i64, _p]),
+                                _p, _i64, _p, _p, _p, _p, _i64, _int, _p]),
     "lpf_ppr_push_host": (_p, [_p, _p, _i64, C.c_double, C.c_double, _int, _p]),
     "lpf_ppr_push_slots": (_i32, [C.c_double, C.c_double]),
     "lpf_ppr_push_scratch_bytes": (_i64, [_i32, _i32]),
@@ -81,7 +81,7 @@ class NzArgs(C.Structure):
                 [(n, _p * 3) for n in ("rpe_w1", "rpe_b1", "rpe_ln_w", "rpe_ln_b", "rpe_mT", "rpe_c")] +
                 [(n, _p) for n in ("att", "att_bias", "post_ln_w", "post_ln_b", "p1T", "pb1", "pln_w", "pln_b", "p2T",
                                    "pb2", "wzT", "off", "w1T", "b1", "ln_w", "ln_b", "w23T", "ws2", "bs2", "prob")] +
-                [("logits", _i32)])
+                [("logits", _i32), ("tab_bf16", _i32)])
 
 
 SIGNATURES["lpf_nz_links_fused"] = (_int, [C.POINTER(NzArgs), _p])

@@ -40,7 +40,12 @@ struct AttendParams {
     float* out;
     int64_t ld_out;
     float* alpha_out;
+    int kv_bf16;          // KV holds bf16 (ld_kv in elements)
 };
+__device__ __forceinline__ float ld_kv(const AttendParams& p, int64_t u, int c) {
+    if (p.kv_bf16) return __uint_as_float((uint32_t)__ldg(reinterpret_cast<const uint16_t*>(p.KV) + u * p.ld_kv + c) << 16);
+    return __ldg(p.KV + u * p.ld_kv + c);
+}
 
 constexpr int kAttWarps = 8;
 constexpr int kAttHeavy = 256;     // a link with more pairs than this is walked by all warps of its CTA
@@ -65,14 +70,13 @@ __device__ __forceinline__ void attend_link(const AttendParams& p, const int64_t
                 for (int j = 0; j < G; ++j) {
                     const int jj = g0 + j < cnt ? g0 + j : g0;          // (a short last group repeats its first pair: weight 0)
                     const int64_t u = __shfl_sync(kFull, my_node, jj);
-                    const float* kv = p.KV + u * p.ld_kv;
                     const float* rr = p.R + (s0 + jj) * p.ld_r;
 #pragma unroll
                     for (int h = 0; h < H; ++h)
 #pragma unroll
                         for (int k = 0; k < KC; ++k) {
                             const int c = lane + 32 * k;
-                            v[j][h][k] = (c < C) ? __ldg(kv + h * C + c) + __ldg(rr + h * C + c) : 0.f;
+                            v[j][h][k] = (c < C) ? ld_kv(p, u, h * C + c) + __ldg(rr + h * C + c) : 0.f;
                         }
                 }
 #pragma unroll
@@ -169,7 +173,6 @@ __global__ void __launch_bounds__(kAttWarps * 32) attend_kernel(const __grid_con
             for (int t = 0; t < 3; ++t) {
                 for (int64_t s = seg_lo[t]; s < seg_hi[t]; ++s) {
                     const int64_t u = __ldg(p.node + s);
-                    const float* kv = p.KV + u * p.ld_kv;
                     const float* rr = p.R + s * p.ld_r;
                     float mean_alpha = 0.f;
 #pragma unroll
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(kAttWarps * 32) attend_kernel(const __grid_con
                         for (int k = 0; k < KC; ++k) {
                             const int c = lane + 32 * k;
                             float val = 0.f;
-                            if (c < C) val = __ldg(kv + h * C + c) + __ldg(rr + h * C + c);
+                            if (c < C) val = ld_kv(p, u, h * C + c) + __ldg(rr + h * C + c);
                             float x = val * q[h][k];
                             x = (x > 0.f) ? x : 0.2f * x;
                             part = fmaf(att[h][k], x, part);
@@ -342,7 +345,7 @@ extern "C" int lpf_attend_fused(const int64_t* ptr, int64_t bs, const int32_t* i
                                 const float* bias, const float* ln_w, const float* ln_b, int32_t heads, int32_t ch,
                                 int mode, int write_counts, float* out, int64_t ld_out, float* alpha_out,
                                 const int64_t* n_dev, const int32_t* seg_start, const int32_t* seg_cnt,
-                                int64_t type_stride, void* stream) {
+                                int64_t type_stride, int kv_bf16, void* stream) {
     LPF_REQUIRE(bs >= 0 && n >= 0, "negative batch size");
     LPF_REQUIRE(idx || n == bs, "n must equal bs when idx is NULL");
     if (n == 0) return LPF_OK;
@@ -355,7 +358,7 @@ extern "C" int lpf_attend_fused(const int64_t* ptr, int64_t bs, const int32_t* i
     LPF_REQUIRE(R == nullptr || ld_r >= hc, "ld_r too small");
     // node / R may be NULL only if every set is empty; the kernel never dereferences them then.
     AttendParams p{ptr, bs, idx, n, n_dev, seg_start, seg_cnt, type_stride, node, KV, ld_kv, R, ld_r, Q, ld_q, att, bias, ln_w, ln_b,
-                   heads, ch, mode, write_counts, out, ld_out, alpha_out};
+                   heads, ch, mode, write_counts, out, ld_out, alpha_out, kv_bf16 ? 1 : 0};
     cudaStream_t st = (cudaStream_t)stream;
     switch (heads) {
         case 1: return launch_attend_h<1>(p, st);

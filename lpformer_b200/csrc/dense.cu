@@ -172,12 +172,12 @@ __global__ void __launch_bounds__(256) gather_links_kernel(const int64_t* __rest
                                                            const float* __restrict__ X, int64_t ldx, int d,
                                                            float* __restrict__ xsum, int64_t lds,
                                                            float* __restrict__ xprod, int64_t ldp,
-                                                           const int64_t* __restrict__ n_dev) {
+                                                           const int64_t* __restrict__ n_dev, int x_bf16) {
     if (n_dev) n = min(n, *n_dev);
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const bool vec = (d % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) &&
+    const bool vec = !x_bf16 && (d % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) &&
                      (!xsum || ((lds % 4 == 0) && (reinterpret_cast<uintptr_t>(xsum) & 15) == 0)) &&
                      (!xprod || ((ldp % 4 == 0) && (reinterpret_cast<uintptr_t>(xprod) & 15) == 0));
     for (int64_t i = warp; i < n; i += nwarps) {
@@ -193,8 +193,11 @@ __global__ void __launch_bounds__(256) gather_links_kernel(const int64_t* __rest
                 if (xprod) *reinterpret_cast<float4*>(xprod + i * ldp + c) = make_float4(u.x * w.x, u.y * w.y, u.z * w.z, u.w * w.w);
             }
         } else {
+            const uint16_t* ha = reinterpret_cast<const uint16_t*>(X) + a * ldx;      // (bf16 table: same row, 2-byte elements)
+            const uint16_t* hb = reinterpret_cast<const uint16_t*>(X) + b * ldx;
             for (int c = lane; c < d; c += 32) {
-                const float u = __ldg(xa + c), w = __ldg(xb + c);
+                const float u = x_bf16 ? __uint_as_float((uint32_t)__ldg(ha + c) << 16) : __ldg(xa + c);
+                const float w = x_bf16 ? __uint_as_float((uint32_t)__ldg(hb + c) << 16) : __ldg(xb + c);
                 if (xsum) xsum[i * lds + c] = u + w;
                 if (xprod) xprod[i * ldp + c] = u * w;
             }
@@ -290,7 +293,7 @@ extern "C" int lpf_layernorm_act(const float* X, int64_t ldx, const float* gamma
 
 extern "C" int lpf_gather_links(const int64_t* links, int64_t bs, const int32_t* idx, int64_t n, const float* X,
                                 int64_t ldx, int32_t d, float* xsum, int64_t ld_sum, float* xprod, int64_t ld_prod,
-                                const int64_t* n_dev, void* stream) {
+                                const int64_t* n_dev, int x_bf16, void* stream) {
     LPF_REQUIRE(bs >= 0 && n >= 0 && d >= 1, "bad shape");
     LPF_REQUIRE(idx || n == bs, "n must equal bs when idx is NULL");
     if (n == 0) return LPF_OK;
@@ -298,7 +301,7 @@ extern "C" int lpf_gather_links(const int64_t* links, int64_t bs, const int32_t*
     LPF_REQUIRE(xsum || xprod, "no output requested");
     LPF_REQUIRE(ldx >= d && (!xsum || ld_sum >= d) && (!xprod || ld_prod >= d), "leading dimension too small");
     gather_links_kernel<<<warp_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(links, bs, idx, n, X, ldx, d, xsum, ld_sum,
-                                                                             xprod, ld_prod, n_dev);
+                                                                             xprod, ld_prod, n_dev, x_bf16);
     return check_launch("lpf_gather_links");
 }
 

@@ -55,8 +55,9 @@ struct Params {
     int64_t bs;
     const int32_t* idx;
     int64_t n;
-    const float* X;
+    const void* X;       // node table [n_nodes, d]: fp32, or bf16 when x_bf16 (ldx in elements either way)
     int64_t ldx;
+    int x_bf16;
     const void* w1p;     // lpf_pack_weight_f16 image of elementwise_lin.linears[0].weight [d, d]
     const float* b1;
     const float* ln_g;   // LayerNorm weight / bias, pre-multiplied by the h scale
@@ -132,6 +133,16 @@ __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ float2 lds_v2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+// four bf16 (two 32-bit words, little endian) -> four fp32
+__device__ __forceinline__ float4 bf16x4(uint32_t w0, uint32_t w1) {
+    return make_float4(__uint_as_float(w0 << 16), __uint_as_float(w0 & 0xffff0000u), __uint_as_float(w1 << 16),
+                       __uint_as_float(w1 & 0xffff0000u));
+}
 __device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 // Packed fp32 pairs (FFMA2 / FADD2 / FMUL2: one issue slot for two lanes' worth — the kernel is bound by instruction
 // issue, not by the fp32 pipe)
@@ -202,6 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) link_heads_f16_kernel(const __gri
     }
     const int64_t n_links = p.n_dev ? min(p.n, *p.n_dev) : p.n;
     const int64_t ntiles = (n_links + kTileM - 1) / kTileM;
+    const int esz = p.x_bf16 ? 2 : 4;                 // bytes per element of the node table (a staged row: D * esz)
     // tile k of this CTA: blockIdx.x + k gridDim.x (every role walks the same sequence by itself)
     if ((int64_t)blockIdx.x >= ntiles) return;       // nothing to do: before any barrier / TMEM / bulk-copy state
     const uint32_t my_tiles = (uint32_t)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
@@ -289,15 +301,14 @@ __global__ void __launch_bounds__(kThreads, 1) link_heads_f16_kernel(const __gri
 #pragma unroll
             for (int r = 0; r < 4; ++r) {                // the source rows into L2 (one row per query in an evaluation batch)
                 if (r == 0 || a[r] != a[0]) {
-                    const char* ra = reinterpret_cast<const char*>(p.X + (int64_t)a[r] * p.ldx);
-#pragma unroll
-                    for (int o = 0; o < D * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(ra + o));
+                    const char* ra = reinterpret_cast<const char*>(p.X) + (int64_t)a[r] * p.ldx * esz;
+                    for (int o = 0; o < D * esz; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(ra + o));
                 }
             }
-            mbar_arrive_expect_tx(&bar_stage[st], 4 * D * 4);
+            mbar_arrive_expect_tx(&bar_stage[st], 4 * D * esz);
             asm volatile(
                 "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-                ::"r"(smem_u32(sStage + st * STAGE_BYTES + lane * (4 * D * 4))), "l"(&xmap), "r"(smem_u32(&bar_stage[st])),
+                ::"r"(smem_u32(sStage + st * STAGE_BYTES + lane * (4 * D * esz))), "l"(&xmap), "r"(smem_u32(&bar_stage[st])),
                 "r"(0), "r"(max(b[0], 0)), "r"(max(b[1], 0)), "r"(max(b[2], 0)), "r"(max(b[3], 0))
                 : "memory");
         }
@@ -376,7 +387,22 @@ __global__ void __launch_bounds__(kThreads, 1) link_heads_f16_kernel(const __gri
             const int r = pass * RPP + row_in_pass;
             return (r & ~6) | ((r & 2) << 1) | ((r & 4) >> 1);
         };
-        auto ld4 = [&](const float* q) -> float4 { return __ldg(reinterpret_cast<const float4*>(q)); };
+        // four consecutive channels of node row `node` from channel c
+        auto ld4 = [&](int64_t node, int c) -> float4 {
+            if (p.x_bf16) {
+                const uint2 w = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p.X) + node * p.ldx + c));
+                return bf16x4(w.x, w.y);
+            }
+            return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.X) + node * p.ldx + c));
+        };
+        // ... of staged row `row`
+        auto lds4 = [&](uint32_t stage, int row, int c) -> float4 {
+            if (p.x_bf16) {
+                const float2 w = lds_v2(stage + row * (D * 2) + c * 2);
+                return bf16x4(__float_as_uint(w.x), __float_as_uint(w.y));
+            }
+            return lds_v4(stage + row * (D * 4) + c * 4);
+        };
         // does every row of this thread in the tile of ring slot `slot` share its source?  (and that source's X row)
         auto tile_source = [&](uint32_t slot, bool& same_a, float4 (&xa)[KBX]) {
             const int32_t a0 = ids[slot][0][rowof(0)];
@@ -384,7 +410,7 @@ __global__ void __launch_bounds__(kThreads, 1) link_heads_f16_kernel(const __gri
 #pragma unroll
             for (int pass = 1; pass < NPASS; ++pass) same_a &= ids[slot][0][rowof(pass)] == a0;
 #pragma unroll
-            for (int kb = 0; kb < KBX; ++kb) xa[kb] = ld4(p.X + (int64_t)a0 * p.ldx + kb * 32 + chunk * 4);
+            for (int kb = 0; kb < KBX; ++kb) xa[kb] = ld4(a0, kb * 32 + chunk * 4);
         };
         mbar_wait(&bar_ids[0], 0);
         float4 xa[KBX];
@@ -423,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) link_heads_f16_kernel(const __gri
                     const int row = rowof(q);
 #pragma unroll
                     for (int kb = 0; kb < KBX; ++kb) {
-                        const float4 v = lds_v4(stage + row * (D * 4) + kb * 128 + chunk * 16);
+                        const float4 v = lds4(stage, row, kb * 32 + chunk * 4);
                         x[q][kb][0] = mul2(make_float2(v.x, v.y), make_float2(xa[kb].x, xa[kb].y));
                         x[q][kb][1] = mul2(make_float2(v.z, v.w), make_float2(xa[kb].z, xa[kb].w));
                     }
@@ -434,8 +460,8 @@ __global__ void __launch_bounds__(kThreads, 1) link_heads_f16_kernel(const __gri
                     const int row = rowof(q);
 #pragma unroll
                     for (int kb = 0; kb < KBX; ++kb) {
-                        const float4 m = ld4(p.X + (int64_t)ids[slot][0][row] * p.ldx + kb * 32 + chunk * 4);
-                        const float4 v = lds_v4(stage + row * (D * 4) + kb * 128 + chunk * 16);
+                        const float4 m = ld4(ids[slot][0][row], kb * 32 + chunk * 4);
+                        const float4 v = lds4(stage, row, kb * 32 + chunk * 4);
                         x[q][kb][0] = mul2(make_float2(v.x, v.y), make_float2(m.x, m.y));
                         x[q][kb][1] = mul2(make_float2(v.z, v.w), make_float2(m.z, m.w));
                     }
@@ -654,16 +680,16 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 // 2-D map of X [n_nodes, D] fp32 (row stride ldx) with a box of one row: a tile::gather4 copy brings four rows
-int make_row_map(CUtensorMap* map, const float* X, int64_t ldx, int64_t n_nodes, int d) {
+int make_row_map(CUtensorMap* map, const void* X, int64_t ldx, int64_t n_nodes, int d, bool bf16) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) {
         set_error("lpf_link_heads_f16: cuTensorMapEncodeTiled not available from this driver");
         return LPF_ERR_CUDA;
     }
     const cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)n_nodes};
-    const cuuint64_t strides[1] = {(cuuint64_t)ldx * 4};
+    const cuuint64_t strides[1] = {(cuuint64_t)ldx * (bf16 ? 2 : 4)};
     const cuuint32_t box[2] = {(cuuint32_t)d, 1}, estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), dims, strides, box, estr,
+    CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(X), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -691,12 +717,12 @@ int launch(const Params& p, int64_t n_nodes, cudaStream_t st) {
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     // the tensor map of the node table: rebuilt only when the table changes (one per calling thread)
-    struct MapKey { const float* X; int64_t ldx, n; };
-    thread_local MapKey key{nullptr, 0, 0};
+    struct MapKey { const void* X; int64_t ldx, n; int bf; };
+    thread_local MapKey key{nullptr, 0, 0, 0};
     alignas(64) thread_local CUtensorMap xmap;
-    if (key.X != p.X || key.ldx != p.ldx || key.n != n_nodes) {
-        if (int rc = make_row_map(&xmap, p.X, p.ldx, n_nodes, D)) return rc;
-        key = MapKey{p.X, p.ldx, n_nodes};
+    if (key.X != p.X || key.ldx != p.ldx || key.n != n_nodes || key.bf != p.x_bf16) {
+        if (int rc = make_row_map(&xmap, p.X, p.ldx, n_nodes, D, p.x_bf16 != 0)) return rc;
+        key = MapKey{p.X, p.ldx, n_nodes, p.x_bf16};
     }
     const int64_t ntiles = (p.n + kTileM - 1) / kTileM;
     const unsigned grid = (unsigned)(ntiles < (int64_t)kNumSMs ? ntiles : (int64_t)kNumSMs);
@@ -735,8 +761,8 @@ extern "C" int lpf_pack_weight_f16(const float* W, int64_t ldw, int32_t N, int32
     return check_launch("lpf_pack_weight_f16");
 }
 
-extern "C" int lpf_link_heads_f16(const int64_t* links, int64_t bs, const int32_t* idx, int64_t n, const float* X,
-                                  int64_t ldx, int64_t n_nodes, int32_t d, const void* w1_packed, float inv_scale_w1, const float* b1,
+extern "C" int lpf_link_heads_f16(const int64_t* links, int64_t bs, const int32_t* idx, int64_t n, const void* X,
+                                  int x_bf16, int64_t ldx, int64_t n_nodes, int32_t d, const void* w1_packed, float inv_scale_w1, const float* b1,
                                   const float* ln_w_scaled, const float* ln_b_scaled, const void* w23_packed,
                                   float inv_scale_h_w23, const float* c3, const float* zb, int64_t ld_zb,
                                   const float* ws2, const float* bs2, float* prob, int logits, const int64_t* n_dev,
@@ -749,12 +775,12 @@ extern "C" int lpf_link_heads_f16(const int64_t* links, int64_t bs, const int32_
     LPF_REQUIRE(ldx >= d && (!zb || ld_zb >= 2 * d), "leading dimension too small");
     LPF_REQUIRE(!zb || ((reinterpret_cast<uintptr_t>(zb) & 15) == 0 && ld_zb % 4 == 0), "zb rows must be 16-byte aligned");
     LPF_REQUIRE(inv_scale_w1 > 0.f && inv_scale_h_w23 > 0.f, "scales must be positive");
-    LPF_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0 && ldx % 4 == 0, "X rows must be 16-byte aligned (TMA)");
+    LPF_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (ldx * (x_bf16 ? 2 : 4)) % 16 == 0, "X rows must be 16-byte aligned (TMA)");
     if (d != 64) {
         set_error("lpf_link_heads_f16: d = %d not supported (64)", d);
         return LPF_ERR_UNSUPPORTED;
     }
-    Params p{links, bs, idx, n, X, ldx, w1_packed, b1, ln_w_scaled, ln_b_scaled, w23_packed, c3, zb, ld_zb, ws2, bs2, prob,
+    Params p{links, bs, idx, n, X, ldx, x_bf16 ? 1 : 0, w1_packed, b1, ln_w_scaled, ln_b_scaled, w23_packed, c3, zb, ld_zb, ws2, bs2, prob,
              logits, n_dev, inv_scale_w1, inv_scale_h_w23, g_heads_dbg_f16};
     cudaStream_t st = (cudaStream_t)stream;
     return zb ? launch<64, true>(p, n_nodes, st) : launch<64, false>(p, n_nodes, st);

@@ -65,7 +65,13 @@ struct NzParams {
     const float* bs2;
     float* prob;
     int logits;
+    int tab_bf16;         // X and KV hold bf16 (ldx / ld_kv in elements)
 };
+// element i of a node table (fp32, or bf16 widened)
+__device__ __forceinline__ float ld_tab(const float* base, int64_t i, int bf) {
+    if (bf) return __uint_as_float((uint32_t)__ldg(reinterpret_cast<const uint16_t*>(base) + i) << 16);
+    return __ldg(base + i);
+}
 
 // Channel layout: a D-wide vector is spread over the lanes with KC = D / 32 ADJACENT channels per lane
 // (channel KC * lane + k), a 2D-wide one with 2 KC adjacent channels per lane — so that a lane's share of a weight row
@@ -258,7 +264,7 @@ __device__ __forceinline__ void attend_pairs(const NzParams& p, int64_t pos, con
                     const int64_t s = s0 + base + (jj < m ? jj : g0);
 #pragma unroll
                     for (int k = 0; k < KC; ++k)
-                        v[j][k] = __ldg(p.KV + u * p.ld_kv + ch<KC>(lane, k)) + __ldg(Rr + s * D + ch<KC>(lane, k));
+                        v[j][k] = ld_tab(p.KV, u * p.ld_kv + ch<KC>(lane, k), p.tab_bf16) + __ldg(Rr + s * D + ch<KC>(lane, k));
                 }
 #pragma unroll
                 for (int j = 0; j < G; ++j) {
@@ -415,10 +421,13 @@ __global__ void __launch_bounds__(32 * kNzWarps, 1) nz_fused_kernel(const __grid
         if (j < n) {
             const int64_t pos = __ldg(p.nz + j);
             const int64_t a = __ldg(p.links + pos), b = __ldg(p.links + p.bs + pos);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.X + a * p.ldx));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.X + a * p.ldx + 32));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.X + b * p.ldx));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.X + b * p.ldx + 32));
+            const int esz = p.tab_bf16 ? 2 : 4;
+            const char* ra = reinterpret_cast<const char*>(p.X) + a * p.ldx * esz;
+            const char* rb = reinterpret_cast<const char*>(p.X) + b * p.ldx * esz;
+            for (int o = 0; o < D * esz; o += 128) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ra + o));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rb + o));
+            }
             for (int t = 0; t < p.ntypes; ++t) {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(p.counts + t * p.bs + pos));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(p.seg_start + t * p.bs + pos));
@@ -458,7 +467,7 @@ __global__ void __launch_bounds__(32 * kNzWarps, 1) nz_fused_kernel(const __grid
 #pragma unroll
             for (int k = 0; k < KC; ++k) {
                 const int c = ch<KC>(lane, k);
-                const float xa = __ldg(p.X + a * p.ldx + c), xb = __ldg(p.X + b * p.ldx + c);
+                const float xa = ld_tab(p.X, a * p.ldx + c, p.tab_bf16), xb = ld_tab(p.X, b * p.ldx + c, p.tab_bf16);
                 xsum[k] = xa + xb;
                 xprod[k] = xa * xb;
                 q[k] = 2.0f * __ldg(p.bl + c);
@@ -545,6 +554,7 @@ extern "C" int lpf_nz_links_fused(const lpf_nz_args* a, void* stream) {
     p.p1T = a->p1T; p.pb1 = a->pb1; p.pln_w = a->pln_w; p.pln_b = a->pln_b; p.p2T = a->p2T; p.pb2 = a->pb2;
     p.wzT = a->wzT; p.off = a->off; p.w1T = a->w1T; p.b1 = a->b1; p.ln_g = a->ln_w; p.ln_b = a->ln_b;
     p.w23T = a->w23T; p.ws2 = a->ws2; p.bs2 = a->bs2; p.prob = a->prob; p.logits = a->logits;
+    p.tab_bf16 = a->tab_bf16 ? 1 : 0;
     LPF_REQUIRE(p.hdr && (p.cap == 0 || p.R), "NULL header / R");
     LPF_REQUIRE(p.links && p.nz && p.X && p.KV && p.seg_start && p.counts && p.wlT && p.bl && p.att && p.att_bias &&
                     p.pn_w && p.pn_b && p.p1T && p.pb1 && p.pln_w && p.pln_b && p.p2T && p.pb2 && p.wzT && p.off &&

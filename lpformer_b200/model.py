@@ -341,6 +341,10 @@ class LinkTransformer(nn.Module):
         self.use_plans = True       # one-pass selection + device-side sizes (plan.py)
         self.use_graphs = True      # ... replayed as a CUDA graph
         # non-empty links below this share of the batch take the one-warp-per-link path (LPF_NZ_FUSED_SHARE: tuning knob)
+        # "bf16": the sync-free plans (score_links / LinkScoreStream at d = 64) read X and KV from bf16 copies — half the
+        # gather bytes; products, contractions and accumulation as in fp32 mode (north star: 1e-2 in bf16)
+        self.node_dtype = os.environ.get("LPF_NODE_DTYPE", "f32")
+        self._tab16 = None
         self.nz_fused_share = float(os.environ.get("LPF_NZ_FUSED_SHARE", 1.0 / 16))
         self.nz_fused_max_links = int(os.environ.get("LPF_NZ_FUSED_MAX_LINKS", 8192))
 
@@ -586,6 +590,15 @@ class LinkTransformer(nn.Module):
                        H, C, write_counts=last, out=feats, alpha_out=alpha if last else None, idx=idx)
         return self.pairwise_lin(feats, out=out), alpha
 
+    def _node_tables(self, X_node, kv):
+        """(X, KV) as the plan's kernels read them: the fp32 tensors, or bf16 copies built once per X_node."""
+        if self.node_dtype != "bf16":
+            return X_node, kv
+        key = (X_node.data_ptr(), X_node._version, kv.data_ptr(), kv._version)
+        if self._tab16 is None or self._tab16[0] != key:
+            self._tab16 = (key, X_node.to(torch.bfloat16).contiguous(), kv.to(torch.bfloat16).contiguous())
+        return self._tab16[1], self._tab16[2]
+
     def _pw_const(self, X_node):
         """[1, dim] pairwise vector of a link with empty node sets; depends on the weights only (cached)."""
         key = self._weights_key()
@@ -686,7 +699,7 @@ class LinkTransformer(nn.Module):
         adj, ppr = self.get_adj(test_set, mask=True), self.get_ppr(test_set)
         if ops.pick_select_algo(adj, ppr, self.thresh_1hop, self.thresh_non1hop, self.mask) == 0:
             return None
-        key = (batch.shape[1], X_node.data_ptr(), X_node._version, bool(test_set), bool(logits), id(consts))
+        key = (batch.shape[1], X_node.data_ptr(), X_node._version, bool(test_set), bool(logits), id(consts), self.node_dtype)
         plan = self._plans.get(key)
         if plan is None:
             from .plan import ScorePlan

@@ -100,12 +100,15 @@ def heads_call(links, bs, idx, n, X, c, zb, ld_zb, prob, logits, n_dev, sched, s
     """One launch of the fused heads with the operand set `c` (model._head_consts): the fp16-split kernel when the
     consts carry its images (d = 64), the 3xTF32 kernel otherwise.  idx / zb / n_dev / sched: raw pointers or None."""
     d = X.shape[1]
-    if "w1h" in c and X.data_ptr() % 16 == 0 and X.stride(0) % 4 == 0:
-        call("lpf_link_heads_f16", ptr(links), bs, idx, n, ptr(X), X.stride(0), X.shape[0], d, ptr(c["w1h"]), c["inv_sw1"], ptr(c["b1"]),
+    bf = X.dtype == torch.bfloat16
+    if "w1h" in c and X.data_ptr() % 16 == 0 and (X.stride(0) * X.element_size()) % 16 == 0:
+        call("lpf_link_heads_f16", ptr(links), bs, idx, n, ptr(X), int(bf), X.stride(0), X.shape[0], d, ptr(c["w1h"]), c["inv_sw1"], ptr(c["b1"]),
              ptr(c["ln_w_s"]), ptr(c["ln_b_s"]), ptr(c["w23h"]), c["inv_s3"], ptr(c["c3"]) if zb is None else None, zb, ld_zb,
              ptr(c["ws2"]), ptr(c["bs2"]), ptr(prob), int(logits), n_dev, st, meta=(n,),
              label=None if zb is None else "non-empty links (per-row offsets)")
     else:
+        if bf:
+            raise _lib.LpfError("bf16 node tables need the fp16-split heads (d = 64, 16-byte aligned rows)")
         call("lpf_link_heads_tc", ptr(links), bs, idx, n, ptr(X), X.stride(0), d, ptr(c["w1p"]), ptr(c["b1"]),
              ptr(c["ln_w"]), ptr(c["ln_b"]), ptr(c["w23p"]), ptr(c["c3"]) if zb is None else None, zb, ld_zb,
              ptr(c["ws2"]), ptr(c["bs2"]), ptr(prob), int(logits), n_dev, sched, st, meta=(n,),
@@ -165,7 +168,7 @@ def gather_links(links, X, want_sum=True, want_prod=True, out_sum=None, out_prod
         out_prod = torch.empty((n, d), dtype=torch.float32, device=X.device)
     call("lpf_gather_links", ptr(links), bs, ptr(idx), n, ptr(X), X.stride(0), d, ptr(out_sum),
          out_sum.stride(0) if out_sum is not None else 0, ptr(out_prod),
-         out_prod.stride(0) if out_prod is not None else 0, None, stream())
+         out_prod.stride(0) if out_prod is not None else 0, None, int(X.dtype == torch.bfloat16), stream())
     return out_sum, out_prod
 
 
@@ -362,8 +365,8 @@ def attend(sel: Selection, KV, R, Q, att, bias, ln_w, ln_b, heads, ch, write_cou
     call("lpf_attend_fused", ptr(sel.ptr), sel.bs, ptr(idx), n, ptr(sel.node), ptr(KV), KV.stride(0),
          ptr(R) if sel.total > 0 else None, R.stride(0) if R is not None and R.dim() == 2 else heads * ch,
          ptr(Q), Q.stride(0), ptr(att), ptr(bias), ptr(ln_w), ptr(ln_b), heads, ch, MODE[sel.mode],
-         int(write_counts), ptr(out), out.stride(0), ptr(alpha_out), None, None, None, 0, stream(),
-         meta=(n, sel.total, heads * ch))
+         int(write_counts), ptr(out), out.stride(0), ptr(alpha_out), None, None, None, 0,
+         int(KV.dtype == torch.bfloat16), stream(), meta=(n, sel.total, heads * ch))
     return out
 
 

@@ -23,7 +23,11 @@ class ScorePlan:
         dev = X_node.device
         self.model, self.bs, self.logits, self.dev = model, bs, bool(logits), dev
         self.score_func, self.test_set = score_func, test_set
-        self.X, self.kv, self.consts = X_node, kv, consts
+        # node tables as the kernels read them: fp32, or bf16 copies (model.node_dtype == "bf16": half the gather bytes,
+        # the arithmetic stays fp32 / fp16-split with fp32 accumulation)
+        self.X, self.kv = model._node_tables(X_node, kv) if "w1h" in consts else (X_node, kv)
+        self.tab_bf16 = int(self.X.dtype == torch.bfloat16)
+        self.consts = consts
         self.adj = model.get_adj(test_set, mask=True)
         self.ppr = model.get_ppr(test_set)
         from . import ops
@@ -84,7 +88,8 @@ class ScorePlan:
                      T(model.elementwise_lin.linears[0].weight), T(consts["w23"])] + [T(m) for m, _ in derived["rpe"]]
         a = _lib.NzArgs()
         a.links, a.bs, a.nz, a.n_cap, a.n_dev = ptr(self.links), bs, ptr(self.nz), bs, self.hdr.data_ptr() + 3 * 8
-        a.X, a.ldx, a.KV, a.ld_kv = ptr(X_node), X_node.stride(0), ptr(kv), kv.stride(0)
+        a.X, a.ldx, a.KV, a.ld_kv = ptr(self.X), self.X.stride(0), ptr(self.kv), self.kv.stride(0)
+        a.tab_bf16 = self.tab_bf16
         a.node, a.src_ppr, a.tgt_ppr = ptr(self.node), ptr(self.pa), ptr(self.pb)
         a.seg_start, a.counts, a.cap, a.d, a.mode = ptr(self.seg_start), ptr(self.counts), cap, d, self.mode
         a.header, a.R = self.hdr.data_ptr(), ptr(self.R)
@@ -168,12 +173,12 @@ class ScorePlan:
             gemm(self.hsum[t * cap:], mp, cvec, 1.0, self.R[t * cap:], cap, HC, d, hp + t * 8)
         # compacted non-empty links: query vectors, attention, pairwise_lin, offset of mlp_score's first layer
         call("lpf_gather_links", ptr(links), bs, ptr(self.nz), bs, ptr(X), X.stride(0), d, ptr(self.xsum),
-             self.xsum.stride(0), None, 0, n_dev, st)
+             self.xsum.stride(0), None, 0, n_dev, self.tab_bf16, st)
         gemm(self.xsum, w["wl"], w["bl"], 2.0, self.Q, bs, HC, d, n_dev)
         call("lpf_attend_fused", None, bs, ptr(self.nz), bs, ptr(self.node), ptr(self.kv), self.kv.stride(0),
              ptr(self.R), self.R.stride(0), ptr(self.Q), self.Q.stride(0), ptr(w["att"]), ptr(w["abias"]),
              ptr(w["pn_w"]), ptr(w["pn_b"]), self.H, self.C, self.mode, 1, ptr(self.feats), self.feats.stride(0), None,
-             n_dev, ptr(self.seg_start), ptr(self.counts), cap, st, meta=(bs, 0, HC))
+             n_dev, ptr(self.seg_start), ptr(self.counts), cap, self.tab_bf16, st, meta=(bs, 0, HC))
         gemm(self.feats, w["p1"], w["pb1"], 1.0, self.hid, bs, pd, pd, n_dev)
         call("lpf_layernorm_act", ptr(self.hid), self.hid.stride(0), ptr(w["pln_w"]), ptr(w["pln_b"]), None, 0,
              ptr(self.hid), self.hid.stride(0), bs, pd, 1, n_dev, st)

@@ -388,7 +388,7 @@ def test_plan_graph_replay_and_overflow():
     np.testing.assert_allclose(out, ref[2], rtol=1e-5, atol=1e-7)
     # overflow: pools of 4 rows per type cannot hold this batch
     model._plans.clear()
-    key = (batches[0].shape[1], X.data_ptr(), X._version, False, False, id(model._head_consts(score, X)))
+    key = (batches[0].shape[1], X.data_ptr(), X._version, False, False, id(model._head_consts(score, X)), model.node_dtype)
     model._plan_cap[key] = 4
     out = model.score_links(batches[0], X, score).cpu().numpy()
     np.testing.assert_allclose(out, ref[0], rtol=1e-5, atol=1e-7)
@@ -720,3 +720,41 @@ def test_link_heads_f16_split_range_and_agreement_with_tf32(xscale):
     np.testing.assert_allclose(ref32.cpu().numpy(), want, rtol=FP32_RTOL, atol=atol)
     e16, e32 = np.abs(got.cpu().numpy() - want).max(), np.abs(ref32.cpu().numpy() - want).max()
     assert e16 <= 4 * e32 + atol / 10, (e16, e32)
+
+
+@pytest.mark.gpu
+def test_bf16_node_tables_within_1e2_of_float64():
+    """node_dtype = "bf16" (north star: logits within 1e-2 in bf16): the plans read X and KV from bf16 copies — the
+    fp16-split heads through a bf16 tensor map, the non-empty-link stage (one warp per link AND the tensor-core
+    sequence) and the attention from 2-byte rows — with fp32 arithmetic; probabilities within 1e-2 of the fp32 plan
+    (itself within 1e-4 of the float64 oracle: test_score_links_*), identical under CUDA-graph replay and through the
+    pipelined stream, and the fp32 mode untouched afterwards."""
+    import lpformer_b200 as L
+    from lpformer_b200 import synthetic as S
+    from lpformer_b200.evaluate import LinkScoreStream
+    dev = torch.device("cuda:0")
+    g = S.make_graph("citation2", seed=3, scale=0.01, heldout=256)
+    torch.manual_seed(1)
+    model = L.LinkTransformer(S.train_args_of(g.cfg), g.data_dict(dev), device=dev).to(dev).eval()
+    score = L.mlp_score(model.out_dim, model.out_dim, 1, 2).to(dev).eval()
+    X = torch.randn(g.n, g.cfg["dim"], device=dev)
+    links = torch.from_numpy(S.citation2_queries(g, 24, 200, seed=7)).to(dev)
+    ref = model.score_links(links, X, score).clone()
+    for share in (1.0, 0.0):                       # one warp per link / the tensor-core sequence
+        model.node_dtype = "bf16"
+        model.nz_fused_share, model.nz_fused_max_links = share, 1 << 30
+        model._plans.clear()
+        model.score_links(links, X, score)                        # (first batch: eager, the regime is picked after it)
+        got = model.score_links(links, X, score).clone()
+        again = model.score_links(links, X, score).clone()       # (CUDA-graph replay)
+        assert torch.equal(got, again)
+        plan = next(iter(model._plans.values()))
+        assert plan.X.dtype == torch.bfloat16 and plan.kv.dtype == torch.bfloat16
+        diff = float((got - ref).abs().max())
+        assert 0.0 < diff < 1e-2, diff
+        stream = LinkScoreStream(model, score, X, links.shape[1] // 4, depth=2)
+        assert float((stream.score(links) - got).abs().max()) < 1e-5     # (its plans pick the regime on their own)
+    model.node_dtype = "f32"
+    model._plans.clear()
+    assert torch.equal(model.score_links(links, X, score), ref)
+
