@@ -54,7 +54,7 @@ constexpr int kAttHeavy = 256;     // a link with more pairs than this is walked
 // come in with one coalesced read, then the G gathered K/V rows and RPE rows are all in flight before the first score
 // is reduced (one pair at a time, every pair paid its own DRAM / L2 round trip), one running-max update per group.
 // `wslot` / `nw`: this warp takes the blocks of 32 pairs wslot, wslot + nw, ... of every type.
-template <int H, int KC, int G>
+template <int H, int KC, int G, bool BF>
 __device__ __forceinline__ void attend_link(const AttendParams& p, const int64_t (&seg_lo)[3], const int64_t (&seg_hi)[3],
                                             const float (&q)[H][KC], const float (&att)[H][KC], int lane, int wslot, int nw,
                                             float (&mx)[H], float (&den)[H], float (&acc)[H][KC]) {
@@ -71,13 +71,25 @@ __device__ __forceinline__ void attend_link(const AttendParams& p, const int64_t
                     const int jj = g0 + j < cnt ? g0 + j : g0;          // (a short last group repeats its first pair: weight 0)
                     const int64_t u = __shfl_sync(kFull, my_node, jj);
                     const float* rr = p.R + (s0 + jj) * p.ld_r;
+                    if constexpr (!BF) {
+                        const float* kv = p.KV + u * p.ld_kv;
 #pragma unroll
-                    for (int h = 0; h < H; ++h)
+                        for (int h = 0; h < H; ++h)
 #pragma unroll
-                        for (int k = 0; k < KC; ++k) {
-                            const int c = lane + 32 * k;
-                            v[j][h][k] = (c < C) ? ld_kv(p, u, h * C + c) + __ldg(rr + h * C + c) : 0.f;
-                        }
+                            for (int k = 0; k < KC; ++k) {
+                                const int c = lane + 32 * k;
+                                v[j][h][k] = (c < C) ? __ldg(kv + h * C + c) + __ldg(rr + h * C + c) : 0.f;
+                            }
+                    } else {
+                        const uint16_t* kv = reinterpret_cast<const uint16_t*>(p.KV) + u * p.ld_kv;
+#pragma unroll
+                        for (int h = 0; h < H; ++h)
+#pragma unroll
+                            for (int k = 0; k < KC; ++k) {
+                                const int c = lane + 32 * k;
+                                v[j][h][k] = (c < C) ? __uint_as_float((uint32_t)__ldg(kv + h * C + c) << 16) + __ldg(rr + h * C + c) : 0.f;
+                            }
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < G; ++j)
@@ -266,7 +278,8 @@ __global__ void __launch_bounds__(kAttWarps * 32) attend_kernel(const __grid_con
 #pragma unroll
                 for (int k = 0; k < KC; ++k) acc[h][k] = 0.f;
             }
-            attend_link<H, KC, G>(p, seg_lo, seg_hi, q, att, lane, 0, 1, mx, den, acc);
+            if (p.kv_bf16) attend_link<H, KC, G, true>(p, seg_lo, seg_hi, q, att, lane, 0, 1, mx, den, acc);
+            else attend_link<H, KC, G, false>(p, seg_lo, seg_hi, q, att, lane, 0, 1, mx, den, acc);
             finish(j, q, seg_lo, seg_hi, mx, den, acc);
         }
         // the heavy links of the slice, one after the other, all warps together
@@ -280,7 +293,8 @@ __global__ void __launch_bounds__(kAttWarps * 32) attend_kernel(const __grid_con
 #pragma unroll
                 for (int k = 0; k < KC; ++k) acc[h][k] = 0.f;
             }
-            attend_link<H, KC, G>(p, seg_lo, seg_hi, q, att, lane, warp, kAttWarps, mx, den, acc);
+            if (p.kv_bf16) attend_link<H, KC, G, true>(p, seg_lo, seg_hi, q, att, lane, warp, kAttWarps, mx, den, acc);
+            else attend_link<H, KC, G, false>(p, seg_lo, seg_hi, q, att, lane, warp, kAttWarps, mx, den, acc);
 #pragma unroll
             for (int h = 0; h < H; ++h) {
 #pragma unroll

@@ -761,7 +761,15 @@ select_screen_packed_kernel(const __grid_constant__ SelectParams2 p, const uint4
         // the list ends at the first link that does not fit (a suffix: the prefix sum is monotone); those links
         // become candidates unscreened
         const unsigned nofit = __ballot_sync(kFull, listed && !fits);
-        unsigned todo = __ballot_sync(kFull, listed && fits);
+        // a link with up to kOwn overflow chunks (most of them: deg <= ~60) is written by its own lane — eight predicated
+        // stores for the whole warp; only the longer rows take the warp-wide loop below (one iteration per link: with every
+        // listed link in it, that loop was 18 % of the kernel's instructions)
+        constexpr int kOwn = 8;
+        const bool own = listed && fits && mine <= kOwn;
+#pragma unroll
+        for (int e = 0; e < kOwn; ++e)
+            if (own && e < mine) W.items[ex + e] = (uint16_t)((l << 11) | (kPkFirst + e));
+        unsigned todo = __ballot_sync(kFull, listed && fits && mine > kOwn);
         long_mask = __ballot_sync(kFull, too_long);
         any_mask = (any_mask | nofit) & ~long_mask;
         const int first_nofit = nofit ? __ffs(nofit) - 1 : 31;
