@@ -16,7 +16,10 @@ for path in sys.argv[1:]:
     col = {h: i for i, h in enumerate(hdr)}
     per = {}
     for r in rows[2:]:
-        name = re.sub(r"<.*", "", re.sub(r"^void ", "", r[col["Kernel Name"]])).split("(")[0].split("::")[-1]
+        raw = r[col["Kernel Name"]]
+        name = re.sub(r"<.*", "", re.sub(r"^void ", "", raw)).split("(")[0].split("::")[-1]
+        if "link_heads" in name and re.search(r"<\s*(\(int\))?\d+\s*,\s*(\(bool\))?(1|true)\s*>", raw):
+            name += "_zb"           # the per-row-offset launch over the non-empty links: not the main launch
         tot = sum(float(r[col[k]]) * units[unit[col[k]]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
         per.setdefault(name, []).append((tot, float(r[col["gpu__time_duration.sum"]])))
     for name, v in per.items():
