@@ -340,6 +340,11 @@ typedef struct lpf_nz_args {
     int32_t tab_bf16;   /* X and KV hold bf16 (leading dimensions in elements) */
 } lpf_nz_args;
 int lpf_nz_links_fused(const lpf_nz_args* args, void* stream);
+/* The pair stage of lpf_nz_links_fused alone: R[t * cap + r] = (h(pa,pb) + h(pb,pa)) (W_pe W2_t)^T + c_t for the
+ * header[t] selected pairs of every type t (models/link_transformer.py:182-211) in ONE launch — what three
+ * lpf_rpe_hidden + three lpf_gemm_tc launches compute in the batched regime.  Reads of `args`: src_ppr, tgt_ppr, cap,
+ * header, R, d, mode and the rpe_* parameters. */
+int lpf_nz_pairs(const lpf_nz_args* args, void* stream);
 
 /* Profiling hook: later lpf_select_onepass_packed launches add per-phase clock64() totals of the screening kernel into
  * device_buffer (int64[48]: [0] source staging, [1] phase A, [2] phase B, [3] phase C, [4] generic fallback,

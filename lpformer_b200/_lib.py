@@ -85,6 +85,7 @@ class NzArgs(C.Structure):
 
 
 SIGNATURES["lpf_nz_links_fused"] = (_int, [C.POINTER(NzArgs), _p])
+SIGNATURES["lpf_nz_pairs"] = (_int, [C.POINTER(NzArgs), _p])
 
 _lib = None
 
@@ -113,7 +114,7 @@ def load():
 # kernels launched per entry point (for bench.py's gpu_launches and per-kernel CUDA-event timing)
 KERNEL_LAUNCHES = {"lpf_select_count": 3, "lpf_scan_counts": 2, "lpf_select_fill": 2, "lpf_rpe_hidden": 1,
                    "lpf_gemm": 1, "lpf_gemm_tc": 1, "lpf_pack_weight": 1, "lpf_layernorm_act": 1, "lpf_gather_links": 1, "lpf_attend_fused": 1,
-                   "lpf_gcn_spmm": 1, "lpf_gcn_layer": 1, "lpf_nz_links_fused": 2, "lpf_select_compact": 2, "lpf_select_onepass": 4, "lpf_select_onepass_packed": 6, "lpf_pack_link_rows": 4, "lpf_scatter_rows": 2, "lpf_link_heads_tc": 1, "lpf_link_heads_f16": 1, "lpf_pack_weight_f16": 1}
+                   "lpf_gcn_spmm": 1, "lpf_gcn_layer": 1, "lpf_nz_links_fused": 2, "lpf_nz_pairs": 1, "lpf_select_compact": 2, "lpf_select_onepass": 4, "lpf_select_onepass_packed": 6, "lpf_pack_link_rows": 4, "lpf_scatter_rows": 2, "lpf_link_heads_tc": 1, "lpf_link_heads_f16": 1, "lpf_pack_weight_f16": 1}
 
 
 class Trace:

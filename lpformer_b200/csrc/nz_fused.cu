@@ -530,7 +530,7 @@ extern "C" int lpf_debug_nz_timing_read(float* ms2_host) {
     return LPF_OK;
 }
 
-extern "C" int lpf_nz_links_fused(const lpf_nz_args* a, void* stream) {
+static int nz_launch(const lpf_nz_args* a, void* stream, bool pairs_only) {
     LPF_REQUIRE(a, "NULL argument block");
     LPF_REQUIRE(a->d == 32 || a->d == 64, "d must be 32 or 64");
     LPF_REQUIRE(a->n_cap >= 0 && a->bs >= 0, "negative size");
@@ -556,10 +556,11 @@ extern "C" int lpf_nz_links_fused(const lpf_nz_args* a, void* stream) {
     p.w23T = a->w23T; p.ws2 = a->ws2; p.bs2 = a->bs2; p.prob = a->prob; p.logits = a->logits;
     p.tab_bf16 = a->tab_bf16 ? 1 : 0;
     LPF_REQUIRE(p.hdr && (p.cap == 0 || p.R), "NULL header / R");
-    LPF_REQUIRE(p.links && p.nz && p.X && p.KV && p.seg_start && p.counts && p.wlT && p.bl && p.att && p.att_bias &&
+    LPF_REQUIRE(pairs_only || (p.links && p.nz && p.X && p.KV && p.seg_start && p.counts && p.wlT && p.bl && p.att && p.att_bias &&
                     p.pn_w && p.pn_b && p.p1T && p.pb1 && p.pln_w && p.pln_b && p.p2T && p.pb2 && p.wzT && p.off &&
-                    p.w1T && p.b1 && p.ln_g && p.ln_b && p.w23T && p.ws2 && p.bs2 && p.prob,
+                    p.w1T && p.b1 && p.ln_g && p.ln_b && p.w23T && p.ws2 && p.bs2 && p.prob),
                 "NULL argument");
+    LPF_REQUIRE(p.cap == 0 || (p.pa && p.pb), "NULL PPR pair values");
     cudaStream_t st = (cudaStream_t)stream;
     // link stage: one CTA of kNzWarps warps per SM (its matrices fill most of the SM's shared memory)
     int64_t blocks = (a->n_cap + kNzWarps - 1) / kNzWarps;
@@ -599,6 +600,7 @@ extern "C" int lpf_nz_links_fused(const lpf_nz_args* a, void* stream) {
     if (timing) cudaEventRecord(g_nz_ev[0], st);
     if (a->d == 64) nz_pairs_kernel<64><<<(unsigned)pblocks, 32 * kNzPairWarps, smem_pairs, st>>>(p);
     else nz_pairs_kernel<32><<<(unsigned)pblocks, 32 * kNzPairWarps, smem_pairs, st>>>(p);
+    if (pairs_only) return check_launch("lpf_nz_pairs");
     if (timing) cudaEventRecord(g_nz_ev[1], st);
     if (a->d == 64) nz_fused_kernel<64><<<(unsigned)blocks, 32 * kNzWarps, smem_links, st>>>(p);
     else nz_fused_kernel<32><<<(unsigned)blocks, 32 * kNzWarps, smem_links, st>>>(p);
@@ -608,3 +610,8 @@ extern "C" int lpf_nz_links_fused(const lpf_nz_args* a, void* stream) {
     }
     return check_launch("lpf_nz_links_fused");
 }
+
+extern "C" int lpf_nz_links_fused(const lpf_nz_args* a, void* stream) { return nz_launch(a, stream, false); }
+
+/* The pair stage alone: R[s] = RPE contraction of every selected pair (all types in one launch). */
+extern "C" int lpf_nz_pairs(const lpf_nz_args* a, void* stream) { return nz_launch(a, stream, true); }

@@ -141,7 +141,8 @@ __device__ __forceinline__ RowView view_row(const uint4* __restrict__ slab, cons
 // Blocked Bloom filter over node ids: two bits of ONE 32-bit word per id (word from the top bits of a multiplicative
 // hash, the two bit positions from its low bits), so a probe is one shared-memory read.
 __device__ __forceinline__ uint32_t bloom_hash(int32_t u) { return (uint32_t)u * 0x9E3779B1u; }
-__device__ __forceinline__ uint32_t bloom_bits(uint32_t h) { return (1u << (h & 31u)) | (1u << ((h >> 5) & 31u)); }
+// (1 << (s & 31) as one funnel shift: the hardware shift clamps, the funnel shift wraps)
+__device__ __forceinline__ uint32_t bloom_bits(uint32_t h) { return __funnelshift_l(0u, 1u, h) | __funnelshift_l(0u, 1u, h >> 5); }
 __device__ __forceinline__ void bloom_insert(uint32_t* bl, int lgw, int32_t u) {
     const uint32_t h = bloom_hash(u);
     atomicOr(bl + (h >> (32 - lgw)), bloom_bits(h));

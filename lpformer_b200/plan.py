@@ -166,11 +166,15 @@ class ScorePlan:
             # few non-empty links: one warp per link, everything from node sets to score in one launch
             call("lpf_nz_links_fused", C.byref(self.nz_args), st, meta=(bs,))
             return
-        # RPE hidden vectors and their contraction, per type pool
-        for t, (w1, b1, g, b, mp, cvec) in enumerate(self.rpe):
-            call("lpf_rpe_hidden", ptr(self.pa), ptr(self.pb), t * cap, cap, ptr(w1), ptr(b1), ptr(g), ptr(b), d,
-                 ptr(self.hsum), self.hsum.stride(0), hp + t * 8, st)
-            gemm(self.hsum[t * cap:], mp, cvec, 1.0, self.R[t * cap:], cap, HC, d, hp + t * 8)
+        # RPE hidden vectors and their contraction: every pair of every type pool in one launch (FFMA, matrices in shared
+        # memory) when the fused kernels cover the configuration; else per type pool rpe_hidden + a tensor-core contraction
+        if self.fused_ok:
+            call("lpf_nz_pairs", C.byref(self.nz_args), st, meta=(bs,))
+        else:
+            for t, (w1, b1, g, b, mp, cvec) in enumerate(self.rpe):
+                call("lpf_rpe_hidden", ptr(self.pa), ptr(self.pb), t * cap, cap, ptr(w1), ptr(b1), ptr(g), ptr(b), d,
+                     ptr(self.hsum), self.hsum.stride(0), hp + t * 8, st)
+                gemm(self.hsum[t * cap:], mp, cvec, 1.0, self.R[t * cap:], cap, HC, d, hp + t * 8)
         # compacted non-empty links: query vectors, attention, pairwise_lin, offset of mlp_score's first layer
         call("lpf_gather_links", ptr(links), bs, ptr(self.nz), bs, ptr(X), X.stride(0), d, ptr(self.xsum),
              self.xsum.stride(0), None, 0, n_dev, self.tab_bf16, st)
