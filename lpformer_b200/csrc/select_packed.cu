@@ -412,26 +412,41 @@ select_resolve_packed_kernel(const __grid_constant__ SelectParams2 p, const uint
     const int lane = threadIdx.x & 31;
     const int n = p.hub[0];
     const int warp0 = (blockIdx.x * kPkResolveThreads + threadIdx.x) >> 5, nwarps = (gridDim.x * kPkResolveThreads) >> 5;
-    for (int q = warp0; q < n; q += nwarps) {
-        const int64_t i = p.hub[4 + q];
-        const int64_t a = __ldg(p.links + i), b = __ldg(p.links + p.bs + i);
-        const uint4 ha = ldg16(slab + (size_t)a * 8), hb = ldg16(slab + (size_t)b * 8);
-        const RowView A = view_row(slab, ovf, a, ha), B = view_row(slab, ovf, b, hb);
-        const bool swapped = A.S < B.S;
-        if (min(A.S, B.S) > kPkResolveSlots) {
-            // a hub-hub pair: a whole CTA walks the shorter row (select_resolve_big_kernel), or — beyond kPkBigSlots —
-            // the deferred-link kernel over the CSR tables
-            if (lane == 0) {
-                if (min(A.S, B.S) <= kPkBigSlots) p.hub[ws_list_words(p.bs) + atomicAdd(p.hub + 1, 1)] = (int32_t)i;
-                else p.heavy[4 + atomicAdd(p.heavy, 1)] = (int32_t)i;
+    // Two passes over this warp's candidates: the common ones (one step of the warp, short PPR rows: resolve_packed_fast)
+    // first, the others (bit k of `slow` = the warp's k-th candidate) after — the two paths are long straight-line code,
+    // and warps that alternate between them keep missing the instruction cache (measured: "no instruction" was the
+    // second stall reason of this kernel).
+    unsigned slow = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        int k = 0;
+        for (int q = warp0; q < n; q += nwarps, ++k) {
+            if (pass == 1 && !(k < 32 && ((slow >> k) & 1u))) continue;
+            const int64_t i = p.hub[4 + q];
+            const int64_t a = __ldg(p.links + i), b = __ldg(p.links + p.bs + i);
+            const uint4 ha = ldg16(slab + (size_t)a * 8), hb = ldg16(slab + (size_t)b * 8);
+            const RowView A = view_row(slab, ovf, a, ha), B = view_row(slab, ovf, b, hb);
+            const bool swapped = A.S < B.S;
+            if (min(A.S, B.S) > kPkResolveSlots) {
+                // a hub-hub pair: a whole CTA walks the shorter row (select_resolve_big_kernel), or — beyond kPkBigSlots —
+                // the deferred-link kernel over the CSR tables
+                if (lane == 0) {
+                    if (min(A.S, B.S) <= kPkBigSlots) p.hub[ws_list_words(p.bs) + atomicAdd(p.hub + 1, 1)] = (int32_t)i;
+                    else p.heavy[4 + atomicAdd(p.heavy, 1)] = (int32_t)i;
+                }
+                continue;
             }
-            continue;
+            const RowView& row = swapped ? A : B;
+            const RowView& src = swapped ? B : A;
+            const bool fast = row.S <= 32 && row.npp <= 32 && src.npp <= 32;
+            if (pass == 0 && !fast && k < 32) {          // (beyond 32 candidates per warp: in place)
+                slow |= 1u << k;
+                continue;
+            }
+            __syncwarp();       // (ids_sm of the previous candidate is no longer read)
+            if (fast) resolve_packed_fast(p, src, row, swapped, i, lane, ids_sm[threadIdx.x >> 5]);
+            else resolve_packed_warp(p, src, row, swapped, i, lane);
         }
-        const RowView& row = swapped ? A : B;
-        const RowView& src = swapped ? B : A;
-        __syncwarp();       // (ids_sm of the previous candidate is no longer read)
-        if (row.S <= 32 && row.npp <= 32 && src.npp <= 32) resolve_packed_fast(p, src, row, swapped, i, lane, ids_sm[threadIdx.x >> 5]);
-        else resolve_packed_warp(p, src, row, swapped, i, lane);
+        if (!slow) break;
     }
 }
 
