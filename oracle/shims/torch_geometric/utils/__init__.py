@@ -27,6 +27,16 @@ def coalesce(edge_index, edge_attr=None, num_nodes=None, reduce="add"):
     return torch.stack([key // N, key % N])
 
 
-def to_undirected(edge_index, num_nodes=None):
+def to_undirected(edge_index, edge_attr=None, num_nodes=None, reduce="add"):
+    """PyG 2.2.0 utils.to_undirected: both directions, sorted, duplicates merged (attributes summed)."""
+    if isinstance(edge_attr, int):
+        edge_attr, num_nodes = None, edge_attr
     both = torch.cat([edge_index, edge_index.flip(0)], dim=1)
-    return coalesce(both, num_nodes=num_nodes)
+    if edge_attr is None:
+        return coalesce(both, num_nodes=num_nodes)
+    assert reduce == "add"
+    N = int(both.max()) + 1 if num_nodes is None else num_nodes
+    uniq, inv = torch.unique(both[0] * N + both[1], sorted=True, return_inverse=True)
+    attr = torch.cat([edge_attr, edge_attr], dim=0)
+    out = torch.zeros((uniq.numel(),) + tuple(attr.shape[1:]), dtype=attr.dtype).index_add_(0, inv, attr)
+    return torch.stack([uniq // N, uniq % N]), out
