@@ -470,7 +470,7 @@ def run_b200(args):
                     M, N, K = meta
                     tot_b += 4.0 * (M * K + M * N + N * K)
                     tot_f += 2.0 * M * N * K
-                elif name == "lpf_attend_fused" and len(meta) == 3:
+                elif name in ("lpf_attend_fused", "lpf_attend_fused_ws") and len(meta) == 3:
                     n_l, S_p, HC = meta          # per pair a K/V row and an RPE row, per link a query row and an output row
                     tot_b += 4.0 * HC * (2 * S_p + 2 * n_l) + 4.0 * S_p
                     tot_f += 8.0 * HC * S_p

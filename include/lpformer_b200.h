@@ -255,6 +255,23 @@ int lpf_attend_fused(const int64_t* ptr, int64_t bs, const int32_t* idx /* NULL 
                      float* out, int64_t ld_out, float* alpha_out,
                      const int64_t* n_dev, const int32_t* seg_start, const int32_t* seg_cnt, int64_t type_stride, int kv_bf16 /* KV holds bf16 (ld_kv in elements) */,
                      void* stream);
+/* The same with a caller-owned DEVICE workspace (16-byte aligned, at least lpf_attend_workspace_min() bytes, no
+ * initialisation needed, private to the call's stream while it runs): a link with more than 1,024 selected pairs (dense
+ * graphs: two hubs of the ogbl-ppa shape share tens of thousands of common neighbours) is then left out of the first
+ * launch, registered in the workspace, and walked in a second launch by many CTAs at once, 256 pairs each — partial
+ * softmax states (running max, denominator, weighted sum) go to the workspace and the CTA that completes a link's
+ * last chunk merges them.  Same results up to fp32 re-association of the softmax sums.  Links that do not fit the
+ * workspace (1,024 links, (bytes - 16 KB) / (4 (2 H + 32 H ceil(C/32))) chunk records) are walked by their own CTA
+ * as without a workspace. */
+int64_t lpf_attend_workspace_min(void);
+int lpf_attend_fused_ws(const int64_t* ptr, int64_t bs, const int32_t* idx, int64_t n, const int32_t* node,
+                        const float* KV, int64_t ld_kv, const float* R, int64_t ld_r,
+                        const float* Q, int64_t ld_q,
+                        const float* att, const float* bias, const float* ln_w, const float* ln_b,
+                        int32_t heads, int32_t ch, int mode, int write_counts,
+                        float* out, int64_t ld_out, float* alpha_out,
+                        const int64_t* n_dev, const int32_t* seg_start, const int32_t* seg_cnt, int64_t type_stride, int kv_bf16,
+                        void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Fused per-link heads on the tensor cores (d in {32, 64}) — the rest of the eval-loop body

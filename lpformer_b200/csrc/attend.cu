@@ -41,7 +41,15 @@ struct AttendParams {
     int64_t ld_out;
     float* alpha_out;
     int kv_bf16;          // KV holds bf16 (ld_kv in elements)
+    // optional workspace for links with thousands of pairs ("giant": split over the grid in a second launch)
+    int32_t* ws;          // [16] header (0: registered links, 1: chunk cursor), then GiantLink[kGiantCap], then the records
+    int32_t pool_cap;     // chunk records the workspace holds
+    int phase;            // 0: every link (giant ones registered in ws and left out); 1: the registered links, chunk by chunk
 };
+struct GiantLink { int32_t j, base, n, done; };
+constexpr int kGiantCap = 1024;    // registered links per launch (more: walked by their CTA, as without a workspace)
+constexpr int kAttGiant = 1024;    // a link with more pairs than this is split over the grid ...
+constexpr int kGiantChunk = 256;   // ... in chunks of this many pairs, one CTA each
 __device__ __forceinline__ float ld_kv(const AttendParams& p, int64_t u, int c) {
     if (p.kv_bf16) return __uint_as_float((uint32_t)__ldg(reinterpret_cast<const uint16_t*>(p.KV) + u * p.ld_kv + c) << 16);
     return __ldg(p.KV + u * p.ld_kv + c);
@@ -258,19 +266,148 @@ __global__ void __launch_bounds__(kAttWarps * 32) attend_kernel(const __grid_con
         }
     };
 
+    // the partial softmax states of the CTA's warps (s_acc / s_mx / s_den) -> one state, in warp 0
+    auto merge_warps = [&](float (&mx)[H], float (&den)[H], float (&acc)[H][KC]) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            float M = -INFINITY;
+#pragma unroll
+            for (int x = 0; x < kAttWarps; ++x) M = fmaxf(M, s_mx[x][h]);
+            den[h] = 0.f;
+#pragma unroll
+            for (int k = 0; k < KC; ++k) acc[h][k] = 0.f;
+#pragma unroll
+            for (int x = 0; x < kAttWarps; ++x) {
+                const float sc = (M == -INFINITY) ? 0.f : expf(s_mx[x][h] - M);   // a warp without pairs: mx = -inf, den = 0
+                den[h] = fmaf(s_den[x][h], sc, den[h]);
+#pragma unroll
+                for (int k = 0; k < KC; ++k) acc[h][k] = fmaf(s_acc[x][(h * KC + k) * 32 + lane], sc, acc[h][k]);
+            }
+            mx[h] = M;
+        }
+    };
+
+    if (p.phase == 1) {
+        // ---- the registered giant links: chunk x = base + c of the launch belongs to CTA x mod gridDim.x; a chunk's
+        // softmax state goes to its record, the CTA that completes a link's last chunk merges the records and finishes
+        constexpr int kRec = 2 * H + H * KC * 32;
+        const int count = min(p.ws[0], kGiantCap);
+        const GiantLink* list = reinterpret_cast<const GiantLink*>(p.ws + 16);
+        float* recs = reinterpret_cast<float*>(p.ws + 16 + 4 * kGiantCap);
+        for (int sidx = 0; sidx < count; ++sidx) {
+            const GiantLink gl = list[sidx];
+            if (gl.j < 0) continue;
+            int c = (int)(((int64_t)blockIdx.x - gl.base) % (int64_t)gridDim.x);
+            if (c < 0) c += gridDim.x;
+            for (; c < gl.n; c += gridDim.x) {
+                float q[H][KC], acc[H][KC], mx[H], den[H];
+                int64_t seg_lo[3], seg_hi[3], lo[3], hi[3];
+                load_link(gl.j, q, seg_lo, seg_hi);
+                int64_t off = 0;
+                const int64_t fs = (int64_t)c * kGiantChunk, fe = fs + kGiantChunk;
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const int64_t len = seg_hi[t] - seg_lo[t];
+                    lo[t] = seg_lo[t] + min(max(fs - off, (int64_t)0), len);
+                    hi[t] = seg_lo[t] + min(max(fe - off, (int64_t)0), len);
+                    off += len;
+                }
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    mx[h] = -INFINITY;
+                    den[h] = 0.f;
+#pragma unroll
+                    for (int k = 0; k < KC; ++k) acc[h][k] = 0.f;
+                }
+                if (p.kv_bf16) attend_link<H, KC, G, true>(p, lo, hi, q, att, lane, warp, kAttWarps, mx, den, acc);
+                else attend_link<H, KC, G, false>(p, lo, hi, q, att, lane, warp, kAttWarps, mx, den, acc);
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+#pragma unroll
+                    for (int k = 0; k < KC; ++k) s_acc[warp][(h * KC + k) * 32 + lane] = acc[h][k];
+                    if (lane == 0) { s_mx[warp][h] = mx[h]; s_den[warp][h] = den[h]; }
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    merge_warps(mx, den, acc);
+                    float* rec = recs + (size_t)(gl.base + c) * kRec;
+#pragma unroll
+                    for (int h = 0; h < H; ++h) {
+                        if (lane == 0) { rec[h] = mx[h]; rec[H + h] = den[h]; }
+#pragma unroll
+                        for (int k = 0; k < KC; ++k) rec[2 * H + (h * KC + k) * 32 + lane] = acc[h][k];
+                    }
+                    __threadfence();
+                    __syncwarp();
+                    int ticket = 0;
+                    if (lane == 0) ticket = atomicAdd(&reinterpret_cast<GiantLink*>(p.ws + 16)[sidx].done, 1);
+                    ticket = __shfl_sync(kFull, ticket, 0);
+                    if (ticket == gl.n - 1) {
+                        __threadfence();
+                        const volatile float* vr = recs + (size_t)gl.base * kRec;
+#pragma unroll
+                        for (int h = 0; h < H; ++h) {
+                            float M = -INFINITY;
+                            for (int x = 0; x < gl.n; ++x) M = fmaxf(M, vr[(size_t)x * kRec + h]);
+                            den[h] = 0.f;
+#pragma unroll
+                            for (int k = 0; k < KC; ++k) acc[h][k] = 0.f;
+                            for (int x = 0; x < gl.n; ++x) {
+                                const float m_x = vr[(size_t)x * kRec + h];
+                                const float sc = (m_x == -INFINITY) ? 0.f : expf(m_x - M);
+                                den[h] = fmaf(vr[(size_t)x * kRec + H + h], sc, den[h]);
+#pragma unroll
+                                for (int k = 0; k < KC; ++k)
+                                    acc[h][k] = fmaf(vr[(size_t)x * kRec + 2 * H + (h * KC + k) * 32 + lane], sc, acc[h][k]);
+                            }
+                            mx[h] = M;
+                        }
+                        finish(gl.j, q, seg_lo, seg_hi, mx, den, acc);
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        return;
+    }
+
     const int64_t n_links = p.n_dev ? min(p.n, *p.n_dev) : p.n;
     for (int64_t j0 = (int64_t)blockIdx.x * kAttWarps; j0 < n_links; j0 += (int64_t)gridDim.x * kAttWarps) {
         const int64_t j = j0 + warp;
         float q[H][KC], acc[H][KC], mx[H], den[H];
         int64_t seg_lo[3] = {0, 0, 0}, seg_hi[3] = {0, 0, 0};
-        bool heavy = false;
+        bool heavy = false, j_skip = false;
         if (j < n_links) {
             load_link(j, q, seg_lo, seg_hi);
-            heavy = (seg_hi[0] - seg_lo[0]) + (seg_hi[1] - seg_lo[1]) + (seg_hi[2] - seg_lo[2]) > kAttHeavy;
+            const int64_t total = (seg_hi[0] - seg_lo[0]) + (seg_hi[1] - seg_lo[1]) + (seg_hi[2] - seg_lo[2]);
+            heavy = total > kAttHeavy;
+            if (p.ws && total > kAttGiant) {
+                // register the link for the second launch (when the list and the record pool have room)
+                int ok = 0;
+                if (lane == 0) {
+                    const int nch = (int)((total + kGiantChunk - 1) / kGiantChunk);
+                    const int slot = atomicAdd(&p.ws[0], 1);
+                    if (slot < kGiantCap) {
+                        GiantLink* e = reinterpret_cast<GiantLink*>(p.ws + 16) + slot;
+                        const int base = atomicAdd(&p.ws[1], nch);
+                        if (base + nch <= p.pool_cap) {
+                            e->base = base; e->n = nch; e->done = 0; e->j = (int32_t)j;
+                            ok = 1;
+                        } else {
+                            e->j = -1;
+                        }
+                    }
+                }
+                if (__shfl_sync(kFull, ok, 0)) {
+                    heavy = false;
+                    seg_hi[0] = seg_lo[0]; seg_hi[1] = seg_lo[1]; seg_hi[2] = seg_lo[2];   // (nothing to do here)
+                    j_skip = true;
+                }
+            }
         }
         if (lane == 0) s_heavy[warp] = heavy ? 1 : 0;
         __syncthreads();
-        if (j < n_links && !heavy) {
+        if (j < n_links && !heavy && !j_skip) {
 #pragma unroll
             for (int h = 0; h < H; ++h) {
                 mx[h] = -INFINITY;
@@ -303,23 +440,7 @@ __global__ void __launch_bounds__(kAttWarps * 32) attend_kernel(const __grid_con
             }
             __syncthreads();
             if (warp == 0) {
-#pragma unroll
-                for (int h = 0; h < H; ++h) {
-                    float M = -INFINITY;
-#pragma unroll
-                    for (int x = 0; x < kAttWarps; ++x) M = fmaxf(M, s_mx[x][h]);
-                    den[h] = 0.f;
-#pragma unroll
-                    for (int k = 0; k < KC; ++k) acc[h][k] = 0.f;
-#pragma unroll
-                    for (int x = 0; x < kAttWarps; ++x) {
-                        const float sc = expf(s_mx[x][h] - M);      // a warp without pairs has mx = -inf, den = 0: weight 0
-                        den[h] = fmaf(s_den[x][h], sc, den[h]);
-#pragma unroll
-                        for (int k = 0; k < KC; ++k) acc[h][k] = fmaf(s_acc[x][(h * KC + k) * 32 + lane], sc, acc[h][k]);
-                    }
-                    mx[h] = M;
-                }
+                merge_warps(mx, den, acc);
                 finish(j0 + w, q, seg_lo, seg_hi, mx, den, acc);
             }
             __syncthreads();
@@ -329,7 +450,7 @@ __global__ void __launch_bounds__(kAttWarps * 32) attend_kernel(const __grid_con
 }
 
 template <int H>
-static int launch_attend_h(const AttendParams& p, cudaStream_t st) {
+static int launch_attend_h(const AttendParams& p, int64_t ws_bytes, cudaStream_t st) {
     int64_t blocks = (p.n + kAttWarps - 1) / kAttWarps;
     const int64_t cap = (int64_t)kNumSMs * 8 * 4;
     if (blocks > cap) blocks = cap;
@@ -341,11 +462,34 @@ static int launch_attend_h(const AttendParams& p, cudaStream_t st) {
     }
     // pairs in flight per warp: as many as 16 registers of gathered values per lane allow, at most 8
     constexpr auto grp = [](int hk) { return hk <= 2 ? 8 : 16 / hk; };
-    if (kc <= 1) attend_kernel<H, 1, grp(H)><<<g, kAttWarps * 32, 0, st>>>(p);
-    else if (kc <= 2) { if constexpr (H * 2 <= 16) attend_kernel<H, 2, grp(H * 2)><<<g, kAttWarps * 32, 0, st>>>(p); }
-    else if (kc <= 4) { if constexpr (H * 4 <= 16) attend_kernel<H, 4, grp(H * 4)><<<g, kAttWarps * 32, 0, st>>>(p); }
-    else if (kc <= 8) { if constexpr (H * 8 <= 16) attend_kernel<H, 8, grp(H * 8)><<<g, kAttWarps * 32, 0, st>>>(p); }
-    else { if constexpr (H * 16 <= 16) attend_kernel<H, 16, 1><<<g, kAttWarps * 32, 0, st>>>(p); }
+    void (*kern)(const AttendParams) = nullptr;
+    if (kc <= 1) kern = attend_kernel<H, 1, grp(H)>;
+    else if (kc <= 2) { if constexpr (H * 2 <= 16) kern = attend_kernel<H, 2, grp(H * 2)>; }
+    else if (kc <= 4) { if constexpr (H * 4 <= 16) kern = attend_kernel<H, 4, grp(H * 4)>; }
+    else if (kc <= 8) { if constexpr (H * 8 <= 16) kern = attend_kernel<H, 8, grp(H * 8)>; }
+    else { if constexpr (H * 16 <= 16) kern = attend_kernel<H, 16, 1>; }
+    if (!kern) {
+        set_error("lpf_attend_fused: heads = %d, ch = %d not instantiated", H, p.ch);
+        return LPF_ERR_UNSUPPORTED;
+    }
+    AttendParams q = p;
+    if (q.ws) {
+        // record pool: what is left of the workspace after the header and the list, in records of this instantiation
+        const int64_t rec = 4 * (2 * H + (int64_t)H * (kc <= 1 ? 1 : kc <= 2 ? 2 : kc <= 4 ? 4 : kc <= 8 ? 8 : 16) * 32);
+        const int64_t pool = (ws_bytes - (int64_t)sizeof(int32_t) * (16 + 4 * kGiantCap)) / rec;
+        if (pool < 8) q.ws = nullptr;
+        else {
+            q.pool_cap = (int32_t)(pool > (1 << 30) ? (1 << 30) : pool);
+            cudaError_t e = cudaMemsetAsync(q.ws, 0, 64, st);
+            if (e != cudaSuccess) { set_error("lpf_attend_fused: cudaMemsetAsync: %s", cudaGetErrorString(e)); return LPF_ERR_CUDA; }
+        }
+    }
+    q.phase = 0;
+    kern<<<g, kAttWarps * 32, 0, st>>>(q);
+    if (q.ws) {
+        q.phase = 1;
+        kern<<<kNumSMs * 4, kAttWarps * 32, 0, st>>>(q);
+    }
     return check_launch("lpf_attend_fused");
 }
 
@@ -353,13 +497,13 @@ static int launch_attend_h(const AttendParams& p, cudaStream_t st) {
 
 using namespace lpf;
 
-extern "C" int lpf_attend_fused(const int64_t* ptr, int64_t bs, const int32_t* idx, int64_t n, const int32_t* node,
-                                const float* KV, int64_t ld_kv,
-                                const float* R, int64_t ld_r, const float* Q, int64_t ld_q, const float* att,
-                                const float* bias, const float* ln_w, const float* ln_b, int32_t heads, int32_t ch,
-                                int mode, int write_counts, float* out, int64_t ld_out, float* alpha_out,
-                                const int64_t* n_dev, const int32_t* seg_start, const int32_t* seg_cnt,
-                                int64_t type_stride, int kv_bf16, void* stream) {
+extern "C" int lpf_attend_fused_ws(const int64_t* ptr, int64_t bs, const int32_t* idx, int64_t n, const int32_t* node,
+                                   const float* KV, int64_t ld_kv,
+                                   const float* R, int64_t ld_r, const float* Q, int64_t ld_q, const float* att,
+                                   const float* bias, const float* ln_w, const float* ln_b, int32_t heads, int32_t ch,
+                                   int mode, int write_counts, float* out, int64_t ld_out, float* alpha_out,
+                                   const int64_t* n_dev, const int32_t* seg_start, const int32_t* seg_cnt,
+                                   int64_t type_stride, int kv_bf16, void* workspace, int64_t workspace_bytes, void* stream) {
     LPF_REQUIRE(bs >= 0 && n >= 0, "negative batch size");
     LPF_REQUIRE(idx || n == bs, "n must equal bs when idx is NULL");
     if (n == 0) return LPF_OK;
@@ -370,17 +514,33 @@ extern "C" int lpf_attend_fused(const int64_t* ptr, int64_t bs, const int32_t* i
     const int cd = !write_counts ? 0 : (mode == LPF_MODE_CN ? 1 : (mode == LPF_MODE_1HOP ? 3 : 4));
     LPF_REQUIRE(ld_kv >= hc && ld_q >= hc && ld_out >= hc + cd, "leading dimension too small");
     LPF_REQUIRE(R == nullptr || ld_r >= hc, "ld_r too small");
+    LPF_REQUIRE(workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
     // node / R may be NULL only if every set is empty; the kernel never dereferences them then.
     AttendParams p{ptr, bs, idx, n, n_dev, seg_start, seg_cnt, type_stride, node, KV, ld_kv, R, ld_r, Q, ld_q, att, bias, ln_w, ln_b,
-                   heads, ch, mode, write_counts, out, ld_out, alpha_out, kv_bf16 ? 1 : 0};
+                   heads, ch, mode, write_counts, out, ld_out, alpha_out, kv_bf16 ? 1 : 0,
+                   workspace_bytes >= lpf_attend_workspace_min() ? static_cast<int32_t*>(workspace) : nullptr, 0, 0};
     cudaStream_t st = (cudaStream_t)stream;
     switch (heads) {
-        case 1: return launch_attend_h<1>(p, st);
-        case 2: return launch_attend_h<2>(p, st);
-        case 4: return launch_attend_h<4>(p, st);
-        case 8: return launch_attend_h<8>(p, st);
+        case 1: return launch_attend_h<1>(p, workspace_bytes, st);
+        case 2: return launch_attend_h<2>(p, workspace_bytes, st);
+        case 4: return launch_attend_h<4>(p, workspace_bytes, st);
+        case 8: return launch_attend_h<8>(p, workspace_bytes, st);
         default:
             set_error("lpf_attend_fused: heads must be 1, 2, 4 or 8 (got %d)", heads);
             return LPF_ERR_UNSUPPORTED;
     }
+}
+
+extern "C" int64_t lpf_attend_workspace_min(void) { return (int64_t)sizeof(int32_t) * (16 + 4 * kGiantCap) + (64 << 10); }
+
+extern "C" int lpf_attend_fused(const int64_t* ptr, int64_t bs, const int32_t* idx, int64_t n, const int32_t* node,
+                                const float* KV, int64_t ld_kv,
+                                const float* R, int64_t ld_r, const float* Q, int64_t ld_q, const float* att,
+                                const float* bias, const float* ln_w, const float* ln_b, int32_t heads, int32_t ch,
+                                int mode, int write_counts, float* out, int64_t ld_out, float* alpha_out,
+                                const int64_t* n_dev, const int32_t* seg_start, const int32_t* seg_cnt,
+                                int64_t type_stride, int kv_bf16, void* stream) {
+    return lpf_attend_fused_ws(ptr, bs, idx, n, node, KV, ld_kv, R, ld_r, Q, ld_q, att, bias, ln_w, ln_b, heads, ch, mode,
+                               write_counts, out, ld_out, alpha_out, n_dev, seg_start, seg_cnt, type_stride, kv_bf16, nullptr, 0,
+                               stream);
 }

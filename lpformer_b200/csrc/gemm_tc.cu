@@ -92,6 +92,30 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(GemmTcParams p) {
     const int row_in_pass = tid >> 3;   // 16 rows per pass
     const uint32_t lane_base = tmem_d + ((uint32_t)(warp * 32) << 16);
 
+    // the thread's share of one A k-block: eight independent 16-byte requests, all in flight together
+    float4 areg[8];
+    auto load_a = [&](int64_t m0, int kb) {
+        const int k0 = kb * 32 + chunk * 4;
+#pragma unroll
+        for (int pass = 0; pass < 8; ++pass) {
+            const int64_t m = m0 + pass * 16 + row_in_pass;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < p.M) {
+                const float* src = p.A + m * p.lda + k0;
+                if (vec_a && k0 + 3 < p.K) {
+                    v = __ldg(reinterpret_cast<const float4*>(src));
+                } else {
+                    if (k0 + 0 < p.K) v.x = __ldg(src + 0);
+                    if (k0 + 1 < p.K) v.y = __ldg(src + 1);
+                    if (k0 + 2 < p.K) v.z = __ldg(src + 2);
+                    if (k0 + 3 < p.K) v.w = __ldg(src + 3);
+                }
+            }
+            areg[pass] = v;
+        }
+    };
+    load_a((int64_t)blockIdx.x * kTileM, 0);
+
     uint32_t it = 0;        // k-blocks issued by this CTA so far (ring position / barrier phases)
     uint32_t tile_it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
@@ -101,36 +125,27 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(GemmTcParams p) {
             const uint32_t use = it >> 1;
             uint8_t* st = smem + (size_t)s * stage_bytes;
             if (it >= 2) mbar_wait(&bar_free[s], (use - 1) & 1);      // MMAs that read this stage have completed
-            if (tid == 0) {
+            if (it == 0 && tid == 0) {          // (every later k-block's weights are requested one k-block ahead, below)
                 mbar_arrive_expect_tx(&bar_w[s], 2 * w_tile);
                 bulk_g2s(st + 2 * kATileBytes, reinterpret_cast<const uint8_t*>(p.Wp) + (size_t)kb * 2 * w_tile,
                          2 * w_tile, &bar_w[s]);
             }
             __syncwarp();
-            // A k-block: rows m0..m0+127, columns kb*32 .. +31
-            const int k0 = kb * 32 + chunk * 4;
+            // A k-block: rows m0..m0+127, columns kb*32 .. +31 — the thread's eight 16-byte pieces are in registers
+            // already (requested one k-block ahead); split, store in the UMMA layout, then request the next k-block's
+            // so that their DRAM round trip runs under this k-block's barrier, MMAs and the next wait
 #pragma unroll
             for (int pass = 0; pass < 8; ++pass) {
                 const int r = pass * 16 + row_in_pass;
-                const int64_t m = m0 + r;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (m < p.M) {
-                    const float* src = p.A + m * p.lda + k0;
-                    if (vec_a && k0 + 3 < p.K) {
-                        v = __ldg(reinterpret_cast<const float4*>(src));
-                    } else {
-                        if (k0 + 0 < p.K) v.x = __ldg(src + 0);
-                        if (k0 + 1 < p.K) v.y = __ldg(src + 1);
-                        if (k0 + 2 < p.K) v.z = __ldg(src + 2);
-                        if (k0 + 3 < p.K) v.w = __ldg(src + 3);
-                    }
-                }
+                const float4 v = areg[pass];
                 const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
                 const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
                 const uint32_t off = swz_chunk_off(r, chunk);
                 *reinterpret_cast<float4*>(st + off) = hi;
                 *reinterpret_cast<float4*>(st + kATileBytes + off) = lo;
             }
+            if (kb + 1 < p.KB) load_a(m0, kb + 1);
+            else if (tile + gridDim.x < ntiles) load_a((tile + gridDim.x) * kTileM, 0);
             fence_async_smem();
             __syncthreads();
             if (tid == 0) {
@@ -141,6 +156,19 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_tc_kernel(GemmTcParams p) {
                 issue_kblock_3x(tmem_d, a_hi, a_lo, b_hi, b_lo, idesc, kb == 0);
                 umma_commit(&bar_free[s]);
                 if (kb == p.KB - 1) umma_commit(&bar_acc);
+                // the next k-block's weights (of this tile, or the first of the CTA's next tile) into the other stage as
+                // soon as the MMAs issued one k-block ago have drained it: a whole k-block of lead for the bulk copy (issued
+                // at the top of its own k-block its 2 NP x 128 bytes arrived ~2 us after the request, every k-block)
+                const bool more = kb + 1 < p.KB || tile + gridDim.x < ntiles;
+                if (more) {
+                    const uint32_t nit = it + 1;
+                    const int ns = nit & 1;
+                    if (nit >= 2) mbar_wait(&bar_free[ns], ((nit >> 1) - 1) & 1);
+                    const int nkb = kb + 1 < p.KB ? kb + 1 : 0;
+                    mbar_arrive_expect_tx(&bar_w[ns], 2 * w_tile);
+                    bulk_g2s(smem + (size_t)ns * stage_bytes + 2 * kATileBytes,
+                             reinterpret_cast<const uint8_t*>(p.Wp) + (size_t)nkb * 2 * w_tile, 2 * w_tile, &bar_w[ns]);
+                }
             }
             __syncwarp();
         }
@@ -235,12 +263,12 @@ extern "C" int lpf_gemm_tc(const float* A, int64_t lda, const float* Wpacked, co
             return LPF_ERR_CUDA;
         }
     }
-    // one CTA per tile; with a device-side row count the host M is only a capacity, so cap the grid at a few
-    // CTAs per SM and let them walk the tiles that really exist
+    // a persistent grid of a few CTAs per SM walks the tiles (the A pieces of a CTA's next tile are requested during
+    // its current tile's last k-block); with a device-side row count the host M is only a capacity
     int64_t grid = (M + tc::kTileM - 1) / tc::kTileM;
     const int64_t per_sm = (int64_t)(227 * 1024) / (int64_t)(smem + 1024);
     const int64_t persistent = (int64_t)kNumSMs * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
-    if (m_dev && grid > persistent) grid = persistent;
+    if (grid > persistent) grid = persistent;
     gemm_tc_kernel<<<(unsigned)grid, kGemmThreads, smem, (cudaStream_t)stream>>>(p);
     return check_launch("lpf_gemm_tc");
 }

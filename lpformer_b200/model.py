@@ -347,6 +347,7 @@ class LinkTransformer(nn.Module):
         self._tab16 = None
         self.nz_fused_share = float(os.environ.get("LPF_NZ_FUSED_SHARE", 1.0 / 16))
         self.nz_fused_max_links = int(os.environ.get("LPF_NZ_FUSED_MAX_LINKS", 8192))
+        self.nz_pairs_tc_min = int(os.environ.get("LPF_NZ_PAIRS_TC_MIN", 150000))   # pairs per batch: RPE stage on the tensor cores
 
     # ------------------------------------------------------------------ graph tables
     def _dev(self):

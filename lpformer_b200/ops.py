@@ -251,8 +251,14 @@ def pick_select_algo(adj: CSR, ppr: CSR, th_1hop, th_non1hop, mode: str) -> int:
         ppr.unit_range = bool(ppr.val.numel() == 0 or (float(ppr.val.min()) > 0.0 and float(ppr.val.max()) <= 1.0))
     if not ppr.unit_range:
         return _lib.ALGO_GENERIC
-    mean_deg = adj.nnz / max(1, adj.n)
-    return _lib.ALGO_INTERSECT32 if mean_deg >= 96 else _lib.ALGO_INTERSECT8
+    # rows walked per link: adjacency rows, and the PPR rows when the mode has PPR-derived sets — a group defers a link
+    # whose shorter row exceeds 16 elements per lane to the CTA-wide kernel, so long PPR rows (ogbl-collab shape: ~325
+    # entries) on a sparse graph want full warps too (measured there: every link deferred with groups of 8, 1.5 ms of
+    # CTA-wide walks per 32,565-link batch)
+    mean_row = adj.nnz / max(1, adj.n)
+    if mode != "cn":
+        mean_row = max(mean_row, ppr.nnz / max(1, ppr.n))
+    return _lib.ALGO_INTERSECT32 if mean_row >= 96 else _lib.ALGO_INTERSECT8
 
 
 def select(links, adj: CSR, ppr: CSR, th_cn, th_1hop, th_non1hop, mode: str, want_link=False, algo=None) -> Selection:
@@ -358,15 +364,20 @@ def rpe_hidden(sel: Selection, t: int, w1, b1, ln_w, ln_b, hsum):
              ptr(ln_b), hsum.shape[1], ptr(hsum), hsum.stride(0), None, stream())
 
 
+ATTEND_WS_BYTES = 4 << 20     # chunk records of the grid-wide split of giant links (lpf_attend_fused_ws)
+
+
 def attend(sel: Selection, KV, R, Q, att, bias, ln_w, ln_b, heads, ch, write_counts, out, alpha_out=None, idx=None):
     """K4 over every link of the batch, or over the batch positions in idx (rows of Q / out follow idx)."""
     require_cuda(KV, R, Q, out, idx)
     n = sel.bs if idx is None else idx.numel()
-    call("lpf_attend_fused", ptr(sel.ptr), sel.bs, ptr(idx), n, ptr(sel.node), ptr(KV), KV.stride(0),
+    # links with thousands of pairs are split over the grid through a workspace (lpf_attend_fused_ws)
+    ws = torch.empty(ATTEND_WS_BYTES, dtype=torch.uint8, device=KV.device)
+    call("lpf_attend_fused_ws", ptr(sel.ptr), sel.bs, ptr(idx), n, ptr(sel.node), ptr(KV), KV.stride(0),
          ptr(R) if sel.total > 0 else None, R.stride(0) if R is not None and R.dim() == 2 else heads * ch,
          ptr(Q), Q.stride(0), ptr(att), ptr(bias), ptr(ln_w), ptr(ln_b), heads, ch, MODE[sel.mode],
          int(write_counts), ptr(out), out.stride(0), ptr(alpha_out), None, None, None, 0,
-         int(KV.dtype == torch.bfloat16), stream(), meta=(n, sel.total, heads * ch))
+         int(KV.dtype == torch.bfloat16), ptr(ws), ws.numel(), stream(), meta=(n, sel.total, heads * ch))
     return out
 
 

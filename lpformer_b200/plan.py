@@ -58,6 +58,7 @@ class ScorePlan:
         pd = HC + model.count_dim
         self.pd = pd
         self.xsum, self.Q, self.feats, self.hid, self.pw, self.zb = e(bs, d), e(bs, HC), e(bs, pd), e(bs, pd), e(bs, d), e(bs, 2 * d)
+        self.att_ws = torch.empty(4 << 20, dtype=torch.uint8, device=dev)    # lpf_attend_fused_ws: giant links' chunk records
         derived = model._get_derived()[0]
         self.rpe = []
         for enc, (m, c) in zip(model._encoders(), derived["rpe"]):
@@ -168,7 +169,7 @@ class ScorePlan:
             return
         # RPE hidden vectors and their contraction: every pair of every type pool in one launch (FFMA, matrices in shared
         # memory) when the fused kernels cover the configuration; else per type pool rpe_hidden + a tensor-core contraction
-        if self.fused_ok:
+        if self.fused_ok and self.nz_mode != "batched_tc":
             call("lpf_nz_pairs", C.byref(self.nz_args), st, meta=(bs,))
         else:
             for t, (w1, b1, g, b, mp, cvec) in enumerate(self.rpe):
@@ -179,10 +180,11 @@ class ScorePlan:
         call("lpf_gather_links", ptr(links), bs, ptr(self.nz), bs, ptr(X), X.stride(0), d, ptr(self.xsum),
              self.xsum.stride(0), None, 0, n_dev, self.tab_bf16, st)
         gemm(self.xsum, w["wl"], w["bl"], 2.0, self.Q, bs, HC, d, n_dev)
-        call("lpf_attend_fused", None, bs, ptr(self.nz), bs, ptr(self.node), ptr(self.kv), self.kv.stride(0),
+        call("lpf_attend_fused_ws", None, bs, ptr(self.nz), bs, ptr(self.node), ptr(self.kv), self.kv.stride(0),
              ptr(self.R), self.R.stride(0), ptr(self.Q), self.Q.stride(0), ptr(w["att"]), ptr(w["abias"]),
              ptr(w["pn_w"]), ptr(w["pn_b"]), self.H, self.C, self.mode, 1, ptr(self.feats), self.feats.stride(0), None,
-             n_dev, ptr(self.seg_start), ptr(self.counts), cap, self.tab_bf16, st, meta=(bs, 0, HC))
+             n_dev, ptr(self.seg_start), ptr(self.counts), cap, self.tab_bf16, ptr(self.att_ws), self.att_ws.numel(), st,
+             meta=(bs, 0, HC))
         gemm(self.feats, w["p1"], w["pb1"], 1.0, self.hid, bs, pd, pd, n_dev)
         call("lpf_layernorm_act", ptr(self.hid), self.hid.stride(0), ptr(w["pln_w"]), ptr(w["pln_b"]), None, 0,
              ptr(self.hid), self.hid.stride(0), bs, pd, 1, n_dev, st)
@@ -235,6 +237,11 @@ class ScorePlan:
             # 13 k non-empty links, 140 vs 186 us at 3 k)
             self.nz_mode = "fused" if (h[3] < self.model.nz_fused_share * self.bs and
                                        h[3] <= self.model.nz_fused_max_links) else "batched"
+            # hundreds of thousands of selected pairs (dense graphs: ogbl-ppa shape, 540 k per 32,565-link batch): the FFMA
+            # pair stage streams its d x d matrix through shared memory once per pair (0.8 ns per pair); the hidden
+            # vectors written out and contracted on the tensor cores cost less from here on
+            if self.nz_mode == "batched" and h[0] + h[1] + h[2] > self.model.nz_pairs_tc_min:
+                self.nz_mode = "batched_tc"
         return bool(h[4])
 
     def run(self, links):

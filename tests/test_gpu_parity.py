@@ -758,3 +758,86 @@ def test_bf16_node_tables_within_1e2_of_float64():
     model._plans.clear()
     assert torch.equal(model.score_links(links, X, score), ref)
 
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("workload", ["ppa", "collab"])
+def test_attention_of_giant_links_split_over_the_grid(workload):
+    """Links with thousands of selected pairs (two hubs of a dense graph: ogbl-ppa's largest pair shares 29,513 common
+    neighbours) leave the first attention launch and are walked chunk by chunk by many CTAs (lpf_attend_fused_ws:
+    partial softmax states merged by the CTA that completes the last chunk).  Hubs 0 / 1 / 2 share 3,000 / 1,500 / 1,100
+    neighbours pairwise (12, 6 and 5 chunks), hub 3 stays below the split (700: the CTA-wide walk); logits against the
+    float64 oracle at 1e-4, through score_links (sync-free plan where the width has one) and calc_pairwise."""
+    import lpformer_b200 as L
+    from lpformer_b200 import synthetic as S
+    cfg = dict(S.CONFIGS[workload])
+    n = 6000
+    rng = np.random.default_rng(5)
+    base = S.chung_lu_edges(n, 20000, 3)
+    hubs = [np.stack([np.full(k, h), 10 + np.arange(k)]) for h, k in ((0, 3000), (1, 3000), (2, 1500), (3, 700))]
+    hubs.append(np.stack([np.full(1100, 2), 3000 + np.arange(1100)]))          # hub 2 also reaches 3000..4099
+    hubs.append(np.stack([np.full(1100, 1), 3000 + np.arange(1100)]))          # and hub 1 too: (1, 2) share 1,500 + 1,100
+    e = np.concatenate([base] + hubs, 1)
+    e = np.stack([e.min(0), e.max(0)])
+    e = e[:, e[0] != e[1]]
+    key = np.unique(e[0].astype(np.int64) * n + e[1])
+    edges = np.stack([key // n, key % n])
+    indptr, indices = S.symmetric_csr(edges, n)
+    ppr = S.ppr_push(indptr, indices, 0.15, 1e-4)
+    x = rng.standard_normal((n, cfg["feat"]), dtype=np.float32)
+    g = S.SyntheticGraph(workload, cfg, n, edges, edges[:, :8], indptr, indices, ppr, x)
+    targs = S.train_args_of(cfg)
+    dev = torch.device("cuda:0")
+    torch.manual_seed(11)
+    model = L.LinkTransformer(targs, g.data_dict(dev), device=dev).to(dev).eval()
+    score = L.mlp_score(model.out_dim, model.out_dim, 1, 2).to(dev).eval()
+    with torch.no_grad():
+        for p in list(model.parameters()) + list(score.parameters()):
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    special = np.array([[0, 0, 1, 0, 3, 1], [1, 2, 2, 3, 2, 0]])
+    links_np = np.concatenate([special, rng.integers(0, n, (2, 400)), edges[:, rng.integers(0, edges.shape[1], 100)],
+                               special[::-1]], 1).astype(np.int64)
+    links = torch.from_numpy(links_np).to(dev)
+    X = model.propagate()
+    logit = model.score_links(links, X, score, return_logits=True).cpu().numpy()
+    pw, _ = model.calc_pairwise(links, X)
+    P = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in model.state_dict().items()}
+    Sd = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in score.state_dict().items()}
+    adj_o = O.CSR(g.indptr, g.indices, None, g.n)
+    ppr_o = O.CSR(g.ppr[0], g.ppr[1], g.ppr[2], g.n)
+    feats, (mode, sets), counts, _ = O.link_features(links_np, X.cpu().numpy().astype(np.float64), adj_o, ppr_o, P, dict(targs))
+    ref_logit, _ = O.mlp_score(feats, Sd)
+    total = counts[:, :3].sum(1) if counts.shape[1] >= 3 else counts.sum(1)
+    assert total[0] >= 3000 and total[1] >= 1500 and total[2] >= 2600 and 256 < total[3] <= 1024, total[:6]
+    d = cfg["dim"]
+    np.testing.assert_allclose(pw.cpu().numpy(), feats[:, d:], rtol=FP32_RTOL, atol=2e-5)
+    np.testing.assert_allclose(logit, ref_logit, rtol=FP32_RTOL, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_plan_pair_stage_on_tensor_cores_for_large_pair_counts():
+    """Batches with hundreds of thousands of selected pairs (dense graphs) switch the plan's RPE stage from the FFMA
+    pair kernel (lpf_nz_pairs) to rpe_hidden + tensor-core contractions with device-side sizes ("batched_tc"); forced
+    here by the threshold, scores against the host-sized path."""
+    import lpformer_b200 as L
+    from lpformer_b200 import synthetic as S
+    g = S.make_graph("ppa", seed=6, scale=0.004, heldout=256)
+    targs = S.train_args_of(g.cfg)
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    model = L.LinkTransformer(targs, g.data_dict(dev), device=dev).to(dev).eval()
+    score = L.mlp_score(model.out_dim, model.out_dim, 1, 2).to(dev).eval()
+    X = model.propagate()
+    batches = [torch.from_numpy(S.heart_queries(g, 6, 200, seed=s).astype(np.int64)).to(dev) for s in range(3)]
+    model.use_plans = False
+    ref = [model.score_links(b, X, score, return_logits=True).cpu().numpy() for b in batches]
+    model.use_plans = True
+    model.nz_fused_share = 0.0          # never the one-warp-per-link kernel
+    model.nz_pairs_tc_min = 0
+    for rep in range(2):
+        for b, r in zip(batches, ref):
+            out = model.score_links(b, X, score, return_logits=True).cpu().numpy()
+            np.testing.assert_allclose(out, r, rtol=5e-5, atol=1e-5)
+    plan = next(iter(model._plans.values()))
+    assert plan.nz_mode == "batched_tc" and "batched_tc" in plan.graphs and sum(plan.stats()["pairs"]) > 0
