@@ -334,6 +334,13 @@ def run_b200(args):
     timed_host = torch.cat([torch.from_numpy(l) for l in host_links[args.warmup:]], dim=1).pin_memory()
     out_host = torch.empty(timed_host.shape[1], dtype=torch.float32).pin_memory()
     scorer.score(warm_links)
+    prewarmed = scorer.plans is None
+    if prewarmed:
+        # host-sized path (no plans: d = 128 / 256 or a threshold of 0 on the 1-hop / >1-hop sets): every batch allocates
+        # pair-sized buffers (gigabytes on the ogbl-ddi shape) through torch's caching allocator, and a batch larger than
+        # any before costs cudaMallocs inside the timed region (measured: 21 vs 8 ms per step).  One untimed pass over the
+        # timed batches brings the allocator to the steady state the >= 200-batch e2e loop measures in anyway.
+        scorer.score(timed_dev)
     barrier()
     if sampler:
         sampler.mark()           # (started long ago; no idle gap here — the GPU would drop its clocks)
@@ -525,6 +532,12 @@ def run_b200(args):
         if not args.no_cpu_baseline:
             cpu_base = cpu_baseline(args, g, negs, model, score, X, targs)
 
+        table_gb = (g.indices.nbytes + g.ppr[1].nbytes * 2 + 2 * g.n * d * 4) / 1e9
+        l2_policy = "distinct link batch every step; node/graph tables (%.2f GB) %s the 126 MB L2" % (
+            table_gb, "exceed" if table_gb > 0.126 else "FIT in (the per-batch pair buffers, %.2f GB, do not)"
+            % (sel_stats["pairs_per_link"] * nlinks * 2 * d * 4 / 1e9))
+        if prewarmed:
+            l2_policy += "; host-sized path: one untimed pass over the timed batches first (allocator steady state)"
         line = {"metric": "scored links/sec", "value": value, "unit": "links/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -532,8 +545,7 @@ def run_b200(args):
                            "scale": args.scale, "graph": g.stats(), "queries_per_step_per_gpu": nq,
                            "links_per_step_per_gpu": nlinks, "dim": d, "mode": model.mask, "node_table_dtype": args.node_dtype,
                            "thresholds": [cfg["thresh_cn"], cfg["thresh_1hop"], cfg["thresh_non1hop"]],
-                           "l2_policy": "distinct link batch every step; node/graph tables (%.2f GB) exceed the 126 MB L2"
-                                        % ((g.indices.nbytes + g.ppr[1].nbytes * 2 + 2 * g.n * d * 4) / 1e9),
+                           "l2_policy": l2_policy,
                            "set_stats": sel_stats, "parallelism": f"links sharded over {world} GPU(s), tables replicated"},
                 "e2e": {"value": e2e_val, "unit": "links/s", "h2d_bytes_per_step": int(host_links[0].nbytes),
                         "d2h_bytes_per_step": int(nlinks * 4), "ms_per_step": e2e_ms / args.steps},

@@ -262,7 +262,11 @@ int lpf_attend_fused(const int64_t* ptr, int64_t bs, const int32_t* idx /* NULL 
  * softmax states (running max, denominator, weighted sum) go to the workspace and the CTA that completes a link's
  * last chunk merges them.  Same results up to fp32 re-association of the softmax sums.  Links that do not fit the
  * workspace (1,024 links, (bytes - 16 KB) / (4 (2 H + 32 H ceil(C/32))) chunk records) are walked by their own CTA
- * as without a workspace. */
+ * as without a workspace.
+ * r_map / r_const: pairs whose two (quantised) PPR values are 0 — most common neighbours of a dense graph under
+ * thresh_cn = 0 have no PPR entry — share ONE relative-positional-encoding row per node type (the RPE MLP sees (0, 0),
+ * models/link_transformer.py:182-211); with a row map the caller computes R only for the other pairs (compacted) and the
+ * kernel reads the per-type constant row for the rest. */
 int64_t lpf_attend_workspace_min(void);
 int lpf_attend_fused_ws(const int64_t* ptr, int64_t bs, const int32_t* idx, int64_t n, const int32_t* node,
                         const float* KV, int64_t ld_kv, const float* R, int64_t ld_r,
@@ -271,6 +275,8 @@ int lpf_attend_fused_ws(const int64_t* ptr, int64_t bs, const int32_t* idx, int6
                         int32_t heads, int32_t ch, int mode, int write_counts,
                         float* out, int64_t ld_out, float* alpha_out,
                         const int64_t* n_dev, const int32_t* seg_start, const int32_t* seg_cnt, int64_t type_stride, int kv_bf16,
+                        const int32_t* r_map /* NULL, or [S]: pair s reads R[r_map[s]] if >= 0, else r_const[-1 - r_map[s]] */,
+                        const float* r_const /* [3, ld_r]: the RPE row of a pair with two zero PPR values, per node type */,
                         void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------- *

@@ -63,7 +63,7 @@ SIGNATURES = {
     "lpf_attend_fused": (_int, [_p, _i64, _p, _i64, _p, _p, _i64, _p, _i64, _p, _i64, _p, _p, _p, _p, _i32, _i32, _int, _int,
                                 _p, _i64, _p, _p, _p, _p, _i64, _int, _p]),
     "lpf_attend_fused_ws": (_int, [_p, _i64, _p, _i64, _p, _p, _i64, _p, _i64, _p, _i64, _p, _p, _p, _p, _i32, _i32, _int, _int,
-                                   _p, _i64, _p, _p, _p, _p, _i64, _int, _p, _i64, _p]),
+                                   _p, _i64, _p, _p, _p, _p, _i64, _int, _p, _p, _p, _i64, _p]),
     "lpf_attend_workspace_min": (_i64, []),
     "lpf_ppr_push_host": (_p, [_p, _p, _i64, C.c_double, C.c_double, _int, _p]),
     "lpf_ppr_push_slots": (_i32, [C.c_double, C.c_double]),

@@ -42,6 +42,11 @@ struct AttendParams {
     float* alpha_out;
     int kv_bf16;          // KV holds bf16 (ld_kv in elements)
     // optional workspace for links with thousands of pairs ("giant": split over the grid in a second launch)
+    // optional row map of R (pairs whose two PPR values are 0 share one RPE vector per type: dense graphs with
+    // thresh_cn = 0, where most common neighbours have no PPR entry at all): pair s reads R[r_map[s]] when r_map[s] >= 0
+    // and r_const[-1 - r_map[s]] (one row per node type) otherwise
+    const int32_t* r_map;
+    const float* r_const;
     int32_t* ws;          // [16] header (0: registered links, 1: chunk cursor), then GiantLink[kGiantCap], then the records
     int32_t pool_cap;     // chunk records the workspace holds
     int phase;            // 0: every link (giant ones registered in ws and left out); 1: the registered links, chunk by chunk
@@ -72,6 +77,7 @@ __device__ __forceinline__ void attend_link(const AttendParams& p, const int64_t
         for (int64_t s0 = seg_lo[t] + 32 * wslot; s0 < seg_hi[t]; s0 += 32 * nw) {
             const int cnt = (int)min((int64_t)32, seg_hi[t] - s0);
             const int32_t my_node = (lane < cnt) ? __ldg(p.node + s0 + lane) : 0;
+            const int32_t my_map = (p.r_map && lane < cnt) ? __ldg(p.r_map + s0 + lane) : 0;
             for (int g0 = 0; g0 < cnt; g0 += G) {
                 float v[G][H][KC], sc[G][H];
 #pragma unroll
@@ -79,6 +85,10 @@ __device__ __forceinline__ void attend_link(const AttendParams& p, const int64_t
                     const int jj = g0 + j < cnt ? g0 + j : g0;          // (a short last group repeats its first pair: weight 0)
                     const int64_t u = __shfl_sync(kFull, my_node, jj);
                     const float* rr = p.R + (s0 + jj) * p.ld_r;
+                    if (p.r_map) {
+                        const int ri = __shfl_sync(kFull, my_map, jj);
+                        rr = ri >= 0 ? p.R + (int64_t)ri * p.ld_r : p.r_const + (int64_t)(-1 - ri) * p.ld_r;
+                    }
                     if constexpr (!BF) {
                         const float* kv = p.KV + u * p.ld_kv;
 #pragma unroll
@@ -194,6 +204,10 @@ __global__ void __launch_bounds__(kAttWarps * 32) attend_kernel(const __grid_con
                 for (int64_t s = seg_lo[t]; s < seg_hi[t]; ++s) {
                     const int64_t u = __ldg(p.node + s);
                     const float* rr = p.R + s * p.ld_r;
+                    if (p.r_map) {
+                        const int ri = __ldg(p.r_map + s);
+                        rr = ri >= 0 ? p.R + (int64_t)ri * p.ld_r : p.r_const + (int64_t)(-1 - ri) * p.ld_r;
+                    }
                     float mean_alpha = 0.f;
 #pragma unroll
                     for (int h = 0; h < H; ++h) {
@@ -503,7 +517,8 @@ extern "C" int lpf_attend_fused_ws(const int64_t* ptr, int64_t bs, const int32_t
                                    const float* bias, const float* ln_w, const float* ln_b, int32_t heads, int32_t ch,
                                    int mode, int write_counts, float* out, int64_t ld_out, float* alpha_out,
                                    const int64_t* n_dev, const int32_t* seg_start, const int32_t* seg_cnt,
-                                   int64_t type_stride, int kv_bf16, void* workspace, int64_t workspace_bytes, void* stream) {
+                                   int64_t type_stride, int kv_bf16, const int32_t* r_map, const float* r_const,
+                                   void* workspace, int64_t workspace_bytes, void* stream) {
     LPF_REQUIRE(bs >= 0 && n >= 0, "negative batch size");
     LPF_REQUIRE(idx || n == bs, "n must equal bs when idx is NULL");
     if (n == 0) return LPF_OK;
@@ -514,10 +529,11 @@ extern "C" int lpf_attend_fused_ws(const int64_t* ptr, int64_t bs, const int32_t
     const int cd = !write_counts ? 0 : (mode == LPF_MODE_CN ? 1 : (mode == LPF_MODE_1HOP ? 3 : 4));
     LPF_REQUIRE(ld_kv >= hc && ld_q >= hc && ld_out >= hc + cd, "leading dimension too small");
     LPF_REQUIRE(R == nullptr || ld_r >= hc, "ld_r too small");
+    LPF_REQUIRE(r_map == nullptr || (r_const != nullptr && R != nullptr), "r_map needs r_const and R");
     LPF_REQUIRE(workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
     // node / R may be NULL only if every set is empty; the kernel never dereferences them then.
     AttendParams p{ptr, bs, idx, n, n_dev, seg_start, seg_cnt, type_stride, node, KV, ld_kv, R, ld_r, Q, ld_q, att, bias, ln_w, ln_b,
-                   heads, ch, mode, write_counts, out, ld_out, alpha_out, kv_bf16 ? 1 : 0,
+                   heads, ch, mode, write_counts, out, ld_out, alpha_out, kv_bf16 ? 1 : 0, r_map, r_const,
                    workspace_bytes >= lpf_attend_workspace_min() ? static_cast<int32_t*>(workspace) : nullptr, 0, 0};
     cudaStream_t st = (cudaStream_t)stream;
     switch (heads) {
@@ -541,6 +557,6 @@ extern "C" int lpf_attend_fused(const int64_t* ptr, int64_t bs, const int32_t* i
                                 const int64_t* n_dev, const int32_t* seg_start, const int32_t* seg_cnt,
                                 int64_t type_stride, int kv_bf16, void* stream) {
     return lpf_attend_fused_ws(ptr, bs, idx, n, node, KV, ld_kv, R, ld_r, Q, ld_q, att, bias, ln_w, ln_b, heads, ch, mode,
-                               write_counts, out, ld_out, alpha_out, n_dev, seg_start, seg_cnt, type_stride, kv_bf16, nullptr, 0,
-                               stream);
+                               write_counts, out, ld_out, alpha_out, n_dev, seg_start, seg_cnt, type_stride, kv_bf16, nullptr,
+                               nullptr, nullptr, 0, stream);
 }

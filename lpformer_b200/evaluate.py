@@ -295,9 +295,14 @@ class LinkScoreStream:
                         out_host[k * bs:k * bs + pr.numel()].copy_(pr)
             finally:
                 self.model.use_plans = use
-            if any(k < nb for k in redo):     # larger pools for the batches to come
-                for P in self.plans:
-                    P.grow()
+            full = [k for k in redo if k < nb]
+            if full:                          # larger pools for the batches to come: grown until a batch that overflowed fits
+                probe = links[:, full[0] * bs:(full[0] + 1) * bs].to(self.dev)
+                while True:
+                    for P in self.plans:
+                        P.grow()
+                    if self.plans[0].cap >= 64 * bs or not self.plans[0].run(probe)[1]:
+                        break
             main.synchronize()
         return out_dev
 

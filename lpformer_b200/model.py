@@ -347,6 +347,7 @@ class LinkTransformer(nn.Module):
         self._tab16 = None
         self.nz_fused_share = float(os.environ.get("LPF_NZ_FUSED_SHARE", 1.0 / 16))
         self.nz_fused_max_links = int(os.environ.get("LPF_NZ_FUSED_MAX_LINKS", 8192))
+        self.rpe_map_min_pairs = int(os.environ.get("LPF_RPE_MAP_MIN_PAIRS", 1 << 18))   # pairs per batch: (0, 0) pairs share an RPE row
         self.nz_pairs_tc_min = int(os.environ.get("LPF_NZ_PAIRS_TC_MIN", 150000))   # pairs per batch: RPE stage on the tensor cores
 
     # ------------------------------------------------------------------ graph tables
@@ -563,10 +564,37 @@ class LinkTransformer(nn.Module):
         derived = self._get_derived()
         kvs = self._get_kv(X_node)
 
+        # Pairs whose two PPR values are 0 see the RPE MLP at (0, 0): one row per node type instead of one per pair.  On
+        # dense graphs with thresh_cn = 0 (ogbl-ddi shape: 285 common neighbours per link, 45 PPR entries per row) that
+        # is most of the pairs, so large batches compute R only for the others and hand K4 a row map.  (Two more host
+        # reads on this host-sized path; the rows are bit-identical either way: every row of rpe_hidden / gemm_tc is
+        # computed on its own.)
+        r_map = r_const = None
+        pa, pb, bounds = sel.src_ppr, sel.tgt_ppr, sel.bounds
+        if S >= self.rpe_map_min_pairs:
+            live = (pa != 0) | (pb != 0)
+            keep = torch.nonzero(live).reshape(-1)                      # host read 1: its size
+            if keep.numel() <= S // 2:
+                cb = torch.searchsorted(keep, torch.tensor(bounds, dtype=torch.int64, device=dev)).tolist()   # host read 2
+                r_map = torch.cumsum(live, 0, dtype=torch.int32) - 1
+                for t in range(3):
+                    r0, r1 = bounds[t], bounds[t + 1]
+                    if r1 > r0:
+                        r_map[r0:r1].masked_fill_(~live[r0:r1], -1 - t)
+                pa, pb, bounds = pa[keep].contiguous(), pb[keep].contiguous(), tuple(cb)
+        Sc = bounds[3]
+        csel = sel if r_map is None else ops.Selection(sel.mode, sel.bs, sel.ptr, sel.node, pa, pb, None, bounds, sel.nz)
+
         # RPE hidden vectors (shared by all layers)
-        hsum = torch.empty((S, d), dtype=torch.float32, device=dev)
+        hsum = torch.empty((Sc, d), dtype=torch.float32, device=dev)
         for t, enc in enumerate(self._encoders()):
-            ops.rpe_hidden(sel, t, enc.linears[0].weight, enc.linears[0].bias, enc.norm.weight, enc.norm.bias, hsum)
+            ops.rpe_hidden(csel, t, enc.linears[0].weight, enc.linears[0].bias, enc.norm.weight, enc.norm.bias, hsum)
+        if r_map is not None:       # the hidden vector of (0, 0), per type
+            zsel = ops.Selection(sel.mode, 1, sel.ptr, sel.node, torch.zeros(3, device=dev), torch.zeros(3, device=dev), None,
+                                 (0, 1, 2, 3), None)
+            h0 = torch.zeros((3, d), dtype=torch.float32, device=dev)
+            for t, enc in enumerate(self._encoders()):
+                ops.rpe_hidden(zsel, t, enc.linears[0].weight, enc.linears[0].bias, enc.norm.weight, enc.norm.bias, h0)
 
         xsum, _ = ops.gather_links(batch, X_node, want_sum=True, want_prod=False, idx=idx)   # e1 + e2 of layer 0
         alpha = torch.empty(S, dtype=torch.float32, device=dev) if want_alpha else None
@@ -580,15 +608,20 @@ class LinkTransformer(nn.Module):
                 Q = ops.linear(xsum, att.lin_l.weight, att.lin_l.bias, bias_scale=2.0)
             else:   # e1, e2 = chunk(2) of the previous layer's output (reference modules/layers.py:211)
                 Q = ops.linear(feats, derived[l]["w_l_cat"], att.lin_l.bias, bias_scale=2.0)
-            R = torch.empty((S, HC), dtype=torch.float32, device=dev)
+            R = torch.empty((Sc, HC), dtype=torch.float32, device=dev)
+            if r_map is not None:
+                r_const = torch.zeros((3, HC), dtype=torch.float32, device=dev)
             for t, (m, c) in enumerate(derived[l]["rpe"]):
-                r0, r1 = sel.type_range(t)
+                r0, r1 = csel.type_range(t)
                 if r1 > r0:
                     ops.linear(hsum[r0:r1], m, c, out=R[r0:r1])
+                if r_map is not None:
+                    ops.linear(h0[t:t + 1], m, c, out=r_const[t:t + 1])
             width = HC + (self.count_dim if last else 0)
             feats = torch.empty((n, width), dtype=torch.float32, device=dev)
             ops.attend(sel, kvs[l], R, Q, att.att, att.bias, layer.post_att_norm.weight, layer.post_att_norm.bias,
-                       H, C, write_counts=last, out=feats, alpha_out=alpha if last else None, idx=idx)
+                       H, C, write_counts=last, out=feats, alpha_out=alpha if last else None, idx=idx,
+                       r_map=r_map, r_const=r_const)
         return self.pairwise_lin(feats, out=out), alpha
 
     def _node_tables(self, X_node, kv):

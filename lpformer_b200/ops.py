@@ -367,9 +367,11 @@ def rpe_hidden(sel: Selection, t: int, w1, b1, ln_w, ln_b, hsum):
 ATTEND_WS_BYTES = 4 << 20     # chunk records of the grid-wide split of giant links (lpf_attend_fused_ws)
 
 
-def attend(sel: Selection, KV, R, Q, att, bias, ln_w, ln_b, heads, ch, write_counts, out, alpha_out=None, idx=None):
-    """K4 over every link of the batch, or over the batch positions in idx (rows of Q / out follow idx)."""
-    require_cuda(KV, R, Q, out, idx)
+def attend(sel: Selection, KV, R, Q, att, bias, ln_w, ln_b, heads, ch, write_counts, out, alpha_out=None, idx=None,
+           r_map=None, r_const=None):
+    """K4 over every link of the batch, or over the batch positions in idx (rows of Q / out follow idx).  With r_map
+    (int32 [S]) R holds only the rows of the pairs the map points to; the others read r_const [3, H*C] by type."""
+    require_cuda(KV, R, Q, out, idx, r_map, r_const)
     n = sel.bs if idx is None else idx.numel()
     # links with thousands of pairs are split over the grid through a workspace (lpf_attend_fused_ws)
     ws = torch.empty(ATTEND_WS_BYTES, dtype=torch.uint8, device=KV.device)
@@ -377,7 +379,8 @@ def attend(sel: Selection, KV, R, Q, att, bias, ln_w, ln_b, heads, ch, write_cou
          ptr(R) if sel.total > 0 else None, R.stride(0) if R is not None and R.dim() == 2 else heads * ch,
          ptr(Q), Q.stride(0), ptr(att), ptr(bias), ptr(ln_w), ptr(ln_b), heads, ch, MODE[sel.mode],
          int(write_counts), ptr(out), out.stride(0), ptr(alpha_out), None, None, None, 0,
-         int(KV.dtype == torch.bfloat16), ptr(ws), ws.numel(), stream(), meta=(n, sel.total, heads * ch))
+         int(KV.dtype == torch.bfloat16), ptr(r_map), ptr(r_const), ptr(ws), ws.numel(), stream(),
+         meta=(n, sel.total, heads * ch))
     return out
 
 

@@ -183,7 +183,7 @@ class ScorePlan:
         call("lpf_attend_fused_ws", None, bs, ptr(self.nz), bs, ptr(self.node), ptr(self.kv), self.kv.stride(0),
              ptr(self.R), self.R.stride(0), ptr(self.Q), self.Q.stride(0), ptr(w["att"]), ptr(w["abias"]),
              ptr(w["pn_w"]), ptr(w["pn_b"]), self.H, self.C, self.mode, 1, ptr(self.feats), self.feats.stride(0), None,
-             n_dev, ptr(self.seg_start), ptr(self.counts), cap, self.tab_bf16, ptr(self.att_ws), self.att_ws.numel(), st,
+             n_dev, ptr(self.seg_start), ptr(self.counts), cap, self.tab_bf16, None, None, ptr(self.att_ws), self.att_ws.numel(), st,
              meta=(bs, 0, HC))
         gemm(self.feats, w["p1"], w["pb1"], 1.0, self.hid, bs, pd, pd, n_dev)
         call("lpf_layernorm_act", ptr(self.hid), self.hid.stride(0), ptr(w["pln_w"]), ptr(w["pln_b"]), None, 0,

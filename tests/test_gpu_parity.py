@@ -348,6 +348,17 @@ def test_score_links_wide_dims_vs_oracle(workload, scale, nq, negs):
         assert mode == "1-hop" and counts[:, 0].mean() > 20            # dense graph: tens of common neighbours per link
     np.testing.assert_allclose(logit, ref_logit, rtol=FP32_RTOL, atol=1e-5)
     np.testing.assert_allclose(prob, ref_prob, rtol=FP32_RTOL, atol=1e-6)
+    # pairs with two zero PPR values sharing one RPE row per type (the row map of lpf_attend_fused_ws; large batches
+    # only by default): the same bits, with attention weights
+    pw0, aw0 = model.calc_pairwise(links, X, return_weights=True)
+    model.rpe_map_min_pairs = 0
+    logit_map = model.score_links(links, X, score, return_logits=True).cpu().numpy()
+    pw1, aw1 = model.calc_pairwise(links, X, return_weights=True)
+    model.rpe_map_min_pairs = 1 << 18
+    zero_share = float(((sets["cn"][2] == 0) & (sets["cn"][3] == 0)).mean())
+    if workload == "ddi":
+        assert zero_share > 0.5            # the map is really in use
+    assert np.array_equal(logit_map, logit) and torch.equal(pw0, pw1) and torch.equal(aw0, aw1), zero_share
     # the GCN itself at these widths against the float64 oracle
     adj_w = O.CSR(g.indptr, g.indices, np.ones(g.indices.size), g.n)
     Xo = O.propagate(g.x.astype(np.float64), adj_w, P, dict(targs))
