@@ -529,7 +529,7 @@ extern "C" int lpf_attend_fused_ws(const int64_t* ptr, int64_t bs, const int32_t
     const int cd = !write_counts ? 0 : (mode == LPF_MODE_CN ? 1 : (mode == LPF_MODE_1HOP ? 3 : 4));
     LPF_REQUIRE(ld_kv >= hc && ld_q >= hc && ld_out >= hc + cd, "leading dimension too small");
     LPF_REQUIRE(R == nullptr || ld_r >= hc, "ld_r too small");
-    LPF_REQUIRE(r_map == nullptr || (r_const != nullptr && R != nullptr), "r_map needs r_const and R");
+    LPF_REQUIRE(r_map == nullptr || r_const != nullptr, "r_map needs r_const");      // (R may be NULL: no mapped row at all)
     LPF_REQUIRE(workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
     // node / R may be NULL only if every set is empty; the kernel never dereferences them then.
     AttendParams p{ptr, bs, idx, n, n_dev, seg_start, seg_cnt, type_stride, node, KV, ld_kv, R, ld_r, Q, ld_q, att, bias, ln_w, ln_b,
