@@ -67,7 +67,7 @@ constexpr int kAttHeavy = 256;     // a link with more pairs than this is walked
 // come in with one coalesced read, then the G gathered K/V rows and RPE rows are all in flight before the first score
 // is reduced (one pair at a time, every pair paid its own DRAM / L2 round trip), one running-max update per group.
 // `wslot` / `nw`: this warp takes the blocks of 32 pairs wslot, wslot + nw, ... of every type.
-template <int H, int KC, int G, bool BF>
+template <int H, int KC, int G, bool BF, bool MAP>
 __device__ __forceinline__ void attend_link(const AttendParams& p, const int64_t (&seg_lo)[3], const int64_t (&seg_hi)[3],
                                             const float (&q)[H][KC], const float (&att)[H][KC], int lane, int wslot, int nw,
                                             float (&mx)[H], float (&den)[H], float (&acc)[H][KC]) {
@@ -77,7 +77,8 @@ __device__ __forceinline__ void attend_link(const AttendParams& p, const int64_t
         for (int64_t s0 = seg_lo[t] + 32 * wslot; s0 < seg_hi[t]; s0 += 32 * nw) {
             const int cnt = (int)min((int64_t)32, seg_hi[t] - s0);
             const int32_t my_node = (lane < cnt) ? __ldg(p.node + s0 + lane) : 0;
-            const int32_t my_map = (p.r_map && lane < cnt) ? __ldg(p.r_map + s0 + lane) : 0;
+            int32_t my_map = 0;
+            if constexpr (MAP) my_map = (lane < cnt) ? __ldg(p.r_map + s0 + lane) : 0;
             for (int g0 = 0; g0 < cnt; g0 += G) {
                 float v[G][H][KC], sc[G][H];
 #pragma unroll
@@ -85,7 +86,7 @@ __device__ __forceinline__ void attend_link(const AttendParams& p, const int64_t
                     const int jj = g0 + j < cnt ? g0 + j : g0;          // (a short last group repeats its first pair: weight 0)
                     const int64_t u = __shfl_sync(kFull, my_node, jj);
                     const float* rr = p.R + (s0 + jj) * p.ld_r;
-                    if (p.r_map) {
+                    if constexpr (MAP) {
                         const int ri = __shfl_sync(kFull, my_map, jj);
                         rr = ri >= 0 ? p.R + (int64_t)ri * p.ld_r : p.r_const + (int64_t)(-1 - ri) * p.ld_r;
                     }
@@ -333,8 +334,9 @@ __global__ void __launch_bounds__(kAttWarps * 32) attend_kernel(const __grid_con
 #pragma unroll
                     for (int k = 0; k < KC; ++k) acc[h][k] = 0.f;
                 }
-                if (p.kv_bf16) attend_link<H, KC, G, true>(p, lo, hi, q, att, lane, warp, kAttWarps, mx, den, acc);
-                else attend_link<H, KC, G, false>(p, lo, hi, q, att, lane, warp, kAttWarps, mx, den, acc);
+                if (p.r_map) { if (p.kv_bf16) attend_link<H, KC, G, true, true>(p, lo, hi, q, att, lane, warp, kAttWarps, mx, den, acc); else attend_link<H, KC, G, false, true>(p, lo, hi, q, att, lane, warp, kAttWarps, mx, den, acc); }
+            else if (p.kv_bf16) attend_link<H, KC, G, true, false>(p, lo, hi, q, att, lane, warp, kAttWarps, mx, den, acc);
+            else attend_link<H, KC, G, false, false>(p, lo, hi, q, att, lane, warp, kAttWarps, mx, den, acc);
 #pragma unroll
                 for (int h = 0; h < H; ++h) {
 #pragma unroll
@@ -429,8 +431,9 @@ __global__ void __launch_bounds__(kAttWarps * 32) attend_kernel(const __grid_con
 #pragma unroll
                 for (int k = 0; k < KC; ++k) acc[h][k] = 0.f;
             }
-            if (p.kv_bf16) attend_link<H, KC, G, true>(p, seg_lo, seg_hi, q, att, lane, 0, 1, mx, den, acc);
-            else attend_link<H, KC, G, false>(p, seg_lo, seg_hi, q, att, lane, 0, 1, mx, den, acc);
+            if (p.r_map) { if (p.kv_bf16) attend_link<H, KC, G, true, true>(p, seg_lo, seg_hi, q, att, lane, 0, 1, mx, den, acc); else attend_link<H, KC, G, false, true>(p, seg_lo, seg_hi, q, att, lane, 0, 1, mx, den, acc); }
+            else if (p.kv_bf16) attend_link<H, KC, G, true, false>(p, seg_lo, seg_hi, q, att, lane, 0, 1, mx, den, acc);
+            else attend_link<H, KC, G, false, false>(p, seg_lo, seg_hi, q, att, lane, 0, 1, mx, den, acc);
             finish(j, q, seg_lo, seg_hi, mx, den, acc);
         }
         // the heavy links of the slice, one after the other, all warps together
@@ -444,8 +447,9 @@ __global__ void __launch_bounds__(kAttWarps * 32) attend_kernel(const __grid_con
 #pragma unroll
                 for (int k = 0; k < KC; ++k) acc[h][k] = 0.f;
             }
-            if (p.kv_bf16) attend_link<H, KC, G, true>(p, seg_lo, seg_hi, q, att, lane, warp, kAttWarps, mx, den, acc);
-            else attend_link<H, KC, G, false>(p, seg_lo, seg_hi, q, att, lane, warp, kAttWarps, mx, den, acc);
+            if (p.r_map) { if (p.kv_bf16) attend_link<H, KC, G, true, true>(p, seg_lo, seg_hi, q, att, lane, warp, kAttWarps, mx, den, acc); else attend_link<H, KC, G, false, true>(p, seg_lo, seg_hi, q, att, lane, warp, kAttWarps, mx, den, acc); }
+            else if (p.kv_bf16) attend_link<H, KC, G, true, false>(p, seg_lo, seg_hi, q, att, lane, warp, kAttWarps, mx, den, acc);
+            else attend_link<H, KC, G, false, false>(p, seg_lo, seg_hi, q, att, lane, warp, kAttWarps, mx, den, acc);
 #pragma unroll
             for (int h = 0; h < H; ++h) {
 #pragma unroll

@@ -12,9 +12,10 @@ for r in rows[1:]:
     v=float(r[vi].replace(',','')); u=r[ui]
     v = v/1e3 if u=='ns' else (v*1e3 if u=='ms' else v)
     seq.append((name,v))
-idx=[i for i,(n,_) in enumerate(seq) if 'link_heads' in n]
+idx=[i for i,(n,_) in enumerate(seq) if 'link_heads' in n and ', 0>' in n]      # the all-links heads launch opens a step
 tot=0
-for n,v in seq[idx[-1]:idx[-1]+9]:
+for n,v in seq[idx[-1]:]:
+    if 'elementwise' in n or 'at::' in n: continue
     print("%-50s %.1f us"%(n[:50],v)); tot+=v
 print("sum %.1f us"%tot)
 PY
