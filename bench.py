@@ -498,6 +498,8 @@ def run_b200(args):
             m = re.search(r"\((\w+)", top_name)                 # "entry point/part (kernel, ...)" -> kernel
             kname = m.group(1) if m else top_name.replace("lpf_", "") + "_kernel"
             traffic = json.load(open(tpath)).get(kname) if grouped else None
+        # (a shape whose node / graph tables fit the 126 MB L2 — ogbl-ddi: 4.4 MB of K/V rows — serves its gathers from L2:
+        # `achieved` then counts L2-served bytes and `frac` relates them to the HBM peak for reference only)
         roof = {"bound": "hbm", "kernel": top_name, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
                 "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": avg_ms,
                 "share_of_kernel_time": top_ms / sum(t for _, _, t in kern)}

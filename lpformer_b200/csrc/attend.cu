@@ -10,6 +10,11 @@
 //   out_i = LN( sum_s softmax_s(sc)_h v_s[h,:] + bias )     (empty set -> LN(bias))
 // The softmax is evaluated online (running max / sum), which is the same quantity as the
 // reference's max-subtracted form exp(sc-max)/(sum+1e-16).
+//
+// lpf_attend_fused_ws adds two things for dense graphs: a link with more than kAttGiant pairs is registered in a caller-owned
+// workspace by the first launch and walked by a second launch of the same kernel (phase 1), kGiantChunk pairs per CTA,
+// the partial softmax states merged by the CTA that completes the link's last chunk; and an optional row map of R, through
+// which the pairs whose two PPR values are 0 read one shared RPE row per node type (AttendParams::r_map / r_const).
 #include "common.cuh"
 
 namespace lpf {
